@@ -1,0 +1,212 @@
+/*
+ * mqgan_b200.h — C ABI of libmqgan_b200.so, the sm_100a (B200) kernels behind the
+ * PreEncoder re-encode path of ZDisket/MQGAN.
+ *
+ * The reference has no FFI: every op on this path is a PyTorch/ATen call inside
+ * preencoder.py / attentions.py / quantizer.py.  Each entry point below names the
+ * reference call site(s) (file:line under the reference root) whose arithmetic it
+ * replaces.  All pointers are DEVICE pointers unless marked host; the caller owns
+ * every buffer (inputs, outputs, workspace) and passes the CUDA stream to launch
+ * on.  Functions return 0 on success, non-zero on error (1 = bad argument,
+ * 2 = CUDA error, 3 = unsupported device); mq_last_error() returns a
+ * thread-local message.  Nothing throws across this boundary and the library
+ * keeps no per-call global state (re-entrant across per-GPU workers).
+ *
+ * Layouts are channel-last everywhere: 1-D activations (B, T, C); refiner
+ * activations (B, T', F, C).  "row_mask" arrays are uint8, one byte per (b, t)
+ * row at that tensor's time resolution, 1 = padded (the reference's x_mask,
+ * preencoder.py:15-24).
+ */
+#ifndef MQGAN_B200_H_
+#define MQGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mq_stream_t; /* cudaStream_t */
+
+#define MQ_MAX_TAPS 9
+#define MQ_MAX_SEGS 6
+
+/* ---- library ------------------------------------------------------------- */
+int mq_version(void);                 /* 10000*major + 100*minor + patch */
+const char* mq_last_error(void);      /* thread-local, never NULL */
+/* 0 if the current device is sm_100 (B200); 3 otherwise. */
+int mq_device_check(void);
+int mq_sm_count(void);
+
+/* ---- K1/K3/K4/K9/K10/K11: implicit-GEMM convolution on tcgen05 ------------ */
+/*
+ * out[n,h,w,co] = epi( sum_tap sum_seg sum_c  in[n, h+dh[tap], w+dw[tap], a_coff[seg]+c]
+ *                                           * wpack[co, ((tap*nseg+seg)*kchunks*64 + c)] )
+ * Zero padding comes from TMA out-of-bounds fill.  bf16 operands, fp32 accumulate
+ * in TMEM.  nseg = 1 is a plain bf16 convolution; nseg = 6 with the input stored
+ * as three bf16 terms [x0|x1|x2] along channels is the fp32-grade "bf16x3" mode
+ * (products x0w0,x0w1,x1w0,x0w2,x1w1,x2w0).
+ *
+ * Replaces: F.linear preencoder.py:433,486,490; F.conv1d attentions.py:532,533,541
+ * (same padding) and :471-474 (causal); F.conv2d preencoder.py:97-98; with the
+ * following element-wise tail fused: bias; masked_fill attentions.py:536-537,547-548,
+ * preencoder.py:101; APTx attentions.py:34-35; residual adds attentions.py:545,
+ * preencoder.py:99-100.
+ *
+ * epilogue:  v = acc + bias[co]
+ *            if res_mode == 1: v += res           (ResidualBlock1D: before mask/act)
+ *            if mask_pre  && row_mask[n*H+h]: v = 0
+ *            if act: v = (1 + tanh(beta v)) * gamma * v
+ *            if res_mode == 2: v += res           (ConvBlock: y + x after act)
+ *            if mask_post && row_mask[n*H+h]: v = 0
+ */
+typedef struct mq_conv_params {
+  /* input activation: bf16, (N, H, W, in_ld) channel-last, in_ld = channel pitch */
+  const void* in;
+  int N, H, W;
+  int in_ld;
+  /* packed weights: bf16 [cout_pad][K], K = taps*nseg*kchunks*64, K-major */
+  const void* wpack;
+  int cout;      /* real output channels */
+  int cout_pad;  /* rows of wpack: multiple of bn */
+  int bn;        /* N tile: multiple of 32, <= 256 */
+  int taps, nseg, kchunks;
+  int tap_dh[MQ_MAX_TAPS];
+  int tap_dw[MQ_MAX_TAPS];
+  int a_coff[MQ_MAX_SEGS];
+  int bh, bw;    /* pixel tile, bh*bw <= 128 */
+  /* epilogue */
+  const float* bias;       /* [cout] or NULL */
+  const uint8_t* row_mask; /* [N*H] or NULL */
+  int mask_pre, mask_post;
+  int act;                 /* 0 none, 1 APTx */
+  int fast_tanh;           /* 1: tanh.approx, 0: ~1e-7 abs-error tanh */
+  float beta, gamma;
+  int res_mode;            /* 0 none, 1 before mask/act, 2 after act */
+  const void* res;         /* (N,H,W,res_ld) */
+  int res_is_bf16, res_ld, res_coff;
+  float* out_f32;  int f32_ld, f32_coff;      /* optional fp32 output */
+  void* out_bf16;  int bf16_ld, bf16_coff;    /* optional bf16 output */
+  void* out_split; int split_ld, split_seg;   /* optional bf16x3 output: term j at channel j*split_seg + co */
+} mq_conv_params;
+
+int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream);
+
+/* ---- input staging: fp32 -> bf16 / bf16x3 (feeds K1) ---------------------- */
+/* x (rows, C) fp32 -> out (rows, nterms*C) bf16, term j at [j*C, (j+1)*C). nterms in {1,3}. */
+int mq_split_bf16(const float* x, void* out, int64_t rows, int C, int nterms, mq_stream_t stream);
+
+/* ---- K2: ConvBlock2D `pre` / `post` (preencoder.py:277-301) ---------------- */
+/*
+ * x (B, T, C) -> y (B, T, C):  s = dw5x5 over the (channel, time) plane (+bias),
+ * zero at padded rows; y = sum_k wout[k] * aptx(wpw[k]*s + bpw[k]; 1, .5) + bout,
+ * and y = bout at padded rows.  The (B, C, C, T) expansion of the reference
+ * (preencoder.py:288-295) is never materialised.
+ * dw: 25 floats [i over channel][j over time] then the dw bias (26 total, folded
+ * weight-norm); pw: C x {wpw, bpw, wout} interleaved as float4-padded triples.
+ */
+typedef struct mq_cb2d_params {
+  const void* x; int x_is_bf16;   /* fp32 or bf16 input */
+  int B, T, C;
+  const float* dw;                /* [26] */
+  const float* pw;                /* [C][4]: wpw, bpw, wout, 0 */
+  float bout;
+  const uint8_t* row_mask;        /* [B*T] or NULL */
+  int fast_tanh;
+  float* out_f32;                 /* optional (B,T,C) */
+  void* out_bf16;                 /* optional (B,T,C) */
+  void* out_split;                /* optional (B,T,3C) bf16x3 */
+} mq_cb2d_params;
+int mq_convblock2d(const mq_cb2d_params* p, mq_stream_t stream);
+
+/* ---- K5/K6: CBAM1D (attentions.py:217-273, 310-365, 393-419) + block tail --- */
+/* pass 1: per (b, c) max over ALL t (quirk App. B1) and masked sum over valid t,
+ * deterministic two-stage reduction.  o (B,T,C) fp32; part: workspace
+ * [B][nchunk][2][C] fp32 with nchunk = mq_cam_chunks(T). */
+int mq_cam_chunks(int T);
+int mq_cam_reduce(const float* o, const uint8_t* row_mask, int B, int T, int C, float* part,
+                  mq_stream_t stream);
+/* pass 1b: finish the reduction, shared MLP on max and mean, sigmoid -> gate (B,C).
+ * w0 (R,C), b0 (R), w2 (C,R), b2 (C). */
+int mq_cam_gate(const float* part, const uint8_t* row_mask, int B, int T, int C, int R,
+                const float* w0, const float* b0, const float* w2, const float* b2, float* gate,
+                mq_stream_t stream);
+/* pass 2: SAM pools (max / mean over C of gate*o, unmasked), conv k7 (no bias),
+ * sigmoid; y = aptx(mask(sam*gate*o + o + r); beta, gamma)   (attentions.py:545-549).
+ * r: residual (B,T,C) fp32.  Outputs: y fp32 and/or bf16 / bf16x3. */
+typedef struct mq_cbam_apply_params {
+  const float* o; const float* gate; const float* res;
+  const uint8_t* row_mask;
+  int B, T, C;
+  const float* sam_w;  /* [2][7] */
+  float beta, gamma;
+  float* out_f32; void* out_bf16; void* out_split;
+} mq_cbam_apply_params;
+int mq_cbam_apply(const mq_cbam_apply_params* p, mq_stream_t stream);
+
+/* ---- K7: q_in_proj + FSQ (preencoder.py:448-451, quantizer.py:109-114,137,177-181) */
+/* y (rows, C) fp32 -> z = y W^T + b (fp32 FMA), bound/round-half-even/mixed-radix
+ * index -> idx int64 (rows).  Optionally also writes z (rows, D) fp32.  D <= 8.
+ * half_l / shift / offset / half_w / basis: host arrays of D entries. */
+typedef struct mq_fsq_params {
+  int D;
+  float half_l[8], shift[8], offset[8];
+  int half_w[8], basis[8], levels[8];
+} mq_fsq_params;
+int mq_qin_fsq(const float* y, int64_t rows, int C, const float* w, const float* b,
+               const mq_fsq_params* fsq, int64_t* idx, float* z_out, mq_stream_t stream);
+/* FSQ alone on latents z (rows, D): the quantizer.py eval path. */
+int mq_fsq_quantize(const float* z, int64_t rows, const mq_fsq_params* fsq, int64_t* idx,
+                    float* codes_out, mq_stream_t stream);
+
+/* ---- K8: indices_to_codes + q_out_proj as a table gather (quantizer.py:183-205,
+ *          preencoder.py:464-466) -------------------------------------------- */
+/* table (n_codes, C) fp32 = q_out_proj(implicit_codebook); idx (rows) int64;
+ * out (rows, C) bf16 and/or fp32.  Indices outside [0, n_codes) are an error flag
+ * written to *bad (device int, optional) and the row is zero-filled. */
+int mq_code_gather(const int64_t* idx, int64_t rows, const float* table, int n_codes, int C,
+                   void* out_bf16, float* out_f32, int* bad, mq_stream_t stream);
+
+/* ---- a19/K13: refiner masks and resampling ---------------------------------- */
+/* mask (B,T) -> all refiner masks.  Level l has H_l = T8 >> l rows per batch
+ * element, T8 = T rounded up to a multiple of 2^depth.  Both outputs are flat
+ * uint8 buffers holding levels 0..depth back to back; level l starts at byte
+ * offset B * sum_{j<l} H_j  (total B * sum_l H_l bytes each).
+ *   down[0]   = mask padded with ones to T8             (preencoder.py:29-47)
+ *   down[l]   = max-pool(2) of down[l-1]                (preencoder.py:63-65)
+ *   up[depth] = down[depth];  up[l] = nearest-up(2) of up[l+1]   (preencoder.py:68-70)
+ * mask may be NULL (= all valid, preencoder.py:471-472). */
+int mq_refiner_masks(const uint8_t* mask, int B, int T, int depth, uint8_t* down, uint8_t* up,
+                     mq_stream_t stream);
+/* AvgPool2d((2,1)) + masked_fill by the pooled mask (preencoder.py:111-114, :96).
+ * x (B, H, F, C) bf16 -> y (B, H/2, F, C) bf16; mask_out (B*H/2). */
+int mq_avgpool_mask(const void* x, void* y, const uint8_t* mask_out, int B, int H, int F, int C,
+                    mq_stream_t stream);
+/* Upsample((2,1), nearest) + cat([up, skip], channel) + masked_fill (preencoder.py:123-130, :96).
+ * x (B, H/2, F, Cx), skip (B, H, F, Cs) -> y (B, H, F, Cx+Cs) bf16. */
+int mq_upcat_mask(const void* x, const void* skip, void* y, const uint8_t* mask_out, int B, int H,
+                  int F, int Cx, int Cs, mq_stream_t stream);
+
+/* ---- K12: thin refiner convolutions --------------------------------------- */
+/* refiner.pre.conv1 (1 -> C, 3x3, pad 1) + APTx on the masked, T-padded refiner
+ * input (preencoder.py:172-175, 96-97).  r (B, T, F) fp32 = cat[x_recon, hidden];
+ * w (C, 9) folded, b (C).  y (B, T8, F, C) bf16. */
+int mq_refiner_stem(const float* r, const uint8_t* mask, int B, int T, int T8, int F, int C,
+                    const float* w, const float* b, int fast_tanh, void* y, mq_stream_t stream);
+/* refiner.post (C -> 1, 3x3) + crop + mask + reproj (F -> M, no bias) + x_recon add
+ * (preencoder.py:191-200, 499).  x (B, T8, F, C) bf16 (already masked), w (9, C)
+ * folded (tap = 3*(dt+1) + (df+1)), reproj_t (F, M) = reproj.weight transposed;
+ * r (B, T, F) fp32 whose first M columns are x_recon; mask (B*T) or NULL;
+ * out (B, T, M) fp32 = x_post. */
+int mq_refiner_tail(const void* x, const uint8_t* mask, int B, int T, int T8, int F, int C,
+                    const float* w, float bias, const float* reproj_t, int M, const float* r,
+                    float* out, mq_stream_t stream);
+
+/* ---- sequence mask (preencoder.py:15-24) ----------------------------------- */
+int mq_sequence_mask(const int64_t* lengths, int B, int T, uint8_t* mask, mq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MQGAN_B200_H_ */

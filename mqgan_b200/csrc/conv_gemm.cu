@@ -1,0 +1,484 @@
+// Implicit-GEMM convolution on tcgen05 / TMEM, fed by TMA.  One kernel serves every
+// dense contraction of the PreEncoder path:
+// a convolution is a sum over filter taps of shifted GEMMs; the shift is a TMA box
+// coordinate and the zero padding is TMA's out-of-bounds fill, so no im2col buffer
+// and no padded copy of the activation ever exists.
+//
+// Shape of one CTA tile: M = 128 output pixels (a bh x bw patch of the (H, W) grid
+// of one batch element, pixels on TMEM lanes), N = bn output channels (TMEM
+// columns), K = taps * nseg * kchunks * 64 bf16.  Persistent CTAs (one per SM),
+// warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+// tcgen05.mma issuer, warps 2-5 = epilogue (tcgen05.ld -> bias / mask / APTx /
+// residual -> global).  The accumulator is double-buffered in TMEM (2 x 256
+// columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/mqgan_b200.h"
+#include "common.cuh"
+
+namespace mq {
+
+constexpr int kBlockK = 64;                 // bf16 per K block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;                  // K per tcgen05.mma (kind::f16)
+constexpr int kTileM = 128;                 // UMMA M, cta_group::1
+constexpr int kThreads = 192;               // 6 warps
+constexpr int kEpiThreads = 128;
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;             // TMEM columns per accumulator buffer
+constexpr int kATileBytes = kTileM * kBlockK * 2;   // 16 KiB
+constexpr int kSmemBudget = 227 * 1024;
+
+struct ConvArgs {
+  int N, H, W;
+  int tiles_h, tiles_w, tiles_n, num_tiles;
+  int bh, bw, bn, cout;
+  int taps, nseg, kchunks;
+  int tap_dh[MQ_MAX_TAPS], tap_dw[MQ_MAX_TAPS], a_coff[MQ_MAX_SEGS];
+  int stages;
+  uint32_t a_tx_bytes, b_tile_bytes;
+  // epilogue
+  const float* bias;
+  const uint8_t* row_mask;
+  int mask_pre, mask_post, act, res_mode;
+  float beta, gamma;
+  const void* res;
+  int res_is_bf16, res_ld, res_coff;
+  float* out_f32;
+  int f32_ld, f32_coff;
+  __nv_bfloat16* out_bf16;
+  int bf16_ld, bf16_coff;
+  __nv_bfloat16* out_split;
+  int split_ld, split_seg;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void decode_tile(const ConvArgs& a, int tile, int& n_idx, int& h0,
+                                            int& w0, int& n0) {
+  int tn = tile % a.tiles_n;
+  int tm = tile / a.tiles_n;
+  int tw = tm % a.tiles_w;
+  int t2 = tm / a.tiles_w;
+  int th = t2 % a.tiles_h;
+  n_idx = t2 / a.tiles_h;
+  h0 = th * a.bh;
+  w0 = tw * a.bw;
+  n0 = tn * a.bn;
+}
+
+template <bool kFast>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                 const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment (in the shared window).
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const int stages = a.stages;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + stages * kATileBytes;
+  uint8_t* tail = smem_b + stages * a.b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [2][256]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);     // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_s, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int kblocks = a.taps * a.nseg * a.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        int n_idx, h0, w0, n0;
+        decode_tile(a, tile, n_idx, h0, w0, n0);
+        int kb = 0;
+        for (int tap = 0; tap < a.taps; ++tap) {
+          const int hh = h0 + a.tap_dh[tap];
+          const int ww = w0 + a.tap_dw[tap];
+          for (int seg = 0; seg < a.nseg; ++seg) {
+            const int cbase = a.a_coff[seg];
+            for (int kc = 0; kc < a.kchunks; ++kc, ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], a.a_tx_bytes + a.b_tile_bytes);
+              tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * kATileBytes,
+                          cbase + kc * kBlockK, ww, hh, n_idx);
+              tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * a.b_tile_bytes,
+                          kb * kBlockK, n0);
+              if (++stage == stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kTileM, a.bn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kAccStride;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
+          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * a.b_tile_bytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[buf]);         // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps) =====================
+    const int q = warp & 3;                   // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;              // accumulator row == pixel within the tile
+    const int lh = r / a.bw;
+    const int lw = r - lh * a.bw;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      int n_idx, h0, w0, n0;
+      decode_tile(a, tile, n_idx, h0, w0, n0);
+      const uint32_t buf = it & 1;
+      float* bs = bias_s + buf * 256;
+      for (int j = et; j < a.bn; j += kEpiThreads)
+        bs[j] = (a.bias != nullptr && n0 + j < a.cout) ? a.bias[n0 + j] : 0.0f;
+      named_bar_sync(1, kEpiThreads);
+
+      const int h = h0 + lh, w = w0 + lw;
+      const bool valid = (r < a.bh * a.bw) && (h < a.H) && (w < a.W);
+      const int64_t row = static_cast<int64_t>(n_idx) * a.H + h;
+      const int64_t pix = row * a.W + w;
+      const bool masked = valid && a.row_mask != nullptr && a.row_mask[row] != 0;
+
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride;
+
+      for (int c = 0; c < a.bn; c += 32) {
+        uint32_t v[32];
+        __syncwarp();                         // tcgen05.ld is .sync.aligned: reconverge first
+        tmem_ld_32x32(t_row + c, v);
+        tmem_ld_wait();
+        const int co0 = n0 + c;
+        if (!valid || co0 >= a.cout) continue;
+        const int nvalid = min(32, a.cout - co0);
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + bs[c + j];
+
+        float rr[32];
+        if (a.res_mode != 0) {
+          if (a.res_is_bf16) {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) +
+                                      pix * a.res_ld + a.res_coff + co0;
+            if (nvalid == 32) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 u = *reinterpret_cast<const uint4*>(rp + 8 * g);
+                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(b2[e]);
+                  rr[8 * g + 2 * e] = f.x;
+                  rr[8 * g + 2 * e + 1] = f.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) rr[j] = j < nvalid ? __bfloat162float(rp[j]) : 0.0f;
+            }
+          } else {
+            const float* rp = reinterpret_cast<const float*>(a.res) + pix * a.res_ld + a.res_coff + co0;
+            if (nvalid == 32) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                float4 f = *reinterpret_cast<const float4*>(rp + 4 * g);
+                rr[4 * g] = f.x; rr[4 * g + 1] = f.y; rr[4 * g + 2] = f.z; rr[4 * g + 3] = f.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) rr[j] = j < nvalid ? rp[j] : 0.0f;
+            }
+          }
+        }
+        if (a.res_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] += rr[j];
+        }
+        if (a.mask_pre && masked) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+        }
+        if (a.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = aptx<kFast>(x[j], a.beta, a.gamma);
+        }
+        if (a.res_mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] += rr[j];
+        }
+        if (a.mask_post && masked) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+        }
+
+        if (a.out_f32 != nullptr) {
+          float* op = a.out_f32 + pix * a.f32_ld + a.f32_coff + co0;
+          if (nvalid == 32) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(op + 4 * g) =
+                  make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) op[j] = x[j];
+          }
+        }
+        if (a.out_bf16 != nullptr) {
+          __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
+          if (nvalid == 32) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_bf16x2(x[8 * g], x[8 * g + 1]);
+              u.y = pack_bf16x2(x[8 * g + 2], x[8 * g + 3]);
+              u.z = pack_bf16x2(x[8 * g + 4], x[8 * g + 5]);
+              u.w = pack_bf16x2(x[8 * g + 6], x[8 * g + 7]);
+              *reinterpret_cast<uint4*>(op + 8 * g) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) op[j] = __float2bfloat16_rn(x[j]);
+          }
+        }
+        if (a.out_split != nullptr) {
+          __nv_bfloat16* op = a.out_split + pix * a.split_ld + co0;
+          if (nvalid == 32) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat16 a0, a1, a2, b0, b1, b2;
+                split3(x[8 * g + 2 * e], a0, a1, a2);
+                split3(x[8 * g + 2 * e + 1], b0, b1, b2);
+                w0[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a0)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(b0)) << 16);
+                w1[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a1)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
+                w2[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a2)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(b2)) << 16);
+              }
+              *reinterpret_cast<uint4*>(op + 8 * g) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+              *reinterpret_cast<uint4*>(op + a.split_seg + 8 * g) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+              *reinterpret_cast<uint4*>(op + 2 * a.split_seg + 8 * g) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) {
+                __nv_bfloat16 a0, a1, a2;
+                split3(x[j], a0, a1, a2);
+                op[j] = a0;
+                op[a.split_seg + j] = a1;
+                op[2 * a.split_seg + j] = a2;
+              }
+          }
+        }
+      }
+      // all TMEM reads of this buffer are complete (tcgen05.wait::ld above)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int conv_smem_bytes(int stages, int b_tile_bytes) {
+  return 1024 /*alignment slack*/ + stages * (kATileBytes + b_tile_bytes) +
+         (2 * kMaxStages + 4) * 8 + 16 + 2 * 256 * 4;
+}
+
+}  // namespace mq
+
+using namespace mq;
+
+extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MQ_REQUIRE(p != nullptr, "mq_conv_gemm: null params");
+  MQ_REQUIRE(p->in && p->wpack, "mq_conv_gemm: null in/wpack");
+  MQ_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "mq_conv_gemm: bad N/H/W %d %d %d", p->N, p->H, p->W);
+  MQ_REQUIRE(p->bn >= 32 && p->bn <= 256 && p->bn % 32 == 0, "mq_conv_gemm: bn=%d must be a multiple of 32 in [32,256]", p->bn);
+  MQ_REQUIRE(p->cout > 0 && p->cout_pad >= p->cout && p->cout_pad % p->bn == 0, "mq_conv_gemm: cout=%d cout_pad=%d bn=%d", p->cout, p->cout_pad, p->bn);
+  MQ_REQUIRE(p->taps >= 1 && p->taps <= MQ_MAX_TAPS, "mq_conv_gemm: taps=%d", p->taps);
+  MQ_REQUIRE(p->nseg >= 1 && p->nseg <= MQ_MAX_SEGS, "mq_conv_gemm: nseg=%d", p->nseg);
+  MQ_REQUIRE(p->kchunks >= 1, "mq_conv_gemm: kchunks=%d", p->kchunks);
+  MQ_REQUIRE(p->bh >= 1 && p->bw >= 1 && p->bh * p->bw <= kTileM && p->bh <= 256 && p->bw <= 256, "mq_conv_gemm: tile %dx%d", p->bh, p->bw);
+  MQ_REQUIRE(p->in_ld % 8 == 0, "mq_conv_gemm: in_ld=%d must be a multiple of 8 (16-byte TMA strides)", p->in_ld);
+  MQ_REQUIRE((reinterpret_cast<uintptr_t>(p->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->wpack) & 15) == 0, "mq_conv_gemm: in/wpack must be 16-byte aligned");
+  MQ_REQUIRE(p->out_f32 || p->out_bf16 || p->out_split, "mq_conv_gemm: no output");
+  MQ_REQUIRE(p->res_mode == 0 || p->res != nullptr, "mq_conv_gemm: res_mode without res");
+  MQ_REQUIRE(!(p->mask_pre || p->mask_post) || p->row_mask != nullptr, "mq_conv_gemm: mask flag without row_mask");
+  if (p->out_f32) MQ_REQUIRE(p->f32_ld % 4 == 0 && p->f32_coff % 4 == 0, "mq_conv_gemm: f32 ld/coff must be multiples of 4");
+  if (p->out_bf16) MQ_REQUIRE(p->bf16_ld % 8 == 0 && p->bf16_coff % 8 == 0, "mq_conv_gemm: bf16 ld/coff must be multiples of 8");
+  if (p->out_split) MQ_REQUIRE(p->split_ld % 8 == 0 && p->split_seg % 8 == 0, "mq_conv_gemm: split ld/seg must be multiples of 8");
+  if (p->res_mode) MQ_REQUIRE(p->res_ld % 8 == 0 && p->res_coff % 8 == 0, "mq_conv_gemm: res ld/coff must be multiples of 8");
+
+  EncodeTiledFn encode = get_encode_fn();
+  MQ_REQUIRE(encode != nullptr, "mq_conv_gemm: cuTensorMapEncodeTiled not available from the driver");
+
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = p->N; a.H = p->H; a.W = p->W;
+  a.bh = p->bh; a.bw = p->bw; a.bn = p->bn; a.cout = p->cout;
+  a.tiles_h = (p->H + p->bh - 1) / p->bh;
+  a.tiles_w = (p->W + p->bw - 1) / p->bw;
+  a.tiles_n = p->cout_pad / p->bn;
+  const long long nt = 1LL * p->N * a.tiles_h * a.tiles_w * a.tiles_n;
+  MQ_REQUIRE(nt < (1LL << 31), "mq_conv_gemm: too many tiles");
+  a.num_tiles = static_cast<int>(nt);
+  a.taps = p->taps; a.nseg = p->nseg; a.kchunks = p->kchunks;
+  for (int i = 0; i < MQ_MAX_TAPS; ++i) { a.tap_dh[i] = p->tap_dh[i]; a.tap_dw[i] = p->tap_dw[i]; }
+  for (int i = 0; i < MQ_MAX_SEGS; ++i) a.a_coff[i] = p->a_coff[i];
+  a.a_tx_bytes = static_cast<uint32_t>(p->bh * p->bw * kBlockK * 2);
+  a.b_tile_bytes = static_cast<uint32_t>(p->bn * kBlockK * 2);
+  int stages = (kSmemBudget - 1024 - 4096) / (kATileBytes + static_cast<int>(a.b_tile_bytes));
+  if (stages > kMaxStages) stages = kMaxStages;
+  MQ_REQUIRE(stages >= 2, "mq_conv_gemm: not enough shared memory for 2 stages");
+  a.stages = stages;
+  a.bias = p->bias; a.row_mask = p->row_mask;
+  a.mask_pre = p->mask_pre; a.mask_post = p->mask_post; a.act = p->act; a.res_mode = p->res_mode;
+  a.beta = p->beta; a.gamma = p->gamma;
+  a.res = p->res; a.res_is_bf16 = p->res_is_bf16; a.res_ld = p->res_ld; a.res_coff = p->res_coff;
+  a.out_f32 = p->out_f32; a.f32_ld = p->f32_ld; a.f32_coff = p->f32_coff;
+  a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16); a.bf16_ld = p->bf16_ld; a.bf16_coff = p->bf16_coff;
+  a.out_split = reinterpret_cast<__nv_bfloat16*>(p->out_split); a.split_ld = p->split_ld; a.split_seg = p->split_seg;
+
+  // --- tensor maps ---
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(p->in_ld), static_cast<cuuint64_t>(p->W),
+                          static_cast<cuuint64_t>(p->H), static_cast<cuuint64_t>(p->N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(p->in_ld) * 2,
+                             static_cast<cuuint64_t>(p->W) * p->in_ld * 2,
+                             static_cast<cuuint64_t>(p->H) * p->W * p->in_ld * 2};
+    cuuint32_t box[4] = {kBlockK, static_cast<cuuint32_t>(p->bw), static_cast<cuuint32_t>(p->bh), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->in), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MQ_REQUIRE(r == CUDA_SUCCESS, "mq_conv_gemm: cuTensorMapEncodeTiled(A) failed with %d (in_ld=%d W=%d H=%d N=%d)", (int)r, p->in_ld, p->W, p->H, p->N);
+  }
+  {
+    const cuuint64_t K = static_cast<cuuint64_t>(p->taps) * p->nseg * p->kchunks * kBlockK;
+    cuuint64_t dims[2] = {K, static_cast<cuuint64_t>(p->cout_pad)};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(p->bn)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->wpack), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MQ_REQUIRE(r == CUDA_SUCCESS, "mq_conv_gemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+
+  int dev = 0, sms = 0;
+  MQ_CUDA_OK(cudaGetDevice(&dev));
+  MQ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int smem = conv_smem_bytes(stages, static_cast<int>(a.b_tile_bytes));
+  const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+  if (p->fast_tanh) {
+    MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv_gemm_kernel<true><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+  } else {
+    MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv_gemm_kernel<false><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+  }
+  MQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}

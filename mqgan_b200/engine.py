@@ -1,0 +1,352 @@
+"""Kernel schedule of the PreEncoder re-encode pass on one B200.
+
+``PreEncoderEngine`` packs a reference state-dict once (weight-norm folded, conv
+weights in the tcgen05 kernel's K order, bf16 / bf16x3 split, FSQ code table) and
+then runs ``encode`` / ``decode`` as a fixed sequence of C-ABI launches on the
+caller's CUDA stream.  Op order follows the reference exactly
+(preencoder.py:420-504); what differs is layout (channel-last
+everywhere, so the reference's permutes vanish) and fusion (bias / mask / APTx /
+residual live in the GEMM epilogues; ConvBlock2D's C-fold expansion is never
+materialised).
+
+Precision modes
+  encoder "bf16x3": every encoder GEMM runs as six bf16 products of 3-term splits
+      (24 significant bits per operand, fp32 accumulate in TMEM) and all
+      element-wise encoder math is fp32 -> indices equal the fp32 reference except
+      within rounding distance of an FSQ boundary.
+  encoder "bf16": single bf16 pass (index agreement rate is reported, not exact).
+  decoder: bf16 operands, fp32 accumulate, bf16 activations between layers.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .ops import PackedConv, pack_conv
+from .spec import PreEncoderConfig
+
+
+def _fold(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """w = g * v / ||v||_2 over all dims but 0 (weight_norm, dim=0)."""
+    try:
+        return torch._weight_norm(v.float(), g.float(), 0)
+    except Exception:  # pragma: no cover - private op missing
+        n = v.float().reshape(v.shape[0], -1).norm(dim=1).reshape(g.shape)
+        return v.float() * (g.float() / n)
+
+
+def folded_weights(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Plain weights from either weight-norm flavour or already-stripped keys."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, t in sd.items():
+        t = t.detach().cpu()
+        if k.endswith(".parametrizations.weight.original1"):
+            base = k[: -len(".parametrizations.weight.original1")]
+            out[base + ".weight"] = _fold(sd[base + ".parametrizations.weight.original0"].detach().cpu(), t)
+        elif k.endswith(".weight_v"):
+            base = k[: -len(".weight_v")]
+            out[base + ".weight"] = _fold(sd[base + ".weight_g"].detach().cpu(), t)
+        elif k.endswith("original0") or k.endswith(".weight_g"):
+            continue
+        else:
+            out[k] = t.float()
+    return out
+
+
+class _CB2D:
+    """Packed ConvBlock2D parameters (preencoder.py:251-268)."""
+
+    def __init__(self, w: Dict[str, torch.Tensor], prefix: str, device):
+        dw = torch.cat([w[prefix + ".dw.weight"].reshape(25), w[prefix + ".dw.bias"].reshape(1)])
+        c = w[prefix + ".pw.weight"].shape[0]
+        pw = torch.zeros(c, 4)
+        pw[:, 0] = w[prefix + ".pw.weight"].reshape(c)
+        pw[:, 1] = w[prefix + ".pw.bias"].reshape(c)
+        pw[:, 2] = w[prefix + ".conv_out.weight"].reshape(c)
+        self.dw = dw.float().contiguous().to(device)
+        self.pw = pw.float().contiguous().to(device)
+        self.bout = float(w[prefix + ".conv_out.bias"].reshape(()))
+        self.c = c
+
+
+class PreEncoderEngine:
+    def __init__(self, cfg: PreEncoderConfig, state_dict: Dict[str, torch.Tensor], device="cuda",
+                 encoder_precision: str = "bf16x3", max_chunk_frames: int = 32768):
+        if encoder_precision not in ("bf16x3", "bf16"):
+            raise ValueError("encoder_precision must be 'bf16x3' or 'bf16'")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("PreEncoderEngine needs a CUDA device (no CPU fallback)")
+        self.enc_split = encoder_precision == "bf16x3"
+        self.encoder_precision = encoder_precision
+        self.max_chunk_frames = int(max_chunk_frames)
+        self.fsq = ops.fsq_params(cfg.fsq_levels)
+        w = folded_weights(state_dict)
+        dev = self.device
+        sp = self.enc_split
+
+        def f32(name):
+            return w[name].float().contiguous().to(dev)
+
+        # ---------------- encoder ----------------
+        self.proj = pack_conv(w["proj.weight"], w["proj.bias"], "linear", sp).to(dev)
+        self.pre = _CB2D(w, "pre", dev)
+        self.enc = []
+        for i, (cin, cout, k) in enumerate(cfg.encoder_layers):
+            p = f"encoder_blocks.{i}"
+            blk = {
+                "cin": cin, "cout": cout,
+                "conv1": pack_conv(w[p + ".conv1.weight"], w[p + ".conv1.bias"], "same1d", sp).to(dev),
+                "conv2": pack_conv(w[p + ".conv2.weight"], w[p + ".conv2.bias"], "same1d", sp).to(dev),
+                "res": None,
+                "mlp_w0": f32(p + ".cbam.channel_attention.mlp.0.weight"),
+                "mlp_b0": f32(p + ".cbam.channel_attention.mlp.0.bias"),
+                "mlp_w2": f32(p + ".cbam.channel_attention.mlp.2.weight"),
+                "mlp_b2": f32(p + ".cbam.channel_attention.mlp.2.bias"),
+                "sam_w": w[p + ".cbam.spatial_attention.conv.weight"].reshape(14).float().contiguous().to(dev),
+                "beta": float(w[p + ".relu.beta"]), "gamma": float(w[p + ".relu.gamma"]),
+            }
+            if (p + ".residual.weight") in w:
+                blk["res"] = pack_conv(w[p + ".residual.weight"].squeeze(-1), w[p + ".residual.bias"],
+                                       "linear", sp).to(dev)
+            self.enc.append(blk)
+        self.qin_w = f32("q_in_proj.weight")
+        self.qin_b = f32("q_in_proj.bias")
+
+        # ---------------- decoder ----------------
+        # K8: indices_to_codes + q_out_proj == gather from q_out_proj(implicit_codebook)
+        n = cfg.codebook_size
+        lv = torch.tensor(cfg.fsq_levels, dtype=torch.int64)
+        basis = torch.cumprod(torch.tensor([1] + list(cfg.fsq_levels[:-1])), dim=0)
+        digits = (torch.arange(n)[:, None] // basis) % lv                 # quantizer.py:186
+        hw = lv // 2
+        codes = ((digits - hw) / hw).float()                              # quantizer.py:170
+        table = torch.nn.functional.linear(codes, w["q_out_proj.weight"].float(), w["q_out_proj.bias"].float())
+        self.code_table = table.contiguous().to(dev)
+        self.dec = []
+        for i, (cin, cout, k) in enumerate(cfg.decoder_layers):
+            p = f"decoder_blocks.{i}"
+            blk = {
+                "cin": cin, "cout": cout,
+                "conv1": pack_conv(w[p + ".conv1.weight"], w[p + ".conv1.bias"], "causal1d", False).to(dev),
+                "conv2": pack_conv(w[p + ".conv2.weight"], w[p + ".conv2.bias"], "causal1d", False).to(dev),
+                "res": None,
+                "beta": float(w[p + ".relu.beta"]), "gamma": float(w[p + ".relu.gamma"]),
+            }
+            if (p + ".residual.weight") in w:
+                blk["res"] = pack_conv(w[p + ".residual.weight"].squeeze(-1), w[p + ".residual.bias"],
+                                       "linear", False).to(dev)
+            self.dec.append(blk)
+        self.post = _CB2D(w, "post", dev)
+        self.out_proj = pack_conv(w["out_proj.weight"], w["out_proj.bias"], "linear", False).to(dev)
+        self.hidden_proj = pack_conv(w["hidden_proj.weight"], w["hidden_proj.bias"], "linear", False).to(dev)
+
+        # ---------------- refiner ----------------
+        chs = cfg.refiner_channels
+        d = cfg.refiner_depth
+        self.stem_w = w["refiner.pre.conv1.weight"].reshape(chs[0], 9).float().contiguous().to(dev)
+        self.stem_b = f32("refiner.pre.conv1.bias")
+
+        def cb(prefix, first=True):
+            out = {}
+            if first:
+                out["conv1"] = pack_conv(w[prefix + ".conv1.weight"], w[prefix + ".conv1.bias"], "conv2d3", False).to(dev)
+            out["conv2"] = pack_conv(w[prefix + ".conv2.weight"], w[prefix + ".conv2.bias"], "conv2d3", False).to(dev)
+            return out
+
+        self.ref_pre = cb("refiner.pre", first=False)
+        self.ref_downs = [cb(f"refiner.downs.{i}.conv") for i in range(d)]
+        self.ref_mid = cb("refiner.mid")
+        self.ref_ups = [cb(f"refiner.ups.{i}.conv") for i in range(d)]
+        # refiner.post: (1, C, 3, 3) -> (9, C) with tap = 3*(dt+1) + (df+1)
+        self.tail_w = w["refiner.post.weight"].reshape(chs[0], 9).t().float().contiguous().to(dev)
+        self.tail_b = float(w["refiner.post.bias"].reshape(()))
+        self.reproj_t = w["refiner.reproj.weight"].t().float().contiguous().to(dev)       # (F, M)
+
+    # ------------------------------------------------------------------
+    def _chunks(self, B: int, T: int):
+        per = max(1, self.max_chunk_frames // max(T, 1))
+        for b0 in range(0, B, per):
+            yield b0, min(B, b0 + per)
+
+    @staticmethod
+    def _mask_u8(mask: Optional[torch.Tensor], B: int, T: int, device) -> Optional[torch.Tensor]:
+        """(B,1,T) / (B,T) bool or uint8, True = padded -> contiguous uint8 (B,T) on device."""
+        if mask is None:
+            return None
+        m = mask.reshape(B, T)
+        if m.dtype != torch.uint8:
+            m = m.to(torch.uint8)
+        return m.to(device).contiguous()
+
+    # ------------------------------------------------------------------
+    def encode(self, mel: torch.Tensor, mask: Optional[torch.Tensor] = None, return_latents: bool = False,
+               taps: Optional[dict] = None):
+        """mel (B,T,n_mels) fp32 on device; mask (B,1,T)|(B,T), True = padded -> (B,T) int64."""
+        if mel.dim() != 3 or mel.shape[2] != self.cfg.mel_channels:
+            raise ValueError(f"mel must be (B, T, {self.cfg.mel_channels}), got {tuple(mel.shape)}")
+        B, T, _ = mel.shape
+        mel = mel.to(self.device, torch.float32).contiguous()
+        m8 = self._mask_u8(mask, B, T, self.device)
+        idx = torch.empty(B, T, dtype=torch.int64, device=self.device)
+        zs = torch.empty(B, T, self.cfg.quantizer_dim, dtype=torch.float32, device=self.device) if return_latents else None
+        for b0, b1 in self._chunks(B, T):
+            i, z = self._encode_chunk(mel[b0:b1], None if m8 is None else m8[b0:b1], return_latents, taps)
+            idx[b0:b1] = i
+            if return_latents:
+                zs[b0:b1] = z
+        return (idx, zs) if return_latents else idx
+
+    def _encode_chunk(self, mel, m8, want_z, taps):
+        cfg, dev, sp = self.cfg, self.device, self.enc_split
+        B, T, M = mel.shape
+        rows = B * T
+        nt = 3 if sp else 1
+
+        def act_buf(c):
+            return torch.empty(rows, nt * c, dtype=torch.bfloat16, device=dev)
+
+        def kw_out(buf):
+            return {"out_split": buf} if sp else {"out_bf16": buf}
+
+        a0 = ops.split_bf16(mel.reshape(rows, M), nt)
+        h = torch.empty(rows, cfg.c0, dtype=torch.float32, device=dev)
+        ops.conv_gemm(a0, self.proj, B, T, 1, out_f32=h)                                   # preencoder.py:433
+        x32 = torch.empty(rows, cfg.c0, dtype=torch.float32, device=dev)
+        xs = act_buf(cfg.c0)
+        ops.convblock2d(h, B, T, cfg.c0, self.pre.dw, self.pre.pw, self.pre.bout, m8, False,
+                        out_f32=x32, **kw_out(xs))                                          # :440
+        if taps is not None:
+            taps["proj"], taps["pre"] = h, x32
+        for i, blk in enumerate(self.enc):                                                  # :443-444
+            cout = blk["cout"]
+            o1 = act_buf(cout)
+            ops.conv_gemm(xs, blk["conv1"], B, T, 1, row_mask=m8, mask_pre=m8 is not None, act=True,
+                          beta=blk["beta"], gamma=blk["gamma"], fast_tanh=False, **kw_out(o1))
+            o = torch.empty(rows, cout, dtype=torch.float32, device=dev)
+            ops.conv_gemm(o1, blk["conv2"], B, T, 1, out_f32=o)
+            if blk["res"] is not None:
+                r = torch.empty(rows, cout, dtype=torch.float32, device=dev)
+                ops.conv_gemm(xs, blk["res"], B, T, 1, out_f32=r)
+            else:
+                r = x32
+            gate = ops.cam_gate(o, m8, B, T, cout, blk["mlp_w0"], blk["mlp_b0"], blk["mlp_w2"], blk["mlp_b2"])
+            y32 = torch.empty(rows, cout, dtype=torch.float32, device=dev)
+            last = i == len(self.enc) - 1
+            ys = None if last else act_buf(cout)
+            ops.cbam_apply(o, gate, r, m8, B, T, cout, blk["sam_w"], blk["beta"], blk["gamma"],
+                           out_f32=y32, **({} if last else kw_out(ys)))
+            x32, xs = y32, ys
+            if taps is not None:
+                taps[f"enc{i}"] = y32
+        out = ops.qin_fsq(x32, self.qin_w, self.qin_b, self.fsq, want_z=want_z)            # :448-451
+        if want_z:
+            return out[0].view(B, T), out[1].view(B, T, -1)
+        return out.view(B, T), None
+
+    # ------------------------------------------------------------------
+    def decode(self, indices: torch.Tensor, mask: Optional[torch.Tensor] = None, return_hidden: bool = False,
+               taps: Optional[dict] = None, return_recon: bool = False):
+        """indices (B,T) int -> x_post (B,T,n_mels) fp32 [, decoder_out (B,C0,T)] [, x_recon (B,T,n_mels)]."""
+        if indices.dim() != 2:
+            raise ValueError(f"indices must be (B, T), got {tuple(indices.shape)}")
+        B, T = indices.shape
+        idx = indices.to(self.device, torch.int64).contiguous()
+        m8 = self._mask_u8(mask, B, T, self.device)
+        out = torch.empty(B, T, self.cfg.mel_channels, dtype=torch.float32, device=self.device)
+        hid = torch.empty(B, T, self.cfg.c0, dtype=torch.float32, device=self.device) if return_hidden else None
+        recon = torch.empty_like(out) if return_recon else None
+        for b0, b1 in self._chunks(B, T):
+            h, R = self._decode_chunk(idx[b0:b1], None if m8 is None else m8[b0:b1], out[b0:b1], return_hidden, taps)
+            if return_hidden:
+                hid[b0:b1] = h
+            if return_recon:
+                recon[b0:b1] = R.view(b1 - b0, T, -1)[..., : self.cfg.mel_channels]
+        res = [out]
+        if return_hidden:
+            res.append(hid.permute(0, 2, 1))          # reference layout (B, C0, T), preencoder.py:480
+        if return_recon:
+            res.append(recon)
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def _decode_chunk(self, idx, m8, out, want_hidden, taps):
+        cfg, dev = self.cfg, self.device
+        B, T = idx.shape
+        rows = B * T
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        x, _ = ops.code_gather(idx.reshape(rows), self.code_table, bad=bad)                # preencoder.py:464-466
+        for i, blk in enumerate(self.dec):                                                  # :476-477
+            cout = blk["cout"]
+            o1 = torch.empty(rows, cout, dtype=torch.bfloat16, device=dev)
+            ops.conv_gemm(x, blk["conv1"], B, T, 1, row_mask=m8, mask_pre=m8 is not None, act=True,
+                          beta=blk["beta"], gamma=blk["gamma"], out_bf16=o1)
+            if blk["res"] is not None:
+                r = torch.empty(rows, cout, dtype=torch.bfloat16, device=dev)
+                ops.conv_gemm(x, blk["res"], B, T, 1, out_bf16=r)
+            else:
+                r = x
+            y = torch.empty(rows, cout, dtype=torch.bfloat16, device=dev)
+            ops.conv_gemm(o1, blk["conv2"], B, T, 1, row_mask=m8, mask_pre=m8 is not None, act=True,
+                          beta=blk["beta"], gamma=blk["gamma"], res=r, res_mode=1, out_bf16=y)
+            x = y
+            if taps is not None:
+                taps[f"dec{i}"] = y
+        dec_out = x
+        pz = torch.empty(rows, cfg.c0, dtype=torch.bfloat16, device=dev)
+        ops.convblock2d(dec_out, B, T, cfg.c0, self.post.dw, self.post.pw, self.post.bout, m8, True,
+                        out_bf16=pz)                                                        # :482
+        F, M = cfg.refiner_width, cfg.mel_channels
+        R = torch.empty(rows, F, dtype=torch.float32, device=dev)
+        ops.conv_gemm(pz, self.out_proj, B, T, 1, out_f32=R, f32_coff=0)                    # :486
+        ops.conv_gemm(dec_out, self.hidden_proj, B, T, 1, out_f32=R, f32_coff=M)            # :490-492
+        if taps is not None:
+            taps["refiner_in"] = R
+        self._refiner(R, m8, B, T, out, taps)                                               # :496-499
+        if int(bad.item()) != 0:
+            raise IndexError("decode: index outside [0, codebook_size)")
+        return (dec_out.view(B, T, cfg.c0).float() if want_hidden else None), R
+
+    def _refiner(self, R, m8, B, T, out, taps):
+        cfg, dev = self.cfg, self.device
+        d = cfg.refiner_depth
+        chs = cfg.refiner_channels
+        F = cfg.refiner_width
+        T8, down, up = ops.refiner_masks(m8, B, T, d, dev)
+        H = [T8 >> l for l in range(d + 1)]
+
+        def convblock(x, blk, l, mask, cin, cout, first=True):
+            if first:
+                t = torch.empty(B, H[l], F, cout, dtype=torch.bfloat16, device=dev)
+                ops.conv_gemm(x, blk["conv1"], B, H[l], F, act=True, out_bf16=t)          # preencoder.py:97
+            else:
+                t = x
+            y = torch.empty(B, H[l], F, cout, dtype=torch.bfloat16, device=dev)
+            match = first and cin == cout
+            ops.conv_gemm(t, blk["conv2"], B, H[l], F, act=True, row_mask=mask, mask_post=True,
+                          res=x if match else None, res_mode=2 if match else 0, out_bf16=y)  # :98-101
+            return y
+
+        s1 = ops.refiner_stem(R, m8, B, T, T8, F, chs[0], self.stem_w, self.stem_b, True)   # :172-175, :97
+        x = convblock(s1, self.ref_pre, 0, down[0], 1, chs[0], first=False)
+        skips = []
+        for i in range(d):                                                                  # :179-181
+            skips.append(x)
+            p = ops.avgpool_mask(x, down[i + 1], B, H[i], F, chs[i])
+            x = convblock(p, self.ref_downs[i], i + 1, down[i + 1], chs[i], chs[i + 1])
+            if taps is not None:
+                taps[f"refiner.downs.{i}"] = x
+        x = convblock(x, self.ref_mid, d, down[d], chs[d], chs[d])                          # :184
+        if taps is not None:
+            taps["refiner.mid"] = x
+        for i in range(d):                                                                  # :187-189
+            l = d - 1 - i
+            skip = skips.pop()
+            u = ops.upcat_mask(x, skip, up[l], B, H[l], F, chs[l + 1], chs[l])
+            x = convblock(u, self.ref_ups[i], l, up[l], chs[l + 1] + chs[l], chs[l])
+            if taps is not None:
+                taps[f"refiner.ups.{i}"] = x
+        ops.refiner_tail(x, m8, B, T, T8, F, chs[0], self.tail_w, self.tail_b, self.reproj_t,
+                         cfg.mel_channels, R, out=out)                                      # :191-200, :499

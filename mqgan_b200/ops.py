@@ -1,0 +1,392 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per entry point) plus
+the host-side weight packing for the tcgen05 convolution kernel.
+
+PyTorch is plumbing here: it owns device memory and the stream; every byte of
+arithmetic on the hot path happens inside libmqgan_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvParams, Cb2dParams, CbamApplyParams, FsqParams
+
+BLOCK_K = 64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (this path has no CPU fallback)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+# ---------------------------------------------------------------------------
+# weight packing for mq_conv_gemm
+# ---------------------------------------------------------------------------
+@dataclass
+class PackedConv:
+    wpack: torch.Tensor            # bf16 [cout_pad, K]
+    bias: Optional[torch.Tensor]   # fp32 [cout]
+    cin: int
+    cout: int
+    cout_pad: int
+    bn: int
+    taps: int
+    nseg: int
+    kchunks: int
+    tap_dh: List[int]
+    tap_dw: List[int]
+    a_coff: List[int]
+    split: bool
+
+    def to(self, device):
+        self.wpack = self.wpack.to(device)
+        if self.bias is not None:
+            self.bias = self.bias.to(device)
+        return self
+
+
+def split3_bf16(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """fp32 -> three bf16 terms with x0 + x1 + x2 == x (host-side weight prep)."""
+    x = x.float()
+    x0 = x.to(torch.bfloat16)
+    r = x - x0.float()
+    x1 = r.to(torch.bfloat16)
+    r = r - x1.float()
+    x2 = r.to(torch.bfloat16)
+    return x0, x1, x2
+
+
+def choose_bn(cout: int) -> Tuple[int, int]:
+    """N tile (multiple of 32, <= 256) and padded cout."""
+    if cout <= 256:
+        bn = (cout + 31) // 32 * 32
+        return bn, bn
+    best = None
+    for bn in (256, 224, 192, 160, 128):
+        pad = (cout + bn - 1) // bn * bn
+        key = (pad, -bn)
+        if best is None or key < best[0]:
+            best = (key, bn, pad)
+    return best[1], best[2]
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, split: bool,
+              in_seg_stride: Optional[int] = None) -> PackedConv:
+    """Pack a folded conv/linear weight for mq_conv_gemm.
+
+    kind: "linear" (Cout, Cin) | "same1d" / "causal1d" (Cout, Cin, k) | "conv2d3" (Cout, Cin, 3, 3).
+    split=True builds the six bf16x3 product segments; the activation is then
+    expected as [x0 | x1 | x2] along channels with term stride ``in_seg_stride``
+    (default Cin).  K order is (tap, segment, channel chunk), matching the kernel.
+    """
+    w = weight.detach().float().cpu()
+    if kind == "linear":
+        cout, cin = w.shape
+        wt = w.reshape(cout, cin, 1)
+        dh, dw = [0], [0]
+    elif kind in ("same1d", "causal1d"):
+        cout, cin, k = w.shape
+        wt = w
+        if kind == "same1d":
+            if k % 2 != 1:
+                raise ValueError("same-padded conv1d needs an odd kernel")
+            dh = [j - (k - 1) // 2 for j in range(k)]
+        else:
+            dh = [j - (k - 1) for j in range(k)]
+        dw = [0] * k
+    elif kind == "conv2d3":
+        cout, cin, kh, kw = w.shape
+        if (kh, kw) != (3, 3):
+            raise ValueError("conv2d3 expects a 3x3 kernel")
+        wt = w.reshape(cout, cin, 9)
+        dh = [i - 1 for i in range(3) for _ in range(3)]
+        dw = [j - 1 for _ in range(3) for j in range(3)]
+    else:
+        raise ValueError(kind)
+    taps = wt.shape[2]
+    if taps > _lib.MQ_MAX_TAPS:
+        raise ValueError(f"{taps} taps > MQ_MAX_TAPS")
+    kchunks = (cin + BLOCK_K - 1) // BLOCK_K
+    cpad = kchunks * BLOCK_K
+    bn, cout_pad = choose_bn(cout)
+    if split:
+        w0, w1, w2 = split3_bf16(wt)
+        seg_w = [w0, w1, w2, w0, w1, w0]          # smallest products first
+        seg_a = [2, 1, 0, 1, 0, 0]
+        stride = cin if in_seg_stride is None else in_seg_stride
+        a_coff = [t * stride for t in seg_a]
+    else:
+        seg_w = [wt.to(torch.bfloat16)]
+        a_coff = [0]
+    nseg = len(seg_w)
+    wp = torch.zeros(cout_pad, taps, nseg, cpad, dtype=torch.bfloat16)
+    for s, ws in enumerate(seg_w):
+        wp[:cout, :, s, :cin] = ws.permute(0, 2, 1)      # (cout, taps, cin)
+    wp = wp.reshape(cout_pad, taps * nseg * cpad).contiguous()
+    b = None if bias is None else bias.detach().float().cpu().contiguous()
+    return PackedConv(wp, b, cin, cout, cout_pad, bn, taps, nseg, kchunks, dh, dw,
+                      a_coff + [0] * (_lib.MQ_MAX_SEGS - len(a_coff)), split)
+
+
+def choose_tile(H: int, W: int) -> Tuple[int, int]:
+    """(bh, bw) with bh*bw <= 128 minimising out-of-bounds waste; prefers wide rows."""
+    if W == 1:
+        return 128, 1
+    best = None
+    for bw in range(1, min(W, 128) + 1):
+        bh = min(128 // bw, 256)
+        if bh < 1:
+            continue
+        covered = math.ceil(W / bw) * bw * math.ceil(H / bh) * bh
+        util = (H * W) / covered * (bh * bw / 128.0)
+        key = (-util, -bw)
+        if best is None or key < best[0]:
+            best = (key, bh, bw)
+    return best[1], best[2]
+
+
+def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
+              row_mask: Optional[torch.Tensor] = None, mask_pre=False, mask_post=False,
+              act=False, beta=1.0, gamma=0.5, fast_tanh=True,
+              res: Optional[torch.Tensor] = None, res_mode=0, res_coff=0,
+              out_f32: Optional[torch.Tensor] = None, f32_coff=0,
+              out_bf16: Optional[torch.Tensor] = None, bf16_coff=0,
+              out_split: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None) -> None:
+    """Launch mq_conv_gemm.  x: bf16 (N*H*W, in_ld) channel-last (any leading shape)."""
+    _chk(x, torch.bfloat16, "x")
+    in_ld = x.shape[-1]
+    if x.numel() != N * H * W * in_ld:
+        raise ValueError(f"x has {x.numel()} elements, expected N*H*W*in_ld = {N * H * W * in_ld}")
+    p = ConvParams()
+    p.inp = x.data_ptr()
+    p.N, p.H, p.W, p.in_ld = N, H, W, in_ld
+    p.wpack = _chk(pc.wpack, torch.bfloat16, "wpack").data_ptr()
+    p.cout, p.cout_pad, p.bn = pc.cout, pc.cout_pad, pc.bn
+    p.taps, p.nseg, p.kchunks = pc.taps, pc.nseg, pc.kchunks
+    for i in range(pc.taps):
+        p.tap_dh[i] = pc.tap_dh[i]
+        p.tap_dw[i] = pc.tap_dw[i]
+    for i in range(_lib.MQ_MAX_SEGS):
+        p.a_coff[i] = pc.a_coff[i]
+    bh, bw = tile if tile is not None else choose_tile(H, W)
+    p.bh, p.bw = bh, bw
+    p.bias = _ptr(pc.bias)
+    if row_mask is not None:
+        _chk(row_mask, torch.uint8, "row_mask")
+        if row_mask.numel() != N * H:
+            raise ValueError("row_mask must have N*H entries")
+    p.row_mask = _ptr(row_mask)
+    p.mask_pre, p.mask_post = int(mask_pre), int(mask_post)
+    p.act, p.fast_tanh = int(act), int(fast_tanh)
+    p.beta, p.gamma = float(beta), float(gamma)
+    p.res_mode = int(res_mode)
+    if res is not None:
+        if res.dtype not in (torch.bfloat16, torch.float32):
+            raise TypeError("res must be bf16 or fp32")
+        p.res = res.data_ptr()
+        p.res_is_bf16 = int(res.dtype == torch.bfloat16)
+        p.res_ld = res.shape[-1]
+        p.res_coff = res_coff
+    if out_f32 is not None:
+        _chk(out_f32, torch.float32, "out_f32")
+        p.out_f32, p.f32_ld, p.f32_coff = out_f32.data_ptr(), out_f32.shape[-1], f32_coff
+    if out_bf16 is not None:
+        _chk(out_bf16, torch.bfloat16, "out_bf16")
+        p.out_bf16, p.bf16_ld, p.bf16_coff = out_bf16.data_ptr(), out_bf16.shape[-1], bf16_coff
+    if out_split is not None:
+        _chk(out_split, torch.bfloat16, "out_split")
+        if out_split.shape[-1] % 3:
+            raise ValueError("out_split last dim must be 3*C")
+        p.out_split, p.split_ld, p.split_seg = out_split.data_ptr(), out_split.shape[-1], out_split.shape[-1] // 3
+    _lib.call("mq_conv_gemm", C.byref(p), _stream())
+
+
+# ---------------------------------------------------------------------------
+# element-wise / reduction entry points
+# ---------------------------------------------------------------------------
+def split_bf16(x: torch.Tensor, nterms: int) -> torch.Tensor:
+    _chk(x, torch.float32, "x")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    out = torch.empty(*x.shape[:-1], nterms * Cc, dtype=torch.bfloat16, device=x.device)
+    _lib.call("mq_split_bf16", x.data_ptr(), out.data_ptr(), rows, Cc, nterms, _stream())
+    return out
+
+
+def convblock2d(x: torch.Tensor, B: int, T: int, Cc: int, dw: torch.Tensor, pw: torch.Tensor, bout: float,
+                row_mask: Optional[torch.Tensor], fast_tanh: bool, *, out_f32=None, out_bf16=None,
+                out_split=None) -> None:
+    p = Cb2dParams()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("x must be fp32 or bf16")
+    p.x, p.x_is_bf16 = x.data_ptr(), int(x.dtype == torch.bfloat16)
+    p.B, p.T, p.C = B, T, Cc
+    p.dw, p.pw = _chk(dw, torch.float32, "dw").data_ptr(), _chk(pw, torch.float32, "pw").data_ptr()
+    p.bout = float(bout)
+    p.row_mask = _ptr(row_mask)
+    p.fast_tanh = int(fast_tanh)
+    p.out_f32, p.out_bf16, p.out_split = _ptr(out_f32), _ptr(out_bf16), _ptr(out_split)
+    _lib.call("mq_convblock2d", C.byref(p), _stream())
+
+
+def cam_chunks(T: int) -> int:
+    return _lib.lib().mq_cam_chunks(T)
+
+
+def cam_gate(o: torch.Tensor, row_mask: Optional[torch.Tensor], B: int, T: int, Cc: int,
+             w0, b0, w2, b2) -> torch.Tensor:
+    _chk(o, torch.float32, "o")
+    nchunk = cam_chunks(T)
+    part = torch.empty(B, nchunk, 2, Cc, dtype=torch.float32, device=o.device)
+    _lib.call("mq_cam_reduce", o.data_ptr(), _ptr(row_mask), B, T, Cc, part.data_ptr(), _stream())
+    gate = torch.empty(B, Cc, dtype=torch.float32, device=o.device)
+    _lib.call("mq_cam_gate", part.data_ptr(), _ptr(row_mask), B, T, Cc, w0.shape[0], w0.data_ptr(),
+              b0.data_ptr(), w2.data_ptr(), b2.data_ptr(), gate.data_ptr(), _stream())
+    return gate
+
+
+def cbam_apply(o, gate, res, row_mask, B, T, Cc, sam_w, beta, gamma, *, out_f32=None, out_bf16=None,
+               out_split=None) -> None:
+    p = CbamApplyParams()
+    p.o, p.gate, p.res = _chk(o, torch.float32, "o").data_ptr(), gate.data_ptr(), _chk(res, torch.float32, "res").data_ptr()
+    p.row_mask = _ptr(row_mask)
+    p.B, p.T, p.C = B, T, Cc
+    p.sam_w = _chk(sam_w, torch.float32, "sam_w").data_ptr()
+    p.beta, p.gamma = float(beta), float(gamma)
+    p.out_f32, p.out_bf16, p.out_split = _ptr(out_f32), _ptr(out_bf16), _ptr(out_split)
+    _lib.call("mq_cbam_apply", C.byref(p), _stream())
+
+
+def fsq_params(levels: Sequence[int]) -> FsqParams:
+    """FSQ constants exactly as quantizer.py:68-72,109-114,132 computes them (fp32)."""
+    f = FsqParams()
+    D = len(levels)
+    if D > 8:
+        raise ValueError("at most 8 FSQ dims")
+    lv = torch.tensor(list(levels), dtype=torch.int32)
+    half_l = (lv - 1) * (1 + 1e-3) / 2
+    offset = torch.where(lv % 2 == 0, 0.5, 0.0)
+    shift = (offset / half_l).atanh()
+    basis = torch.cumprod(torch.tensor([1] + list(levels[:-1])), dim=0)
+    f.D = D
+    for i in range(D):
+        f.half_l[i] = float(half_l[i])
+        f.offset[i] = float(offset[i])
+        f.shift[i] = float(shift[i])
+        f.half_w[i] = int(levels[i]) // 2
+        f.basis[i] = int(basis[i])
+        f.levels[i] = int(levels[i])
+    return f
+
+
+def qin_fsq(y: torch.Tensor, w: torch.Tensor, b: torch.Tensor, fsq: FsqParams, want_z=False):
+    _chk(y, torch.float32, "y")
+    Cc = y.shape[-1]
+    rows = y.numel() // Cc
+    idx = torch.empty(y.shape[:-1], dtype=torch.int64, device=y.device)
+    z = torch.empty(*y.shape[:-1], fsq.D, dtype=torch.float32, device=y.device) if want_z else None
+    _lib.call("mq_qin_fsq", y.data_ptr(), rows, Cc, _chk(w, torch.float32, "w").data_ptr(),
+              _chk(b, torch.float32, "b").data_ptr(), C.byref(fsq), idx.data_ptr(), _ptr(z), _stream())
+    return (idx, z) if want_z else idx
+
+
+def fsq_quantize(z: torch.Tensor, fsq: FsqParams, want_codes=False):
+    _chk(z, torch.float32, "z")
+    rows = z.numel() // fsq.D
+    idx = torch.empty(z.shape[:-1], dtype=torch.int64, device=z.device)
+    codes = torch.empty_like(z) if want_codes else None
+    _lib.call("mq_fsq_quantize", z.data_ptr(), rows, C.byref(fsq), idx.data_ptr(), _ptr(codes), _stream())
+    return (idx, codes) if want_codes else idx
+
+
+def code_gather(idx: torch.Tensor, table: torch.Tensor, *, bf16=True, f32=False, bad: Optional[torch.Tensor] = None):
+    _chk(idx, torch.int64, "idx")
+    _chk(table, torch.float32, "table")
+    rows, Cc = idx.numel(), table.shape[1]
+    ob = torch.empty(*idx.shape, Cc, dtype=torch.bfloat16, device=idx.device) if bf16 else None
+    of = torch.empty(*idx.shape, Cc, dtype=torch.float32, device=idx.device) if f32 else None
+    _lib.call("mq_code_gather", idx.data_ptr(), rows, table.data_ptr(), table.shape[0], Cc, _ptr(ob), _ptr(of),
+              _ptr(bad), _stream())
+    return ob, of
+
+
+def sequence_mask(lengths: torch.Tensor, T: int) -> torch.Tensor:
+    _chk(lengths, torch.int64, "lengths")
+    B = lengths.numel()
+    m = torch.empty(B, T, dtype=torch.uint8, device=lengths.device)
+    _lib.call("mq_sequence_mask", lengths.data_ptr(), B, T, m.data_ptr(), _stream())
+    return m
+
+
+def refiner_level_rows(T: int, depth: int) -> Tuple[int, List[int]]:
+    mult = 1 << depth
+    T8 = (T + mult - 1) // mult * mult
+    return T8, [T8 >> l for l in range(depth + 1)]
+
+
+def refiner_masks(mask: Optional[torch.Tensor], B: int, T: int, depth: int, device):
+    """Returns (T8, down[l], up[l]) with per-level (B, H_l) uint8 views."""
+    T8, rows = refiner_level_rows(T, depth)
+    total = B * sum(rows)
+    down = torch.empty(total, dtype=torch.uint8, device=device)
+    up = torch.empty(total, dtype=torch.uint8, device=device)
+    _lib.call("mq_refiner_masks", _ptr(mask), B, T, depth, down.data_ptr(), up.data_ptr(), _stream())
+    dl, ul, off = [], [], 0
+    for h in rows:
+        dl.append(down[off:off + B * h].view(B, h))
+        ul.append(up[off:off + B * h].view(B, h))
+        off += B * h
+    return T8, dl, ul
+
+
+def avgpool_mask(x: torch.Tensor, mask_out: Optional[torch.Tensor], B, H, F, Cc) -> torch.Tensor:
+    _chk(x, torch.bfloat16, "x")
+    y = torch.empty(B, H // 2, F, Cc, dtype=torch.bfloat16, device=x.device)
+    _lib.call("mq_avgpool_mask", x.data_ptr(), y.data_ptr(), _ptr(mask_out), B, H, F, Cc, _stream())
+    return y
+
+
+def upcat_mask(x: torch.Tensor, skip: torch.Tensor, mask_out: Optional[torch.Tensor], B, H, F, Cx, Cs) -> torch.Tensor:
+    _chk(x, torch.bfloat16, "x")
+    _chk(skip, torch.bfloat16, "skip")
+    y = torch.empty(B, H, F, Cx + Cs, dtype=torch.bfloat16, device=x.device)
+    _lib.call("mq_upcat_mask", x.data_ptr(), skip.data_ptr(), y.data_ptr(), _ptr(mask_out), B, H, F, Cx, Cs, _stream())
+    return y
+
+
+def refiner_stem(r: torch.Tensor, mask: Optional[torch.Tensor], B, T, T8, F, Cc, w, b, fast_tanh) -> torch.Tensor:
+    _chk(r, torch.float32, "r")
+    y = torch.empty(B, T8, F, Cc, dtype=torch.bfloat16, device=r.device)
+    _lib.call("mq_refiner_stem", r.data_ptr(), _ptr(mask), B, T, T8, F, Cc, w.data_ptr(), b.data_ptr(),
+              int(fast_tanh), y.data_ptr(), _stream())
+    return y
+
+
+def refiner_tail(x: torch.Tensor, mask: Optional[torch.Tensor], B, T, T8, F, Cc, w, bias: float, reproj_t, M,
+                 r: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, torch.bfloat16, "x")
+    if out is None:
+        out = torch.empty(B, T, M, dtype=torch.float32, device=x.device)
+    _lib.call("mq_refiner_tail", x.data_ptr(), _ptr(mask), B, T, T8, F, Cc, w.data_ptr(), float(bias),
+              reproj_t.data_ptr(), M, r.data_ptr(), out.data_ptr(), _stream())
+    return out

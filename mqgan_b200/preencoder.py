@@ -1,0 +1,208 @@
+"""Drop-in ``PreEncoder`` boundary (reference: preencoder.py:304-599).
+
+Same constructor, attributes, state-dict keys (both weight-norm flavours,
+SURVEY App. B4), ``encode`` / ``decode`` / ``forward`` signatures and loader as
+the reference, but the arithmetic runs in libmqgan_b200.so on a B200.  The
+module owns ordinary ``nn.Parameter``s so ``load_state_dict(strict=True)`` /
+``state_dict()`` / ``.to()`` behave as users expect; kernels read a packed copy
+that is rebuilt whenever a parameter changes.
+
+There is no CPU path: calling ``encode`` / ``decode`` on a module that is not on
+a CUDA device raises.
+"""
+from __future__ import annotations
+
+import math
+import os
+from collections import OrderedDict
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .engine import PreEncoderEngine
+from .spec import PreEncoderConfig, param_spec
+
+
+def sequence_mask(max_length, x_lengths):
+    """(B, max_length) bool, True = padded (preencoder.py:15-24)."""
+    ar = torch.arange(max_length, device=x_lengths.device)
+    return ar.unsqueeze(0) >= x_lengths.unsqueeze(1)
+
+
+class _Node(nn.Module):
+    """Bare container so dotted reference key names resolve to real parameters."""
+
+
+def _attach(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
+    parts = dotted.split(".")
+    mod = root
+    for name in parts[:-1]:
+        nxt = mod._modules.get(name)
+        if nxt is None:
+            nxt = _Node()
+            mod.add_module(name, nxt)
+        mod = nxt
+    mod.register_parameter(parts[-1], param)
+
+
+class PreEncoder(nn.Module):
+    def __init__(self, mel_channels, channels, kernel_sizes, fsq_levels=[8, 8, 5, 5, 5], dropout=0.1,
+                 refiner_base_channels=128, refiner_depth=3, refiner_hidden_proj_divisor=8,
+                 encoder_precision: str = "bf16x3"):
+        super().__init__()
+        self.cfg = PreEncoderConfig(int(mel_channels), tuple(channels), tuple(kernel_sizes), tuple(fsq_levels),
+                                    int(refiner_base_channels), int(refiner_depth),
+                                    int(refiner_hidden_proj_divisor))
+        self.dropout_p = dropout            # eval-only path: dropout is the identity
+        self.encoder_precision = encoder_precision
+        # attributes the reference exposes (preencoder.py:323, 337-341, 355)
+        self.quantizer_dim = self.cfg.quantizer_dim
+        self.codebook_size = self.cfg.codebook_size
+        self.bos_token_id = self.codebook_size + 1
+        self.eos_token_id = self.codebook_size + 2
+        self.refiner_hidden_channels = self.cfg.refiner_hidden_channels
+        spec = param_spec(self.cfg)
+        shapes = dict(spec)
+        for key, shape in spec:
+            _attach(self, key, nn.Parameter(self._init(key, shape, shapes)))
+        # weight-norm g starts as ||v|| (what weight_norm does when it wraps a conv)
+        with torch.no_grad():
+            sd = dict(self.named_parameters())
+            for key, _ in spec:
+                if key.endswith("original0"):
+                    v = sd[key[: -len("original0")] + "original1"]
+                elif key.endswith("weight_g"):
+                    v = sd[key[: -len("weight_g")] + "weight_v"]
+                else:
+                    continue
+                sd[key].copy_(v.reshape(v.shape[0], -1).norm(dim=1).reshape(sd[key].shape))
+        self._engine: Optional[PreEncoderEngine] = None
+        self._engine_key = None
+        self.eval()
+
+    @staticmethod
+    def _init(key, shape, shapes):
+        if key.endswith(".relu.beta"):
+            return torch.tensor(1.0)
+        if key.endswith(".relu.gamma"):
+            return torch.tensor(0.5)
+        wshape = shape
+        if key.endswith(".bias"):
+            base = key[: -len(".bias")]
+            for cand in (base + ".weight", base + ".parametrizations.weight.original1", base + ".weight_v"):
+                if cand in shapes:
+                    wshape = shapes[cand]
+                    break
+        fan_in = 1
+        for d in wshape[1:]:
+            fan_in *= d
+        bound = 1.0 / math.sqrt(max(fan_in, 1))
+        return (torch.rand(shape) * 2.0 - 1.0) * bound
+
+    # ------------------------------------------------------------------
+    def _device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    def engine(self) -> PreEncoderEngine:
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("mqgan_b200.PreEncoder runs on CUDA (B200) only - there is no CPU fallback; "
+                               "move the module with .to('cuda')")
+        key = (dev, self.encoder_precision) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._engine is None or key != self._engine_key:
+            self._engine = PreEncoderEngine(self.cfg, self.state_dict(), dev, self.encoder_precision)
+            self._engine_key = key
+        return self._engine
+
+    def _no_training(self, what):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError(
+                f"{what}: the training step (backward kernels, SURVEY 8-f4) is not part of this build; "
+                "call .eval() / torch.no_grad() for inference")
+
+    @torch.no_grad()
+    def encode(self, x, x_mask=None):
+        """(B, T, mel) [+ (B,1,T) bool, True = padded] -> (B, T) int64 (preencoder.py:420-451)."""
+        return self.engine().encode(x.to(self._device()), x_mask)
+
+    @torch.no_grad()
+    def decode(self, indices, x_mask=None, return_hidden=False):
+        """(B, T) int -> (B, T, mel) [, (B, C0, T)] (preencoder.py:453-504)."""
+        return self.engine().decode(indices.to(self._device()), x_mask, return_hidden=return_hidden)
+
+    def forward(self, x, x_lengths):
+        """(x_recon, x_post) as preencoder.py:363-418, inference only."""
+        self._no_training("PreEncoder.forward")
+        with torch.no_grad():
+            x = x.to(self._device())
+            mask = sequence_mask(x.size(1), x_lengths.to(x.device)).unsqueeze(1)
+            eng = self.engine()
+            idx = eng.encode(x, mask)
+            x_post, x_recon = eng.decode(idx, mask, return_recon=True)
+            return x_recon, x_post
+
+
+def strip_weight_norm(module):
+    """Reference: preencoder.py:507-514.  Weight-norm is folded once when the
+    kernels' packed weights are built, so there is nothing to strip; kept for
+    call-site compatibility."""
+    return module
+
+
+def get_pre_encoder(model_path: str, device, channels=[384, 512, 768], kernel_sizes=[7, 5, 3],
+                    mel_channels=88, fsq_levels=[8, 5, 5, 5], refiner_base_channels=128, refiner_depth=3,
+                    refiner_hidden_proj_divisor=8, inference=False):
+    """Load a checkpoint written by the reference's train.py (preencoder.py:517-599):
+    needs ``checkpoint['model_state_dict']``, strips a ``module.`` prefix, strict load,
+    ``.to(device).eval()``.  Raises FileNotFoundError / KeyError / RuntimeError as the reference."""
+    if not os.path.isfile(model_path):
+        raise FileNotFoundError(f"Checkpoint file not found: {model_path}")
+    print(f"Loading checkpoint from: {model_path}")
+    checkpoint = torch.load(model_path, map_location="cpu", weights_only=False)
+    try:
+        model = PreEncoder(mel_channels=mel_channels, channels=channels, kernel_sizes=kernel_sizes, dropout=0.0,
+                           fsq_levels=fsq_levels, refiner_base_channels=refiner_base_channels,
+                           refiner_depth=refiner_depth, refiner_hidden_proj_divisor=refiner_hidden_proj_divisor)
+    except Exception as e:
+        raise RuntimeError(f"Failed to instantiate model with loaded config: {e}")
+    if "model_state_dict" not in checkpoint:
+        raise KeyError("Checkpoint missing 'model_state_dict' key containing weights.")
+    weights = OrderedDict()
+    stripped = False
+    for k, v in checkpoint["model_state_dict"].items():
+        if k.startswith("module."):
+            stripped = True
+            k = k[7:]
+        weights[k] = v
+    if stripped:
+        print("Removed 'module.' prefix from weight keys.")
+    weights = _accept_stripped_weight_norm(model, weights)
+    try:
+        model.load_state_dict(weights, strict=True)
+        print("Successfully loaded model weights.")
+    except RuntimeError as e:
+        print(f"Error loading state_dict (likely architecture mismatch): {e}")
+        raise
+    model.to(device)
+    model.eval()
+    if inference:
+        strip_weight_norm(model)
+    print(f"Model loaded onto {device} and set to evaluation mode.")
+    return model
+
+
+def _accept_stripped_weight_norm(model: "PreEncoder", weights):
+    """A state-dict harvested from an ``inference=True`` reference model / TorchScript
+    export has plain ``decoder_blocks.*.conv*.weight`` (legacy weight-norm removed,
+    SURVEY App. B4).  Re-express it as g = ||w||, v = w so the strict load still holds."""
+    own = set(k for k, _ in model.named_parameters())
+    out = OrderedDict()
+    for k, v in weights.items():
+        if k not in own and k.endswith(".weight") and (k[: -len("weight")] + "weight_v") in own:
+            base = k[: -len("weight")]
+            out[base + "weight_v"] = v
+            out[base + "weight_g"] = v.reshape(v.shape[0], -1).norm(dim=1).reshape(v.shape[0], *([1] * (v.dim() - 1)))
+        else:
+            out[k] = v
+    return out

@@ -1,0 +1,298 @@
+"""Per-kernel parity on the GPU, through the C ABI (ops.py -> libmqgan_b200.so).
+
+Each kernel is compared with a float64 CPU restatement of the same reference op
+on the same seeded inputs.  Tolerances are written beside each assert.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from mqgan_b200 import ops  # noqa: E402
+from oracle import preencoder_oracle as O  # noqa: E402
+
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def _ref_conv(x, w, b, kind):
+    """x (N,H,W,C) float64 channel-last -> (N,H,W,Cout) float64."""
+    N, H, W, Cc = x.shape
+    if kind == "linear":
+        return F.linear(x, w, b)
+    if kind in ("same1d", "causal1d"):
+        assert W == 1
+        k = w.shape[2]
+        xi = x.reshape(N, H, Cc).permute(0, 2, 1)
+        if kind == "causal1d":
+            y = F.conv1d(F.pad(xi, (k - 1, 0)), w, b)
+        else:
+            y = F.conv1d(xi, w, b, padding=(k - 1) // 2)
+        return y.permute(0, 2, 1).reshape(N, H, 1, -1)
+    if kind == "conv2d3":
+        y = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1)
+        return y.permute(0, 2, 3, 1)
+    raise ValueError(kind)
+
+
+CONV_CASES = [
+    # kind, N, H, W, Cin, Cout, wshape-tail
+    ("linear", 1, 256, 1, 128, 64, ()),
+    ("linear", 2, 77, 1, 512, 144, ()),          # cout not a multiple of 32; ragged M
+    ("same1d", 2, 300, 1, 64, 96, (3,)),
+    ("same1d", 1, 130, 1, 192, 256, (5,)),
+    ("causal1d", 2, 200, 1, 768, 512, (7,)),     # two N tiles, K = 7*768
+    ("conv2d3", 2, 24, 144, 64, 128, (3, 3)),
+    ("conv2d3", 1, 7, 36, 96, 192, (3, 3)),      # Cin not a multiple of 64 (hifimusic-like), small H
+    ("conv2d3", 1, 16, 144, 192, 64, (3, 3)),
+]
+
+
+@pytest.mark.parametrize("kind,N,H,W,Cin,Cout,tail", CONV_CASES)
+def test_conv_gemm_bf16(kind, N, H, W, Cin, Cout, tail):
+    x = _rand(N, H, W, Cin, seed=1).to(torch.bfloat16)
+    w = (_rand(Cout, Cin, *tail, seed=2) / (Cin * max(1, int(np.prod(tail)))) ** 0.5).to(torch.bfloat16)
+    b = _rand(Cout, seed=3)
+    ref = _ref_conv(x.double(), w.double(), b.double(), kind)
+    pc = ops.pack_conv(w.float(), b, kind, split=False).to(DEV)
+    out = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
+    ops.conv_gemm(x.to(DEV), pc, N, H, W, out_f32=out)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    # bf16 inputs are exact on both sides; only fp32 accumulation order differs
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+def test_conv_gemm_epilogue_variants():
+    N, H, W, Cin, Cout = 2, 16, 48, 128, 128
+    x = _rand(N, H, W, Cin, seed=4).to(torch.bfloat16)
+    w = (_rand(Cout, Cin, 3, 3, seed=5) / (9 * Cin) ** 0.5).to(torch.bfloat16)
+    b = _rand(Cout, seed=6)
+    res = _rand(N, H, W, Cout, seed=7).to(torch.bfloat16)
+    mask = torch.zeros(N, H, dtype=torch.uint8)
+    mask[0, 11:] = 1
+    mask[1, 5:] = 1
+    acc = _ref_conv(x.double(), w.double(), b.double(), "conv2d3")
+    m = mask.bool()[:, :, None, None]
+    beta, gamma = 0.9, 0.6
+    pc = ops.pack_conv(w.float(), b, "conv2d3", split=False).to(DEV)
+    xd, rd, md = x.to(DEV), res.to(DEV), mask.to(DEV)
+
+    # ConvBlock conv2: act -> + x -> mask (preencoder.py:98-101)
+    ref = (O.aptx(acc, beta, gamma) + res.double()).masked_fill(m, 0.0)
+    o32 = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
+    o16 = torch.empty(N, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv_gemm(xd, pc, N, H, W, row_mask=md, mask_post=True, act=True, beta=beta, gamma=gamma,
+                  fast_tanh=False, res=rd, res_mode=2, out_f32=o32, out_bf16=o16)
+    assert (o32.cpu().double() - ref).abs().max().item() < 1e-4
+    assert (o16.cpu().double() - ref).abs().max().item() < 2e-2          # bf16 rounding of the output
+    # fast tanh (tanh.approx): looser
+    ops.conv_gemm(xd, pc, N, H, W, row_mask=md, mask_post=True, act=True, beta=beta, gamma=gamma,
+                  fast_tanh=True, res=rd, res_mode=2, out_f32=o32)
+    assert (o32.cpu().double() - ref).abs().max().item() < 5e-3
+
+    # ResidualBlock1D tail: (+ res) -> mask -> act (attentions.py:545-549), fp32 residual, split output
+    res32 = res.float()
+    ref = O.aptx((acc + res32.double()).masked_fill(m, 0.0), beta, gamma)
+    osp = torch.empty(N, H, W, 3 * Cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv_gemm(xd, pc, N, H, W, row_mask=md, mask_pre=True, act=True, beta=beta, gamma=gamma,
+                  fast_tanh=False, res=res32.to(DEV), res_mode=1, out_f32=o32, out_split=osp)
+    assert (o32.cpu().double() - ref).abs().max().item() < 1e-4
+    s = osp.cpu().float().reshape(N, H, W, 3, Cout).sum(dim=3)
+    assert (s - o32.cpu()).abs().max().item() < 1e-6                      # 3-term split carries fp32
+
+    # strided fp32 output with a channel offset (out_proj / hidden_proj writing one buffer)
+    big = torch.zeros(N, H, W, Cout + 32, dtype=torch.float32, device=DEV)
+    ops.conv_gemm(xd, pc, N, H, W, out_f32=big, f32_coff=32)
+    assert (big[..., 32:].cpu().double() - acc).abs().max().item() < 1e-4
+    assert big[..., :32].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("kind,N,H,W,Cin,Cout,tail", [
+    ("linear", 2, 100, 1, 128, 512, ()),
+    ("same1d", 1, 257, 1, 512, 768, (5,)),
+    ("linear", 1, 64, 1, 32, 64, ()),            # Cin < 64: segment over-read hits zero weights
+])
+def test_conv_gemm_bf16x3_is_fp32_grade(kind, N, H, W, Cin, Cout, tail):
+    x = _rand(N, H, W, Cin, seed=8)
+    w = _rand(Cout, Cin, *tail, seed=9) / (Cin * max(1, int(np.prod(tail)))) ** 0.5
+    b = _rand(Cout, seed=10)
+    ref = _ref_conv(x.double(), w.double(), b.double(), kind)
+    pc = ops.pack_conv(w, b, kind, split=True).to(DEV)
+    xs = ops.split_bf16(x.reshape(-1, Cin).to(DEV), 3)
+    out = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
+    ops.conv_gemm(xs, pc, N, H, W, out_f32=out)
+    err = (out.cpu().double() - ref).abs().max().item()
+    ref32 = _ref_conv(x, w, b, kind)
+    err32 = (ref32.double() - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
+    # as accurate as an fp32 CPU convolution (within 4x of its error, floor 2e-6 relative)
+    assert err < max(4 * err32, 2e-6 * scale), (err, err32)
+
+
+def test_convblock2d_matches_reference_op():
+    B, T, Cc = 2, 37, 96
+    x = _rand(B, T, Cc, seed=11)
+    w = {"p.dw.weight": _rand(1, 1, 5, 5, seed=12) * 0.2, "p.dw.bias": _rand(1, seed=13) * 0.1,
+         "p.pw.weight": _rand(Cc, 1, 1, 1, seed=14), "p.pw.bias": _rand(Cc, seed=15),
+         "p.conv_out.weight": _rand(1, Cc, 1, 1, seed=16) / Cc ** 0.5, "p.conv_out.bias": _rand(1, seed=17)}
+    lengths = torch.tensor([T, 20])
+    mask = O.sequence_mask(T, lengths)
+    ref = O.convblock2d(x.permute(0, 2, 1).double(), mask.unsqueeze(1), {k: v.double() for k, v in w.items()}, "p")
+    ref = ref.permute(0, 2, 1)
+    dw = torch.cat([w["p.dw.weight"].reshape(25), w["p.dw.bias"]]).to(DEV)
+    pw = torch.zeros(Cc, 4)
+    pw[:, 0], pw[:, 1], pw[:, 2] = w["p.pw.weight"].reshape(Cc), w["p.pw.bias"], w["p.conv_out.weight"].reshape(Cc)
+    m8 = mask.to(torch.uint8).to(DEV)
+    o32 = torch.empty(B, T, Cc, dtype=torch.float32, device=DEV)
+    osp = torch.empty(B, T, 3 * Cc, dtype=torch.bfloat16, device=DEV)
+    ops.convblock2d(x.to(DEV), B, T, Cc, dw, pw.to(DEV), float(w["p.conv_out.bias"]), m8, False,
+                    out_f32=o32, out_split=osp)
+    err = (o32.cpu().double() - ref).abs().max().item()
+    assert err < 5e-6 * max(1.0, ref.abs().max().item()), err
+    assert (osp.cpu().float().reshape(B, T, 3, Cc).sum(2) - o32.cpu()).abs().max().item() < 1e-6
+    # padded rows equal conv_out.bias exactly
+    assert torch.all(o32[1, 20:] == float(w["p.conv_out.bias"]))
+    # fast-tanh / bf16 input variant (decoder `post`)
+    o16 = torch.empty(B, T, Cc, dtype=torch.bfloat16, device=DEV)
+    xb = x.to(torch.bfloat16)
+    refb = O.convblock2d(xb.permute(0, 2, 1).double(), mask.unsqueeze(1), {k: v.double() for k, v in w.items()}, "p").permute(0, 2, 1)
+    ops.convblock2d(xb.to(DEV), B, T, Cc, dw, pw.to(DEV), float(w["p.conv_out.bias"]), m8, True, out_bf16=o16)
+    assert (o16.cpu().double() - refb).abs().max().item() < 2e-2 * max(1.0, refb.abs().max().item())
+
+
+def test_cbam_block_tail_matches_reference_op():
+    B, T, Cc, R = 3, 150, 64, 8
+    o = _rand(B, T, Cc, seed=20)
+    r = _rand(B, T, Cc, seed=21)
+    lengths = torch.tensor([150, 97, 31])
+    mask = O.sequence_mask(T, lengths).unsqueeze(1)
+    w = {"c.channel_attention.mlp.0.weight": _rand(R, Cc, seed=22) * 0.2, "c.channel_attention.mlp.0.bias": _rand(R, seed=23) * 0.1,
+         "c.channel_attention.mlp.2.weight": _rand(Cc, R, seed=24) * 0.3, "c.channel_attention.mlp.2.bias": _rand(Cc, seed=25) * 0.1,
+         "c.spatial_attention.conv.weight": _rand(1, 2, 7, seed=26) * 0.3}
+    wd = {k: v.double() for k, v in w.items()}
+    beta, gamma = 1.1, 0.45
+    cb = O.cbam(o.permute(0, 2, 1).double(), mask, wd, "c")
+    ref = O.aptx((cb + r.permute(0, 2, 1).double()).masked_fill(mask, 0), beta, gamma).permute(0, 2, 1)
+    m8 = mask.squeeze(1).to(torch.uint8).to(DEV)
+    od = o.to(DEV)
+    gate = ops.cam_gate(od, m8, B, T, Cc, *(w[k].to(DEV).contiguous() for k in list(w)[:4]))
+    y = torch.empty(B, T, Cc, dtype=torch.float32, device=DEV)
+    ops.cbam_apply(od, gate, r.to(DEV), m8, B, T, Cc, w["c.spatial_attention.conv.weight"].reshape(14).to(DEV),
+                   beta, gamma, out_f32=y)
+    err = (y.cpu().double() - ref).abs().max().item()
+    assert err < 5e-6 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("levels", [[8, 5, 5, 5], [8, 8, 5, 5, 5]])
+def test_fsq_bit_exact_vs_reference_vectors(levels, golden_dir):
+    fx = np.load(os.path.join(golden_dir, "fsq_" + "_".join(map(str, levels)) + ".npz"))
+    z = torch.from_numpy(fx["z"]).reshape(-1, len(levels)).contiguous()
+    fsq = ops.fsq_params(levels)
+    idx, codes = ops.fsq_quantize(z.to(DEV), fsq, want_codes=True)
+    ref_idx = torch.from_numpy(fx["indices"].astype(np.int64)).reshape(-1)
+    # integer work: bit-exact except where CUDA tanhf and the host tanh differ by an ulp exactly at a
+    # rounding boundary; the fixture is random so demand exact equality
+    assert torch.equal(idx.cpu(), ref_idx)
+    assert torch.equal(codes.cpu(), torch.from_numpy(fx["codes"]).reshape(-1, len(levels)))
+    # adversarial: exact half-way points in bounded space round half-to-even like torch.round
+    lv, basis, half_l, offset, shift, half_w = O.fsq_constants(levels)
+    n = int(np.prod(levels))
+    table = torch.from_numpy(fx["all_codes"])
+    zero = torch.zeros(1, len(levels))
+    i0 = ops.fsq_quantize(zero.to(DEV), fsq)
+    assert int(i0) == int(O.fsq_quantize(zero, levels)[1])
+
+
+def test_qin_fsq_and_gather():
+    levels = [8, 5, 5, 5]
+    rows, Cc = 1000, 768
+    y = _rand(rows, Cc, seed=30)
+    w = _rand(4, Cc, seed=31) / Cc ** 0.5
+    b = _rand(4, seed=32) * 0.1
+    fsq = ops.fsq_params(levels)
+    idx, z = ops.qin_fsq(y.to(DEV), w.to(DEV), b.to(DEV), fsq, want_z=True)
+    z64 = F.linear(y.double(), w.double(), b.double())
+    assert (z.cpu().double() - z64).abs().max().item() < 1e-6
+    ref_idx = O.fsq_quantize(z.cpu(), levels)[1]
+    assert torch.equal(idx.cpu(), ref_idx)
+    # K8: gather == indices_to_codes + q_out_proj
+    wq, bq = _rand(Cc, 4, seed=33), _rand(Cc, seed=34)
+    codes = O.fsq_indices_to_codes(torch.arange(1000), levels)
+    table = F.linear(codes, wq, bq).contiguous()
+    ob, of = ops.code_gather(idx, table.to(DEV), bf16=True, f32=True)
+    ref = F.linear(O.fsq_indices_to_codes(idx.cpu(), levels), wq, bq)
+    assert torch.equal(of.cpu(), ref)
+    assert torch.equal(ob.cpu(), ref.to(torch.bfloat16))
+    bad = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.code_gather(torch.tensor([3, 1001, -1], device=DEV), table.to(DEV), bad=bad)
+    assert int(bad) == 1                                 # bos/eos ids are outside the FSQ range (App. B7)
+
+
+def test_refiner_masks_pool_upcat_stem_tail():
+    B, T, depth, Fw, Cc, M = 2, 21, 3, 20, 16, 16
+    lengths = torch.tensor([21, 13])
+    mask = O.sequence_mask(T, lengths)
+    T8, down, up = ops.refiner_masks(mask.to(torch.uint8).to(DEV), B, T, depth, DEV)
+    assert T8 == 24
+    cur = torch.cat([mask, torch.ones(B, T8 - T, dtype=torch.bool)], 1).reshape(B, 1, T8, 1)
+    downs_ref = [cur]
+    for _ in range(depth):
+        cur = F.max_pool2d(cur.float(), kernel_size=(2, 1), stride=(2, 1)).bool()
+        downs_ref.append(cur)
+    ups_ref = {depth: cur}
+    for l in range(depth - 1, -1, -1):
+        cur = F.interpolate(cur.float(), scale_factor=(2, 1), mode="nearest").bool()
+        ups_ref[l] = cur
+    for l in range(depth + 1):
+        assert torch.equal(down[l].cpu().bool(), downs_ref[l].reshape(B, -1))
+        assert torch.equal(up[l].cpu().bool(), ups_ref[l].reshape(B, -1))
+    # no mask -> only the T padding is masked
+    _, d0, _ = ops.refiner_masks(None, B, T, depth, DEV)
+    assert d0[0][:, :T].sum().item() == 0 and d0[0][:, T:].all()
+
+    x = _rand(B, T8, Fw, Cc, seed=40).to(torch.bfloat16)
+    y = ops.avgpool_mask(x.to(DEV), down[1], B, T8, Fw, Cc)
+    ref = F.avg_pool2d(x.float().permute(0, 3, 1, 2), kernel_size=(2, 1)).masked_fill(downs_ref[1], 0.0).permute(0, 2, 3, 1)
+    assert torch.equal(y.cpu(), ref.to(torch.bfloat16))
+    lo = _rand(B, T8 // 2, Fw, 2 * Cc, seed=41).to(torch.bfloat16)
+    u = ops.upcat_mask(lo.to(DEV), x.to(DEV), up[0], B, T8, Fw, 2 * Cc, Cc)
+    ref = torch.cat([F.interpolate(lo.float().permute(0, 3, 1, 2), scale_factor=(2, 1), mode="nearest"),
+                     x.float().permute(0, 3, 1, 2)], 1).masked_fill(ups_ref[0], 0.0).permute(0, 2, 3, 1)
+    assert torch.equal(u.cpu(), ref.to(torch.bfloat16))
+
+    # stem: conv 1->C over the masked, T-padded image + APTx
+    r = _rand(B, T, Fw, seed=42)
+    w1, b1 = _rand(Cc, 1, 3, 3, seed=43) * 0.3, _rand(Cc, seed=44) * 0.1
+    img = torch.cat([r, torch.zeros(B, T8 - T, Fw)], 1).unsqueeze(1).masked_fill(downs_ref[0], 0.0)
+    ref = O.aptx(F.conv2d(img.double(), w1.double(), b1.double(), padding=1), 1, 0.5).permute(0, 2, 3, 1)
+    s = ops.refiner_stem(r.to(DEV), mask.to(torch.uint8).to(DEV), B, T, T8, Fw, Cc,
+                         w1.reshape(Cc, 9).contiguous().to(DEV), b1.to(DEV), False)
+    assert (s.cpu().double() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+    # tail: conv C->1 + crop + mask + reproj + x_recon add
+    xin = _rand(B, T8, Fw, Cc, seed=45).to(torch.bfloat16)
+    wp, bp = _rand(1, Cc, 3, 3, seed=46) / (9 * Cc) ** 0.5, _rand(1, seed=47)
+    wr = _rand(M, Fw, seed=48) / Fw ** 0.5
+    o = F.conv2d(xin.double().permute(0, 3, 1, 2), wp.double(), bp.double(), padding=1).squeeze(1)[:, :T]
+    o = o.masked_fill(mask.unsqueeze(-1), 0.0)
+    ref = r[..., :M].double() + F.linear(o, wr.double())
+    out = ops.refiner_tail(xin.to(DEV), mask.to(torch.uint8).to(DEV), B, T, T8, Fw, Cc,
+                           wp.reshape(Cc, 9).t().contiguous().to(DEV), float(bp), wr.t().contiguous().to(DEV), M,
+                           r.to(DEV))
+    assert (out.cpu().double() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_sequence_mask_kernel():
+    lengths = torch.tensor([5, 0, 9, 3])
+    m = ops.sequence_mask(lengths.to(DEV), 9)
+    assert torch.equal(m.cpu().bool(), O.sequence_mask(9, lengths))

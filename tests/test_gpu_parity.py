@@ -1,0 +1,179 @@
+"""End-to-end parity of the CUDA path (PreEncoder API -> C ABI) against the CPU
+oracle and the committed reference outputs (tests/golden/).
+
+Gates (BASELINE north_star):
+  * fp32 mode ("bf16x3" encoder): indices equal to the reference on every frame
+    whose float64 distance to an FSQ rounding boundary exceeds TAU; raw agreement
+    reported and required >= 99.5 %.
+  * bf16 encoder mode: agreement rate reported, required >= 80 %.
+  * reconstructed mels (bf16 operands, fp32 accumulate, bf16 activations):
+    max-abs error <= MEL_ATOL + MEL_RTOL * max|ref|.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from mqgan_b200.preencoder import PreEncoder, sequence_mask  # noqa: E402
+from mqgan_b200.synth import synth_mels, synth_lengths  # noqa: E402
+from oracle import preencoder_oracle as O  # noqa: E402
+from tests.helpers import load_golden, index_report  # noqa: E402
+
+TAU = 2e-4          # bounded-latent units (rounding boundaries are 1 apart)
+MEL_ATOL = 2e-2
+MEL_RTOL = 2e-2
+
+REPORT = {}
+
+
+def _dump():
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1)
+
+
+def _model(cfg, sd, precision="bf16x3"):
+    m = PreEncoder(cfg.mel_channels, list(cfg.channels), list(cfg.kernel_sizes), fsq_levels=list(cfg.fsq_levels),
+                   dropout=0.0, refiner_base_channels=cfg.refiner_base_channels, refiner_depth=cfg.refiner_depth,
+                   refiner_hidden_proj_divisor=cfg.refiner_hidden_proj_divisor, encoder_precision=precision)
+    m.load_state_dict(sd, strict=True)
+    return m.to("cuda").eval()
+
+
+@pytest.mark.parametrize("name", ["tiny", "hifispeech", "hifimusic"])
+def test_encode_indices_vs_reference(name):
+    cfg, sd, mel, lengths, fx = load_golden(name)
+    T = mel.shape[1]
+    mask = sequence_mask(T, lengths).unsqueeze(1)
+    model = _model(cfg, sd)
+    idx, z = model.engine().encode(mel.cuda(), mask.cuda(), return_latents=True)
+    ref_idx = torch.from_numpy(fx["indices"].astype(np.int64))
+    ref_z = torch.from_numpy(fx["z"])
+    z64 = O.encode_latents(sd, cfg, mel, mask, dtype=torch.float64)
+    margin = O.fsq_round_margin(z64, cfg.fsq_levels)
+    rep = index_report(idx, ref_idx, margin, TAU)
+    rep["z_maxabs_vs_ref32"] = float((z.cpu() - ref_z).abs().max())
+    rep["z_maxabs_vs_fp64"] = float((z.cpu().double() - z64).abs().max())
+    rep["ref32_maxabs_vs_fp64"] = float((ref_z.double() - z64).abs().max())
+    REPORT[f"encode/{name}"] = rep
+    _dump()
+    print(name, rep)
+    assert rep["safe_mismatch"] == 0, rep
+    assert rep["agree"] >= 0.995, rep
+    # fp32-grade: our latents are as close to float64 as the reference's own fp32 ones (x4 slack)
+    assert rep["z_maxabs_vs_fp64"] <= max(4 * rep["ref32_maxabs_vs_fp64"], 2e-5), rep
+    # API contract: (B, T) int64 on the module's device
+    out = model.encode(mel, mask)
+    assert out.dtype == torch.int64 and tuple(out.shape) == tuple(mel.shape[:2]) and out.is_cuda
+    assert torch.equal(out, idx)
+
+
+@pytest.mark.parametrize("name", ["tiny", "hifispeech", "hifimusic"])
+def test_decode_mels_vs_reference(name):
+    cfg, sd, mel, lengths, fx = load_golden(name)
+    T = mel.shape[1]
+    mask = sequence_mask(T, lengths).unsqueeze(1)
+    model = _model(cfg, sd)
+    for ik, rk in (("indices", "recon"), ("rand_indices", "rand_recon")):
+        idx = torch.from_numpy(fx[ik].astype(np.int64))
+        ref = torch.from_numpy(fx[rk])
+        out = model.decode(idx.cuda(), mask.cuda()).cpu()
+        assert out.shape == ref.shape and out.dtype == torch.float32
+        err = float((out - ref).abs().max())
+        scale = float(ref.abs().max())
+        rel = float((out - ref).norm() / ref.norm())
+        REPORT[f"decode/{name}/{ik}"] = {"max_abs_err": err, "ref_max": scale, "rel_l2": rel}
+        _dump()
+        print(name, ik, REPORT[f"decode/{name}/{ik}"])
+        assert err <= MEL_ATOL + MEL_RTOL * scale, (err, scale)
+    # return_hidden: (x_post, last_hid (B, C0, T))
+    x_post, hid = model.decode(idx.cuda(), mask.cuda(), return_hidden=True)
+    assert tuple(hid.shape) == (mel.shape[0], cfg.c0, T)
+    # padded frames are not zeroed (App. B8)
+    pad = mask.squeeze(1)
+    if pad.any():
+        assert float(x_post.cpu()[pad].abs().max()) > 0
+
+
+def test_no_mask_and_forward():
+    cfg, sd, mel, lengths, fx = load_golden("tiny")
+    model = _model(cfg, sd)
+    idx = model.encode(mel[:1].cuda(), None)
+    ref = torch.from_numpy(fx["nomask_indices"].astype(np.int64))
+    assert float((idx.cpu() == ref).float().mean()) >= 0.99
+    out = model.decode(idx, None).cpu()
+    refm = torch.from_numpy(fx["nomask_recon"])
+    if torch.equal(idx.cpu(), ref):
+        assert float((out - refm).abs().max()) <= MEL_ATOL + MEL_RTOL * float(refm.abs().max())
+    x_recon, x_post = model(mel.cuda(), lengths.cuda())
+    assert x_recon.shape == x_post.shape == mel.shape
+
+
+def test_bf16_encoder_mode_reports_agreement():
+    cfg, sd, mel, lengths, fx = load_golden("hifispeech")
+    mask = sequence_mask(mel.shape[1], lengths).unsqueeze(1)
+    model = _model(cfg, sd, precision="bf16")
+    idx = model.encode(mel.cuda(), mask.cuda())
+    rep = index_report(idx, torch.from_numpy(fx["indices"].astype(np.int64)))
+    REPORT["encode_bf16/hifispeech"] = rep
+    _dump()
+    print("bf16 encoder agreement", rep)
+    assert rep["agree"] >= 0.80
+
+
+def test_batch_invariance_and_determinism():
+    """Utterances are independent given the padded length: encoding a
+    sub-batch alone gives the same indices bit for bit; chunked execution too."""
+    cfg, sd, mel, lengths, fx = load_golden("tiny")
+    T = mel.shape[1]
+    mask = sequence_mask(T, lengths).unsqueeze(1)
+    model = _model(cfg, sd)
+    a = model.encode(mel.cuda(), mask.cuda())
+    b = model.encode(mel[1:3].cuda(), mask[1:3].cuda())
+    assert torch.equal(a[1:3], b)
+    assert torch.equal(a, model.encode(mel.cuda(), mask.cuda()))
+    eng = model.engine()
+    old = eng.max_chunk_frames
+    eng.max_chunk_frames = T            # one utterance per chunk
+    try:
+        assert torch.equal(a, model.encode(mel.cuda(), mask.cuda()))
+        d1 = model.decode(a, mask.cuda())
+    finally:
+        eng.max_chunk_frames = old
+    d2 = model.decode(a, mask.cuda())
+    assert torch.equal(d1, d2)
+
+
+def test_hifispeech_longer_ragged_batch_vs_oracle():
+    """A larger seeded case than the fixtures (B=4, T=200, ragged), checked against the oracle run here."""
+    cfg, sd, _, _, _ = load_golden("hifispeech")
+    B, T = 4, 200
+    mel = synth_mels(B, T, cfg.mel_channels, seed=7)
+    lengths = synth_lengths(B, T, seed=7)
+    pad = torch.arange(T)[None, :] >= lengths[:, None]
+    mel = mel.masked_fill(pad.unsqueeze(-1), 0.0)
+    mask = pad.unsqueeze(1)
+    w = O.effective_weights(sd)
+    z32 = O.encode_latents(w, cfg, mel, mask, folded=True)
+    ref_idx = O.fsq_quantize(z32, cfg.fsq_levels)[1]
+    z64 = O.encode_latents(sd, cfg, mel, mask, dtype=torch.float64)
+    margin = O.fsq_round_margin(z64, cfg.fsq_levels)
+    model = _model(cfg, sd)
+    idx = model.encode(mel.cuda(), mask.cuda())
+    rep = index_report(idx, ref_idx, margin, TAU)
+    REPORT["encode/hifispeech_4x200"] = rep
+    print(rep)
+    assert rep["safe_mismatch"] == 0 and rep["agree"] >= 0.995, rep
+    ref = O.decode(w, cfg, ref_idx, mask, folded=True)
+    out = model.decode(ref_idx.cuda(), mask.cuda()).cpu()
+    err, scale = float((out - ref).abs().max()), float(ref.abs().max())
+    REPORT["decode/hifispeech_4x200"] = {"max_abs_err": err, "ref_max": scale,
+                                         "rel_l2": float((out - ref).norm() / ref.norm())}
+    _dump()
+    print(REPORT["decode/hifispeech_4x200"])
+    assert err <= MEL_ATOL + MEL_RTOL * scale
