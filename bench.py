@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the PreEncoder re-encode pass (encode + FSQ + decode) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port of the reference)
+
+One "step" = one re-encode pass over one batch of synthetic mels of the workload
+BASELINE.json's metric is quoted on (configs[1]: hifispeech PreEncoder, 256 x 1024
+frames, fp32-grade encoder so the VQ indices equal the fp32 reference).  Rank 0
+prints ONE JSON line (contract in the task statement).  For N > 1 every rank runs the
+same per-GPU workload on its own shard of utterances (weak scaling, no data-path
+collective; NCCL only for the timing barrier and the max-over-ranks reduction).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (config attr, B per GPU, T, encoder precision)
+    "hifispeech_256x1024_fp32idx": ("HIFISPEECH", 256, 1024, "bf16x3"),
+    "hifimusic_32x8192_bf16": ("HIFIMUSIC", 32, 8192, "bf16"),
+    "hifispeech_16x512_fp32idx": ("HIFISPEECH", 16, 512, "bf16x3"),
+    "tiny_8x256": ("TINY", 8, 256, "bf16x3"),
+}
+DEFAULT_WORKLOAD = "hifispeech_256x1024_fp32idx"
+CPU_SAMPLE = (2, 1024)       # utterances x frames timed on the host cores (bounded sample)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], 0.0, set(), 0.0
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+                power = max(power, float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "power_w_max": power or None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(cfg, precision, device, seed=0):
+    """Random-init weights of the reference architecture + the SURVEY-D4 q_in_proj
+    recalibration, computed with the CUDA encoder itself on a fixed calibration batch."""
+    from mqgan_b200.preencoder import PreEncoder
+    from mqgan_b200.synth import synth_state_dict, synth_mels, recalibrate_q_in_proj
+
+    sd = synth_state_dict(cfg, seed=seed)
+
+    def make(sd_):
+        m = PreEncoder(cfg.mel_channels, list(cfg.channels), list(cfg.kernel_sizes), fsq_levels=list(cfg.fsq_levels),
+                       dropout=0.0, refiner_base_channels=cfg.refiner_base_channels, refiner_depth=cfg.refiner_depth,
+                       refiner_hidden_proj_divisor=cfg.refiner_hidden_proj_divisor, encoder_precision=precision)
+        m.load_state_dict(sd_, strict=True)
+        return m.to(device).eval()
+
+    m = make(sd)
+    cal = synth_mels(8, 512, cfg.mel_channels, seed=100).to(device)
+    _, z = m.engine().encode(cal, None, return_latents=True)
+    recalibrate_q_in_proj(sd, z.cpu())
+    return make(sd), sd
+
+
+def run_cpu_sample(cfg, sd, mel, lengths, threads):
+    """Times the oracle port (torch CPU restatement of the reference) on a bounded sample."""
+    from oracle import preencoder_oracle as O
+    torch.set_num_threads(threads)
+    w = O.effective_weights(sd)
+    mask = O.sequence_mask(mel.shape[1], lengths).unsqueeze(1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        idx = O.encode(w, cfg, mel, mask, folded=True)
+        out = O.decode(w, cfg, idx, mask, folded=True)
+    dt = time.perf_counter() - t0
+    return idx, out, dt
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the
+    Python reference itself cannot travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mqgan_b200 import spec as S
+    from mqgan_b200.synth import synth_state_dict, synth_mels
+    cfg_name, B, T, precision = WORKLOADS[args.workload]
+    cfg = getattr(S, cfg_name)
+    sd = synth_state_dict(cfg, seed=0)
+    threads = os.cpu_count() or 1
+    sb, st = CPU_SAMPLE[0], min(CPU_SAMPLE[1], T)
+    mel = synth_mels(sb, st, cfg.mel_channels, seed=1)
+    lengths = torch.full((sb,), st, dtype=torch.long)
+    for _ in range(min(args.warmup, 1)):
+        run_cpu_sample(cfg, sd, mel, lengths, threads)
+    times = []
+    for _ in range(args.steps):
+        _, _, dt = run_cpu_sample(cfg, sd, mel, lengths, threads)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    fps = sb * st / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "mel frames/sec re-encoded (encode+VQ+decode)", "value": fps,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "sample": f"{sb}x{st} frames per step on host CPU", "device": "cpu"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{sb} utterances x {st} frames, oracle/preencoder_oracle.py, torch {torch.__version__} CPU"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", default=None, help="write the per-layer kernel table (markdown) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    from mqgan_b200 import spec as S, _lib
+    from mqgan_b200.synth import synth_mels
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib().mq_device_check(), "mq_device_check")
+
+    cfg_name, B, T, precision = WORKLOADS[args.workload]
+    cfg = getattr(S, cfg_name)
+    model, sd = build_model(cfg, precision, dev)
+    eng = model.engine()
+    mel_host = synth_mels(B, T, cfg.mel_channels, seed=1 + rank).pin_memory()
+    out_host = torch.empty(B, T, cfg.mel_channels, dtype=torch.float32).pin_memory()
+    idx_host = torch.empty(B, T, dtype=torch.int64).pin_memory()
+    mel_dev = mel_host.to(dev, non_blocking=True)
+    frames = B * T
+
+    def step_resident():
+        idx = eng.encode(mel_dev, None)
+        return idx, eng.decode(idx, None)
+
+    def step_e2e():
+        x = mel_host.to(dev, non_blocking=True)
+        idx = model.encode(x, None)
+        out = model.decode(idx, None)
+        out_host.copy_(out, non_blocking=True)
+        idx_host.copy_(idx, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    ms_total = timed(step_resident, args.steps)
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- per-kernel table (one instrumented step; CUDA events on the launching stream) ----
+    _lib.profiler = _lib.LaunchProfiler()
+    step_resident()
+    table = _lib.profiler.summary()
+    _lib.profiler = None
+    peaks = load_peaks()
+    conv = [r for r in table if r[0] == "mq_conv_gemm"]
+    conv_ms = sum(r[3] for r in conv)
+    conv_flops = sum(r[4] for r in conv)
+    conv_mma = sum(r[5] for r in conv)
+    conv_launches = sum(r[2] for r in conv)
+    total_ms = sum(r[3] for r in table)
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv, all %d launches of one step)" % conv_launches,
+        "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " bf16 sustained",
+        "traffic": None,
+        "issued_mma_tflops": conv_mma / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
+        "share_of_step": conv_ms / total_ms if total_ms > 0 else None,
+        "flops_per_launch_avg": conv_flops / max(conv_launches, 1),
+        "ms_per_launch_avg": conv_ms / max(conv_launches, 1),
+    }
+
+    if rank == 0 and args.layer_table:
+        rows = sorted(table, key=lambda r: -r[3])
+        with open(args.layer_table, "w") as f:
+            f.write(f"# per-kernel table, workload {args.workload}, one step, CUDA events on the launching stream\n\n")
+            f.write("| entry point | layer | launches | ms | share | algorithmic TFLOP/s | issued MMA TFLOP/s |\n|---|---|---|---|---|---|---|\n")
+            for name, tag, n, ms, fl, mma in rows:
+                tf = f"{fl / (ms * 1e-3) / 1e12:.1f}" if fl > 0 and ms > 0 else ""
+                tm = f"{mma / (ms * 1e-3) / 1e12:.1f}" if mma > 0 and ms > 0 else ""
+                f.write(f"| {name} | {tag} | {n} | {ms:.3f} | {100 * ms / total_ms:.1f}% | {tf} | {tm} |\n")
+            f.write(f"\ntotal {total_ms:.3f} ms for {frames} frames\n")
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline + parity spot-check on a sub-batch of the same workload ----
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline and world >= 1:
+        sb, st = min(CPU_SAMPLE[0], B), T if T <= CPU_SAMPLE[1] else CPU_SAMPLE[1]
+        threads = os.cpu_count() or 1
+        sub = mel_host[:sb, :st].clone()
+        lengths = torch.full((sb,), st, dtype=torch.long)
+        ref_idx, ref_out, dt = run_cpu_sample(cfg, sd, sub, lengths, threads)
+        cpu = {"value": sb * st / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"first {sb} utterances x {st} frames of the workload, oracle port, 1 run of {dt:.1f} s"}
+        g_idx = model.encode(sub.to(dev), None)
+        g_out = model.decode(ref_idx.to(dev), None).cpu()
+        parity = {"frames": sb * st, "index_match": float((g_idx.cpu() == ref_idx).float().mean()),
+                  "index_mismatches": int((g_idx.cpu() != ref_idx).sum()),
+                  "mel_max_abs_err": float((g_out - ref_out).abs().max()), "mel_ref_max_abs": float(ref_out.abs().max())}
+
+    ms_step = ms_total / args.steps
+    value = world * frames / (ms_step * 1e-3)
+    e2e_value = world * frames / (ms_e2e / args.steps * 1e-3)
+    from mqgan_b200.spec import flops_per_frame
+    fpf = flops_per_frame(cfg)["total"]
+    line = {
+        "metric": "mel frames/sec re-encoded (encode+VQ+decode)", "value": value, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": ("bf16x3 (fp32-grade) encoder" if precision == "bf16x3" else "bf16 encoder") + " + bf16 decoder, fp32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "model": cfg_name.lower(), "batch_per_gpu": B, "frames": T,
+                   "weights": "random-init (seed 0) + q_in_proj recalibration", "l2": "inputs and intermediates exceed L2 (134 MB mels, GBs of activations per step)",
+                   "parallelism": f"utterance shards x{world}, no collective"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": mel_host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4 + idx_host.numel() * 8, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "pass_frac_of_tensor_roofline": value / world * fpf / (peaks["bf16_tflops_sustained"] * 1e12),
+        "cpu_baseline": cpu,
+        "parity": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -153,10 +153,52 @@ def check(rc: int, what: str) -> None:
         raise MqError(f"{what} failed (rc={rc}): {msg}")
 
 
-def call(name: str, *args) -> None:
+class LaunchProfiler:
+    """Times every launch with CUDA events on the launching (current) stream.
+    ``bench.py`` uses it for the per-kernel roofline table; off by default."""
+
+    def __init__(self):
+        self.records = []          # (entry point, meta dict, start event, end event)
+
+    def begin(self, name, meta):
+        import torch
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._cur = (name, meta or {}, ev)
+
+    def end(self):
+        import torch
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        name, meta, ev0 = self._cur
+        self.records.append((name, meta, ev0, ev))
+
+    def summary(self):
+        """[(name, tag, launches, total ms, total algorithmic flops)] after a device sync."""
+        import torch
+        torch.cuda.synchronize()
+        agg = {}
+        for name, meta, e0, e1 in self.records:
+            key = (name, meta.get("tag", ""))
+            a = agg.setdefault(key, [0, 0.0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += float(meta.get("flops", 0.0))
+            a[3] += float(meta.get("mma_flops", 0.0))
+        return [(k[0], k[1], v[0], v[1], v[2], v[3]) for k, v in agg.items()]
+
+
+profiler = None
+
+
+def call(name: str, *args, meta=None) -> None:
     """Invoke a launching entry point and raise on a non-zero status."""
     global launch_count
+    if profiler is not None:
+        profiler.begin(name, meta)
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         check(rc, name)
     launch_count += 1
+    if profiler is not None:
+        profiler.end()

@@ -214,7 +214,7 @@ class PreEncoderEngine:
 
         a0 = ops.split_bf16(mel.reshape(rows, M), nt)
         h = torch.empty(rows, cfg.c0, dtype=torch.float32, device=dev)
-        ops.conv_gemm(a0, self.proj, B, T, 1, out_f32=h)                                   # preencoder.py:433
+        ops.conv_gemm(a0, self.proj, B, T, 1, out_f32=h, tag="enc.proj")                                   # preencoder.py:433
         x32 = torch.empty(rows, cfg.c0, dtype=torch.float32, device=dev)
         xs = act_buf(cfg.c0)
         ops.convblock2d(h, B, T, cfg.c0, self.pre.dw, self.pre.pw, self.pre.bout, m8, False,
@@ -225,12 +225,12 @@ class PreEncoderEngine:
             cout = blk["cout"]
             o1 = act_buf(cout)
             ops.conv_gemm(xs, blk["conv1"], B, T, 1, row_mask=m8, mask_pre=m8 is not None, act=True,
-                          beta=blk["beta"], gamma=blk["gamma"], fast_tanh=False, **kw_out(o1))
+                          beta=blk["beta"], gamma=blk["gamma"], fast_tanh=False, tag=f"enc{i}.conv1", **kw_out(o1))
             o = torch.empty(rows, cout, dtype=torch.float32, device=dev)
-            ops.conv_gemm(o1, blk["conv2"], B, T, 1, out_f32=o)
+            ops.conv_gemm(o1, blk["conv2"], B, T, 1, out_f32=o, tag=f"enc{i}.conv2")
             if blk["res"] is not None:
                 r = torch.empty(rows, cout, dtype=torch.float32, device=dev)
-                ops.conv_gemm(xs, blk["res"], B, T, 1, out_f32=r)
+                ops.conv_gemm(xs, blk["res"], B, T, 1, out_f32=r, tag=f"enc{i}.res")
             else:
                 r = x32
             gate = ops.cam_gate(o, m8, B, T, cout, blk["mlp_w0"], blk["mlp_b0"], blk["mlp_w2"], blk["mlp_b2"])
@@ -282,15 +282,15 @@ class PreEncoderEngine:
             cout = blk["cout"]
             o1 = torch.empty(rows, cout, dtype=torch.bfloat16, device=dev)
             ops.conv_gemm(x, blk["conv1"], B, T, 1, row_mask=m8, mask_pre=m8 is not None, act=True,
-                          beta=blk["beta"], gamma=blk["gamma"], out_bf16=o1)
+                          beta=blk["beta"], gamma=blk["gamma"], out_bf16=o1, tag=f"dec{i}.conv1")
             if blk["res"] is not None:
                 r = torch.empty(rows, cout, dtype=torch.bfloat16, device=dev)
-                ops.conv_gemm(x, blk["res"], B, T, 1, out_bf16=r)
+                ops.conv_gemm(x, blk["res"], B, T, 1, out_bf16=r, tag=f"dec{i}.res")
             else:
                 r = x
             y = torch.empty(rows, cout, dtype=torch.bfloat16, device=dev)
             ops.conv_gemm(o1, blk["conv2"], B, T, 1, row_mask=m8, mask_pre=m8 is not None, act=True,
-                          beta=blk["beta"], gamma=blk["gamma"], res=r, res_mode=1, out_bf16=y)
+                          beta=blk["beta"], gamma=blk["gamma"], res=r, res_mode=1, out_bf16=y, tag=f"dec{i}.conv2")
             x = y
             if taps is not None:
                 taps[f"dec{i}"] = y
@@ -300,8 +300,8 @@ class PreEncoderEngine:
                         out_bf16=pz)                                                        # :482
         F, M = cfg.refiner_width, cfg.mel_channels
         R = torch.empty(rows, F, dtype=torch.float32, device=dev)
-        ops.conv_gemm(pz, self.out_proj, B, T, 1, out_f32=R, f32_coff=0)                    # :486
-        ops.conv_gemm(dec_out, self.hidden_proj, B, T, 1, out_f32=R, f32_coff=M)            # :490-492
+        ops.conv_gemm(pz, self.out_proj, B, T, 1, out_f32=R, f32_coff=0, tag="dec.out_proj")                    # :486
+        ops.conv_gemm(dec_out, self.hidden_proj, B, T, 1, out_f32=R, f32_coff=M, tag="dec.hidden_proj")            # :490-492
         if taps is not None:
             taps["refiner_in"] = R
         self._refiner(R, m8, B, T, out, taps)                                               # :496-499
@@ -317,35 +317,36 @@ class PreEncoderEngine:
         T8, down, up = ops.refiner_masks(m8, B, T, d, dev)
         H = [T8 >> l for l in range(d + 1)]
 
-        def convblock(x, blk, l, mask, cin, cout, first=True):
+        def convblock(x, blk, l, mask, cin, cout, first=True, tag=""):
             if first:
                 t = torch.empty(B, H[l], F, cout, dtype=torch.bfloat16, device=dev)
-                ops.conv_gemm(x, blk["conv1"], B, H[l], F, act=True, out_bf16=t)          # preencoder.py:97
+                ops.conv_gemm(x, blk["conv1"], B, H[l], F, act=True, out_bf16=t, tag=tag + ".conv1")   # preencoder.py:97
             else:
                 t = x
             y = torch.empty(B, H[l], F, cout, dtype=torch.bfloat16, device=dev)
             match = first and cin == cout
             ops.conv_gemm(t, blk["conv2"], B, H[l], F, act=True, row_mask=mask, mask_post=True,
-                          res=x if match else None, res_mode=2 if match else 0, out_bf16=y)  # :98-101
+                          res=x if match else None, res_mode=2 if match else 0, out_bf16=y,
+                          tag=tag + ".conv2")                                               # :98-101
             return y
 
         s1 = ops.refiner_stem(R, m8, B, T, T8, F, chs[0], self.stem_w, self.stem_b, True)   # :172-175, :97
-        x = convblock(s1, self.ref_pre, 0, down[0], 1, chs[0], first=False)
+        x = convblock(s1, self.ref_pre, 0, down[0], 1, chs[0], first=False, tag="ref.pre")
         skips = []
         for i in range(d):                                                                  # :179-181
             skips.append(x)
             p = ops.avgpool_mask(x, down[i + 1], B, H[i], F, chs[i])
-            x = convblock(p, self.ref_downs[i], i + 1, down[i + 1], chs[i], chs[i + 1])
+            x = convblock(p, self.ref_downs[i], i + 1, down[i + 1], chs[i], chs[i + 1], tag=f"ref.down{i}")
             if taps is not None:
                 taps[f"refiner.downs.{i}"] = x
-        x = convblock(x, self.ref_mid, d, down[d], chs[d], chs[d])                          # :184
+        x = convblock(x, self.ref_mid, d, down[d], chs[d], chs[d], tag="ref.mid")                          # :184
         if taps is not None:
             taps["refiner.mid"] = x
         for i in range(d):                                                                  # :187-189
             l = d - 1 - i
             skip = skips.pop()
             u = ops.upcat_mask(x, skip, up[l], B, H[l], F, chs[l + 1], chs[l])
-            x = convblock(u, self.ref_ups[i], l, up[l], chs[l + 1] + chs[l], chs[l])
+            x = convblock(u, self.ref_ups[i], l, up[l], chs[l + 1] + chs[l], chs[l], tag=f"ref.up{i}")
             if taps is not None:
                 taps[f"refiner.ups.{i}"] = x
         ops.refiner_tail(x, m8, B, T, T8, F, chs[0], self.tail_w, self.tail_b, self.reproj_t,

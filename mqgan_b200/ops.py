@@ -171,7 +171,8 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
               res: Optional[torch.Tensor] = None, res_mode=0, res_coff=0,
               out_f32: Optional[torch.Tensor] = None, f32_coff=0,
               out_bf16: Optional[torch.Tensor] = None, bf16_coff=0,
-              out_split: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None) -> None:
+              out_split: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None,
+              tag: str = "") -> None:
     """Launch mq_conv_gemm.  x: bf16 (N*H*W, in_ld) channel-last (any leading shape)."""
     _chk(x, torch.bfloat16, "x")
     in_ld = x.shape[-1]
@@ -218,7 +219,12 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         if out_split.shape[-1] % 3:
             raise ValueError("out_split last dim must be 3*C")
         p.out_split, p.split_ld, p.split_seg = out_split.data_ptr(), out_split.shape[-1], out_split.shape[-1] // 3
-    _lib.call("mq_conv_gemm", C.byref(p), _stream())
+    meta = None
+    if _lib.profiler is not None:
+        pix = float(N) * H * W
+        meta = {"tag": tag, "flops": 2.0 * pix * pc.cout * pc.cin * pc.taps,            # algorithmic
+                "mma_flops": 2.0 * pix * pc.cout_pad * pc.taps * pc.nseg * pc.kchunks * BLOCK_K}  # issued
+    _lib.call("mq_conv_gemm", C.byref(p), _stream(), meta=meta)
 
 
 # ---------------------------------------------------------------------------
