@@ -1,0 +1,206 @@
+"""Host side of the re-encode CLIs (reference: reencode_spectrograms.py:8-88 and
+reencode_spectrograms_from_checkpoint.py:9-108).
+
+Same observable behaviour: walk ``input_dir`` for ``*.npy`` in ``os.walk`` order,
+form consecutive ``batch_size`` chunks, zero-pad each chunk to its longest
+utterance, ``encode`` -> ``decode`` with the lengths, trim, and save float32
+``(T, n_mels)`` arrays under the mirrored relative path; a failing batch is
+reported and skipped.
+
+Added (additive, never changes results): the unit of sharding is the reference's
+batch (SURVEY §8e - batch composition influences the encoder through padding), so
+with ``world`` workers batch ``i`` goes to worker ``i % world`` and every worker
+writes a disjoint set of files; there is no data-path collective.  Reading and
+writing happen on background threads so disk I/O overlaps the GPU.
+"""
+from __future__ import annotations
+
+import os
+import queue
+import threading
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+def list_npy_files(input_dir: str) -> List[str]:
+    """Recursive *.npy listing in the reference's order (reencode_spectrograms.py:30-34)."""
+    out = []
+    for root, _, files in os.walk(input_dir):
+        for file in files:
+            if file.endswith(".npy"):
+                out.append(os.path.join(root, file))
+    return out
+
+
+def make_batches(files: Sequence[str], batch_size: int) -> List[List[str]]:
+    """Consecutive chunks (reencode_spectrograms.py:43)."""
+    if batch_size < 1:
+        raise ValueError("batch_size must be >= 1")
+    return [list(files[i:i + batch_size]) for i in range(0, len(files), batch_size)]
+
+
+def shard_indices(n_batches: int, rank: int, world: int) -> List[int]:
+    """Batch indices owned by ``rank``: round-robin, disjoint, covering."""
+    if not (0 <= rank < world):
+        raise ValueError("need 0 <= rank < world")
+    return list(range(rank, n_batches, world))
+
+
+def load_and_pad(paths: Sequence[str]) -> Tuple[torch.Tensor, List[int]]:
+    """np.load each file, zero-pad to the longest, stack, float32 (reencode_spectrograms.py:49-62)."""
+    specs = [np.load(p) for p in paths]
+    lengths = [int(s.shape[0]) for s in specs]
+    max_len = max(lengths)
+    n_mels = specs[0].shape[1]
+    batch = np.zeros((len(specs), max_len, n_mels), dtype=np.float32)
+    for i, s in enumerate(specs):
+        if s.shape[1] != n_mels:
+            raise ValueError(f"{paths[i]}: {s.shape[1]} mel channels, expected {n_mels}")
+        batch[i, : s.shape[0]] = s
+    return torch.from_numpy(batch), lengths
+
+
+def save_outputs(reencoded: torch.Tensor, lengths: Sequence[int], paths: Sequence[str], input_dir: str,
+                 output_dir: str) -> None:
+    """Trim to the original length and save under the mirrored path (:69-81)."""
+    arr = reencoded.numpy() if not reencoded.is_cuda else reencoded.cpu().numpy()
+    for i, p in enumerate(paths):
+        out_path = os.path.join(output_dir, os.path.relpath(p, input_dir))
+        os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+        np.save(out_path, np.ascontiguousarray(arr[i, : lengths[i], :], dtype=np.float32))
+
+
+def reencode_tree(run_batch: Callable[[torch.Tensor, List[int]], torch.Tensor], input_dir: str, output_dir: str,
+                  batch_size: int, rank: int = 0, world: int = 1, progress: bool = True,
+                  prefetch: int = 2) -> Tuple[int, int]:
+    """Process this worker's share of the tree.  ``run_batch(batch (B,T,M) float32 CPU, lengths)``
+    returns the re-encoded (B,T,M) tensor (any device).  Returns (files done, batches failed)."""
+    files = list_npy_files(input_dir)
+    if not files:
+        print("Warning: No .npy files were found.")
+        return 0, 0
+    if rank == 0:
+        print(f"Found {len(files)} spectrogram files to process.")
+    batches = make_batches(files, batch_size)
+    mine = shard_indices(len(batches), rank, world)
+
+    in_q: "queue.Queue" = queue.Queue(maxsize=max(1, prefetch))
+    out_q: "queue.Queue" = queue.Queue(maxsize=max(1, prefetch))
+
+    def reader():
+        for bi in mine:
+            paths = batches[bi]
+            try:
+                batch, lengths = load_and_pad(paths)
+                if torch.cuda.is_available():
+                    batch = batch.pin_memory()
+                in_q.put((paths, batch, lengths, None))
+            except Exception as e:  # noqa: BLE001 - mirror the reference's catch-all (:83-85)
+                in_q.put((paths, None, None, e))
+        in_q.put(None)
+
+    failed = [0]
+
+    def writer():
+        while True:
+            item = out_q.get()
+            if item is None:
+                return
+            paths, out, lengths = item
+            try:
+                save_outputs(out, lengths, paths, input_dir, output_dir)
+            except Exception as e:  # noqa: BLE001
+                failed[0] += 1
+                print(f"\nCould not save batch starting with {paths[0]}. Error: {e}")
+
+    rt = threading.Thread(target=reader, daemon=True)
+    wt = threading.Thread(target=writer, daemon=True)
+    rt.start()
+    wt.start()
+    it: Iterable = range(len(mine))
+    if progress and rank == 0:
+        try:
+            from tqdm import tqdm
+            it = tqdm(it, desc="Re-encoding Spectrograms")
+        except Exception:
+            pass
+    done = 0
+    for _ in it:
+        item = in_q.get()
+        if item is None:
+            break
+        paths, batch, lengths, err = item
+        try:
+            if err is not None:
+                raise err
+            out = run_batch(batch, lengths)
+            if out.is_cuda:
+                host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+                host.copy_(out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                out = host
+            out_q.put((paths, out, lengths))
+            done += len(paths)
+        except Exception as e:  # noqa: BLE001
+            failed[0] += 1
+            print(f"\nCould not process batch starting with {paths[0]}. Error: {e}")
+            continue
+    out_q.put(None)
+    wt.join()
+    return done, failed[0]
+
+
+def dist_env() -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from torchrun's environment, (0, 1, 0) otherwise."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def finish_distributed(done: int, failed: int, backend: Optional[str] = None) -> Tuple[int, int]:
+    """Sum the per-worker counters (the only exchange on this path) when launched under torchrun."""
+    rank, world, _ = dist_env()
+    if world == 1:
+        return done, failed
+    import torch.distributed as dist
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group(backend or ("nccl" if torch.cuda.is_available() else "gloo"))
+        created = True
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([done, failed], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    if created:
+        dist.destroy_process_group()
+    return int(t[0]), int(t[1])
+
+
+def _worker(rank: int, world: int, make_model: Callable[[str], object], input_dir: str, output_dir: str,
+            batch_size: int, ret) -> None:
+    torch.cuda.set_device(rank)
+    model = make_model(f"cuda:{rank}")
+
+    def run(batch, lengths):
+        idx = model.encode(batch, lengths=lengths)
+        return model.decode(idx, lengths=lengths)
+
+    ret[rank] = reencode_tree(run, input_dir, output_dir, batch_size, rank, world, progress=(rank == 0))
+
+
+def run_multi_gpu(make_model: Callable[[str], object], input_dir: str, output_dir: str, batch_size: int,
+                  gpus: int) -> Tuple[int, int]:
+    """One worker process per GPU (``--gpus N``); each builds its own model copy."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        procs = [ctx.Process(target=_worker, args=(r, gpus, make_model, input_dir, output_dir, batch_size, ret))
+                 for r in range(gpus)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join()
+        done = sum(v[0] for v in ret.values())
+        failed = sum(v[1] for v in ret.values()) + sum(1 for p in procs if p.exitcode != 0)
+    return done, failed

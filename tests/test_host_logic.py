@@ -1,0 +1,213 @@
+"""CPU tests of the host side: state-dict surface, loaders, CLI batching/sharding,
+C-ABI symbol table (no compute calls - there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from mqgan_b200 import _lib, spec as S, reencode as R, ops
+from mqgan_b200.preencoder import PreEncoder, get_pre_encoder, sequence_mask
+from mqgan_b200.synth import synth_state_dict
+from mqgan_b200.engine import folded_weights
+from oracle import preencoder_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    _lib.build()
+    header = open(os.path.join(ROOT, "include", "mqgan_b200.h")).read()
+    declared = set(re.findall(r"\b(mq_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mq_stream_t"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.mq_version() == 100
+    assert lib.mq_cam_chunks(1000) == 16            # pure host helper, safe without a GPU
+    assert isinstance(lib.mq_last_error(), bytes)
+
+
+def test_ctypes_structs_match_header_sizes(tmp_path):
+    """Compile a tiny C program against the header and compare sizeof() with the ctypes mirrors."""
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "mqgan_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
+                   'sizeof(mq_conv_params),sizeof(mq_cb2d_params),sizeof(mq_cbam_apply_params),sizeof(mq_fsq_params));return 0;}')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = list(map(int, subprocess.check_output([str(exe)]).split()))
+    assert sizes == [ctypes.sizeof(_lib.ConvParams), ctypes.sizeof(_lib.Cb2dParams),
+                     ctypes.sizeof(_lib.CbamApplyParams), ctypes.sizeof(_lib.FsqParams)]
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.MqError, match="no CPU/PyTorch fallback"):
+        _lib.lib()
+
+
+def test_state_dict_surface_and_attributes():
+    cfg = S.HIFISPEECH
+    m = PreEncoder(cfg.mel_channels, list(cfg.channels), list(cfg.kernel_sizes), fsq_levels=list(cfg.fsq_levels),
+                   refiner_base_channels=cfg.refiner_base_channels)
+    keys = [k for k, _ in S.param_spec(cfg)]
+    assert list(m.state_dict().keys()) == keys and len(keys) == 145
+    assert m.codebook_size == 1000 and m.bos_token_id == 1001 and m.eos_token_id == 1002
+    assert m.quantizer_dim == 4 and m.refiner_hidden_channels == 16
+    assert sum(p.numel() for p in m.parameters()) == 30599524      # 30.60 M
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.encode(torch.zeros(1, 8, cfg.mel_channels))
+    assert S.flops_per_frame(cfg)["total"] == pytest.approx(738.78e6, rel=1e-4)
+    assert S.flops_per_frame(S.HIFIMUSIC)["total"] == pytest.approx(1996.02e6, rel=1e-4)
+
+
+def test_get_pre_encoder_errors_and_loading(tmp_path):
+    cfg = S.TINY
+    kw = dict(channels=list(cfg.channels), kernel_sizes=list(cfg.kernel_sizes), mel_channels=cfg.mel_channels,
+              fsq_levels=list(cfg.fsq_levels), refiner_base_channels=cfg.refiner_base_channels)
+    with pytest.raises(FileNotFoundError):
+        get_pre_encoder(str(tmp_path / "missing.pth"), "cpu", **kw)
+    sd = synth_state_dict(cfg)
+    p = tmp_path / "a.pth"
+    torch.save({"not_weights": 1}, p)
+    with pytest.raises(KeyError):
+        get_pre_encoder(str(p), "cpu", **kw)
+    torch.save({"model_state_dict": {"module." + k: v for k, v in sd.items()}}, p)
+    m = get_pre_encoder(str(p), "cpu", inference=True, **kw)
+    assert not m.training and all(torch.equal(m.state_dict()[k], v) for k, v in sd.items())
+    bad = dict(sd)
+    bad.pop("proj.bias")
+    torch.save({"model_state_dict": bad}, p)
+    with pytest.raises(RuntimeError):
+        get_pre_encoder(str(p), "cpu", **kw)
+    # a state-dict with legacy weight-norm already stripped (inference=True export, App. B4) still loads
+    w = folded_weights(sd)
+    stripped = {}
+    for k, v in sd.items():
+        if k.endswith("weight_g"):
+            continue
+        if k.endswith("weight_v"):
+            stripped[k[:-2]] = w[k[:-2]]
+        else:
+            stripped[k] = v
+    torch.save({"model_state_dict": stripped}, p)
+    m2 = get_pre_encoder(str(p), "cpu", **kw)
+    w2 = folded_weights(m2.state_dict())
+    for k in w:
+        assert torch.allclose(w[k], w2[k], atol=1e-6), k
+
+
+def test_folded_weights_equal_oracle_folding():
+    sd = synth_state_dict(S.TINY)
+    a, b = folded_weights(sd), O.effective_weights(sd)
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_weight_packing_layout():
+    w = torch.arange(2 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3) / 16
+    pc = ops.pack_conv(w, torch.zeros(2), "causal1d", split=False)
+    assert (pc.taps, pc.kchunks, pc.nseg, pc.bn, pc.cout_pad) == (3, 1, 1, 32, 32)
+    assert pc.tap_dh == [-2, -1, 0] and pc.wpack.shape == (32, 3 * 64)
+    assert torch.equal(pc.wpack[1, 64:67].float(), w[1, :, 1])
+    ps = ops.pack_conv(w, None, "same1d", split=True)
+    assert ps.tap_dh == [-1, 0, 1] and ps.nseg == 6 and ps.a_coff == [6, 3, 0, 3, 0, 0]
+    w0, w1, w2 = ops.split3_bf16(w)
+    assert torch.equal(w0.float() + w1.float() + w2.float(), w)
+    p2 = ops.pack_conv(torch.randn(768, 64, 3, 3), None, "conv2d3", False)
+    assert (p2.bn, p2.cout_pad, p2.taps) == (256, 768, 9) and p2.tap_dh[0] == -1 and p2.tap_dw[2] == 1
+    assert ops.choose_bn(384) == (192, 384) and ops.choose_bn(96) == (96, 96) and ops.choose_bn(16) == (32, 32)
+    assert ops.choose_tile(1024, 1) == (128, 1) and ops.choose_tile(128, 144) == (8, 16)
+
+
+def test_fsq_params_match_reference_constants():
+    f = ops.fsq_params([8, 5, 5, 5])
+    assert [f.basis[i] for i in range(4)] == [1, 8, 40, 200]
+    assert [f.half_w[i] for i in range(4)] == [4, 2, 2, 2]
+    assert f.half_l[0] == pytest.approx(3.5035) and f.half_l[1] == pytest.approx(2.002)
+    assert f.shift[0] == pytest.approx(0.143695, abs=1e-6) and f.shift[1] == 0.0
+
+
+def _make_tree(root, n, seed=0):
+    rng = np.random.default_rng(seed)
+    paths = []
+    for i in range(n):
+        d = os.path.join(root, f"spk{i % 3}", "sub" if i % 2 else "")
+        os.makedirs(d, exist_ok=True)
+        p = os.path.join(d, f"utt{i}.npy")
+        np.save(p, rng.standard_normal((int(rng.integers(5, 40)), 8)).astype(np.float64 if i % 4 == 0 else np.float32))
+        paths.append(p)
+    return paths
+
+
+def _fake_run(batch, lengths):
+    # stands in for encode->decode; depends on the batch composition like the real encoder does
+    return batch * 2.0 + float(batch.shape[1])
+
+
+def test_reencode_tree_matches_reference_batching(tmp_path):
+    src, dst = str(tmp_path / "in"), str(tmp_path / "out")
+    _make_tree(src, 11)
+    files = R.list_npy_files(src)
+    assert len(files) == 11
+    batches = R.make_batches(files, 4)
+    assert [len(b) for b in batches] == [4, 4, 3]
+    done, failed = R.reencode_tree(_fake_run, src, dst, 4, progress=False)
+    assert (done, failed) == (11, 0)
+    for b in batches:
+        tmax = max(np.load(p).shape[0] for p in b)
+        for p in b:
+            x = np.load(p)
+            y = np.load(os.path.join(dst, os.path.relpath(p, src)))
+            assert y.dtype == np.float32 and y.shape == x.shape
+            np.testing.assert_allclose(y, x.astype(np.float32) * 2 + tmax)
+
+
+def test_sharding_is_disjoint_and_order_preserving(tmp_path):
+    src = str(tmp_path / "in")
+    _make_tree(src, 23, seed=1)
+    ref = str(tmp_path / "ref")
+    R.reencode_tree(_fake_run, src, ref, 3, progress=False)
+    for world in (2, 3):
+        dst = str(tmp_path / f"w{world}")
+        total = 0
+        seen = set()
+        for rank in range(world):
+            idxs = R.shard_indices(8, rank, world)
+            assert not (seen & set(idxs))
+            seen |= set(idxs)
+            d, f = R.reencode_tree(_fake_run, src, dst, 3, rank, world, progress=False)
+            total += d
+            assert f == 0
+        assert seen == set(range(8)) and total == 23
+        for p in R.list_npy_files(ref):
+            q = os.path.join(dst, os.path.relpath(p, ref))
+            assert np.array_equal(np.load(p), np.load(q))         # byte-identical to the 1-worker run
+
+
+def test_failing_batch_is_skipped(tmp_path, capsys):
+    src, dst = str(tmp_path / "in"), str(tmp_path / "out")
+    _make_tree(src, 6)
+    calls = {"n": 0}
+
+    def flaky(batch, lengths):
+        calls["n"] += 1
+        if calls["n"] == 2:
+            raise RuntimeError("boom")
+        return batch
+
+    done, failed = R.reencode_tree(flaky, src, dst, 2, progress=False)
+    assert (done, failed) == (4, 1)
+    assert "Could not process batch" in capsys.readouterr().out
+
+
+def test_sequence_mask_matches_reference_definition():
+    lengths = torch.tensor([3, 0, 5])
+    m = sequence_mask(5, lengths)
+    assert m.tolist() == [[False, False, False, True, True], [True] * 5, [False] * 5]
+    assert torch.equal(m, O.sequence_mask(5, lengths))
