@@ -105,6 +105,15 @@ int mq_split_bf16(const float* x, void* out, int64_t rows, int C, int nterms, mq
  * (preencoder.py:288-295) is never materialised.
  * dw: 25 floats [i over channel][j over time] then the dw bias (26 total, folded
  * weight-norm); pw: C x {wpw, bpw, wout} interleaved as float4-padded triples.
+ *
+ * y depends on the pixel only through the scalar s, so the C-term sum
+ * g(s) = sum_k wout[k]*aptx(wpw[k]*s + bpw[k]) + bout is a fixed univariate function
+ * of the model.  If `table` is non-NULL it holds per-interval cubic coefficients of g
+ * on a uniform grid: interval i covers s*table_inv_h in [i - table_off, i - table_off + 1),
+ * g ~= c0 + t*(c1 + t*(c2 + t*c3)), t = frac(s*table_inv_h); table_inv_h must be a power
+ * of two so t is exact.  Pixels whose s falls outside the grid use the exact C-term sum.
+ * The host builds the table in float64 and verifies it against the exact sum
+ * (mqgan_b200/engine.py:_CB2D); with table == NULL every pixel is evaluated exactly.
  */
 typedef struct mq_cb2d_params {
   const void* x; int x_is_bf16;   /* fp32 or bf16 input */
@@ -117,6 +126,9 @@ typedef struct mq_cb2d_params {
   float* out_f32;                 /* optional (B,T,C) */
   void* out_bf16;                 /* optional (B,T,C) */
   void* out_split;                /* optional (B,T,3C) bf16x3 */
+  const float* table;             /* optional [table_n][4] cubic coefficients of g */
+  int table_n, table_off;
+  float table_inv_h;
 } mq_cb2d_params;
 int mq_convblock2d(const mq_cb2d_params* p, mq_stream_t stream);
 

@@ -58,6 +58,7 @@ class Cb2dParams(C.Structure):
         ("row_mask", C.c_void_p),
         ("fast_tanh", C.c_int),
         ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("out_split", C.c_void_p),
+        ("table", C.c_void_p), ("table_n", C.c_int), ("table_off", C.c_int), ("table_inv_h", C.c_float),
     ]
 
 

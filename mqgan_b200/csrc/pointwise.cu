@@ -141,6 +141,101 @@ convblock2d_kernel(const void* __restrict__ xin, int B, int T, int C, const floa
   }
 }
 
+// K2, table mode: g(s) from per-interval cubics (HBM-bound instead of MUFU-bound).
+// Block = (b, 8 frames, 128 channels); thread = 4 consecutive channels of one frame.
+constexpr int kCtT = 8, kCtC = 128;
+
+template <bool kFast, bool kInBf16>
+__global__ void __launch_bounds__(256)
+convblock2d_table_kernel(const void* __restrict__ xin, int B, int T, int C, const float* __restrict__ dw,
+                         const float4* __restrict__ pw, float bout, const uint8_t* __restrict__ row_mask,
+                         const float4* __restrict__ table, int table_n, int table_off, float inv_h,
+                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
+                         __nv_bfloat16* __restrict__ out_split) {
+  __shared__ float tile[kCtT + 4][kCtC + 4];
+  __shared__ float dws[26];
+  const int ctiles = (C + kCtC - 1) / kCtC;
+  const int ttiles = (T + kCtT - 1) / kCtT;
+  int bid = blockIdx.x;
+  const int ct = bid % ctiles; bid /= ctiles;
+  const int tt = bid % ttiles;
+  const int b = bid / ttiles;
+  const int t0 = tt * kCtT, c0 = ct * kCtC;
+  if (threadIdx.x < 26) dws[threadIdx.x] = dw[threadIdx.x];
+  for (int i = threadIdx.x; i < (kCtT + 4) * (kCtC + 4); i += blockDim.x) {
+    const int lt = i / (kCtC + 4), lc = i - lt * (kCtC + 4);
+    const int t = t0 + lt - 2, c = c0 + lc - 2;
+    float v = 0.0f;
+    if (t >= 0 && t < T && c >= 0 && c < C) {
+      const int64_t off = (static_cast<int64_t>(b) * T + t) * C + c;
+      v = kInBf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(xin)[off])
+                  : reinterpret_cast<const float*>(xin)[off];
+    }
+    tile[lt][lc] = v;
+  }
+  __syncthreads();
+  const int lt = threadIdx.x >> 5;              // 8 frames
+  const int lc = (threadIdx.x & 31) * 4;        // 32 x 4 channels
+  const int t = t0 + lt, c = c0 + lc;
+  if (t >= T || c >= C) return;
+  const int64_t row = static_cast<int64_t>(b) * T + t;
+  const bool masked = row_mask != nullptr && row_mask[row] != 0;
+  float y[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float acc = dws[25];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) acc = fmaf(dws[i * 5 + j], tile[lt + j][lc + e + i], acc);
+    const float s = acc;
+    const float u = s * inv_h;                  // inv_h is a power of two: exact
+    const float fl = floorf(u);
+    const int idx = static_cast<int>(fl) + table_off;
+    float g;
+    if (idx >= 0 && idx < table_n) {
+      const float tt_ = u - fl;                 // exact
+      const float4 cf = __ldg(table + idx);
+      g = fmaf(tt_, fmaf(tt_, fmaf(tt_, cf.w, cf.z), cf.y), cf.x);
+    } else {                                    // outside the grid (or NaN): exact C-term sum
+      float a = 0.0f;
+      for (int k = 0; k < C; ++k) {
+        const float4 p = __ldg(pw + k);
+        const float uu = fmaf(p.x, s, p.y);
+        const float th = kFast ? tanh_fast(uu) : tanh_precise(uu);
+        a = fmaf(fmaf(uu, th, uu), 0.5f * p.z, a);
+      }
+      g = a + bout;
+    }
+    y[e] = masked ? bout : g;
+  }
+  const int nv = min(4, C - c);
+  if (nv == 4) {
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out_bf16) {
+      uint2 u2;
+      u2.x = pack_bf16x2(y[0], y[1]);
+      u2.y = pack_bf16x2(y[2], y[3]);
+      *reinterpret_cast<uint2*>(out_bf16 + row * C + c) = u2;
+    }
+    if (out_split) {
+      __nv_bfloat16 tq[3][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split3(y[e], tq[0][e], tq[1][e], tq[2][e]);
+      __nv_bfloat16* op = out_split + row * 3 * C + c;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        *reinterpret_cast<uint2*>(op + static_cast<int64_t>(j) * C) = *reinterpret_cast<uint2*>(tq[j]);
+    }
+  } else {
+    for (int e = 0; e < nv; ++e) {
+      if (out_f32) out_f32[row * C + c + e] = y[e];
+      if (out_bf16) out_bf16[row * C + c + e] = __float2bfloat16_rn(y[e]);
+      if (out_split) store_split3(out_split + row * 3 * C + c + e, C, y[e]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K5: CAM reduce / gate
 // ---------------------------------------------------------------------------
@@ -677,6 +772,26 @@ extern "C" int mq_convblock2d(const mq_cb2d_params* p, mq_stream_t stream) {
   auto* ob = reinterpret_cast<__nv_bfloat16*>(p->out_bf16);
   auto* os = reinterpret_cast<__nv_bfloat16*>(p->out_split);
   const float4* pw = reinterpret_cast<const float4*>(p->pw);
+  if (p->table != nullptr) {
+    MQ_REQUIRE(p->table_n > 0 && p->table_inv_h > 0.0f, "mq_convblock2d: bad table");
+    MQ_REQUIRE(p->C % 4 == 0, "mq_convblock2d: table mode needs C %% 4 == 0");
+    const int ct2 = (p->C + kCtC - 1) / kCtC, tt2 = (p->T + kCtT - 1) / kCtT;
+    const long long nb = 1LL * p->B * tt2 * ct2;
+    MQ_REQUIRE(nb < (1LL << 31), "mq_convblock2d: grid too large");
+    const float4* tb = reinterpret_cast<const float4*>(p->table);
+#define LAUNCH_CT(FAST, INBF)                                                                     \
+  convblock2d_table_kernel<FAST, INBF><<<static_cast<unsigned>(nb), 256, 0, STREAM(stream)>>>(    \
+      p->x, p->B, p->T, p->C, p->dw, pw, p->bout, p->row_mask, tb, p->table_n, p->table_off,      \
+      p->table_inv_h, p->out_f32, ob, os)
+    if (p->fast_tanh) {
+      if (p->x_is_bf16) LAUNCH_CT(true, true); else LAUNCH_CT(true, false);
+    } else {
+      if (p->x_is_bf16) LAUNCH_CT(false, true); else LAUNCH_CT(false, false);
+    }
+#undef LAUNCH_CT
+    MQ_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   dim3 grid(static_cast<unsigned>(blocks));
 #define LAUNCH_CB(FAST, INBF)                                                                     \
   convblock2d_kernel<FAST, INBF><<<grid, 256, smem, STREAM(stream)>>>(                            \

@@ -55,10 +55,48 @@ def folded_weights(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return out
 
 
+def cb2d_exact_g(s: torch.Tensor, wpw, bpw, wout, bout) -> torch.Tensor:
+    """g(s) = sum_k wout_k * aptx(wpw_k s + bpw_k; 1, .5) + bout in the dtype of ``s``
+    (preencoder.py:288-295 restated for one scalar pixel value)."""
+    u = s[:, None] * wpw[None, :] + bpw[None, :]
+    return ((1 + torch.tanh(u)) * 0.5 * u) @ wout + bout
+
+
+def build_cb2d_table(wpw, bpw, wout, bout, s_max: float = 64.0, tol: float = 2.5e-7, max_intervals: int = 1 << 17,
+                     device="cpu"):
+    """Per-interval cubic fit of g on [-s_max, s_max) (Chebyshev nodes, float64), refined
+    until the float32-evaluated cubic matches the float64 exact sum to ``tol`` * max(1, |g|)
+    (about two fp32 ulps) at interior test points.  Load-time work, done with torch float64
+    on ``device``.  Returns (coeffs float32 [n,4], offset, inv_h, max_err) or None."""
+    wpw, bpw, wout = wpw.double().to(device), bpw.double().to(device), wout.double().to(device)
+    nodes = 0.5 - 0.5 * torch.cos((2 * torch.arange(4, dtype=torch.float64, device=device) + 1) * torch.pi / 8)
+    V = torch.stack([nodes ** j for j in range(4)], dim=1)                                          # (4 nodes, 4 coeffs)
+    Vinv = torch.linalg.inv(V)
+    tests = torch.tensor([0.0, 0.21, 0.5, 0.79, 0.999], dtype=torch.float64, device=device)
+    inv_h = 32.0
+    while True:
+        n = int(2 * s_max * inv_h)
+        if n > max_intervals:
+            return None
+        left = (torch.arange(n, dtype=torch.float64, device=device) - n // 2) / inv_h
+        pts = (left[:, None] + nodes[None, :] / inv_h).reshape(-1)
+        g = torch.cat([cb2d_exact_g(c, wpw, bpw, wout, bout) for c in pts.split(1 << 14)]).reshape(n, 4)
+        coef = (g @ Vinv.T).float()                                                                 # (n, 4)
+        tp = (left[:, None] + tests[None, :] / inv_h).reshape(-1)
+        ref = torch.cat([cb2d_exact_g(c, wpw, bpw, wout, bout) for c in tp.split(1 << 14)]).reshape(n, -1)
+        t32 = tests.float()[None, :]
+        c = coef
+        approx = torch.addcmul(c[:, 0:1], t32, torch.addcmul(c[:, 1:2], t32, torch.addcmul(c[:, 2:3], t32, c[:, 3:4])))
+        err = ((approx.double() - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
+        if err <= tol:
+            return coef.contiguous(), n // 2, inv_h, err
+        inv_h *= 2.0
+
+
 class _CB2D:
     """Packed ConvBlock2D parameters (preencoder.py:251-268)."""
 
-    def __init__(self, w: Dict[str, torch.Tensor], prefix: str, device):
+    def __init__(self, w: Dict[str, torch.Tensor], prefix: str, device, use_table: bool = True):
         dw = torch.cat([w[prefix + ".dw.weight"].reshape(25), w[prefix + ".dw.bias"].reshape(1)])
         c = w[prefix + ".pw.weight"].shape[0]
         pw = torch.zeros(c, 4)
@@ -69,11 +107,22 @@ class _CB2D:
         self.pw = pw.float().contiguous().to(device)
         self.bout = float(w[prefix + ".conv_out.bias"].reshape(()))
         self.c = c
+        self.table, self.table_off, self.table_inv_h, self.table_err = None, 0, 0.0, None
+        if use_table and c % 4 == 0:
+            t = build_cb2d_table(pw[:, 0], pw[:, 1], pw[:, 2], self.bout, device=device)
+            if t is not None:
+                self.table = t[0].to(device)
+                self.table_off, self.table_inv_h, self.table_err = t[1], t[2], t[3]
+
+    def kwargs(self):
+        if self.table is None:
+            return {}
+        return {"table": self.table, "table_off": self.table_off, "table_inv_h": self.table_inv_h}
 
 
 class PreEncoderEngine:
     def __init__(self, cfg: PreEncoderConfig, state_dict: Dict[str, torch.Tensor], device="cuda",
-                 encoder_precision: str = "bf16x3", max_chunk_frames: int = 32768):
+                 encoder_precision: str = "bf16x3", max_chunk_frames: int = 32768, cb2d_table: bool = True):
         if encoder_precision not in ("bf16x3", "bf16"):
             raise ValueError("encoder_precision must be 'bf16x3' or 'bf16'")
         self.cfg = cfg
@@ -93,7 +142,7 @@ class PreEncoderEngine:
 
         # ---------------- encoder ----------------
         self.proj = pack_conv(w["proj.weight"], w["proj.bias"], "linear", sp).to(dev)
-        self.pre = _CB2D(w, "pre", dev)
+        self.pre = _CB2D(w, "pre", dev, cb2d_table)
         self.enc = []
         for i, (cin, cout, k) in enumerate(cfg.encoder_layers):
             p = f"encoder_blocks.{i}"
@@ -140,7 +189,7 @@ class PreEncoderEngine:
                 blk["res"] = pack_conv(w[p + ".residual.weight"].squeeze(-1), w[p + ".residual.bias"],
                                        "linear", False).to(dev)
             self.dec.append(blk)
-        self.post = _CB2D(w, "post", dev)
+        self.post = _CB2D(w, "post", dev, cb2d_table)
         self.out_proj = pack_conv(w["out_proj.weight"], w["out_proj.bias"], "linear", False).to(dev)
         self.hidden_proj = pack_conv(w["hidden_proj.weight"], w["hidden_proj.bias"], "linear", False).to(dev)
 
@@ -218,7 +267,7 @@ class PreEncoderEngine:
         x32 = torch.empty(rows, cfg.c0, dtype=torch.float32, device=dev)
         xs = act_buf(cfg.c0)
         ops.convblock2d(h, B, T, cfg.c0, self.pre.dw, self.pre.pw, self.pre.bout, m8, False,
-                        out_f32=x32, **kw_out(xs))                                          # :440
+                        out_f32=x32, **kw_out(xs), **self.pre.kwargs())                                          # :440
         if taps is not None:
             taps["proj"], taps["pre"] = h, x32
         for i, blk in enumerate(self.enc):                                                  # :443-444
@@ -297,7 +346,7 @@ class PreEncoderEngine:
         dec_out = x
         pz = torch.empty(rows, cfg.c0, dtype=torch.bfloat16, device=dev)
         ops.convblock2d(dec_out, B, T, cfg.c0, self.post.dw, self.post.pw, self.post.bout, m8, True,
-                        out_bf16=pz)                                                        # :482
+                        out_bf16=pz, **self.post.kwargs())                                                        # :482
         F, M = cfg.refiner_width, cfg.mel_channels
         R = torch.empty(rows, F, dtype=torch.float32, device=dev)
         ops.conv_gemm(pz, self.out_proj, B, T, 1, out_f32=R, f32_coff=0, tag="dec.out_proj")                    # :486

@@ -241,7 +241,8 @@ def split_bf16(x: torch.Tensor, nterms: int) -> torch.Tensor:
 
 def convblock2d(x: torch.Tensor, B: int, T: int, Cc: int, dw: torch.Tensor, pw: torch.Tensor, bout: float,
                 row_mask: Optional[torch.Tensor], fast_tanh: bool, *, out_f32=None, out_bf16=None,
-                out_split=None) -> None:
+                out_split=None, table: Optional[torch.Tensor] = None, table_off: int = 0,
+                table_inv_h: float = 0.0) -> None:
     p = Cb2dParams()
     if x.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("x must be fp32 or bf16")
@@ -252,6 +253,9 @@ def convblock2d(x: torch.Tensor, B: int, T: int, Cc: int, dw: torch.Tensor, pw: 
     p.row_mask = _ptr(row_mask)
     p.fast_tanh = int(fast_tanh)
     p.out_f32, p.out_bf16, p.out_split = _ptr(out_f32), _ptr(out_bf16), _ptr(out_split)
+    if table is not None:
+        _chk(table, torch.float32, "table")
+        p.table, p.table_n, p.table_off, p.table_inv_h = table.data_ptr(), table.shape[0], int(table_off), float(table_inv_h)
     _lib.call("mq_convblock2d", C.byref(p), _stream())
 
 

@@ -297,3 +297,38 @@ def test_sequence_mask_kernel():
     lengths = torch.tensor([5, 0, 9, 3])
     m = ops.sequence_mask(lengths.to(DEV), 9)
     assert torch.equal(m.cpu().bool(), O.sequence_mask(9, lengths))
+
+
+def test_convblock2d_table_mode_matches_exact_sum():
+    """The tabulated g(s) (per-interval cubics, built in float64) against the float64 oracle and
+    the exact-sum kernel, including pixels outside the table range (exact fallback)."""
+    from mqgan_b200.engine import build_cb2d_table
+    B, T, Cc = 2, 45, 128
+    x = _rand(B, T, Cc, seed=50) * 3.0
+    x[0, 7, 40:48] = 400.0           # pushes some s beyond +-64 -> exact fallback path
+    w = {"p.dw.weight": _rand(1, 1, 5, 5, seed=51) * 0.3, "p.dw.bias": _rand(1, seed=52) * 0.1,
+         "p.pw.weight": _rand(Cc, 1, 1, 1, seed=53), "p.pw.bias": _rand(Cc, seed=54),
+         "p.conv_out.weight": _rand(1, Cc, 1, 1, seed=55) / Cc ** 0.5, "p.conv_out.bias": _rand(1, seed=56)}
+    lengths = torch.tensor([T, 30])
+    mask = O.sequence_mask(T, lengths)
+    ref = O.convblock2d(x.permute(0, 2, 1).double(), mask.unsqueeze(1), {k: v.double() for k, v in w.items()}, "p").permute(0, 2, 1)
+    dw = torch.cat([w["p.dw.weight"].reshape(25), w["p.dw.bias"]]).to(DEV)
+    pw = torch.zeros(Cc, 4)
+    pw[:, 0], pw[:, 1], pw[:, 2] = w["p.pw.weight"].reshape(Cc), w["p.pw.bias"], w["p.conv_out.weight"].reshape(Cc)
+    bout = float(w["p.conv_out.bias"])
+    coef, off, inv_h, terr = build_cb2d_table(pw[:, 0], pw[:, 1], pw[:, 2], bout, device=DEV)
+    assert terr <= 2.5e-7
+    m8 = mask.to(torch.uint8).to(DEV)
+    ot = torch.empty(B, T, Cc, dtype=torch.float32, device=DEV)
+    oe = torch.empty(B, T, Cc, dtype=torch.float32, device=DEV)
+    osp = torch.empty(B, T, 3 * Cc, dtype=torch.bfloat16, device=DEV)
+    ops.convblock2d(x.to(DEV), B, T, Cc, dw, pw.to(DEV), bout, m8, False, out_f32=ot, out_split=osp,
+                    table=coef.to(DEV), table_off=off, table_inv_h=inv_h)
+    ops.convblock2d(x.to(DEV), B, T, Cc, dw, pw.to(DEV), bout, m8, False, out_f32=oe)
+    scale = max(1.0, ref.abs().max().item())
+    e_t = (ot.cpu().double() - ref).abs().max().item()
+    e_e = (oe.cpu().double() - ref).abs().max().item()
+    print("table err", e_t, "exact-kernel err", e_e, "scale", scale)
+    assert e_t < 5e-6 * scale and e_e < 5e-6 * scale
+    assert (osp.cpu().float().reshape(B, T, 3, Cc).sum(2) - ot.cpu()).abs().max().item() < 1e-6 * scale
+    assert torch.all(ot[1, 30:] == bout)
