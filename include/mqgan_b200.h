@@ -75,7 +75,9 @@ typedef struct mq_conv_params {
   int tap_dh[MQ_MAX_TAPS];
   int tap_dw[MQ_MAX_TAPS];
   int a_coff[MQ_MAX_SEGS];
-  int bh, bw;    /* pixel tile, bh*bw <= 128 */
+  int bh, bw;    /* pixel sub-tile, bh*bw <= 128 */
+  int msub;      /* sub-tiles (stacked along H) per CTA tile sharing one weight tile: 1, 2 or 4
+                    with msub*bn <= 256; 0 = 1.  Cuts L2->SM weight traffic for narrow layers. */
   /* epilogue */
   const float* bias;       /* [cout] or NULL */
   const uint8_t* row_mask; /* [N*H] or NULL */

@@ -34,7 +34,7 @@ class ConvParams(C.Structure):
         ("tap_dh", C.c_int * MQ_MAX_TAPS),
         ("tap_dw", C.c_int * MQ_MAX_TAPS),
         ("a_coff", C.c_int * MQ_MAX_SEGS),
-        ("bh", C.c_int), ("bw", C.c_int),
+        ("bh", C.c_int), ("bw", C.c_int), ("msub", C.c_int),
         ("bias", C.c_void_p),
         ("row_mask", C.c_void_p),
         ("mask_pre", C.c_int), ("mask_post", C.c_int),

@@ -37,6 +37,7 @@ struct ConvArgs {
   int N, H, W;
   int tiles_h, tiles_w, tiles_n, num_tiles;
   int bh, bw, bn, cout;
+  int msub;                       // 128-pixel sub-tiles per CTA tile (share one B tile); msub*bn <= 256
   int taps, nseg, kchunks;
   int tap_dh[MQ_MAX_TAPS], tap_dw[MQ_MAX_TAPS], a_coff[MQ_MAX_SEGS];
   int stages;
@@ -68,7 +69,7 @@ __device__ __forceinline__ void decode_tile(const ConvArgs& a, int tile, int& n_
   int t2 = tm / a.tiles_w;
   int th = t2 % a.tiles_h;
   n_idx = t2 / a.tiles_h;
-  h0 = th * a.bh;
+  h0 = th * a.bh * a.msub;
   w0 = tw * a.bw;
   n0 = tn * a.bn;
 }
@@ -83,8 +84,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   const int stages = a.stages;
+  const int a_stage_bytes = a.msub * kATileBytes;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + stages * kATileBytes;
+  uint8_t* smem_b = smem + stages * a_stage_bytes;
   uint8_t* tail = smem_b + stages * a.b_tile_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -136,9 +138,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
             const int cbase = a.a_coff[seg];
             for (int kc = 0; kc < a.kchunks; ++kc, ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_expect_tx(&full_bar[stage], a.a_tx_bytes + a.b_tile_bytes);
-              tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * kATileBytes,
-                          cbase + kc * kBlockK, ww, hh, n_idx);
+              mbar_expect_tx(&full_bar[stage], a.msub * a.a_tx_bytes + a.b_tile_bytes);
+              for (int sub = 0; sub < a.msub; ++sub)
+                tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * a_stage_bytes + sub * kATileBytes,
+                            cbase + kc * kBlockK, ww, hh + sub * a.bh, n_idx);
               tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * a.b_tile_bytes,
                           kb * kBlockK, n0);
               if (++stage == stages) {
@@ -165,12 +168,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
           const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * a.b_tile_bytes));
+          for (int sub = 0; sub < a.msub; ++sub) {
+            const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * a_stage_bytes + sub * kATileBytes));
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 field
+              umma_bf16(d_tmem + sub * a.bn, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
           if (++stage == stages) {
@@ -198,15 +203,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
         bs[j] = (a.bias != nullptr && n0 + j < a.cout) ? a.bias[n0 + j] : 0.0f;
       named_bar_sync(1, kEpiThreads);
 
-      const int h = h0 + lh, w = w0 + lw;
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      for (int sub = 0; sub < a.msub; ++sub) {
+      const int h = h0 + sub * a.bh + lh, w = w0 + lw;
       const bool valid = (r < a.bh * a.bw) && (h < a.H) && (w < a.W);
       const int64_t row = static_cast<int64_t>(n_idx) * a.H + h;
       const int64_t pix = row * a.W + w;
       const bool masked = valid && a.row_mask != nullptr && a.row_mask[row] != 0;
-
-      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride + sub * a.bn;
 
       for (int c = 0; c < a.bn; c += 32) {
         uint32_t v[32];
@@ -342,6 +347,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
           }
         }
       }
+      }  // sub
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld above)
       tc_fence_before();
       __syncwarp();
@@ -378,8 +384,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int conv_smem_bytes(int stages, int b_tile_bytes) {
-  return 1024 /*alignment slack*/ + stages * (kATileBytes + b_tile_bytes) +
+static int conv_smem_bytes(int stages, int a_stage_bytes, int b_tile_bytes) {
+  return 1024 /*alignment slack*/ + stages * (a_stage_bytes + b_tile_bytes) +
          (2 * kMaxStages + 4) * 8 + 16 + 2 * 256 * 4;
 }
 
@@ -415,7 +421,9 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   memset(&a, 0, sizeof(a));
   a.N = p->N; a.H = p->H; a.W = p->W;
   a.bh = p->bh; a.bw = p->bw; a.bn = p->bn; a.cout = p->cout;
-  a.tiles_h = (p->H + p->bh - 1) / p->bh;
+  a.msub = p->msub > 0 ? p->msub : 1;
+  MQ_REQUIRE(a.msub * p->bn <= kAccStride && a.msub <= 4, "mq_conv_gemm: msub=%d * bn=%d exceeds %d TMEM columns", a.msub, p->bn, kAccStride);
+  a.tiles_h = (p->H + p->bh * a.msub - 1) / (p->bh * a.msub);
   a.tiles_w = (p->W + p->bw - 1) / p->bw;
   a.tiles_n = p->cout_pad / p->bn;
   const long long nt = 1LL * p->N * a.tiles_h * a.tiles_w * a.tiles_n;
@@ -426,7 +434,8 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   for (int i = 0; i < MQ_MAX_SEGS; ++i) a.a_coff[i] = p->a_coff[i];
   a.a_tx_bytes = static_cast<uint32_t>(p->bh * p->bw * kBlockK * 2);
   a.b_tile_bytes = static_cast<uint32_t>(p->bn * kBlockK * 2);
-  int stages = (kSmemBudget - 1024 - 4096) / (kATileBytes + static_cast<int>(a.b_tile_bytes));
+  const int a_stage_bytes = a.msub * kATileBytes;
+  int stages = (kSmemBudget - 1024 - 4096) / (a_stage_bytes + static_cast<int>(a.b_tile_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
   MQ_REQUIRE(stages >= 2, "mq_conv_gemm: not enough shared memory for 2 stages");
   a.stages = stages;
@@ -470,7 +479,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   int dev = 0, sms = 0;
   MQ_CUDA_OK(cudaGetDevice(&dev));
   MQ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int smem = conv_smem_bytes(stages, static_cast<int>(a.b_tile_bytes));
+  const int smem = conv_smem_bytes(stages, a_stage_bytes, static_cast<int>(a.b_tile_bytes));
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
   if (p->fast_tanh) {
     MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -165,6 +166,21 @@ def choose_tile(H: int, W: int) -> Tuple[int, int]:
     return best[1], best[2]
 
 
+def choose_msub(bn: int, N: int, H: int, W: int, bh: int, bw: int) -> int:
+    """Sub-tiles per CTA tile.  Narrow layers (bn <= 128) are bound by L2->SM operand traffic:
+    stacking 2-4 pixel sub-tiles on one weight tile amortises the weight loads.
+    Only when there are still >= 2 waves of tiles for 148 SMs."""
+    override = os.environ.get("MQ_MSUB")
+    if override:
+        m = int(override)
+        return m if m * bn <= 256 else 1
+    m = 4 if bn <= 64 else (2 if bn <= 128 else 1)
+    tiles_w = math.ceil(W / bw)
+    while m > 1 and N * math.ceil(H / (bh * m)) * tiles_w < 2 * 148:
+        m //= 2
+    return m
+
+
 def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
               row_mask: Optional[torch.Tensor] = None, mask_pre=False, mask_post=False,
               act=False, beta=1.0, gamma=0.5, fast_tanh=True,
@@ -172,7 +188,7 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
               out_f32: Optional[torch.Tensor] = None, f32_coff=0,
               out_bf16: Optional[torch.Tensor] = None, bf16_coff=0,
               out_split: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None,
-              tag: str = "") -> None:
+              msub: Optional[int] = None, tag: str = "") -> None:
     """Launch mq_conv_gemm.  x: bf16 (N*H*W, in_ld) channel-last (any leading shape)."""
     _chk(x, torch.bfloat16, "x")
     in_ld = x.shape[-1]
@@ -191,6 +207,7 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         p.a_coff[i] = pc.a_coff[i]
     bh, bw = tile if tile is not None else choose_tile(H, W)
     p.bh, p.bw = bh, bw
+    p.msub = choose_msub(pc.bn, N, H, W, bh, bw) if msub is None else msub
     p.bias = _ptr(pc.bias)
     if row_mask is not None:
         _chk(row_mask, torch.uint8, "row_mask")

@@ -332,3 +332,25 @@ def test_convblock2d_table_mode_matches_exact_sum():
     assert e_t < 5e-6 * scale and e_e < 5e-6 * scale
     assert (osp.cpu().float().reshape(B, T, 3, Cc).sum(2) - ot.cpu()).abs().max().item() < 1e-6 * scale
     assert torch.all(ot[1, 30:] == bout)
+
+
+@pytest.mark.parametrize("kind,N,H,W,Cin,Cout,tail,msub", [
+    ("conv2d3", 2, 40, 144, 64, 64, (3, 3), 4),      # narrow layer: 4 sub-tiles share one weight tile
+    ("conv2d3", 1, 21, 36, 128, 128, (3, 3), 2),     # H not a multiple of msub*bh
+    ("same1d", 2, 700, 1, 64, 96, (3,), 2),
+    ("causal1d", 1, 513, 1, 128, 32, (5,), 4),
+])
+def test_conv_gemm_multi_subtile(kind, N, H, W, Cin, Cout, tail, msub):
+    x = _rand(N, H, W, Cin, seed=61).to(torch.bfloat16)
+    w = (_rand(Cout, Cin, *tail, seed=62) / (Cin * max(1, int(np.prod(tail)))) ** 0.5).to(torch.bfloat16)
+    b = _rand(Cout, seed=63)
+    mask = torch.zeros(N, H, dtype=torch.uint8)
+    mask[0, H // 2:] = 1
+    ref = O.aptx(_ref_conv(x.double(), w.double(), b.double(), kind), 1.0, 0.5)
+    ref = ref.masked_fill(mask.bool()[:, :, None, None], 0.0)
+    pc = ops.pack_conv(w.float(), b, kind, split=False).to(DEV)
+    out = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
+    ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, fast_tanh=False,
+                  out_f32=out, msub=msub)
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
