@@ -209,13 +209,14 @@ int mq_upcat_mask(const void* x, const void* skip, void* y, const uint8_t* mask_
 int mq_refiner_stem(const float* r, const uint8_t* mask, int B, int T, int T8, int F, int C,
                     const float* w, const float* b, int fast_tanh, void* y, mq_stream_t stream);
 /* refiner.post (C -> 1, 3x3) + crop + mask + reproj (F -> M, no bias) + x_recon add
- * (preencoder.py:191-200, 499).  x (B, T8, F, C) bf16 (already masked), w (9, C)
- * folded (tap = 3*(dt+1) + (df+1)), reproj_t (F, M) = reproj.weight transposed;
- * r (B, T, F) fp32 whose first M columns are x_recon; mask (B*T) or NULL;
- * out (B, T, M) fp32 = x_post. */
-int mq_refiner_tail(const void* x, const uint8_t* mask, int B, int T, int T8, int F, int C,
-                    const float* w, float bias, const float* reproj_t, int M, const float* r,
-                    float* out, mq_stream_t stream);
+ * (preencoder.py:191-200, 499).  The C -> 1 3x3 convolution is split into a 1x1 tcgen05 GEMM
+ * C -> 9 (mq_conv_gemm with the (9, C) folded weight, tap k = 3*(dt+1) + (df+1)) producing
+ * taps (B, T8, F, ldp) fp32, and this kernel: post[t,f] = bias + sum_k taps[t+dt, f+df, k]
+ * (zero outside the image), crop to T, mask, reproj_t (F, M) = reproj.weight transposed,
+ * out (B, T, M) fp32 = r[..., :M] + residual, r (B, T, F) = cat[x_recon, hidden]. */
+int mq_refiner_tail(const float* taps, int ldp, const uint8_t* mask, int B, int T, int T8, int F,
+                    float bias, const float* reproj_t, int M, const float* r, float* out,
+                    mq_stream_t stream);
 
 /* ---- sequence mask (preencoder.py:15-24) ----------------------------------- */
 int mq_sequence_mask(const int64_t* lengths, int B, int T, uint8_t* mask, mq_stream_t stream);

@@ -25,8 +25,8 @@ namespace mq {
 constexpr int kBlockK = 64;                 // bf16 per K block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;                  // K per tcgen05.mma (kind::f16)
 constexpr int kTileM = 128;                 // UMMA M, cta_group::1
-constexpr int kThreads = 192;               // 6 warps
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 384;               // WG0: producer, MMA issuer (+2 idle warps); WG1-2: 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // TMEM columns per accumulator buffer
@@ -74,7 +74,200 @@ __device__ __forceinline__ void decode_tile(const ConvArgs& a, int tile, int& n_
   n0 = tn * a.bn;
 }
 
+// ---------------------------------------------------------------------------
+// epilogue bodies: one 32-column chunk of one accumulator row (pixel) per call
+// ---------------------------------------------------------------------------
 template <bool kFast>
+__device__ __forceinline__ void epilogue_generic(const ConvArgs& a, const uint32_t (&v)[32], const float* bs,
+                                                 int64_t pix, int co0, bool masked) {
+    const int nvalid = min(32, a.cout - co0);
+    float x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + bs[j];
+
+    float rr[32];
+    if (a.res_mode != 0) {
+      if (a.res_is_bf16) {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) +
+                                  pix * a.res_ld + a.res_coff + co0;
+        if (nvalid == 32) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u = *reinterpret_cast<const uint4*>(rp + 8 * g);
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(b2[e]);
+              rr[8 * g + 2 * e] = f.x;
+              rr[8 * g + 2 * e + 1] = f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rr[j] = j < nvalid ? __bfloat162float(rp[j]) : 0.0f;
+        }
+      } else {
+        const float* rp = reinterpret_cast<const float*>(a.res) + pix * a.res_ld + a.res_coff + co0;
+        if (nvalid == 32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 f = *reinterpret_cast<const float4*>(rp + 4 * g);
+            rr[4 * g] = f.x; rr[4 * g + 1] = f.y; rr[4 * g + 2] = f.z; rr[4 * g + 3] = f.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rr[j] = j < nvalid ? rp[j] : 0.0f;
+        }
+      }
+    }
+    if (a.res_mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] += rr[j];
+    }
+    if (a.mask_pre && masked) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+    }
+    if (a.act) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = aptx<kFast>(x[j], a.beta, a.gamma);
+    }
+    if (a.res_mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] += rr[j];
+    }
+    if (a.mask_post && masked) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+    }
+
+    if (a.out_f32 != nullptr) {
+      float* op = a.out_f32 + pix * a.f32_ld + a.f32_coff + co0;
+      if (nvalid == 32) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(op + 4 * g) =
+              make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) op[j] = x[j];
+      }
+    }
+    if (a.out_bf16 != nullptr) {
+      __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
+      if (nvalid == 32) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(x[8 * g], x[8 * g + 1]);
+          u.y = pack_bf16x2(x[8 * g + 2], x[8 * g + 3]);
+          u.z = pack_bf16x2(x[8 * g + 4], x[8 * g + 5]);
+          u.w = pack_bf16x2(x[8 * g + 6], x[8 * g + 7]);
+          *reinterpret_cast<uint4*>(op + 8 * g) = u;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) op[j] = __float2bfloat16_rn(x[j]);
+      }
+    }
+    if (a.out_split != nullptr) {
+      __nv_bfloat16* op = a.out_split + pix * a.split_ld + co0;
+      if (nvalid == 32) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 a0, a1, a2, b0, b1, b2;
+            split3(x[8 * g + 2 * e], a0, a1, a2);
+            split3(x[8 * g + 2 * e + 1], b0, b1, b2);
+            w0[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a0)) |
+                    (static_cast<uint32_t>(__bfloat16_as_ushort(b0)) << 16);
+            w1[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a1)) |
+                    (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
+            w2[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a2)) |
+                    (static_cast<uint32_t>(__bfloat16_as_ushort(b2)) << 16);
+          }
+          *reinterpret_cast<uint4*>(op + 8 * g) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+          *reinterpret_cast<uint4*>(op + a.split_seg + 8 * g) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+          *reinterpret_cast<uint4*>(op + 2 * a.split_seg + 8 * g) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) {
+            __nv_bfloat16 a0, a1, a2;
+            split3(x[j], a0, a1, a2);
+            op[j] = a0;
+            op[a.split_seg + j] = a1;
+            op[2 * a.split_seg + j] = a2;
+          }
+      }
+    }
+}
+
+// Lean variant for the bf16 decoder / refiner layers: cout % 32 == 0, bf16 output only, optional
+// bf16 residual.  Dead branches of the generic body are compiled out (narrow layers are
+// epilogue-issue bound, ncu profiles/ncu_conv_small_r01).
+template <bool kFast>
+__device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t (&v)[32], const float* bs,
+                                              int64_t pix, int co0, bool masked) {
+  float x[32];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * g);
+    x[4 * g] = __uint_as_float(v[4 * g]) + b4.x;
+    x[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b4.y;
+    x[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b4.z;
+    x[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b4.w;
+  }
+  float rr[32];
+  if (a.res_mode != 0) {
+    const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.res_ld + a.res_coff + co0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 u = *reinterpret_cast<const uint4*>(rp + 8 * g);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(b2[e]);
+        rr[8 * g + 2 * e] = f.x;
+        rr[8 * g + 2 * e + 1] = f.y;
+      }
+    }
+    if (a.res_mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] += rr[j];
+    }
+  }
+  const bool zero_pre = a.mask_pre && masked;
+  const bool zero_post = a.mask_post && masked;
+  if (a.act) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = aptx<kFast>(zero_pre ? 0.0f : x[j], a.beta, a.gamma);
+  } else if (zero_pre) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+  }
+  if (a.res_mode == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] += rr[j];
+  }
+  __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 u;
+    u.x = zero_post ? 0u : pack_bf16x2(x[8 * g], x[8 * g + 1]);
+    u.y = zero_post ? 0u : pack_bf16x2(x[8 * g + 2], x[8 * g + 3]);
+    u.z = zero_post ? 0u : pack_bf16x2(x[8 * g + 4], x[8 * g + 5]);
+    u.w = zero_post ? 0u : pack_bf16x2(x[8 * g + 6], x[8 * g + 7]);
+    *reinterpret_cast<uint4*>(op + 8 * g) = u;
+  }
+}
+
+template <bool kFast, bool kLean>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
@@ -107,7 +300,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);     // one arrive per epilogue warp
+      mbar_init(&tempty_bar[b], kEpiThreads / 32);     // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -186,13 +379,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
         umma_commit(&tfull_bar[buf]);         // accumulator ready for the epilogue
       }
     }
-  } else {
-    // ===================== epilogue (4 warps) =====================
-    const int q = warp & 3;                   // TMEM lane quarter this warp may read
-    const int r = q * 32 + lane;              // accumulator row == pixel within the tile
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps) =====================
+    // Warp w may only read TMEM lanes [32*(w%4), +32); warps w and w+4 share a lane quarter and
+    // split the 32-column chunks of the accumulator between them.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int r = q * 32 + lane;              // accumulator row == pixel within the sub-tile
     const int lh = r / a.bw;
     const int lw = r - lh * a.bw;
-    const int et = threadIdx.x - 64;
+    const int et = threadIdx.x - 128;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       int n_idx, h0, w0, n0;
@@ -201,153 +397,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
       float* bs = bias_s + buf * 256;
       for (int j = et; j < a.bn; j += kEpiThreads)
         bs[j] = (a.bias != nullptr && n0 + j < a.cout) ? a.bias[n0 + j] : 0.0f;
+      // row masks of every sub-tile, fetched before the accumulator wait so the latency overlaps it
+      bool mflag[4];
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        const int h = h0 + sub * a.bh + lh;
+        mflag[sub] = false;
+        if (sub < a.msub && a.row_mask != nullptr && r < a.bh * a.bw && h < a.H)
+          mflag[sub] = a.row_mask[static_cast<int64_t>(n_idx) * a.H + h] != 0;
+      }
       named_bar_sync(1, kEpiThreads);
 
       mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
       tc_fence_after();
+#pragma unroll 1
       for (int sub = 0; sub < a.msub; ++sub) {
-      const int h = h0 + sub * a.bh + lh, w = w0 + lw;
-      const bool valid = (r < a.bh * a.bw) && (h < a.H) && (w < a.W);
-      const int64_t row = static_cast<int64_t>(n_idx) * a.H + h;
-      const int64_t pix = row * a.W + w;
-      const bool masked = valid && a.row_mask != nullptr && a.row_mask[row] != 0;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride + sub * a.bn;
-
-      for (int c = 0; c < a.bn; c += 32) {
-        uint32_t v[32];
-        __syncwarp();                         // tcgen05.ld is .sync.aligned: reconverge first
-        tmem_ld_32x32(t_row + c, v);
-        tmem_ld_wait();
-        const int co0 = n0 + c;
-        if (!valid || co0 >= a.cout) continue;
-        const int nvalid = min(32, a.cout - co0);
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + bs[c + j];
-
-        float rr[32];
-        if (a.res_mode != 0) {
-          if (a.res_is_bf16) {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) +
-                                      pix * a.res_ld + a.res_coff + co0;
-            if (nvalid == 32) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 u = *reinterpret_cast<const uint4*>(rp + 8 * g);
-                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __bfloat1622float2(b2[e]);
-                  rr[8 * g + 2 * e] = f.x;
-                  rr[8 * g + 2 * e + 1] = f.y;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) rr[j] = j < nvalid ? __bfloat162float(rp[j]) : 0.0f;
-            }
+        const int h = h0 + sub * a.bh + lh, w = w0 + lw;
+        const bool valid = (r < a.bh * a.bw) && (h < a.H) && (w < a.W);
+        const int64_t pix = (static_cast<int64_t>(n_idx) * a.H + h) * a.W + w;
+        const bool masked = mflag[sub];
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride + sub * a.bn;
+#pragma unroll 1
+        for (int c = half * 32; c < a.bn; c += 64) {
+          uint32_t v[32];
+          __syncwarp();                         // tcgen05.ld is .sync.aligned: reconverge first
+          tmem_ld_32x32(t_row + c, v);
+          tmem_ld_wait();
+          const int co0 = n0 + c;
+          if (kLean) {
+            if (valid) epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked);
           } else {
-            const float* rp = reinterpret_cast<const float*>(a.res) + pix * a.res_ld + a.res_coff + co0;
-            if (nvalid == 32) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                float4 f = *reinterpret_cast<const float4*>(rp + 4 * g);
-                rr[4 * g] = f.x; rr[4 * g + 1] = f.y; rr[4 * g + 2] = f.z; rr[4 * g + 3] = f.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) rr[j] = j < nvalid ? rp[j] : 0.0f;
-            }
-          }
-        }
-        if (a.res_mode == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] += rr[j];
-        }
-        if (a.mask_pre && masked) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = 0.0f;
-        }
-        if (a.act) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = aptx<kFast>(x[j], a.beta, a.gamma);
-        }
-        if (a.res_mode == 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] += rr[j];
-        }
-        if (a.mask_post && masked) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = 0.0f;
-        }
-
-        if (a.out_f32 != nullptr) {
-          float* op = a.out_f32 + pix * a.f32_ld + a.f32_coff + co0;
-          if (nvalid == 32) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              *reinterpret_cast<float4*>(op + 4 * g) =
-                  make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) op[j] = x[j];
-          }
-        }
-        if (a.out_bf16 != nullptr) {
-          __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
-          if (nvalid == 32) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 u;
-              u.x = pack_bf16x2(x[8 * g], x[8 * g + 1]);
-              u.y = pack_bf16x2(x[8 * g + 2], x[8 * g + 3]);
-              u.z = pack_bf16x2(x[8 * g + 4], x[8 * g + 5]);
-              u.w = pack_bf16x2(x[8 * g + 6], x[8 * g + 7]);
-              *reinterpret_cast<uint4*>(op + 8 * g) = u;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) op[j] = __float2bfloat16_rn(x[j]);
-          }
-        }
-        if (a.out_split != nullptr) {
-          __nv_bfloat16* op = a.out_split + pix * a.split_ld + co0;
-          if (nvalid == 32) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t w0[4], w1[4], w2[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat16 a0, a1, a2, b0, b1, b2;
-                split3(x[8 * g + 2 * e], a0, a1, a2);
-                split3(x[8 * g + 2 * e + 1], b0, b1, b2);
-                w0[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a0)) |
-                        (static_cast<uint32_t>(__bfloat16_as_ushort(b0)) << 16);
-                w1[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a1)) |
-                        (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
-                w2[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a2)) |
-                        (static_cast<uint32_t>(__bfloat16_as_ushort(b2)) << 16);
-              }
-              *reinterpret_cast<uint4*>(op + 8 * g) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-              *reinterpret_cast<uint4*>(op + a.split_seg + 8 * g) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-              *reinterpret_cast<uint4*>(op + 2 * a.split_seg + 8 * g) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) {
-                __nv_bfloat16 a0, a1, a2;
-                split3(x[j], a0, a1, a2);
-                op[j] = a0;
-                op[a.split_seg + j] = a1;
-                op[2 * a.split_seg + j] = a2;
-              }
+            if (valid && co0 < a.cout) epilogue_generic<kFast>(a, v, bs + c, pix, co0, masked);
           }
         }
       }
-      }  // sub
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld above)
       tc_fence_before();
       __syncwarp();
@@ -481,13 +564,19 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   MQ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int smem = conv_smem_bytes(stages, a_stage_bytes, static_cast<int>(a.b_tile_bytes));
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+  const bool lean = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->out_split == nullptr &&
+                    p->cout % 32 == 0 && (p->res_mode == 0 || p->res_is_bf16);
+#define MQ_LAUNCH_CONV(FAST, LEAN)                                                                          \
+  do {                                                                                                      \
+    MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    conv_gemm_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);                        \
+  } while (0)
   if (p->fast_tanh) {
-    MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv_gemm_kernel<true><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+    if (lean) MQ_LAUNCH_CONV(true, true); else MQ_LAUNCH_CONV(true, false);
   } else {
-    MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv_gemm_kernel<false><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+    if (lean) MQ_LAUNCH_CONV(false, true); else MQ_LAUNCH_CONV(false, false);
   }
+#undef MQ_LAUNCH_CONV
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

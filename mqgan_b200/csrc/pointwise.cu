@@ -636,16 +636,23 @@ __global__ void __launch_bounds__(256)
 refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mask, int B, int T, int T8,
                     int F, int C, const float* __restrict__ w, const float* __restrict__ bias,
                     __nv_bfloat16* __restrict__ y) {
-  extern __shared__ float ws[];                 // [C][9] then bias[C]
-  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) ws[i] = w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) ws[C * 9 + i] = bias[i];
-  __syncthreads();
+  // thread = (pixel slot, group of 8 output channels); the 72 weights + 8 biases of the group stay
+  // in registers for the whole grid-stride loop (the shared-memory version was LDS-issue bound).
   const int C8 = C / 8;
-  const int64_t total = static_cast<int64_t>(B) * T8 * F * C8;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % C8);
-    const int64_t pix = i / C8;
+  const int slots = blockDim.x / C8;                   // pixels per block iteration
+  const int cg = threadIdx.x % C8;
+  const int slot = threadIdx.x / C8;
+  if (slot >= slots) return;
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    br[e] = bias[cg * 8 + e];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[e][k] = w[(cg * 8 + e) * 9 + k];
+  }
+  const int64_t npix = static_cast<int64_t>(B) * T8 * F;
+  for (int64_t pix = static_cast<int64_t>(blockIdx.x) * slots + slot; pix < npix;
+       pix += static_cast<int64_t>(gridDim.x) * slots) {
     const int f = static_cast<int>(pix % F);
     const int64_t row = pix / F;
     const int64_t b = row / T8;
@@ -658,24 +665,19 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
 #pragma unroll
       for (int df = -1; df <= 1; ++df) {
         const int ff = f + df;
-        in[(dt + 1) * 3 + (df + 1)] = (row_ok && ff >= 0 && ff < F) ? r[(b * T + tt) * F + ff] : 0.0f;
+        in[(dt + 1) * 3 + (df + 1)] = (row_ok && ff >= 0 && ff < F) ? __ldg(r + (b * T + tt) * F + ff) : 0.0f;
       }
     }
-    uint32_t packed[4];
+    float v[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float v[2];
+    for (int e = 0; e < 8; ++e) {
+      float acc = br[e];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = cg * 8 + e * 2 + h;
-        float acc = ws[C * 9 + c];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc = fmaf(ws[c * 9 + k], in[k], acc);
-        v[h] = aptx<kFast>(acc, 1.0f, 0.5f);
-      }
-      packed[e] = pack_bf16x2(v[0], v[1]);
+      for (int k = 0; k < 9; ++k) acc = fmaf(wr[e][k], in[k], acc);
+      v[e] = aptx<kFast>(acc, 1.0f, 0.5f);
     }
-    *reinterpret_cast<uint4*>(y + pix * C + cg * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    *reinterpret_cast<uint4*>(y + pix * C + cg * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
 
@@ -685,47 +687,30 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
 // ---------------------------------------------------------------------------
 constexpr int kTailT = 4;
 
+// taps: (B, T8, F, ldp) fp32, channel k = 3*(dt+1)+(df+1) holds sum_c x[.., c] * w[k][c] (a 1x1
+// tcgen05 GEMM, C -> 9).  post(x)[t,f] = bias + sum_k taps[t+dt, f+df, k].
 __global__ void __launch_bounds__(256)
-refiner_tail_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ mask, int T, int T8,
-                    int F, int C, const float* __restrict__ w, float bias,
-                    const float* __restrict__ reproj_t, int M, const float* __restrict__ r,
-                    float* __restrict__ out) {
-  extern __shared__ float sm[];                 // w[9*C], o[kTailT][F]
-  float* wsm = sm;
-  float* osm = sm + 9 * C;
+refiner_tail_kernel(const float* __restrict__ taps, int ldp, const uint8_t* __restrict__ mask, int T, int T8,
+                    int F, float bias, const float* __restrict__ reproj_t, int M,
+                    const float* __restrict__ r, float* __restrict__ out) {
+  extern __shared__ float osm[];                // o[kTailT][F]
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kTailT;
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) wsm[i] = w[i];
-  __syncthreads();
-  const int C8 = C / 8;
   for (int i = threadIdx.x; i < kTailT * F; i += blockDim.x) {
     const int lt = i / F, f = i - lt * F;
     const int t = t0 + lt;
     float acc = 0.0f;
-    if (t < T) {
-      const bool pad = mask != nullptr && mask[static_cast<int64_t>(b) * T + t] != 0;
-      if (!pad) {
-        acc = bias;
-        for (int dt = -1; dt <= 1; ++dt) {
-          const int tt = t + dt;
-          if (tt < 0 || tt >= T8) continue;
-          for (int df = -1; df <= 1; ++df) {
-            const int ff = f + df;
-            if (ff < 0 || ff >= F) continue;
-            const uint4* px = reinterpret_cast<const uint4*>(
-                x + ((static_cast<int64_t>(b) * T8 + tt) * F + ff) * C);
-            const float* wt = wsm + ((dt + 1) * 3 + (df + 1)) * C;
-            for (int g = 0; g < C8; ++g) {
-              const uint4 u = px[g];
-              const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    if (t < T && !(mask != nullptr && mask[static_cast<int64_t>(b) * T + t] != 0)) {
+      acc = bias;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 fv = __bfloat1622float2(p2[e]);
-                acc = fmaf(fv.x, wt[g * 8 + 2 * e], acc);
-                acc = fmaf(fv.y, wt[g * 8 + 2 * e + 1], acc);
-              }
-            }
-          }
+      for (int dt = -1; dt <= 1; ++dt) {
+        const int tt = t + dt;
+        if (tt < 0 || tt >= T8) continue;
+#pragma unroll
+        for (int df = -1; df <= 1; ++df) {
+          const int ff = f + df;
+          if (ff < 0 || ff >= F) continue;
+          acc += __ldg(taps + ((static_cast<int64_t>(b) * T8 + tt) * F + ff) * ldp + (dt + 1) * 3 + (df + 1));
         }
       }
     }
@@ -738,7 +723,7 @@ refiner_tail_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restri
     if (t >= T) continue;
     float acc = 0.0f;
     const float* orow = osm + lt * F;
-    for (int f = 0; f < F; ++f) acc = fmaf(reproj_t[static_cast<int64_t>(f) * M + m], orow[f], acc);
+    for (int f = 0; f < F; ++f) acc = fmaf(__ldg(reproj_t + static_cast<int64_t>(f) * M + m), orow[f], acc);
     const int64_t row = static_cast<int64_t>(b) * T + t;
     out[row * M + m] = r[row * F + m] + acc;       // x_post = x_recon + residual (preencoder.py:499)
   }
@@ -923,27 +908,27 @@ extern "C" int mq_upcat_mask(const void* x, const void* skip, void* y, const uin
 
 extern "C" int mq_refiner_stem(const float* r, const uint8_t* mask, int B, int T, int T8, int F, int C,
                                const float* w, const float* b, int fast_tanh, void* y, mq_stream_t stream) {
-  MQ_REQUIRE(r && w && b && y && B > 0 && T > 0 && T8 >= T && F > 0 && C % 8 == 0, "mq_refiner_stem: bad args");
-  const int64_t total = static_cast<int64_t>(B) * T8 * F * (C / 8);
-  const size_t smem = static_cast<size_t>(C) * 10 * sizeof(float);
-  const int grid = grid_for(total, 256);
+  MQ_REQUIRE(r && w && b && y && B > 0 && T > 0 && T8 >= T && F > 0 && C % 8 == 0 && C / 8 <= 256,
+             "mq_refiner_stem: bad args");
+  const int slots = 256 / (C / 8);
+  const int64_t npix = static_cast<int64_t>(B) * T8 * F;
+  const int grid = grid_for(npix, slots, 16);
   if (fast_tanh)
-    refiner_stem_kernel<true><<<grid, 256, smem, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
+    refiner_stem_kernel<true><<<grid, 256, 0, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
   else
-    refiner_stem_kernel<false><<<grid, 256, smem, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
+    refiner_stem_kernel<false><<<grid, 256, 0, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-extern "C" int mq_refiner_tail(const void* x, const uint8_t* mask, int B, int T, int T8, int F, int C,
-                               const float* w, float bias, const float* reproj_t, int M, const float* r,
-                               float* out, mq_stream_t stream) {
-  MQ_REQUIRE(x && w && reproj_t && r && out && B > 0 && T > 0 && T8 >= T && F >= M && C % 8 == 0,
+extern "C" int mq_refiner_tail(const float* taps, int ldp, const uint8_t* mask, int B, int T, int T8, int F,
+                               float bias, const float* reproj_t, int M, const float* r, float* out,
+                               mq_stream_t stream) {
+  MQ_REQUIRE(taps && reproj_t && r && out && B > 0 && T > 0 && T8 >= T && F >= M && ldp >= 9,
              "mq_refiner_tail: bad args");
-  const size_t smem = (9 * static_cast<size_t>(C) + kTailT * static_cast<size_t>(F)) * sizeof(float);
+  const size_t smem = kTailT * static_cast<size_t>(F) * sizeof(float);
   dim3 grid((T + kTailT - 1) / kTailT, B);
-  refiner_tail_kernel<<<grid, 256, smem, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), mask,
-                                                          T, T8, F, C, w, bias, reproj_t, M, r, out);
+  refiner_tail_kernel<<<grid, 256, smem, STREAM(stream)>>>(taps, ldp, mask, T, T8, F, bias, reproj_t, M, r, out);
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

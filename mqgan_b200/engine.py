@@ -210,8 +210,8 @@ class PreEncoderEngine:
         self.ref_downs = [cb(f"refiner.downs.{i}.conv") for i in range(d)]
         self.ref_mid = cb("refiner.mid")
         self.ref_ups = [cb(f"refiner.ups.{i}.conv") for i in range(d)]
-        # refiner.post: (1, C, 3, 3) -> (9, C) with tap = 3*(dt+1) + (df+1)
-        self.tail_w = w["refiner.post.weight"].reshape(chs[0], 9).t().float().contiguous().to(dev)
+        # refiner.post: (1, C, 3, 3) -> (9, C) with tap = 3*(dt+1) + (df+1), run as a 1x1 GEMM C -> 9
+        self.tail = pack_conv(w["refiner.post.weight"].reshape(chs[0], 9).t().contiguous(), None, "linear", False).to(dev)
         self.tail_b = float(w["refiner.post.bias"].reshape(()))
         self.reproj_t = w["refiner.reproj.weight"].t().float().contiguous().to(dev)       # (F, M)
 
@@ -398,5 +398,6 @@ class PreEncoderEngine:
             x = convblock(u, self.ref_ups[i], l, up[l], chs[l + 1] + chs[l], chs[l], tag=f"ref.up{i}")
             if taps is not None:
                 taps[f"refiner.ups.{i}"] = x
-        ops.refiner_tail(x, m8, B, T, T8, F, chs[0], self.tail_w, self.tail_b, self.reproj_t,
-                         cfg.mel_channels, R, out=out)                                      # :191-200, :499
+        tp = torch.empty(B, T8, F, 12, dtype=torch.float32, device=dev)
+        ops.conv_gemm(x, self.tail, B, T8, F, out_f32=tp, tag="ref.post")                   # :191 as 9 tap planes
+        ops.refiner_tail(tp, m8, B, T, T8, F, self.tail_b, self.reproj_t, cfg.mel_channels, R, out=out)  # :192-200, :499

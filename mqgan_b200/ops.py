@@ -409,11 +409,11 @@ def refiner_stem(r: torch.Tensor, mask: Optional[torch.Tensor], B, T, T8, F, Cc,
     return y
 
 
-def refiner_tail(x: torch.Tensor, mask: Optional[torch.Tensor], B, T, T8, F, Cc, w, bias: float, reproj_t, M,
+def refiner_tail(taps: torch.Tensor, mask: Optional[torch.Tensor], B, T, T8, F, bias: float, reproj_t, M,
                  r: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _chk(x, torch.bfloat16, "x")
+    _chk(taps, torch.float32, "taps")
     if out is None:
-        out = torch.empty(B, T, M, dtype=torch.float32, device=x.device)
-    _lib.call("mq_refiner_tail", x.data_ptr(), _ptr(mask), B, T, T8, F, Cc, w.data_ptr(), float(bias),
+        out = torch.empty(B, T, M, dtype=torch.float32, device=taps.device)
+    _lib.call("mq_refiner_tail", taps.data_ptr(), taps.shape[-1], _ptr(mask), B, T, T8, F, float(bias),
               reproj_t.data_ptr(), M, r.data_ptr(), out.data_ptr(), _stream())
     return out

@@ -287,10 +287,13 @@ def test_refiner_masks_pool_upcat_stem_tail():
     o = F.conv2d(xin.double().permute(0, 3, 1, 2), wp.double(), bp.double(), padding=1).squeeze(1)[:, :T]
     o = o.masked_fill(mask.unsqueeze(-1), 0.0)
     ref = r[..., :M].double() + F.linear(o, wr.double())
-    out = ops.refiner_tail(xin.to(DEV), mask.to(torch.uint8).to(DEV), B, T, T8, Fw, Cc,
-                           wp.reshape(Cc, 9).t().contiguous().to(DEV), float(bp), wr.t().contiguous().to(DEV), M,
+    pc9 = ops.pack_conv(wp.reshape(Cc, 9).t().contiguous(), None, "linear", False).to(DEV)
+    tp = torch.empty(B, T8, Fw, 12, dtype=torch.float32, device=DEV)
+    ops.conv_gemm(xin.to(DEV), pc9, B, T8, Fw, out_f32=tp)
+    out = ops.refiner_tail(tp, mask.to(torch.uint8).to(DEV), B, T, T8, Fw, float(bp), wr.t().contiguous().to(DEV), M,
                            r.to(DEV))
-    assert (out.cpu().double() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    # the 9 tap weights are bf16 inside the GEMM (like every decoder weight): bf16-level tolerance
+    assert (out.cpu().double() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
 
 
 def test_sequence_mask_kernel():
