@@ -29,7 +29,7 @@ extern "C" {
 
 typedef void* mq_stream_t; /* cudaStream_t */
 
-#define MQ_MAX_TAPS 9
+#define MQ_MAX_TAPS 16
 #define MQ_MAX_SEGS 6
 
 /* ---- library ------------------------------------------------------------- */
@@ -91,6 +91,17 @@ typedef struct mq_conv_params {
   float* out_f32;  int f32_ld, f32_coff;      /* optional fp32 output */
   void* out_bf16;  int bf16_ld, bf16_coff;    /* optional bf16 output */
   void* out_split; int split_ld, split_seg;   /* optional bf16x3 output: term j at channel j*split_seg + co */
+  /* Fused nearest Upsample((2,1)) + channel concat of UpBlock (preencoder.py:123-130), optional.
+   * in2 != NULL: `in` is the LOW-resolution tensor (N, H, W, in_ld), in2 the skip tensor
+   * (N, 2H, W, in2_ld); the output (and row_mask / res / out_*) has 2H rows.  Output row 2i+p
+   * reads up(x)[2i+p+dh] = x[(2i+p+dh)>>1], so per row parity p the three row taps collapse to two
+   * with pre-summed weights: taps [0, up_taps) read `in` at half-row offset tap_dh (p = 0) or
+   * tap_dh_odd (p = 1) with kchunks chunks each; taps [up_taps, taps) read in2 at output-row
+   * offset tap_dh with kchunks2 chunks each.  wpack holds [2][cout_pad][K] (parity-major),
+   * K = (up_taps*kchunks + (taps-up_taps)*kchunks2)*64.  nseg must be 1. */
+  const void* in2;
+  int in2_ld, up_taps, kchunks2;
+  int tap_dh_odd[MQ_MAX_TAPS];
 } mq_conv_params;
 
 int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream);
@@ -193,6 +204,11 @@ int mq_code_gather(const int64_t* idx, int64_t rows, const float* table, int n_c
  * mask may be NULL (= all valid, preencoder.py:471-472). */
 int mq_refiner_masks(const uint8_t* mask, int B, int T, int depth, uint8_t* down, uint8_t* up,
                      mq_stream_t stream);
+/* Zero every row (row_bytes each, multiple of 16) with mask_new[row] == 1 and mask_old[row] == 0
+ * (mask_old may be NULL).  Re-masks a skip tensor from the down-path mask to the coarser up-path
+ * mask (preencoder.py:125, :96) before the fused upsample+concat convolution reads it. */
+int mq_zero_rows(void* x, const uint8_t* mask_new, const uint8_t* mask_old, int64_t rows,
+                 int64_t row_bytes, mq_stream_t stream);
 /* AvgPool2d((2,1)) + masked_fill by the pooled mask (preencoder.py:111-114, :96).
  * x (B, H, F, C) bf16 -> y (B, H/2, F, C) bf16; mask_out (B*H/2). */
 int mq_avgpool_mask(const void* x, void* y, const uint8_t* mask_out, int B, int H, int F, int C,

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmqgan_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-MQ_MAX_TAPS = 9
+MQ_MAX_TAPS = 16
 MQ_MAX_SEGS = 6
 
 
@@ -46,6 +46,8 @@ class ConvParams(C.Structure):
         ("out_f32", C.c_void_p), ("f32_ld", C.c_int), ("f32_coff", C.c_int),
         ("out_bf16", C.c_void_p), ("bf16_ld", C.c_int), ("bf16_coff", C.c_int),
         ("out_split", C.c_void_p), ("split_ld", C.c_int), ("split_seg", C.c_int),
+        ("in2", C.c_void_p), ("in2_ld", C.c_int), ("up_taps", C.c_int), ("kchunks2", C.c_int),
+        ("tap_dh_odd", C.c_int * MQ_MAX_TAPS),
     ]
 
 
@@ -101,6 +103,7 @@ SIGNATURES = {
     "mq_code_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_refiner_masks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mq_zero_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "mq_avgpool_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mq_upcat_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]),

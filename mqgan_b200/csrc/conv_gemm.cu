@@ -13,6 +13,7 @@
 // columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -40,7 +41,11 @@ struct ConvArgs {
   int msub;                       // 128-pixel sub-tiles per CTA tile (share one B tile); msub*bn <= 256
   int taps, nseg, kchunks;
   int tap_dh[MQ_MAX_TAPS], tap_dw[MQ_MAX_TAPS], a_coff[MQ_MAX_SEGS];
+  // fused nearest-upsample + concat (UpBlock): output rows 2*H, tiles carry a row parity
+  int up_mode, up_taps, kchunks2, par_tiles, cout_pad;
+  int tap_dh_odd[MQ_MAX_TAPS];
   int stages;
+  int debug;                      // bench-only bottleneck probes (MQ_CONV_DEBUG): 1 no epilogue math/stores, 2 no MMA, 4 no TMA
   uint32_t a_tx_bytes, b_tile_bytes;
   // epilogue
   const float* bias;
@@ -62,9 +67,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 __device__ __forceinline__ void decode_tile(const ConvArgs& a, int tile, int& n_idx, int& h0,
-                                            int& w0, int& n0) {
+                                            int& w0, int& n0, int& par) {
   int tn = tile % a.tiles_n;
   int tm = tile / a.tiles_n;
+  par = tm % a.par_tiles;
+  tm /= a.par_tiles;
   int tw = tm % a.tiles_w;
   int t2 = tm / a.tiles_w;
   int th = t2 % a.tiles_h;
@@ -270,7 +277,8 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
 template <bool kFast, bool kLean>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
-                 const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
+                 const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_a2, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment (in the shared window).
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -294,6 +302,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (a.up_mode) tma_prefetch_desc(&map_a2);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -313,7 +322,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  const int kblocks = a.taps * a.nseg * a.kchunks;
+  const int kblocks = a.up_mode ? a.up_taps * a.kchunks + (a.taps - a.up_taps) * a.kchunks2
+                                : a.taps * a.nseg * a.kchunks;
 
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
@@ -321,22 +331,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        int n_idx, h0, w0, n0;
-        decode_tile(a, tile, n_idx, h0, w0, n0);
+        int n_idx, h0, w0, n0, par;
+        decode_tile(a, tile, n_idx, h0, w0, n0, par);
+        const int brow = n0 + par * a.cout_pad;
         int kb = 0;
         for (int tap = 0; tap < a.taps; ++tap) {
-          const int hh = h0 + a.tap_dh[tap];
+          const bool src2 = a.up_mode && tap >= a.up_taps;
+          const int nch = src2 ? a.kchunks2 : a.kchunks;
           const int ww = w0 + a.tap_dw[tap];
+          int hh, par2 = 0;
+          if (!src2) {
+            hh = h0 + ((a.up_mode && par) ? a.tap_dh_odd[tap] : a.tap_dh[tap]);
+          } else {
+            const int orow = par + a.tap_dh[tap];   // output-row offset -> (parity, half-row) of the skip tensor
+            par2 = orow & 1;
+            hh = h0 + (orow >> 1);
+          }
           for (int seg = 0; seg < a.nseg; ++seg) {
             const int cbase = a.a_coff[seg];
-            for (int kc = 0; kc < a.kchunks; ++kc, ++kb) {
+            for (int kc = 0; kc < nch; ++kc, ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (a.debug & 4) {
+                mbar_arrive(&full_bar[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+                continue;
+              }
               mbar_expect_tx(&full_bar[stage], a.msub * a.a_tx_bytes + a.b_tile_bytes);
-              for (int sub = 0; sub < a.msub; ++sub)
-                tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * a_stage_bytes + sub * kATileBytes,
-                            cbase + kc * kBlockK, ww, hh + sub * a.bh, n_idx);
-              tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * a.b_tile_bytes,
-                          kb * kBlockK, n0);
+              for (int sub = 0; sub < a.msub; ++sub) {
+                uint8_t* dst = smem_a + stage * a_stage_bytes + sub * kATileBytes;
+                if (!src2)
+                  tma_load_4d(&map_a, &full_bar[stage], dst, cbase + kc * kBlockK, ww, hh + sub * a.bh, n_idx);
+                else
+                  tma_load_5d(&map_a2, &full_bar[stage], dst, kc * kBlockK, ww, par2, hh + sub * a.bh, n_idx);
+              }
+              tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * a.b_tile_bytes, kb * kBlockK, brow);
               if (++stage == stages) {
                 stage = 0;
                 phase ^= 1;
@@ -362,7 +390,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * a.b_tile_bytes));
-          for (int sub = 0; sub < a.msub; ++sub) {
+          for (int sub = 0; sub < ((a.debug & 2) ? 0 : a.msub); ++sub) {
             const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * a_stage_bytes + sub * kATileBytes));
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
@@ -391,8 +419,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
     const int et = threadIdx.x - 128;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-      int n_idx, h0, w0, n0;
-      decode_tile(a, tile, n_idx, h0, w0, n0);
+      int n_idx, h0, w0, n0, par;
+      decode_tile(a, tile, n_idx, h0, w0, n0, par);
+      const int hmul = a.up_mode ? 2 : 1;
+      const int Hout = a.H * hmul;
       const uint32_t buf = it & 1;
       float* bs = bias_s + buf * 256;
       for (int j = et; j < a.bn; j += kEpiThreads)
@@ -404,7 +434,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
         const int h = h0 + sub * a.bh + lh;
         mflag[sub] = false;
         if (sub < a.msub && a.row_mask != nullptr && r < a.bh * a.bw && h < a.H)
-          mflag[sub] = a.row_mask[static_cast<int64_t>(n_idx) * a.H + h] != 0;
+          mflag[sub] = a.row_mask[static_cast<int64_t>(n_idx) * Hout + h * hmul + par] != 0;
       }
       named_bar_sync(1, kEpiThreads);
 
@@ -414,7 +444,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
       for (int sub = 0; sub < a.msub; ++sub) {
         const int h = h0 + sub * a.bh + lh, w = w0 + lw;
         const bool valid = (r < a.bh * a.bw) && (h < a.H) && (w < a.W);
-        const int64_t pix = (static_cast<int64_t>(n_idx) * a.H + h) * a.W + w;
+        const int64_t pix = (static_cast<int64_t>(n_idx) * Hout + h * hmul + par) * a.W + w;
         const bool masked = mflag[sub];
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride + sub * a.bn;
 #pragma unroll 1
@@ -424,6 +454,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
           tmem_ld_32x32(t_row + c, v);
           tmem_ld_wait();
           const int co0 = n0 + c;
+          if (a.debug & 1) continue;
           if (kLean) {
             if (valid) epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked);
           } else {
@@ -484,6 +515,11 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   MQ_REQUIRE(p->bn >= 32 && p->bn <= 256 && p->bn % 32 == 0, "mq_conv_gemm: bn=%d must be a multiple of 32 in [32,256]", p->bn);
   MQ_REQUIRE(p->cout > 0 && p->cout_pad >= p->cout && p->cout_pad % p->bn == 0, "mq_conv_gemm: cout=%d cout_pad=%d bn=%d", p->cout, p->cout_pad, p->bn);
   MQ_REQUIRE(p->taps >= 1 && p->taps <= MQ_MAX_TAPS, "mq_conv_gemm: taps=%d", p->taps);
+  const bool up = p->in2 != nullptr;
+  if (up) {
+    MQ_REQUIRE(p->nseg == 1 && p->up_taps >= 1 && p->up_taps < p->taps && p->kchunks2 >= 1 && p->in2_ld % 8 == 0 &&
+               (reinterpret_cast<uintptr_t>(p->in2) & 15) == 0, "mq_conv_gemm: bad upsample-concat arguments");
+  }
   MQ_REQUIRE(p->nseg >= 1 && p->nseg <= MQ_MAX_SEGS, "mq_conv_gemm: nseg=%d", p->nseg);
   MQ_REQUIRE(p->kchunks >= 1, "mq_conv_gemm: kchunks=%d", p->kchunks);
   MQ_REQUIRE(p->bh >= 1 && p->bw >= 1 && p->bh * p->bw <= kTileM && p->bh <= 256 && p->bw <= 256, "mq_conv_gemm: tile %dx%d", p->bh, p->bw);
@@ -509,7 +545,13 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.tiles_h = (p->H + p->bh * a.msub - 1) / (p->bh * a.msub);
   a.tiles_w = (p->W + p->bw - 1) / p->bw;
   a.tiles_n = p->cout_pad / p->bn;
-  const long long nt = 1LL * p->N * a.tiles_h * a.tiles_w * a.tiles_n;
+  a.up_mode = up ? 1 : 0;
+  a.up_taps = up ? p->up_taps : 0;
+  a.kchunks2 = up ? p->kchunks2 : 0;
+  a.par_tiles = up ? 2 : 1;
+  a.cout_pad = p->cout_pad;
+  for (int i = 0; i < MQ_MAX_TAPS; ++i) a.tap_dh_odd[i] = p->tap_dh_odd[i];
+  const long long nt = 1LL * p->N * a.tiles_h * a.tiles_w * a.tiles_n * a.par_tiles;
   MQ_REQUIRE(nt < (1LL << 31), "mq_conv_gemm: too many tiles");
   a.num_tiles = static_cast<int>(nt);
   a.taps = p->taps; a.nseg = p->nseg; a.kchunks = p->kchunks;
@@ -522,6 +564,12 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   if (stages > kMaxStages) stages = kMaxStages;
   MQ_REQUIRE(stages >= 2, "mq_conv_gemm: not enough shared memory for 2 stages");
   a.stages = stages;
+  {
+    const char* dbg = getenv("MQ_CONV_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+    const char* st = getenv("MQ_CONV_STAGES");
+    if (st && atoi(st) >= 2 && atoi(st) <= stages) a.stages = stages = atoi(st);
+  }
   a.bias = p->bias; a.row_mask = p->row_mask;
   a.mask_pre = p->mask_pre; a.mask_post = p->mask_post; a.act = p->act; a.res_mode = p->res_mode;
   a.beta = p->beta; a.gamma = p->gamma;
@@ -531,7 +579,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.out_split = reinterpret_cast<__nv_bfloat16*>(p->out_split); a.split_ld = p->split_ld; a.split_seg = p->split_seg;
 
   // --- tensor maps ---
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_a2;
   {
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(p->in_ld), static_cast<cuuint64_t>(p->W),
                           static_cast<cuuint64_t>(p->H), static_cast<cuuint64_t>(p->N)};
@@ -547,8 +595,10 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     MQ_REQUIRE(r == CUDA_SUCCESS, "mq_conv_gemm: cuTensorMapEncodeTiled(A) failed with %d (in_ld=%d W=%d H=%d N=%d)", (int)r, p->in_ld, p->W, p->H, p->N);
   }
   {
-    const cuuint64_t K = static_cast<cuuint64_t>(p->taps) * p->nseg * p->kchunks * kBlockK;
-    cuuint64_t dims[2] = {K, static_cast<cuuint64_t>(p->cout_pad)};
+    const cuuint64_t K = up ? (static_cast<cuuint64_t>(p->up_taps) * p->kchunks +
+                               static_cast<cuuint64_t>(p->taps - p->up_taps) * p->kchunks2) * kBlockK
+                            : static_cast<cuuint64_t>(p->taps) * p->nseg * p->kchunks * kBlockK;
+    cuuint64_t dims[2] = {K, static_cast<cuuint64_t>(p->cout_pad) * (up ? 2 : 1)};
     cuuint64_t strides[1] = {K * 2};
     cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(p->bn)};
     cuuint32_t estr[2] = {1, 1};
@@ -557,6 +607,22 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MQ_REQUIRE(r == CUDA_SUCCESS, "mq_conv_gemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+
+  if (up) {
+    // skip tensor (N, 2H, W, C2) viewed as (N, H, 2, W, C2): the row parity is its own dimension
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(p->in2_ld), static_cast<cuuint64_t>(p->W), 2,
+                          static_cast<cuuint64_t>(p->H), static_cast<cuuint64_t>(p->N)};
+    const cuuint64_t rowb = static_cast<cuuint64_t>(p->W) * p->in2_ld * 2;
+    cuuint64_t strides[4] = {static_cast<cuuint64_t>(p->in2_ld) * 2, rowb, 2 * rowb, 2 * rowb * p->H};
+    cuuint32_t box[5] = {kBlockK, static_cast<cuuint32_t>(p->bw), 1, static_cast<cuuint32_t>(p->bh), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_a2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p->in2), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MQ_REQUIRE(r == CUDA_SUCCESS, "mq_conv_gemm: cuTensorMapEncodeTiled(A2) failed with %d", (int)r);
+  } else {
+    map_a2 = map_a;
   }
 
   int dev = 0, sms = 0;
@@ -569,7 +635,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
 #define MQ_LAUNCH_CONV(FAST, LEAN)                                                                          \
   do {                                                                                                      \
     MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    conv_gemm_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);                        \
+    conv_gemm_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, map_a2, a);                       \
   } while (0)
   if (p->fast_tanh) {
     if (lean) MQ_LAUNCH_CONV(true, true); else MQ_LAUNCH_CONV(true, false);

@@ -566,6 +566,17 @@ __global__ void refiner_masks_kernel(const uint8_t* __restrict__ mask, int B, in
   }
 }
 
+// zero the rows that are padded under `mask_new` but were valid under `mask_old` (the up-path mask
+// of the refiner is coarser than the down-path mask the skip tensor was written with)
+__global__ void __launch_bounds__(256)
+zero_rows_kernel(uint4* __restrict__ x, const uint8_t* __restrict__ mask_new,
+                 const uint8_t* __restrict__ mask_old, int64_t row_u4) {
+  const int64_t row = blockIdx.x;
+  if (mask_new[row] == 0 || (mask_old != nullptr && mask_old[row] != 0)) return;
+  uint4* p = x + row * row_u4;
+  for (int64_t i = threadIdx.x; i < row_u4; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+}
+
 // ---------------------------------------------------------------------------
 // K13: pooling / upsample+concat (bf16, 8 channels per thread)
 // ---------------------------------------------------------------------------
@@ -880,6 +891,16 @@ extern "C" int mq_refiner_masks(const uint8_t* mask, int B, int T, int depth, ui
   const int mult = 1 << depth;
   const int T8 = (T + mult - 1) / mult * mult;
   refiner_masks_kernel<<<B, 256, 0, STREAM(stream)>>>(mask, B, T, T8, depth, down, up);
+  MQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mq_zero_rows(void* x, const uint8_t* mask_new, const uint8_t* mask_old, int64_t rows,
+                            int64_t row_bytes, mq_stream_t stream) {
+  MQ_REQUIRE(x && mask_new && rows > 0 && rows < (1LL << 31) && row_bytes > 0 && row_bytes % 16 == 0,
+             "mq_zero_rows: bad args");
+  zero_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<uint4*>(x), mask_new, mask_old, row_bytes / 16);
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import ops
-from .ops import PackedConv, pack_conv
+from .ops import PackedConv, pack_conv, pack_upconv
 from .spec import PreEncoderConfig
 
 
@@ -122,7 +122,8 @@ class _CB2D:
 
 class PreEncoderEngine:
     def __init__(self, cfg: PreEncoderConfig, state_dict: Dict[str, torch.Tensor], device="cuda",
-                 encoder_precision: str = "bf16x3", max_chunk_frames: int = 32768, cb2d_table: bool = True):
+                 encoder_precision: str = "bf16x3", max_chunk_frames: int = 32768, cb2d_table: bool = True,
+                 fuse_upcat: bool = True):
         if encoder_precision not in ("bf16x3", "bf16"):
             raise ValueError("encoder_precision must be 'bf16x3' or 'bf16'")
         self.cfg = cfg
@@ -210,6 +211,10 @@ class PreEncoderEngine:
         self.ref_downs = [cb(f"refiner.downs.{i}.conv") for i in range(d)]
         self.ref_mid = cb("refiner.mid")
         self.ref_ups = [cb(f"refiner.ups.{i}.conv") for i in range(d)]
+        self.fuse_upcat = bool(fuse_upcat)
+        for i in range(d):          # fused nearest-upsample + concat variant of ups[i].conv1
+            pfx = f"refiner.ups.{i}.conv.conv1"
+            self.ref_ups[i]["conv1_up"] = pack_upconv(w[pfx + ".weight"], w[pfx + ".bias"], chs[d - i], chs[d - i - 1]).to(dev)
         # refiner.post: (1, C, 3, 3) -> (9, C) with tap = 3*(dt+1) + (df+1), run as a 1x1 GEMM C -> 9
         self.tail = pack_conv(w["refiner.post.weight"].reshape(chs[0], 9).t().contiguous(), None, "linear", False).to(dev)
         self.tail_b = float(w["refiner.post.bias"].reshape(()))
@@ -394,8 +399,16 @@ class PreEncoderEngine:
         for i in range(d):                                                                  # :187-189
             l = d - 1 - i
             skip = skips.pop()
-            u = ops.upcat_mask(x, skip, up[l], B, H[l], F, chs[l + 1], chs[l])
-            x = convblock(u, self.ref_ups[i], l, up[l], chs[l + 1] + chs[l], chs[l], tag=f"ref.up{i}")
+            if self.fuse_upcat:
+                # upsample + cat + mask folded into conv1's operand loads (no (Cx+Cs)-channel copy)
+                ops.zero_rows(skip, up[l], down[l])
+                t = torch.empty(B, H[l], F, chs[l], dtype=torch.bfloat16, device=dev)
+                ops.conv_gemm(x, self.ref_ups[i]["conv1_up"], B, H[l + 1], F, x2=skip, act=True, out_bf16=t,
+                              tag=f"ref.up{i}.conv1")
+                x = convblock(t, self.ref_ups[i], l, up[l], 0, chs[l], first=False, tag=f"ref.up{i}")
+            else:
+                u = ops.upcat_mask(x, skip, up[l], B, H[l], F, chs[l + 1], chs[l])
+                x = convblock(u, self.ref_ups[i], l, up[l], chs[l + 1] + chs[l], chs[l], tag=f"ref.up{i}")
             if taps is not None:
                 taps[f"refiner.ups.{i}"] = x
         tp = torch.empty(B, T8, F, 12, dtype=torch.float32, device=dev)

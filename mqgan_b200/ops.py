@@ -58,6 +58,11 @@ class PackedConv:
     tap_dw: List[int]
     a_coff: List[int]
     split: bool
+    # fused upsample + concat (UpBlock) extras
+    up_taps: int = 0
+    kchunks2: int = 0
+    cin2: int = 0
+    tap_dh_odd: Optional[List[int]] = None
 
     def to(self, device):
         self.wpack = self.wpack.to(device)
@@ -149,6 +154,40 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, spl
                       a_coff + [0] * (_lib.MQ_MAX_SEGS - len(a_coff)), split)
 
 
+def pack_upconv(weight: torch.Tensor, bias: Optional[torch.Tensor], cx: int, cs: int) -> PackedConv:
+    """Pack UpBlock.conv.conv1 (Cout, cx+cs, 3, 3) for the fused nearest-upsample + concat mode of
+    mq_conv_gemm.  Output row 2i+p of conv3x3(cat[up(x), skip]) reads up(x) rows 2i+p-1 .. 2i+p+1,
+    i.e. x rows {i-1, i, i} (p = 0) or {i, i, i+1} (p = 1): two row taps with pre-summed weights
+    per parity (6 taps instead of 9 on the up-sampled half), plus the 9 ordinary taps on the skip."""
+    w = weight.detach().float().cpu()
+    cout = w.shape[0]
+    if w.shape[1] != cx + cs or tuple(w.shape[2:]) != (3, 3):
+        raise ValueError("pack_upconv: weight must be (Cout, cx+cs, 3, 3)")
+    wx, ws = w[:, :cx], w[:, cx:]
+    k1, k2 = (cx + BLOCK_K - 1) // BLOCK_K, (cs + BLOCK_K - 1) // BLOCK_K
+    bn, cout_pad = choose_bn(cout)
+    K = (6 * k1 + 9 * k2) * BLOCK_K
+    wp = torch.zeros(2, cout_pad, K, dtype=torch.bfloat16)
+    rows = {0: [wx[:, :, 0, :], wx[:, :, 1, :] + wx[:, :, 2, :]],       # half-row offsets -1, 0
+            1: [wx[:, :, 0, :] + wx[:, :, 1, :], wx[:, :, 2, :]]}       # half-row offsets 0, +1
+    for p in (0, 1):
+        col = 0
+        for rw in rows[p]:
+            for j in range(3):
+                wp[p, :cout, col:col + cx] = rw[:, :, j].to(torch.bfloat16)
+                col += k1 * BLOCK_K
+        for i in range(3):
+            for j in range(3):
+                wp[p, :cout, col:col + cs] = ws[:, :, i, j].to(torch.bfloat16)
+                col += k2 * BLOCK_K
+    dh = [-1, -1, -1, 0, 0, 0] + [i - 1 for i in range(3) for _ in range(3)]
+    dh_odd = [0, 0, 0, 1, 1, 1] + [0] * 9
+    dw = [-1, 0, 1, -1, 0, 1] + [j - 1 for _ in range(3) for j in range(3)]
+    b = None if bias is None else bias.detach().float().cpu().contiguous()
+    return PackedConv(wp.reshape(2 * cout_pad, K).contiguous(), b, cx, cout, cout_pad, bn, 15, 1, k1, dh, dw,
+                      [0] * _lib.MQ_MAX_SEGS, False, up_taps=6, kchunks2=k2, cin2=cs, tap_dh_odd=dh_odd)
+
+
 def choose_tile(H: int, W: int) -> Tuple[int, int]:
     """(bh, bw) with bh*bw <= 128 minimising out-of-bounds waste; prefers wide rows."""
     if W == 1:
@@ -188,8 +227,9 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
               out_f32: Optional[torch.Tensor] = None, f32_coff=0,
               out_bf16: Optional[torch.Tensor] = None, bf16_coff=0,
               out_split: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None,
-              msub: Optional[int] = None, tag: str = "") -> None:
-    """Launch mq_conv_gemm.  x: bf16 (N*H*W, in_ld) channel-last (any leading shape)."""
+              msub: Optional[int] = None, tag: str = "", x2: Optional[torch.Tensor] = None) -> None:
+    """Launch mq_conv_gemm.  x: bf16 (N*H*W, in_ld) channel-last (any leading shape).
+    x2: skip tensor (N, 2H, W, C2) for a ``pack_upconv`` weight; outputs / masks then have 2H rows."""
     _chk(x, torch.bfloat16, "x")
     in_ld = x.shape[-1]
     if x.numel() != N * H * W * in_ld:
@@ -205,14 +245,25 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         p.tap_dw[i] = pc.tap_dw[i]
     for i in range(_lib.MQ_MAX_SEGS):
         p.a_coff[i] = pc.a_coff[i]
+    hm = 1
+    if pc.up_taps:
+        if x2 is None:
+            raise ValueError("this packed weight needs the skip tensor x2")
+        _chk(x2, torch.bfloat16, "x2")
+        if x2.numel() != N * 2 * H * W * x2.shape[-1]:
+            raise ValueError("x2 must be (N, 2H, W, C2)")
+        p.in2, p.in2_ld, p.up_taps, p.kchunks2 = x2.data_ptr(), x2.shape[-1], pc.up_taps, pc.kchunks2
+        for i in range(pc.taps):
+            p.tap_dh_odd[i] = pc.tap_dh_odd[i]
+        hm = 2
     bh, bw = tile if tile is not None else choose_tile(H, W)
     p.bh, p.bw = bh, bw
     p.msub = choose_msub(pc.bn, N, H, W, bh, bw) if msub is None else msub
     p.bias = _ptr(pc.bias)
     if row_mask is not None:
         _chk(row_mask, torch.uint8, "row_mask")
-        if row_mask.numel() != N * H:
-            raise ValueError("row_mask must have N*H entries")
+        if row_mask.numel() != N * H * hm:
+            raise ValueError("row_mask must have one entry per output row")
     p.row_mask = _ptr(row_mask)
     p.mask_pre, p.mask_post = int(mask_pre), int(mask_post)
     p.act, p.fast_tanh = int(act), int(fast_tanh)
@@ -238,9 +289,13 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         p.out_split, p.split_ld, p.split_seg = out_split.data_ptr(), out_split.shape[-1], out_split.shape[-1] // 3
     meta = None
     if _lib.profiler is not None:
-        pix = float(N) * H * W
-        meta = {"tag": tag, "flops": 2.0 * pix * pc.cout * pc.cin * pc.taps,            # algorithmic
-                "mma_flops": 2.0 * pix * pc.cout_pad * pc.taps * pc.nseg * pc.kchunks * BLOCK_K}  # issued
+        pix = float(N) * H * W * hm
+        if pc.up_taps:
+            meta = {"tag": tag, "flops": 2.0 * pix * pc.cout * (pc.cin + pc.cin2) * 9,  # the reference's conv
+                    "mma_flops": 2.0 * pix * pc.cout_pad * pc.wpack.shape[1]}
+        else:
+            meta = {"tag": tag, "flops": 2.0 * pix * pc.cout * pc.cin * pc.taps,        # algorithmic
+                    "mma_flops": 2.0 * pix * pc.cout_pad * pc.taps * pc.nseg * pc.kchunks * BLOCK_K}  # issued
     _lib.call("mq_conv_gemm", C.byref(p), _stream(), meta=meta)
 
 
@@ -384,6 +439,14 @@ def refiner_masks(mask: Optional[torch.Tensor], B: int, T: int, depth: int, devi
         ul.append(up[off:off + B * h].view(B, h))
         off += B * h
     return T8, dl, ul
+
+
+def zero_rows(x: torch.Tensor, mask_new: torch.Tensor, mask_old: Optional[torch.Tensor]) -> None:
+    """In place: zero rows padded under mask_new but not under mask_old.  x: (rows, ...) bf16."""
+    rows = mask_new.numel()
+    row_bytes = x.numel() // rows * x.element_size()
+    _lib.call("mq_zero_rows", x.data_ptr(), _chk(mask_new, torch.uint8, "mask_new").data_ptr(), _ptr(mask_old),
+              rows, row_bytes, _stream())
 
 
 def avgpool_mask(x: torch.Tensor, mask_out: Optional[torch.Tensor], B, H, F, Cc) -> torch.Tensor:

@@ -357,3 +357,40 @@ def test_conv_gemm_multi_subtile(kind, N, H, W, Cin, Cout, tail, msub):
                   out_f32=out, msub=msub)
     err = (out.cpu().double() - ref).abs().max().item()
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("N,Hl,W,Cx,Cs,Cout,msub", [
+    (2, 8, 48, 128, 64, 64, None),
+    (1, 11, 36, 96, 96, 96, 1),          # odd half-rows, channel counts that are not multiples of 64
+    (2, 20, 144, 256, 128, 128, 2),
+])
+def test_conv_gemm_fused_upsample_concat(N, Hl, W, Cx, Cs, Cout, msub):
+    """UpBlock: conv3x3(mask(cat[nearest_up(x), skip])) without materialising the concat."""
+    H = 2 * Hl
+    x = _rand(N, Hl, W, Cx, seed=70).to(torch.bfloat16)
+    skip = _rand(N, H, W, Cs, seed=71).to(torch.bfloat16)
+    w = (_rand(Cout, Cx + Cs, 3, 3, seed=72) / (9 * (Cx + Cs)) ** 0.5).to(torch.bfloat16)
+    b = _rand(Cout, seed=73)
+    mask_new = torch.zeros(N, H, dtype=torch.uint8)
+    mask_new[0, H - 4:] = 1
+    mask_old = torch.zeros(N, H, dtype=torch.uint8)
+    mask_old[0, H - 2:] = 1
+    x = x.masked_fill(mask_new[:, ::2].bool()[:, :, None, None], 0)      # low-res input is already masked
+    skip = skip.masked_fill(mask_old.bool()[:, :, None, None], 0)        # skip carries the finer down-path mask
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=(2, 1), mode="nearest")
+    cat = torch.cat([up, skip.float().permute(0, 3, 1, 2)], 1).masked_fill(mask_new.bool()[:, None, :, None], 0.0)
+    ref = O.aptx(F.conv2d(cat.double(), w.double(), b.double(), padding=1), 1.0, 0.5).permute(0, 2, 3, 1)
+    pc = ops.pack_upconv(w.float(), b, Cx, Cs).to(DEV)
+    sd = skip.to(DEV)
+    ops.zero_rows(sd, mask_new.to(DEV), mask_old.to(DEV))
+    out = torch.empty(N, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv_gemm(x.to(DEV), pc, N, Hl, W, x2=sd, act=True, fast_tanh=False, out_bf16=out, msub=msub)
+    err = (out.cpu().double() - ref).abs().max().item()
+    # pre-summed tap weights are rounded to bf16 once more; output is bf16
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+    # masked-output variant with fp32 output for a tighter check of the indexing
+    o32 = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
+    ops.conv_gemm(x.to(DEV), pc, N, Hl, W, x2=sd, act=True, fast_tanh=False, row_mask=mask_new.to(DEV),
+                  mask_post=True, out_f32=o32, msub=msub)
+    ref_m = ref.masked_fill(mask_new.bool()[:, :, None, None], 0.0)
+    assert (o32.cpu().double() - ref_m).abs().max().item() < 6e-3 * max(1.0, ref.abs().max().item())
