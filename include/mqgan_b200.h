@@ -42,7 +42,7 @@ int mq_sm_count(void);
 /* ---- K1/K3/K4/K9/K10/K11: implicit-GEMM convolution on tcgen05 ------------ */
 /*
  * out[n,h,w,co] = epi( sum_tap sum_seg sum_c  in[n, h+dh[tap], w+dw[tap], a_coff[seg]+c]
- *                                           * wpack[co, ((tap*nseg+seg)*kchunks*64 + c)] )
+ *                                           * wpack[co, ((seg*taps+tap)*kchunks*64 + c)] )
  * Zero padding comes from TMA out-of-bounds fill.  bf16 operands, fp32 accumulate
  * in TMEM.  nseg = 1 is a plain bf16 convolution; nseg = 6 with the input stored
  * as three bf16 terms [x0|x1|x2] along channels is the fp32-grade "bf16x3" mode
@@ -66,7 +66,7 @@ typedef struct mq_conv_params {
   const void* in;
   int N, H, W;
   int in_ld;
-  /* packed weights: bf16 [cout_pad][K], K = taps*nseg*kchunks*64, K-major */
+  /* packed weights: bf16 [cout_pad][K], K = nseg*taps*kchunks*64 (segment-major), K-major */
   const void* wpack;
   int cout;      /* real output channels */
   int cout_pad;  /* rows of wpack: multiple of bn */

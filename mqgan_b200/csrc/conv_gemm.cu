@@ -335,20 +335,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
         decode_tile(a, tile, n_idx, h0, w0, n0, par);
         const int brow = n0 + par * a.cout_pad;
         int kb = 0;
-        for (int tap = 0; tap < a.taps; ++tap) {
-          const bool src2 = a.up_mode && tap >= a.up_taps;
-          const int nch = src2 ? a.kchunks2 : a.kchunks;
-          const int ww = w0 + a.tap_dw[tap];
-          int hh, par2 = 0;
-          if (!src2) {
-            hh = h0 + ((a.up_mode && par) ? a.tap_dh_odd[tap] : a.tap_dh[tap]);
-          } else {
-            const int orow = par + a.tap_dh[tap];   // output-row offset -> (parity, half-row) of the skip tensor
-            par2 = orow & 1;
-            hh = h0 + (orow >> 1);
-          }
-          for (int seg = 0; seg < a.nseg; ++seg) {
-            const int cbase = a.a_coff[seg];
+        // K order: segment-major (bf16x3: the small products x2w0, x1w1, ... come first, so they
+        // accumulate while |acc| is small and the tensor core's truncating fp32 adds cost nothing;
+        // only the final x0w0 chain sees full-magnitude truncation), then tap, then channel chunk.
+        for (int seg = 0; seg < a.nseg; ++seg) {
+          const int cbase = a.a_coff[seg];
+          for (int tap = 0; tap < a.taps; ++tap) {
+            const bool src2 = a.up_mode && tap >= a.up_taps;
+            const int nch = src2 ? a.kchunks2 : a.kchunks;
+            const int ww = w0 + a.tap_dw[tap];
+            int hh, par2 = 0;
+            if (!src2) {
+              hh = h0 + ((a.up_mode && par) ? a.tap_dh_odd[tap] : a.tap_dh[tap]);
+            } else {
+              const int orow = par + a.tap_dh[tap];   // output-row offset -> (parity, half-row) of the skip tensor
+              par2 = orow & 1;
+              hh = h0 + (orow >> 1);
+            }
             for (int kc = 0; kc < nch; ++kc, ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               if (a.debug & 4) {

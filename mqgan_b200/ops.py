@@ -103,7 +103,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, spl
     kind: "linear" (Cout, Cin) | "same1d" / "causal1d" (Cout, Cin, k) | "conv2d3" (Cout, Cin, 3, 3).
     split=True builds the six bf16x3 product segments; the activation is then
     expected as [x0 | x1 | x2] along channels with term stride ``in_seg_stride``
-    (default Cin).  K order is (tap, segment, channel chunk), matching the kernel.
+    (default Cin).  K order is (segment, tap, channel chunk), matching the kernel.
     """
     w = weight.detach().float().cpu()
     if kind == "linear":
@@ -145,10 +145,10 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, spl
         seg_w = [wt.to(torch.bfloat16)]
         a_coff = [0]
     nseg = len(seg_w)
-    wp = torch.zeros(cout_pad, taps, nseg, cpad, dtype=torch.bfloat16)
+    wp = torch.zeros(cout_pad, nseg, taps, cpad, dtype=torch.bfloat16)
     for s, ws in enumerate(seg_w):
-        wp[:cout, :, s, :cin] = ws.permute(0, 2, 1)      # (cout, taps, cin)
-    wp = wp.reshape(cout_pad, taps * nseg * cpad).contiguous()
+        wp[:cout, s, :, :cin] = ws.permute(0, 2, 1)      # (cout, taps, cin)
+    wp = wp.reshape(cout_pad, nseg * taps * cpad).contiguous()
     b = None if bias is None else bias.detach().float().cpu().contiguous()
     return PackedConv(wp, b, cin, cout, cout_pad, bn, taps, nseg, kchunks, dh, dw,
                       a_coff + [0] * (_lib.MQ_MAX_SEGS - len(a_coff)), split)

@@ -24,7 +24,7 @@ from oracle import preencoder_oracle as O  # noqa: E402
 from tests.helpers import load_golden, index_report  # noqa: E402
 
 TAU = 2e-4          # bounded-latent units (rounding boundaries are 1 apart)
-Z_ATOL = 2e-4       # pre-quantiser latents vs float64 (tensor-core fp32 accumulation truncates)
+Z_ATOL = 5e-5       # pre-quantiser latents (unit std) vs float64; measured 4e-6 .. 1.4e-5 (reference fp32: 4e-6 .. 9e-6)
 MEL_ATOL = 2e-2
 MEL_RTOL = 2e-2
 

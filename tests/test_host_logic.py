@@ -109,12 +109,23 @@ def test_folded_weights_equal_oracle_folding():
     assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
 
 
+def ps_check(w):
+    """segment-major split packing: segment 5 (x0*w0) holds the leading bf16 term of every tap."""
+    ps = ops.pack_conv(w, None, "same1d", split=True)
+    K1 = ps.taps * ps.kchunks * 64
+    lead = ps.wpack[: w.shape[0], 5 * K1:6 * K1].reshape(w.shape[0], ps.taps, -1)[:, :, : w.shape[1]].permute(0, 2, 1).float()
+    rest = ps.wpack[: w.shape[0], 4 * K1:5 * K1].reshape(w.shape[0], ps.taps, -1)[:, :, : w.shape[1]].permute(0, 2, 1).float()
+    last = ps.wpack[: w.shape[0], 2 * K1:3 * K1].reshape(w.shape[0], ps.taps, -1)[:, :, : w.shape[1]].permute(0, 2, 1).float()
+    return lead + rest + last
+
+
 def test_weight_packing_layout():
     w = torch.arange(2 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3) / 16
     pc = ops.pack_conv(w, torch.zeros(2), "causal1d", split=False)
     assert (pc.taps, pc.kchunks, pc.nseg, pc.bn, pc.cout_pad) == (3, 1, 1, 32, 32)
     assert pc.tap_dh == [-2, -1, 0] and pc.wpack.shape == (32, 3 * 64)
     assert torch.equal(pc.wpack[1, 64:67].float(), w[1, :, 1])
+    assert torch.equal(ps_check(w), w)
     ps = ops.pack_conv(w, None, "same1d", split=True)
     assert ps.tap_dh == [-1, 0, 1] and ps.nseg == 6 and ps.a_coff == [6, 3, 0, 3, 0, 0]
     w0, w1, w2 = ops.split3_bf16(w)
