@@ -642,18 +642,29 @@ upcat_mask_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, u
 // ---------------------------------------------------------------------------
 // K12a: refiner.pre.conv1 (1 -> C) + APTx.  Thread = (pixel, 8 channels).
 // ---------------------------------------------------------------------------
+constexpr int kStemRows = 8;
+
 template <bool kFast>
 __global__ void __launch_bounds__(256)
 refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mask, int B, int T, int T8,
                     int F, int C, const float* __restrict__ w, const float* __restrict__ bias,
                     __nv_bfloat16* __restrict__ y) {
-  // thread = (pixel slot, group of 8 output channels); the 72 weights + 8 biases of the group stay
-  // in registers for the whole grid-stride loop (the shared-memory version was LDS-issue bound).
+  // Block = kStemRows output rows of one batch element: the masked / zero-padded input rows go to
+  // shared memory; thread = (pixel, group of 8 output channels) with that group's 72 weights + 8
+  // biases in registers (group = threadIdx.x % (C/8), constant because blockDim.x % (C/8) == 0).
+  extern __shared__ float rows[];               // [kStemRows + 2][F + 2], columns shifted by one
+  const int t0 = blockIdx.x * kStemRows, b = blockIdx.y;
+  const int Fp = F + 2;
+  for (int i = threadIdx.x; i < (kStemRows + 2) * Fp; i += blockDim.x) {
+    const int rr = i / Fp, ff = i - rr * Fp - 1;
+    const int tt = t0 + rr - 1;
+    float v = 0.0f;
+    if (ff >= 0 && ff < F && tt >= 0 && tt < T && (mask == nullptr || mask[b * T + tt] == 0))
+      v = r[(static_cast<int64_t>(b) * T + tt) * F + ff];
+    rows[i] = v;
+  }
   const int C8 = C / 8;
-  const int slots = blockDim.x / C8;                   // pixels per block iteration
   const int cg = threadIdx.x % C8;
-  const int slot = threadIdx.x / C8;
-  if (slot >= slots) return;
   float wr[8][9], br[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -661,24 +672,17 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[e][k] = w[(cg * 8 + e) * 9 + k];
   }
-  const int64_t npix = static_cast<int64_t>(B) * T8 * F;
-  for (int64_t pix = static_cast<int64_t>(blockIdx.x) * slots + slot; pix < npix;
-       pix += static_cast<int64_t>(gridDim.x) * slots) {
-    const int f = static_cast<int>(pix % F);
-    const int64_t row = pix / F;
-    const int64_t b = row / T8;
-    const int t = static_cast<int>(row - b * T8);
+  __syncthreads();
+  const int nrow = min(kStemRows, T8 - t0);
+  __nv_bfloat16* ybase = y + (static_cast<int64_t>(b) * T8 + t0) * F * C;
+  for (int i = threadIdx.x; i < nrow * F * C8; i += blockDim.x) {
+    const int px = i / C8;                      // lt * F + f
+    const int lt = px / F, f = px - lt * F;
     float in[9];
 #pragma unroll
-    for (int dt = -1; dt <= 1; ++dt) {
-      const int tt = t + dt;
-      const bool row_ok = tt >= 0 && tt < T && (mask == nullptr || mask[b * T + tt] == 0);
+    for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
-      for (int df = -1; df <= 1; ++df) {
-        const int ff = f + df;
-        in[(dt + 1) * 3 + (df + 1)] = (row_ok && ff >= 0 && ff < F) ? __ldg(r + (b * T + tt) * F + ff) : 0.0f;
-      }
-    }
+      for (int df = 0; df < 3; ++df) in[rr * 3 + df] = rows[(lt + rr) * Fp + f + df];
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -687,7 +691,7 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
       for (int k = 0; k < 9; ++k) acc = fmaf(wr[e][k], in[k], acc);
       v[e] = aptx<kFast>(acc, 1.0f, 0.5f);
     }
-    *reinterpret_cast<uint4*>(y + pix * C + cg * 8) =
+    *reinterpret_cast<uint4*>(ybase + static_cast<int64_t>(px) * C + cg * 8) =
         make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
@@ -931,13 +935,14 @@ extern "C" int mq_refiner_stem(const float* r, const uint8_t* mask, int B, int T
                                const float* w, const float* b, int fast_tanh, void* y, mq_stream_t stream) {
   MQ_REQUIRE(r && w && b && y && B > 0 && T > 0 && T8 >= T && F > 0 && C % 8 == 0 && C / 8 <= 256,
              "mq_refiner_stem: bad args");
-  const int slots = 256 / (C / 8);
-  const int64_t npix = static_cast<int64_t>(B) * T8 * F;
-  const int grid = grid_for(npix, slots, 16);
+  MQ_REQUIRE(B <= 65535, "mq_refiner_stem: B too large for one launch");
+  const int threads = 256 / (C / 8) * (C / 8);       // multiple of C/8 so a thread keeps its channel group
+  const size_t smem = (kStemRows + 2) * static_cast<size_t>(F + 2) * sizeof(float);
+  dim3 grid((T8 + kStemRows - 1) / kStemRows, B);
   if (fast_tanh)
-    refiner_stem_kernel<true><<<grid, 256, 0, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
+    refiner_stem_kernel<true><<<grid, threads, smem, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
   else
-    refiner_stem_kernel<false><<<grid, 256, 0, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
+    refiner_stem_kernel<false><<<grid, threads, smem, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
