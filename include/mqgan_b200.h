@@ -102,6 +102,11 @@ typedef struct mq_conv_params {
   const void* in2;
   int in2_ld, up_taps, kchunks2;
   int tap_dh_odd[MQ_MAX_TAPS];
+  /* halo != 0: halo-tile main loop for single-source 3x3 / pad-1 convolutions (taps in row-major
+   * (dh, dw) order, nseg == 1, bh == 16, bw == 8): each 64-channel chunk of the activation is
+   * fetched once per CTA tile as a (16*msub + 2) x 10 pixel halo and the nine taps are nine
+   * shifted tensor-core descriptors into it (9x less L2->SM activation traffic). */
+  int halo;
 } mq_conv_params;
 
 int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream);

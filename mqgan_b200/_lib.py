@@ -48,6 +48,7 @@ class ConvParams(C.Structure):
         ("out_split", C.c_void_p), ("split_ld", C.c_int), ("split_seg", C.c_int),
         ("in2", C.c_void_p), ("in2_ld", C.c_int), ("up_taps", C.c_int), ("kchunks2", C.c_int),
         ("tap_dh_odd", C.c_int * MQ_MAX_TAPS),
+        ("halo", C.c_int),
     ]
 
 

@@ -45,6 +45,7 @@ struct ConvArgs {
   int up_mode, up_taps, kchunks2, par_tiles, cout_pad;
   int tap_dh_odd[MQ_MAX_TAPS];
   int stages;
+  int halo_nA, halo_nB, halo_slot_bytes, halo_tx_bytes;   // halo-tile variant (conv_halo_kernel)
   int debug;                      // bench-only bottleneck probes (MQ_CONV_DEBUG): 1 no epilogue math/stores, 2 no MMA, 4 no TMA
   uint32_t a_tx_bytes, b_tile_bytes;
   // epilogue
@@ -274,6 +275,70 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
   }
 }
 
+// The epilogue role (warps 4..11), shared by both main-loop variants.
+template <bool kFast, bool kLean>
+__device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_base, uint64_t* tfull_bar,
+                                             uint64_t* tempty_bar, float* bias_s, int warp, int lane) {
+  // Warp w may only read TMEM lanes [32*(w%4), +32); warps w and w+4 share a lane quarter and
+  // split the 32-column chunks of the accumulator between them.
+  const int q = warp & 3;
+  const int half = (warp - 4) >> 2;
+  const int r = q * 32 + lane;              // accumulator row == pixel within the sub-tile
+  const int lh = r / a.bw;
+  const int lw = r - lh * a.bw;
+  const int et = threadIdx.x - 128;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+    int n_idx, h0, w0, n0, par;
+    decode_tile(a, tile, n_idx, h0, w0, n0, par);
+    const int hmul = a.up_mode ? 2 : 1;
+    const int Hout = a.H * hmul;
+    const uint32_t buf = it & 1;
+    float* bs = bias_s + buf * 256;
+    for (int j = et; j < a.bn; j += kEpiThreads)
+      bs[j] = (a.bias != nullptr && n0 + j < a.cout) ? a.bias[n0 + j] : 0.0f;
+    // row masks of every sub-tile, fetched before the accumulator wait so the latency overlaps it
+    bool mflag[4];
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      const int h = h0 + sub * a.bh + lh;
+      mflag[sub] = false;
+      if (sub < a.msub && a.row_mask != nullptr && r < a.bh * a.bw && h < a.H)
+        mflag[sub] = a.row_mask[static_cast<int64_t>(n_idx) * Hout + h * hmul + par] != 0;
+    }
+    named_bar_sync(1, kEpiThreads);
+
+    mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int sub = 0; sub < a.msub; ++sub) {
+      const int h = h0 + sub * a.bh + lh, w = w0 + lw;
+      const bool valid = (r < a.bh * a.bw) && (h < a.H) && (w < a.W);
+      const int64_t pix = (static_cast<int64_t>(n_idx) * Hout + h * hmul + par) * a.W + w;
+      const bool masked = mflag[sub];
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride + sub * a.bn;
+#pragma unroll 1
+      for (int c = half * 32; c < a.bn; c += 64) {
+        uint32_t v[32];
+        __syncwarp();                         // tcgen05.ld is .sync.aligned: reconverge first
+        tmem_ld_32x32(t_row + c, v);
+        tmem_ld_wait();
+        const int co0 = n0 + c;
+        if (a.debug & 1) continue;
+        if (kLean) {
+          if (valid) epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked);
+        } else {
+          if (valid && co0 < a.cout) epilogue_generic<kFast>(a, v, bs + c, pix, co0, masked);
+        }
+      }
+    }
+    // all TMEM reads of this buffer are complete (tcgen05.wait::ld above)
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+  }
+}
+
 template <bool kFast, bool kLean>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -412,64 +477,139 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
-    // Warp w may only read TMEM lanes [32*(w%4), +32); warps w and w+4 share a lane quarter and
-    // split the 32-column chunks of the accumulator between them.
-    const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
-    const int r = q * 32 + lane;              // accumulator row == pixel within the sub-tile
-    const int lh = r / a.bw;
-    const int lw = r - lh * a.bw;
-    const int et = threadIdx.x - 128;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-      int n_idx, h0, w0, n0, par;
-      decode_tile(a, tile, n_idx, h0, w0, n0, par);
-      const int hmul = a.up_mode ? 2 : 1;
-      const int Hout = a.H * hmul;
-      const uint32_t buf = it & 1;
-      float* bs = bias_s + buf * 256;
-      for (int j = et; j < a.bn; j += kEpiThreads)
-        bs[j] = (a.bias != nullptr && n0 + j < a.cout) ? a.bias[n0 + j] : 0.0f;
-      // row masks of every sub-tile, fetched before the accumulator wait so the latency overlaps it
-      bool mflag[4];
-#pragma unroll
-      for (int sub = 0; sub < 4; ++sub) {
-        const int h = h0 + sub * a.bh + lh;
-        mflag[sub] = false;
-        if (sub < a.msub && a.row_mask != nullptr && r < a.bh * a.bw && h < a.H)
-          mflag[sub] = a.row_mask[static_cast<int64_t>(n_idx) * Hout + h * hmul + par] != 0;
-      }
-      named_bar_sync(1, kEpiThreads);
+    run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, tempty_bar, bias_s, warp, lane);
+  }
 
-      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int sub = 0; sub < a.msub; ++sub) {
-        const int h = h0 + sub * a.bh + lh, w = w0 + lw;
-        const bool valid = (r < a.bh * a.bw) && (h < a.H) && (w < a.W);
-        const int64_t pix = (static_cast<int64_t>(n_idx) * Hout + h * hmul + par) * a.W + w;
-        const bool masked = mflag[sub];
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride + sub * a.bn;
-#pragma unroll 1
-        for (int c = half * 32; c < a.bn; c += 64) {
-          uint32_t v[32];
-          __syncwarp();                         // tcgen05.ld is .sync.aligned: reconverge first
-          tmem_ld_32x32(t_row + c, v);
-          tmem_ld_wait();
-          const int co0 = n0 + c;
-          if (a.debug & 1) continue;
-          if (kLean) {
-            if (valid) epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked);
-          } else {
-            if (valid && co0 < a.cout) epilogue_generic<kFast>(a, v, bs + c, pix, co0, masked);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Halo-tile variant for 3x3 / pad-1 convolutions (single source, nseg == 1).
+//
+// The tap-shifted kernel above fetches every activation tile nine times (once per tap), and narrow
+// layers are bound by that L2->SM traffic.  Here a CTA tile is msub sub-tiles of 16 rows x 8
+// columns stacked along H; per 64-channel chunk ONE halo box (16*msub + 2) x 10 pixels is loaded,
+// and the nine taps are nine UMMA descriptors into it: pixel (y, x) of the halo sits at row
+// y*10 + x (128 B per row, SWIZZLE_128B), so the 8 pixels of an image row are one 8-row group and
+// consecutive image rows are 1280 B apart (SBO = 1280).  Tap (dh, dw) only moves the descriptor
+// start by ((1+dh)*10 + (1+dw)) rows.  The swizzle XOR is a function of the absolute shared-memory
+// address bits, so unaligned starts need no descriptor base offset (probe: tools/umma_offset_probe.cu).
+// Activations and weights run in two independent TMA rings (A: per chunk, B: per chunk x tap).
+// ---------------------------------------------------------------------------
+constexpr int kHaloW = 10, kHaloSubRows = 16, kHaloMaxA = 4, kHaloMaxB = 16;
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <bool kFast, bool kLean>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
+                 const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int nA = a.halo_nA, nB = a.halo_nB;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + nA * a.halo_slot_bytes;
+  uint8_t* tail = smem_b + nB * a.b_tile_bytes;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* emptyA = fullA + kHaloMaxA;
+  uint64_t* fullB = emptyA + kHaloMaxA;
+  uint64_t* emptyB = fullB + kHaloMaxB;
+  uint64_t* tfull_bar = emptyB + kHaloMaxB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_s + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < nA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < nB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiThreads / 32); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_s, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        int n_idx, h0, w0, n0, par;
+        decode_tile(a, tile, n_idx, h0, w0, n0, par);
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&emptyA[sa], pa ^ 1);
+          mbar_expect_tx(&fullA[sa], a.halo_tx_bytes);
+          tma_load_4d(&map_a, &fullA[sa], smem_a + sa * a.halo_slot_bytes, kc * kBlockK, w0 - 1, h0 - 1, n_idx);
+          if (++sa == nA) { sa = 0; pa ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&emptyB[sb], pb ^ 1);
+            mbar_expect_tx(&fullB[sb], a.b_tile_bytes);
+            tma_load_2d(&map_b, &fullB[sb], smem_b + sb * a.b_tile_bytes, (tap * a.kchunks + kc) * kBlockK, n0);
+            if (++sb == nB) { sb = 0; pb ^= 1; }
           }
         }
       }
-      // all TMEM reads of this buffer are complete (tcgen05.wait::ld above)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kTileM, a.bn);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kAccStride;
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&fullA[sa], pa);
+          const uint32_t a_base = smem_u32(smem_a + sa * a.halo_slot_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&fullB[sb], pb);
+            tc_fence_after();
+            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + sb * a.b_tile_bytes));
+            const int ty = tap / 3, tx = tap - ty * 3;          // 1 + dh, 1 + dw
+            for (int sub = 0; sub < a.msub; ++sub) {
+              const uint32_t start = a_base + static_cast<uint32_t>(((sub * kHaloSubRows + ty) * kHaloW + tx) * 128);
+              const uint64_t da = umma_desc_sw128_sbo(start, kHaloW * 128);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16(d_tmem + sub * a.bn, da + 2 * k, db + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&emptyB[sb]);
+            if (++sb == nB) { sb = 0; pb ^= 1; }
+          }
+          umma_commit(&emptyA[sa]);
+          if (++sa == nA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, tempty_bar, bias_s, warp, lane);
   }
 
   tc_fence_before();
@@ -560,6 +700,13 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.taps = p->taps; a.nseg = p->nseg; a.kchunks = p->kchunks;
   for (int i = 0; i < MQ_MAX_TAPS; ++i) { a.tap_dh[i] = p->tap_dh[i]; a.tap_dw[i] = p->tap_dw[i]; }
   for (int i = 0; i < MQ_MAX_SEGS; ++i) a.a_coff[i] = p->a_coff[i];
+  const bool halo = p->halo != 0;
+  if (halo) {
+    MQ_REQUIRE(!up && p->nseg == 1 && p->taps == 9 && p->bw == 8 && p->bh == kHaloSubRows,
+               "mq_conv_gemm: halo mode needs a single-source 3x3 conv with an 16x8 sub-tile");
+    for (int t = 0; t < 9; ++t)
+      MQ_REQUIRE(p->tap_dh[t] == t / 3 - 1 && p->tap_dw[t] == t % 3 - 1, "mq_conv_gemm: halo mode needs the standard 3x3 tap order");
+  }
   a.a_tx_bytes = static_cast<uint32_t>(p->bh * p->bw * kBlockK * 2);
   a.b_tile_bytes = static_cast<uint32_t>(p->bn * kBlockK * 2);
   const int a_stage_bytes = a.msub * kATileBytes;
@@ -590,6 +737,10 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
                              static_cast<cuuint64_t>(p->W) * p->in_ld * 2,
                              static_cast<cuuint64_t>(p->H) * p->W * p->in_ld * 2};
     cuuint32_t box[4] = {kBlockK, static_cast<cuuint32_t>(p->bw), static_cast<cuuint32_t>(p->bh), 1};
+    if (halo) {                       // one (16*msub + 2) x 10 pixel halo box per channel chunk
+      box[1] = kHaloW;
+      box[2] = static_cast<cuuint32_t>(kHaloSubRows * a.msub + 2);
+    }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->in), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -631,7 +782,21 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   int dev = 0, sms = 0;
   MQ_CUDA_OK(cudaGetDevice(&dev));
   MQ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int smem = conv_smem_bytes(stages, a_stage_bytes, static_cast<int>(a.b_tile_bytes));
+  int smem = conv_smem_bytes(stages, a_stage_bytes, static_cast<int>(a.b_tile_bytes));
+  if (halo) {
+    const int halo_px = (kHaloSubRows * a.msub + 2) * kHaloW;
+    a.halo_tx_bytes = halo_px * 128;
+    a.halo_slot_bytes = (a.halo_tx_bytes + 1023) / 1024 * 1024;
+    const int tail_bytes = (2 * kHaloMaxA + 2 * kHaloMaxB + 4) * 8 + 16 + 2 * 256 * 4;
+    const int budget = kSmemBudget - 1024 - tail_bytes - 256;
+    int nA = a.kchunks >= 3 ? 3 : 2;
+    while (nA > 2 && budget - nA * a.halo_slot_bytes < 4 * static_cast<int>(a.b_tile_bytes)) --nA;
+    int nB = (budget - nA * a.halo_slot_bytes) / static_cast<int>(a.b_tile_bytes);
+    if (nB > kHaloMaxB) nB = kHaloMaxB;
+    MQ_REQUIRE(nB >= 3, "mq_conv_gemm: halo mode does not fit shared memory (msub=%d bn=%d)", a.msub, p->bn);
+    a.halo_nA = nA; a.halo_nB = nB;
+    smem = 1024 + nA * a.halo_slot_bytes + nB * static_cast<int>(a.b_tile_bytes) + tail_bytes;
+  }
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
   const bool lean = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->out_split == nullptr &&
                     p->cout % 32 == 0 && (p->res_mode == 0 || p->res_is_bf16);
@@ -640,12 +805,24 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
     conv_gemm_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, map_a2, a);                       \
   } while (0)
-  if (p->fast_tanh) {
+#define MQ_LAUNCH_HALO(FAST, LEAN)                                                                          \
+  do {                                                                                                      \
+    MQ_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    conv_halo_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);                        \
+  } while (0)
+  if (halo) {
+    if (p->fast_tanh) {
+      if (lean) MQ_LAUNCH_HALO(true, true); else MQ_LAUNCH_HALO(true, false);
+    } else {
+      if (lean) MQ_LAUNCH_HALO(false, true); else MQ_LAUNCH_HALO(false, false);
+    }
+  } else if (p->fast_tanh) {
     if (lean) MQ_LAUNCH_CONV(true, true); else MQ_LAUNCH_CONV(true, false);
   } else {
     if (lean) MQ_LAUNCH_CONV(false, true); else MQ_LAUNCH_CONV(false, false);
   }
 #undef MQ_LAUNCH_CONV
+#undef MQ_LAUNCH_HALO
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

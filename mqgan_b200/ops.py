@@ -18,6 +18,7 @@ from . import _lib
 from ._lib import ConvParams, Cb2dParams, CbamApplyParams, FsqParams
 
 BLOCK_K = 64
+HALO_DEFAULT = os.environ.get("MQ_HALO", "1") != "0"   # halo-tile main loop for 3x3 convs
 
 
 def _stream() -> int:
@@ -227,7 +228,8 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
               out_f32: Optional[torch.Tensor] = None, f32_coff=0,
               out_bf16: Optional[torch.Tensor] = None, bf16_coff=0,
               out_split: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None,
-              msub: Optional[int] = None, tag: str = "", x2: Optional[torch.Tensor] = None) -> None:
+              msub: Optional[int] = None, tag: str = "", x2: Optional[torch.Tensor] = None,
+              halo: Optional[bool] = None) -> None:
     """Launch mq_conv_gemm.  x: bf16 (N*H*W, in_ld) channel-last (any leading shape).
     x2: skip tensor (N, 2H, W, C2) for a ``pack_upconv`` weight; outputs / masks then have 2H rows."""
     _chk(x, torch.bfloat16, "x")
@@ -256,7 +258,13 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         for i in range(pc.taps):
             p.tap_dh_odd[i] = pc.tap_dh_odd[i]
         hm = 2
-    bh, bw = tile if tile is not None else choose_tile(H, W)
+    if halo is None:
+        halo = HALO_DEFAULT and pc.taps == 9 and pc.nseg == 1 and not pc.up_taps and W >= 8 and tile is None
+    if halo:
+        bh, bw = 16, 8
+    else:
+        bh, bw = tile if tile is not None else choose_tile(H, W)
+    p.halo = int(bool(halo))
     p.bh, p.bw = bh, bw
     p.msub = choose_msub(pc.bn, N, H, W, bh, bw) if msub is None else msub
     p.bias = _ptr(pc.bias)

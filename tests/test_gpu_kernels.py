@@ -394,3 +394,39 @@ def test_conv_gemm_fused_upsample_concat(N, Hl, W, Cx, Cs, Cout, msub):
                   mask_post=True, out_f32=o32, msub=msub)
     ref_m = ref.masked_fill(mask_new.bool()[:, :, None, None], 0.0)
     assert (o32.cpu().double() - ref_m).abs().max().item() < 6e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,msub", [
+    (2, 40, 144, 64, 64, 4),
+    (1, 37, 36, 128, 128, 2),        # H not a multiple of the tile; W = 36 -> 5 column tiles (last one ragged)
+    (2, 16, 144, 256, 256, 1),
+    (1, 9, 20, 96, 192, 1),          # Cin padded to 128, tiny image
+    (3, 128, 144, 192, 64, None),    # automatic msub
+])
+def test_conv_halo_mode_matches_tap_mode(N, H, W, Cin, Cout, msub):
+    """Halo-tile main loop (one activation fetch, 9 shifted descriptors) against the float64 conv and
+    against the tap-shifted main loop (must agree bit for bit: same K order per output)."""
+    x = _rand(N, H, W, Cin, seed=81).to(torch.bfloat16)
+    w = (_rand(Cout, Cin, 3, 3, seed=82) / (9 * Cin) ** 0.5).to(torch.bfloat16)
+    b = _rand(Cout, seed=83)
+    res = _rand(N, H, W, Cout, seed=84).to(torch.bfloat16)
+    mask = torch.zeros(N, H, dtype=torch.uint8)
+    mask[0, H // 3:] = 1
+    ref = (O.aptx(_ref_conv(x.double(), w.double(), b.double(), "conv2d3"), 1.0, 0.5) + res.double())
+    ref = ref.masked_fill(mask.bool()[:, :, None, None], 0.0)
+    pc = ops.pack_conv(w.float(), b, "conv2d3", split=False).to(DEV)
+    outs = {}
+    for halo in (True, False):
+        o = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
+        ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, fast_tanh=False,
+                      res=res.to(DEV), res_mode=2, out_f32=o, msub=msub if halo else None, halo=halo)
+        outs[halo] = o.cpu()
+    err = (outs[True].double() - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+    # tap-mode accumulates (tap, chunk) and halo-mode (chunk, tap): tiny fp32 reordering differences only
+    assert (outs[True] - outs[False]).abs().max().item() < 1e-4
+    ob = torch.empty(N, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, out_bf16=ob, halo=True,
+                  msub=msub)
+    ref2 = O.aptx(_ref_conv(x.double(), w.double(), b.double(), "conv2d3"), 1.0, 0.5).masked_fill(mask.bool()[:, :, None, None], 0.0)
+    assert (ob.cpu().double() - ref2).abs().max().item() < 2e-2 * max(1.0, ref2.abs().max().item())
