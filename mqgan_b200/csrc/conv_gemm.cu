@@ -38,7 +38,8 @@ struct ConvArgs {
   int N, H, W;
   int tiles_h, tiles_w, tiles_n, num_tiles;
   int bh, bw, bn, cout;
-  int msub;                       // 128-pixel sub-tiles per CTA tile (share one B tile); msub*bn <= 256
+  int msub;                       // 128-pixel sub-tiles per CTA tile (share one B tile)
+  int nbuf;                       // TMEM accumulator buffers: 2 if msub*bn <= 256, else 1 (msub*bn <= 512)
   int taps, nseg, kchunks;
   int tap_dh[MQ_MAX_TAPS], tap_dw[MQ_MAX_TAPS], a_coff[MQ_MAX_SEGS];
   // fused nearest-upsample + concat (UpBlock): output rows 2*H, tiles carry a row parity
@@ -293,7 +294,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
     decode_tile(a, tile, n_idx, h0, w0, n0, par);
     const int hmul = a.up_mode ? 2 : 1;
     const int Hout = a.H * hmul;
-    const uint32_t buf = it & 1;
+    const uint32_t buf = it % a.nbuf;
     float* bs = bias_s + buf * 256;
     for (int j = et; j < a.bn; j += kEpiThreads)
       bs[j] = (a.bias != nullptr && n0 + j < a.cout) ? a.bias[n0 + j] : 0.0f;
@@ -308,7 +309,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
     }
     named_bar_sync(1, kEpiThreads);
 
-    mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+    mbar_wait(&tfull_bar[buf], (it / a.nbuf) & 1);
     tc_fence_after();
 #pragma unroll 1
     for (int sub = 0; sub < a.msub; ++sub) {
@@ -450,8 +451,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1;
-        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        const uint32_t buf = it % a.nbuf;
+        mbar_wait(&tempty_bar[buf], ((it / a.nbuf) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kAccStride;
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -580,8 +581,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       uint32_t pa = 0, pb = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1;
-        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        const uint32_t buf = it % a.nbuf;
+        mbar_wait(&tempty_bar[buf], ((it / a.nbuf) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kAccStride;
         for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -684,7 +685,8 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.N = p->N; a.H = p->H; a.W = p->W;
   a.bh = p->bh; a.bw = p->bw; a.bn = p->bn; a.cout = p->cout;
   a.msub = p->msub > 0 ? p->msub : 1;
-  MQ_REQUIRE(a.msub * p->bn <= kAccStride && a.msub <= 4, "mq_conv_gemm: msub=%d * bn=%d exceeds %d TMEM columns", a.msub, p->bn, kAccStride);
+  MQ_REQUIRE(a.msub * p->bn <= kTmemCols && a.msub <= 4, "mq_conv_gemm: msub=%d * bn=%d exceeds %d TMEM columns", a.msub, p->bn, kTmemCols);
+  a.nbuf = a.msub * p->bn <= kAccStride ? 2 : 1;   // one accumulator buffer when the tile needs more than 256 columns
   a.tiles_h = (p->H + p->bh * a.msub - 1) / (p->bh * a.msub);
   a.tiles_w = (p->W + p->bw - 1) / p->bw;
   a.tiles_n = p->cout_pad / p->bn;

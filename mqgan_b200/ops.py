@@ -206,15 +206,23 @@ def choose_tile(H: int, W: int) -> Tuple[int, int]:
     return best[1], best[2]
 
 
-def choose_msub(bn: int, N: int, H: int, W: int, bh: int, bw: int) -> int:
+def choose_msub(bn: int, N: int, H: int, W: int, bh: int, bw: int, up: bool = False, kblocks: int = 0,
+                heavy_epilogue: bool = False) -> int:
     """Sub-tiles per CTA tile.  Narrow layers (bn <= 128) are bound by L2->SM operand traffic:
     stacking 2-4 pixel sub-tiles on one weight tile amortises the weight loads.
     Only when there are still >= 2 waves of tiles for 148 SMs."""
     override = os.environ.get("MQ_MSUB")
     if override:
         m = int(override)
-        return m if m * bn <= 256 else 1
-    m = 4 if bn <= 64 else (2 if bn <= 128 else 1)
+        return m if m * bn <= 512 else (2 if 2 * bn <= 512 else 1)
+    # measured on B200 (tools/conv_bench.py): bn <= 64 -> 4; bn <= 128 -> 2 (4 for the fused up-conv);
+    # bn = 256 -> 2 with a single TMEM accumulator buffer (halves the weight traffic per pixel,
+    # worth more than overlapping the epilogue at K >= 2304)
+    # only for long K loops (>= 64 k-blocks) whose epilogue has no residual read
+    wide = 2 if (kblocks >= 64 and not heavy_epilogue) else 1
+    m = 4 if bn <= 64 else ((4 if up else 2) if bn <= 128 else wide)
+    while m * bn > 512:
+        m //= 2
     tiles_w = math.ceil(W / bw)
     while m > 1 and N * math.ceil(H / (bh * m)) * tiles_w < 2 * 148:
         m //= 2
@@ -266,7 +274,11 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         bh, bw = tile if tile is not None else choose_tile(H, W)
     p.halo = int(bool(halo))
     p.bh, p.bw = bh, bw
-    p.msub = choose_msub(pc.bn, N, H, W, bh, bw) if msub is None else msub
+    if msub is None:
+        kblocks = pc.wpack.shape[1] // BLOCK_K
+        msub = choose_msub(pc.bn, N, H, W, bh, bw, bool(pc.up_taps), kblocks,
+                           heavy_epilogue=(res_mode != 0 or out_split is not None or out_f32 is not None))
+    p.msub = msub
     p.bias = _ptr(pc.bias)
     if row_mask is not None:
         _chk(row_mask, torch.uint8, "row_mask")

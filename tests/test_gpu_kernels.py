@@ -402,6 +402,8 @@ def test_conv_gemm_fused_upsample_concat(N, Hl, W, Cx, Cs, Cout, msub):
     (2, 16, 144, 256, 256, 1),
     (1, 9, 20, 96, 192, 1),          # Cin padded to 128, tiny image
     (3, 128, 144, 192, 64, None),    # automatic msub
+    (2, 64, 144, 128, 256, 2),       # bn = 256 with two sub-tiles: single TMEM accumulator buffer
+    (1, 40, 72, 64, 512, 2),         # two N tiles, single-buffered
 ])
 def test_conv_halo_mode_matches_tap_mode(N, H, W, Cin, Cout, msub):
     """Halo-tile main loop (one activation fetch, 9 shifted descriptors) against the float64 conv and
@@ -419,7 +421,7 @@ def test_conv_halo_mode_matches_tap_mode(N, H, W, Cin, Cout, msub):
     for halo in (True, False):
         o = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
         ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, fast_tanh=False,
-                      res=res.to(DEV), res_mode=2, out_f32=o, msub=msub if halo else None, halo=halo)
+                      res=res.to(DEV), res_mode=2, out_f32=o, msub=msub, halo=halo)
         outs[halo] = o.cpu()
     err = (outs[True].double() - ref).abs().max().item()
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
