@@ -29,10 +29,10 @@ import torch  # noqa: E402
 
 WORKLOADS = {
     # name: (config attr, B per GPU, T, encoder precision)
-    "hifispeech_256x1024_fp32idx": ("HIFISPEECH", 256, 1024, "bf16x3"),
+    "hifispeech_256x1024_fp32idx": ("HIFISPEECH", 256, 1024, "f16x2"),
     "hifimusic_32x8192_bf16": ("HIFIMUSIC", 32, 8192, "bf16"),
-    "hifispeech_16x512_fp32idx": ("HIFISPEECH", 16, 512, "bf16x3"),
-    "tiny_8x256": ("TINY", 8, 256, "bf16x3"),
+    "hifispeech_16x512_fp32idx": ("HIFISPEECH", 16, 512, "f16x2"),
+    "tiny_8x256": ("TINY", 8, 256, "f16x2"),
 }
 DEFAULT_WORKLOAD = "hifispeech_256x1024_fp32idx"
 CPU_SAMPLE = (2, 1024)       # utterances x frames timed on the host cores (bounded sample)
@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=None, choices=["f16x2", "bf16x3", "bf16"],
+                    help="override the workload's encoder operand format")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write the per-layer kernel table (markdown) here")
     args = ap.parse_args()
@@ -209,6 +211,7 @@ def main():
     _lib.check(_lib.lib().mq_device_check(), "mq_device_check")
 
     cfg_name, B, T, precision = WORKLOADS[args.workload]
+    precision = args.precision or precision
     cfg = getattr(S, cfg_name)
     model, sd = build_model(cfg, precision, dev)
     eng = model.engine()
@@ -328,9 +331,13 @@ def main():
         "metric": "mel frames/sec re-encoded (encode+VQ+decode)", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": ("bf16x3 (fp32-grade) encoder" if precision == "bf16x3" else "bf16 encoder") + " + bf16 decoder, fp32 accumulate",
+        "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": args.workload, "model": cfg_name.lower(), "batch_per_gpu": B, "frames": T,
+                   "precision": {"f16x2": "encoder GEMMs on 2-term fp16 operand splits (22-bit operands, fp32-grade indices)",
+                                 "bf16x3": "encoder GEMMs on 3-term bf16 operand splits (24-bit operands, fp32-grade indices)",
+                                 "bf16": "encoder GEMMs on bf16 operands (index agreement reported)"}[precision]
+                                + "; decoder/refiner bf16 operands; fp32 accumulate everywhere",
                    "weights": "random-init (seed 0) + q_in_proj recalibration", "l2": "inputs and intermediates exceed L2 (134 MB mels, GBs of activations per step)",
                    "parallelism": f"utterance shards x{world}, no collective"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": mel_host.numel() * 4,

@@ -102,6 +102,15 @@ typedef struct mq_conv_params {
   const void* in2;
   int in2_ld, up_taps, kchunks2;
   int tap_dh_odd[MQ_MAX_TAPS];
+  /* f16x2 mode: op_f16 != 0 means `in` / `in2` / `wpack` hold fp16 (not bf16) operands;
+   * split_kind selects what out_split writes: 0 = three bf16 terms, 1 = two fp16 terms
+   * (term j at channel j*split_seg + co).  With nseg = 3 segments h1*g0, h0*g1, h0*g0 this is the
+   * cheaper fp32-grade mode (22-bit operands, half the MMA work of bf16x3). */
+  int op_f16, split_kind;
+  /* acc_scale: the accumulator is multiplied by this before the bias is added (0 means 1).
+   * f16x2 weights are packed pre-scaled by a power of two so their low terms stay in fp16's
+   * normal range; acc_scale = 2^-s undoes it exactly. */
+  float acc_scale;
   /* halo != 0: halo-tile main loop for single-source 3x3 / pad-1 convolutions (taps in row-major
    * (dh, dw) order, nseg == 1, bh == 16, bw == 8): each 64-channel chunk of the activation is
    * fetched once per CTA tile as a (16*msub + 2) x 10 pixel halo and the nine taps are nine
@@ -112,7 +121,8 @@ typedef struct mq_conv_params {
 int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream);
 
 /* ---- input staging: fp32 -> bf16 / bf16x3 (feeds K1) ---------------------- */
-/* x (rows, C) fp32 -> out (rows, nterms*C) bf16, term j at [j*C, (j+1)*C). nterms in {1,3}. */
+/* x (rows, C) fp32 -> out (rows, nterms*C) 16-bit terms, term j at [j*C, (j+1)*C):
+ * nterms 1 = bf16, 3 = bf16x3, 2 = f16x2 (two fp16 terms). */
 int mq_split_bf16(const float* x, void* out, int64_t rows, int C, int nterms, mq_stream_t stream);
 
 /* ---- K2: ConvBlock2D `pre` / `post` (preencoder.py:277-301) ---------------- */
@@ -147,6 +157,7 @@ typedef struct mq_cb2d_params {
   const float* table;             /* optional [table_n][4] cubic coefficients of g */
   int table_n, table_off;
   float table_inv_h;
+  int split_kind;                 /* out_split format: 0 = bf16x3 (B,T,3C), 1 = f16x2 (B,T,2C) */
 } mq_cb2d_params;
 int mq_convblock2d(const mq_cb2d_params* p, mq_stream_t stream);
 
@@ -172,6 +183,7 @@ typedef struct mq_cbam_apply_params {
   const float* sam_w;  /* [2][7] */
   float beta, gamma;
   float* out_f32; void* out_bf16; void* out_split;
+  int split_kind;      /* 0 = bf16x3, 1 = f16x2 */
 } mq_cbam_apply_params;
 int mq_cbam_apply(const mq_cbam_apply_params* p, mq_stream_t stream);
 

@@ -48,6 +48,8 @@ class ConvParams(C.Structure):
         ("out_split", C.c_void_p), ("split_ld", C.c_int), ("split_seg", C.c_int),
         ("in2", C.c_void_p), ("in2_ld", C.c_int), ("up_taps", C.c_int), ("kchunks2", C.c_int),
         ("tap_dh_odd", C.c_int * MQ_MAX_TAPS),
+        ("op_f16", C.c_int), ("split_kind", C.c_int),
+        ("acc_scale", C.c_float),
         ("halo", C.c_int),
     ]
 
@@ -62,6 +64,7 @@ class Cb2dParams(C.Structure):
         ("fast_tanh", C.c_int),
         ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("out_split", C.c_void_p),
         ("table", C.c_void_p), ("table_n", C.c_int), ("table_off", C.c_int), ("table_inv_h", C.c_float),
+        ("split_kind", C.c_int),
     ]
 
 
@@ -73,6 +76,7 @@ class CbamApplyParams(C.Structure):
         ("sam_w", C.c_void_p),
         ("beta", C.c_float), ("gamma", C.c_float),
         ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("out_split", C.c_void_p),
+        ("split_kind", C.c_int),
     ]
 
 

@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -196,6 +197,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// same with FP16 operands (A/B format 0)
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 
 // ---------------------------------------------------------------------------
 // math
@@ -237,6 +242,52 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& a, __nv_bfloat16&
   b = __float2bfloat16_rn(r);
   r -= __bfloat162float(b);
   c = __float2bfloat16_rn(r);
+}
+
+// Multi-term operand splits for fp32-grade tensor-core GEMMs.  kind 0: three bf16 terms (24 bits);
+// kind 1: two fp16 terms (22 bits; |x| is clamped to the fp16 range, tiny terms bottom out at the
+// fp16 subnormal spacing 2^-24, an absolute error that is irrelevant next to O(1) dot products).
+__device__ __forceinline__ int split_nterms(int kind) { return kind == 1 ? 2 : 3; }
+
+__device__ __forceinline__ void split_terms(float x, int kind, uint16_t (&t)[3]) {
+  if (kind == 1) {
+    const float xs = fminf(fmaxf(x, -65504.0f), 65504.0f);
+    const __half h0 = __float2half_rn(xs);
+    const __half h1 = __float2half_rn(xs - __half2float(h0));
+    t[0] = __half_as_ushort(h0);
+    t[1] = __half_as_ushort(h1);
+    t[2] = 0;
+  } else {
+    __nv_bfloat16 a, b, c;
+    split3(x, a, b, c);
+    t[0] = __bfloat16_as_ushort(a);
+    t[1] = __bfloat16_as_ushort(b);
+    t[2] = __bfloat16_as_ushort(c);
+  }
+}
+
+// four consecutive channels -> nterms 8-byte stores, term j at element offset j*seg
+__device__ __forceinline__ void store_terms4(uint16_t* base, int64_t seg, int kind, const float (&y)[4]) {
+  uint16_t t[4][3];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_terms(y[e], kind, t[e]);
+  const int nt = split_nterms(kind);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j < nt) {
+      uint2 u;
+      u.x = static_cast<uint32_t>(t[0][j]) | (static_cast<uint32_t>(t[1][j]) << 16);
+      u.y = static_cast<uint32_t>(t[2][j]) | (static_cast<uint32_t>(t[3][j]) << 16);
+      *reinterpret_cast<uint2*>(base + j * seg) = u;
+    }
+  }
+}
+
+__device__ __forceinline__ void store_terms1(uint16_t* base, int64_t seg, int kind, float v) {
+  uint16_t t[3];
+  split_terms(v, kind, t);
+  const int nt = split_nterms(kind);
+  for (int j = 0; j < nt; ++j) base[j * seg] = t[j];
 }
 
 }  // namespace mq

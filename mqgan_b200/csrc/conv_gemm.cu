@@ -60,8 +60,10 @@ struct ConvArgs {
   int f32_ld, f32_coff;
   __nv_bfloat16* out_bf16;
   int bf16_ld, bf16_coff;
-  __nv_bfloat16* out_split;
-  int split_ld, split_seg;
+  uint16_t* out_split;
+  int split_ld, split_seg, split_kind;
+  int op_f16;                     // operands are fp16 (f16x2 mode) instead of bf16
+  float acc_scale;                // accumulator scale applied before the bias (undoes the f16x2 weight scale)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -92,7 +94,7 @@ __device__ __forceinline__ void epilogue_generic(const ConvArgs& a, const uint32
     const int nvalid = min(32, a.cout - co0);
     float x[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + bs[j];
+    for (int j = 0; j < 32; ++j) x[j] = fmaf(__uint_as_float(v[j]), a.acc_scale, bs[j]);
 
     float rr[32];
     if (a.res_mode != 0) {
@@ -182,37 +184,17 @@ __device__ __forceinline__ void epilogue_generic(const ConvArgs& a, const uint32
       }
     }
     if (a.out_split != nullptr) {
-      __nv_bfloat16* op = a.out_split + pix * a.split_ld + co0;
+      uint16_t* op = a.out_split + pix * a.split_ld + co0;
       if (nvalid == 32) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w0[4], w1[4], w2[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 a0, a1, a2, b0, b1, b2;
-            split3(x[8 * g + 2 * e], a0, a1, a2);
-            split3(x[8 * g + 2 * e + 1], b0, b1, b2);
-            w0[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a0)) |
-                    (static_cast<uint32_t>(__bfloat16_as_ushort(b0)) << 16);
-            w1[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a1)) |
-                    (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
-            w2[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a2)) |
-                    (static_cast<uint32_t>(__bfloat16_as_ushort(b2)) << 16);
-          }
-          *reinterpret_cast<uint4*>(op + 8 * g) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-          *reinterpret_cast<uint4*>(op + a.split_seg + 8 * g) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-          *reinterpret_cast<uint4*>(op + 2 * a.split_seg + 8 * g) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+        for (int g = 0; g < 8; ++g) {
+          const float y4[4] = {x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]};
+          store_terms4(op + 4 * g, a.split_seg, a.split_kind, y4);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < nvalid) {
-            __nv_bfloat16 a0, a1, a2;
-            split3(x[j], a0, a1, a2);
-            op[j] = a0;
-            op[a.split_seg + j] = a1;
-            op[2 * a.split_seg + j] = a2;
-          }
+          if (j < nvalid) store_terms1(op + j, a.split_seg, a.split_kind, x[j]);
       }
     }
 }
@@ -446,7 +428,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kTileM, a.bn);
+      const uint32_t idesc = a.op_f16 ? umma_idesc_f16(kTileM, a.bn) : umma_idesc_bf16(kTileM, a.bn);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -576,7 +558,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kTileM, a.bn);
+      const uint32_t idesc = a.op_f16 ? umma_idesc_f16(kTileM, a.bn) : umma_idesc_bf16(kTileM, a.bn);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -728,7 +710,10 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.res = p->res; a.res_is_bf16 = p->res_is_bf16; a.res_ld = p->res_ld; a.res_coff = p->res_coff;
   a.out_f32 = p->out_f32; a.f32_ld = p->f32_ld; a.f32_coff = p->f32_coff;
   a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16); a.bf16_ld = p->bf16_ld; a.bf16_coff = p->bf16_coff;
-  a.out_split = reinterpret_cast<__nv_bfloat16*>(p->out_split); a.split_ld = p->split_ld; a.split_seg = p->split_seg;
+  a.out_split = reinterpret_cast<uint16_t*>(p->out_split); a.split_ld = p->split_ld; a.split_seg = p->split_seg;
+  a.split_kind = p->split_kind; a.op_f16 = p->op_f16;
+  a.acc_scale = p->acc_scale != 0.0f ? p->acc_scale : 1.0f;
+  const CUtensorMapDataType op_dt = p->op_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 
   // --- tensor maps ---
   CUtensorMap map_a, map_b, map_a2;
@@ -744,7 +729,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
       box[2] = static_cast<cuuint32_t>(kHaloSubRows * a.msub + 2);
     }
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->in), dims,
+    CUresult r = encode(&map_a, op_dt, 4, const_cast<void*>(p->in), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -758,7 +743,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     cuuint64_t strides[1] = {K * 2};
     cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(p->bn)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->wpack), dims,
+    CUresult r = encode(&map_b, op_dt, 2, const_cast<void*>(p->wpack), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -773,7 +758,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     cuuint64_t strides[4] = {static_cast<cuuint64_t>(p->in2_ld) * 2, rowb, 2 * rowb, 2 * rowb * p->H};
     cuuint32_t box[5] = {kBlockK, static_cast<cuuint32_t>(p->bw), 1, static_cast<cuuint32_t>(p->bh), 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&map_a2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p->in2), dims, strides,
+    CUresult r = encode(&map_a2, op_dt, 5, const_cast<void*>(p->in2), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MQ_REQUIRE(r == CUDA_SUCCESS, "mq_conv_gemm: cuTensorMapEncodeTiled(A2) failed with %d", (int)r);
@@ -801,7 +786,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   }
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
   const bool lean = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->out_split == nullptr &&
-                    p->cout % 32 == 0 && (p->res_mode == 0 || p->res_is_bf16);
+                    p->cout % 32 == 0 && (p->res_mode == 0 || p->res_is_bf16) && a.acc_scale == 1.0f;
 #define MQ_LAUNCH_CONV(FAST, LEAN)                                                                          \
   do {                                                                                                      \
     MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \

@@ -27,19 +27,12 @@ static inline int grid_for(int64_t work_items, int per_block, int waves = 8) {
   return static_cast<int>(need < cap ? need : cap);
 }
 
-__device__ __forceinline__ void store_split3(__nv_bfloat16* base, int seg, float v) {
-  __nv_bfloat16 a, b, c;
-  split3(v, a, b, c);
-  base[0] = a;
-  base[seg] = b;
-  base[2 * seg] = c;
-}
-
 // ---------------------------------------------------------------------------
 // fp32 -> bf16 / bf16x3
 // ---------------------------------------------------------------------------
-__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+__global__ void split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ out,
                                   int64_t rows, int C, int nterms) {
+  // nterms 1: plain bf16; 3: bf16x3; 2: f16x2.  Term j at [j*C, (j+1)*C) of each output row.
   const int64_t total = rows * (C / 4);
   const int c4 = C / 4;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -48,12 +41,15 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __
     const int c = static_cast<int>(i - r * c4) * 4;
     const float4 v = *reinterpret_cast<const float4*>(x + r * C + c);
     const float f[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 t[3][4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) split3(f[e], t[0][e], t[1][e], t[2][e]);
-    __nv_bfloat16* o = out + r * (static_cast<int64_t>(nterms) * C) + c;
-    for (int j = 0; j < nterms; ++j)
-      *reinterpret_cast<uint2*>(o + static_cast<int64_t>(j) * C) = *reinterpret_cast<uint2*>(t[j]);
+    uint16_t* o = out + r * (static_cast<int64_t>(nterms) * C) + c;
+    if (nterms == 1) {
+      uint2 u;
+      u.x = pack_bf16x2(f[0], f[1]);
+      u.y = pack_bf16x2(f[2], f[3]);
+      *reinterpret_cast<uint2*>(o) = u;
+    } else {
+      store_terms4(o, C, nterms == 2 ? 1 : 0, f);
+    }
   }
 }
 
@@ -68,7 +64,7 @@ __global__ void __launch_bounds__(256)
 convblock2d_kernel(const void* __restrict__ xin, int B, int T, int C, const float* __restrict__ dw,
                    const float4* __restrict__ pw, float bout, const uint8_t* __restrict__ row_mask,
                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
-                   __nv_bfloat16* __restrict__ out_split) {
+                   uint16_t* __restrict__ out_split, int split_kind) {
   extern __shared__ float4 smem_pw[];                       // [C] {wpw, bpw, 0.5*wout, 0}
   __shared__ float tile[kCbT + 4][kCbC + 4];
   __shared__ float dws[26];
@@ -137,7 +133,7 @@ convblock2d_kernel(const void* __restrict__ xin, int B, int T, int C, const floa
     const int64_t row = static_cast<int64_t>(b) * T + t;
     if (out_f32) out_f32[row * C + c] = v;
     if (out_bf16) out_bf16[row * C + c] = __float2bfloat16_rn(v);
-    if (out_split) store_split3(out_split + row * 3 * C + c, C, v);
+    if (out_split) store_terms1(out_split + row * split_nterms(split_kind) * C + c, C, split_kind, v);
   }
 }
 
@@ -151,7 +147,7 @@ convblock2d_table_kernel(const void* __restrict__ xin, int B, int T, int C, cons
                          const float4* __restrict__ pw, float bout, const uint8_t* __restrict__ row_mask,
                          const float4* __restrict__ table, int table_n, int table_off, float inv_h,
                          float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
-                         __nv_bfloat16* __restrict__ out_split) {
+                         uint16_t* __restrict__ out_split, int split_kind) {
   __shared__ float tile[kCtT + 4][kCtC + 4];
   __shared__ float dws[26];
   const int ctiles = (C + kCtC - 1) / kCtC;
@@ -218,20 +214,12 @@ convblock2d_table_kernel(const void* __restrict__ xin, int B, int T, int C, cons
       u2.y = pack_bf16x2(y[2], y[3]);
       *reinterpret_cast<uint2*>(out_bf16 + row * C + c) = u2;
     }
-    if (out_split) {
-      __nv_bfloat16 tq[3][4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) split3(y[e], tq[0][e], tq[1][e], tq[2][e]);
-      __nv_bfloat16* op = out_split + row * 3 * C + c;
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        *reinterpret_cast<uint2*>(op + static_cast<int64_t>(j) * C) = *reinterpret_cast<uint2*>(tq[j]);
-    }
+    if (out_split) store_terms4(out_split + row * split_nterms(split_kind) * C + c, C, split_kind, y);
   } else {
     for (int e = 0; e < nv; ++e) {
       if (out_f32) out_f32[row * C + c + e] = y[e];
       if (out_bf16) out_bf16[row * C + c + e] = __float2bfloat16_rn(y[e]);
-      if (out_split) store_split3(out_split + row * 3 * C + c + e, C, y[e]);
+      if (out_split) store_terms1(out_split + row * split_nterms(split_kind) * C + c + e, C, split_kind, y[e]);
     }
   }
 }
@@ -334,7 +322,7 @@ cbam_apply_kernel(const float* __restrict__ o, const float* __restrict__ gate,
                   const float* __restrict__ res, const uint8_t* __restrict__ row_mask, int T, int C,
                   const float* __restrict__ sam_w, float beta, float gamma,
                   float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
-                  __nv_bfloat16* __restrict__ out_split) {
+                  uint16_t* __restrict__ out_split, int split_kind) {
   extern __shared__ float gs[];                   // gate[C]
   __shared__ float pmax[kSamT + 6], pavg[kSamT + 6], sam[kSamT];
   const int b = blockIdx.y;
@@ -404,15 +392,7 @@ cbam_apply_kernel(const float* __restrict__ o, const float* __restrict__ gate,
       u.y = pack_bf16x2(y[2], y[3]);
       *reinterpret_cast<uint2*>(out_bf16 + row * C + c) = u;
     }
-    if (out_split) {
-      __nv_bfloat16 t[3][4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) split3(y[e], t[0][e], t[1][e], t[2][e]);
-      __nv_bfloat16* op = out_split + row * 3 * C + c;
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        *reinterpret_cast<uint2*>(op + static_cast<int64_t>(j) * C) = *reinterpret_cast<uint2*>(t[j]);
-    }
+    if (out_split) store_terms4(out_split + row * split_nterms(split_kind) * C + c, C, split_kind, y);
   }
 }
 
@@ -753,9 +733,9 @@ using namespace mq;
 extern "C" int mq_split_bf16(const float* x, void* out, int64_t rows, int C, int nterms,
                              mq_stream_t stream) {
   MQ_REQUIRE(x && out && rows > 0 && C > 0 && C % 4 == 0, "mq_split_bf16: bad args (C=%d must be a multiple of 4)", C);
-  MQ_REQUIRE(nterms == 1 || nterms == 3, "mq_split_bf16: nterms=%d", nterms);
+  MQ_REQUIRE(nterms >= 1 && nterms <= 3, "mq_split_bf16: nterms=%d", nterms);
   split_bf16_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, STREAM(stream)>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(out), rows, C, nterms);
+      x, reinterpret_cast<uint16_t*>(out), rows, C, nterms);
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -770,7 +750,8 @@ extern "C" int mq_convblock2d(const mq_cb2d_params* p, mq_stream_t stream) {
   const size_t smem = static_cast<size_t>(p->C) * sizeof(float4);
   MQ_REQUIRE(smem <= 40 * 1024, "mq_convblock2d: C=%d too large", p->C);
   auto* ob = reinterpret_cast<__nv_bfloat16*>(p->out_bf16);
-  auto* os = reinterpret_cast<__nv_bfloat16*>(p->out_split);
+  auto* os = reinterpret_cast<uint16_t*>(p->out_split);
+  const int sk = p->split_kind;
   const float4* pw = reinterpret_cast<const float4*>(p->pw);
   if (p->table != nullptr) {
     MQ_REQUIRE(p->table_n > 0 && p->table_inv_h > 0.0f, "mq_convblock2d: bad table");
@@ -782,7 +763,7 @@ extern "C" int mq_convblock2d(const mq_cb2d_params* p, mq_stream_t stream) {
 #define LAUNCH_CT(FAST, INBF)                                                                     \
   convblock2d_table_kernel<FAST, INBF><<<static_cast<unsigned>(nb), 256, 0, STREAM(stream)>>>(    \
       p->x, p->B, p->T, p->C, p->dw, pw, p->bout, p->row_mask, tb, p->table_n, p->table_off,      \
-      p->table_inv_h, p->out_f32, ob, os)
+      p->table_inv_h, p->out_f32, ob, os, sk)
     if (p->fast_tanh) {
       if (p->x_is_bf16) LAUNCH_CT(true, true); else LAUNCH_CT(true, false);
     } else {
@@ -795,7 +776,7 @@ extern "C" int mq_convblock2d(const mq_cb2d_params* p, mq_stream_t stream) {
   dim3 grid(static_cast<unsigned>(blocks));
 #define LAUNCH_CB(FAST, INBF)                                                                     \
   convblock2d_kernel<FAST, INBF><<<grid, 256, smem, STREAM(stream)>>>(                            \
-      p->x, p->B, p->T, p->C, p->dw, pw, p->bout, p->row_mask, p->out_f32, ob, os)
+      p->x, p->B, p->T, p->C, p->dw, pw, p->bout, p->row_mask, p->out_f32, ob, os, sk)
   if (p->fast_tanh) {
     if (p->x_is_bf16) LAUNCH_CB(true, true); else LAUNCH_CB(true, false);
   } else {
@@ -836,7 +817,7 @@ extern "C" int mq_cbam_apply(const mq_cbam_apply_params* p, mq_stream_t stream) 
   dim3 grid((p->T + kSamT - 1) / kSamT, p->B);
   cbam_apply_kernel<<<grid, 256, smem, STREAM(stream)>>>(
       p->o, p->gate, p->res, p->row_mask, p->T, p->C, p->sam_w, p->beta, p->gamma, p->out_f32,
-      reinterpret_cast<__nv_bfloat16*>(p->out_bf16), reinterpret_cast<__nv_bfloat16*>(p->out_split));
+      reinterpret_cast<__nv_bfloat16*>(p->out_bf16), reinterpret_cast<uint16_t*>(p->out_split), p->split_kind);
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

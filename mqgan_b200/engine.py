@@ -10,10 +10,11 @@ residual live in the GEMM epilogues; ConvBlock2D's C-fold expansion is never
 materialised).
 
 Precision modes
-  encoder "bf16x3": every encoder GEMM runs as six bf16 products of 3-term splits
-      (24 significant bits per operand, fp32 accumulate in TMEM) and all
-      element-wise encoder math is fp32 -> indices equal the fp32 reference except
-      within rounding distance of an FSQ boundary.
+  encoder "f16x2" (default): every encoder GEMM runs as three fp16 products of 2-term operand
+      splits (22 significant bits per operand, weights pre-scaled by a power of two, fp32
+      accumulate in TMEM) and all element-wise encoder math is fp32 -> indices equal the fp32
+      reference except within rounding distance of an FSQ boundary.
+  encoder "bf16x3": the same with six bf16 products of 3-term splits (24 bits, twice the MMAs).
   encoder "bf16": single bf16 pass (index agreement rate is reported, not exact).
   decoder: bf16 operands, fp32 accumulate, bf16 activations between layers.
 """
@@ -122,21 +123,21 @@ class _CB2D:
 
 class PreEncoderEngine:
     def __init__(self, cfg: PreEncoderConfig, state_dict: Dict[str, torch.Tensor], device="cuda",
-                 encoder_precision: str = "bf16x3", max_chunk_frames: int = 32768, cb2d_table: bool = True,
+                 encoder_precision: str = "f16x2", max_chunk_frames: int = 32768, cb2d_table: bool = True,
                  fuse_upcat: bool = True):
-        if encoder_precision not in ("bf16x3", "bf16"):
-            raise ValueError("encoder_precision must be 'bf16x3' or 'bf16'")
+        if encoder_precision not in ("f16x2", "bf16x3", "bf16"):
+            raise ValueError("encoder_precision must be 'f16x2', 'bf16x3' or 'bf16'")
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("PreEncoderEngine needs a CUDA device (no CPU fallback)")
-        self.enc_split = encoder_precision == "bf16x3"
+        self.enc_split = encoder_precision != "bf16"
         self.encoder_precision = encoder_precision
         self.max_chunk_frames = int(max_chunk_frames)
         self.fsq = ops.fsq_params(cfg.fsq_levels)
         w = folded_weights(state_dict)
         dev = self.device
-        sp = self.enc_split
+        sp = encoder_precision        # operand format of every encoder GEMM (ops.pack_conv ``split``)
 
         def f32(name):
             return w[name].float().contiguous().to(dev)
@@ -258,10 +259,11 @@ class PreEncoderEngine:
         cfg, dev, sp = self.cfg, self.device, self.enc_split
         B, T, M = mel.shape
         rows = B * T
-        nt = 3 if sp else 1
+        nt = ops.SPLIT_TERMS[self.encoder_precision]
+        op_dt = torch.float16 if self.encoder_precision == "f16x2" else torch.bfloat16
 
         def act_buf(c):
-            return torch.empty(rows, nt * c, dtype=torch.bfloat16, device=dev)
+            return torch.empty(rows, nt * c, dtype=op_dt, device=dev)
 
         def kw_out(buf):
             return {"out_split": buf} if sp else {"out_bf16": buf}

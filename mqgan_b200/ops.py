@@ -64,6 +64,9 @@ class PackedConv:
     kchunks2: int = 0
     cin2: int = 0
     tap_dh_odd: Optional[List[int]] = None
+    # operand format: "bf16" (single pass), "bf16x3" (six segments), "f16x2" (three fp16 segments)
+    mode: str = "bf16"
+    acc_scale: float = 1.0         # epilogue multiplies the accumulator by this (f16x2 weight pre-scale undone)
 
     def to(self, device):
         self.wpack = self.wpack.to(device)
@@ -83,6 +86,29 @@ def split3_bf16(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tens
     return x0, x1, x2
 
 
+def split2_f16(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 -> two fp16 terms with h0 + h1 == x to 22 significant bits (host-side weight prep)."""
+    x = x.float().clamp(-65504.0, 65504.0)
+    h0 = x.to(torch.float16)
+    h1 = (x - h0.float()).to(torch.float16)
+    return h0, h1
+
+
+def split_mode(split) -> str:
+    """Normalise the ``split`` argument of pack_conv: False/None -> "bf16", True -> "bf16x3"."""
+    if split is None or split is False:
+        return "bf16"
+    if split is True:
+        return "bf16x3"
+    if split in ("bf16", "bf16x3", "f16x2"):
+        return split
+    raise ValueError(f"unknown operand split {split!r}")
+
+
+SPLIT_TERMS = {"bf16": 1, "bf16x3": 3, "f16x2": 2}
+SPLIT_KIND = {"bf16x3": 0, "f16x2": 1}
+
+
 def choose_bn(cout: int) -> Tuple[int, int]:
     """N tile (multiple of 32, <= 256) and padded cout."""
     if cout <= 256:
@@ -97,15 +123,19 @@ def choose_bn(cout: int) -> Tuple[int, int]:
     return best[1], best[2]
 
 
-def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, split: bool,
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, split=False,
               in_seg_stride: Optional[int] = None) -> PackedConv:
     """Pack a folded conv/linear weight for mq_conv_gemm.
 
     kind: "linear" (Cout, Cin) | "same1d" / "causal1d" (Cout, Cin, k) | "conv2d3" (Cout, Cin, 3, 3).
-    split=True builds the six bf16x3 product segments; the activation is then
-    expected as [x0 | x1 | x2] along channels with term stride ``in_seg_stride``
-    (default Cin).  K order is (segment, tap, channel chunk), matching the kernel.
+    split: False / "bf16" = one bf16 pass; True / "bf16x3" = the six product segments of 3-term bf16
+    splits (activation expected as [x0 | x1 | x2] along channels); "f16x2" = the three product
+    segments h0*g1, h1*g0, h0*g0 of 2-term fp16 splits (activation [h0 | h1]; weights pre-scaled by a
+    power of two so the low term stays in fp16's normal range, undone by ``acc_scale``).  The term
+    stride of the activation is ``in_seg_stride`` (default Cin).  K order is (segment, tap, channel
+    chunk), matching the kernel.
     """
+    mode = split_mode(split)
     w = weight.detach().float().cpu()
     if kind == "linear":
         cout, cin = w.shape
@@ -136,23 +166,36 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, spl
     kchunks = (cin + BLOCK_K - 1) // BLOCK_K
     cpad = kchunks * BLOCK_K
     bn, cout_pad = choose_bn(cout)
-    if split:
+    acc_scale = 1.0
+    stride = cin if in_seg_stride is None else in_seg_stride
+    if mode == "bf16x3":
         w0, w1, w2 = split3_bf16(wt)
         seg_w = [w0, w1, w2, w0, w1, w0]          # smallest products first
         seg_a = [2, 1, 0, 1, 0, 0]
-        stride = cin if in_seg_stride is None else in_seg_stride
+        a_coff = [t * stride for t in seg_a]
+    elif mode == "f16x2":
+        # scale so max|w| lands in [2^13, 2^14): the low term g1 (<= 2^-11 |w|) is then a normal fp16
+        # number for every weight above 2^-16 of the largest, and accumulators stay far from fp32 limits
+        wmax = float(wt.abs().max())
+        e = 0 if wmax == 0.0 else 13 - math.floor(math.log2(wmax))
+        e = max(-24, min(24, e))
+        g0, g1 = split2_f16(wt * (2.0 ** e))
+        acc_scale = 2.0 ** (-e)
+        seg_w = [g1, g0, g0]                      # smallest products first
+        seg_a = [0, 1, 0]
         a_coff = [t * stride for t in seg_a]
     else:
         seg_w = [wt.to(torch.bfloat16)]
         a_coff = [0]
     nseg = len(seg_w)
-    wp = torch.zeros(cout_pad, nseg, taps, cpad, dtype=torch.bfloat16)
+    wp = torch.zeros(cout_pad, nseg, taps, cpad, dtype=torch.float16 if mode == "f16x2" else torch.bfloat16)
     for s, ws in enumerate(seg_w):
         wp[:cout, s, :, :cin] = ws.permute(0, 2, 1)      # (cout, taps, cin)
     wp = wp.reshape(cout_pad, nseg * taps * cpad).contiguous()
     b = None if bias is None else bias.detach().float().cpu().contiguous()
     return PackedConv(wp, b, cin, cout, cout_pad, bn, taps, nseg, kchunks, dh, dw,
-                      a_coff + [0] * (_lib.MQ_MAX_SEGS - len(a_coff)), split)
+                      a_coff + [0] * (_lib.MQ_MAX_SEGS - len(a_coff)), mode != "bf16", mode=mode,
+                      acc_scale=acc_scale)
 
 
 def pack_upconv(weight: torch.Tensor, bias: Optional[torch.Tensor], cx: int, cs: int) -> PackedConv:
@@ -238,16 +281,20 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
               out_split: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None,
               msub: Optional[int] = None, tag: str = "", x2: Optional[torch.Tensor] = None,
               halo: Optional[bool] = None) -> None:
-    """Launch mq_conv_gemm.  x: bf16 (N*H*W, in_ld) channel-last (any leading shape).
-    x2: skip tensor (N, 2H, W, C2) for a ``pack_upconv`` weight; outputs / masks then have 2H rows."""
-    _chk(x, torch.bfloat16, "x")
+    """Launch mq_conv_gemm.  x: bf16 (fp16 for an "f16x2" weight) (N*H*W, in_ld) channel-last (any
+    leading shape).  x2: skip tensor (N, 2H, W, C2) for a ``pack_upconv`` weight; outputs / masks then
+    have 2H rows.  out_split: bf16 (.., 3C) or fp16 (.., 2C) multi-term output for the next split GEMM."""
+    op_dt = torch.float16 if pc.mode == "f16x2" else torch.bfloat16
+    _chk(x, op_dt, "x")
     in_ld = x.shape[-1]
     if x.numel() != N * H * W * in_ld:
         raise ValueError(f"x has {x.numel()} elements, expected N*H*W*in_ld = {N * H * W * in_ld}")
     p = ConvParams()
     p.inp = x.data_ptr()
     p.N, p.H, p.W, p.in_ld = N, H, W, in_ld
-    p.wpack = _chk(pc.wpack, torch.bfloat16, "wpack").data_ptr()
+    p.wpack = _chk(pc.wpack, op_dt, "wpack").data_ptr()
+    p.op_f16 = int(pc.mode == "f16x2")
+    p.acc_scale = float(pc.acc_scale)
     p.cout, p.cout_pad, p.bn = pc.cout, pc.cout_pad, pc.bn
     p.taps, p.nseg, p.kchunks = pc.taps, pc.nseg, pc.kchunks
     for i in range(pc.taps):
@@ -303,10 +350,11 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         _chk(out_bf16, torch.bfloat16, "out_bf16")
         p.out_bf16, p.bf16_ld, p.bf16_coff = out_bf16.data_ptr(), out_bf16.shape[-1], bf16_coff
     if out_split is not None:
-        _chk(out_split, torch.bfloat16, "out_split")
-        if out_split.shape[-1] % 3:
-            raise ValueError("out_split last dim must be 3*C")
-        p.out_split, p.split_ld, p.split_seg = out_split.data_ptr(), out_split.shape[-1], out_split.shape[-1] // 3
+        nt = _split_terms_of(out_split)
+        if out_split.shape[-1] % nt:
+            raise ValueError(f"out_split last dim must be {nt}*C")
+        p.out_split, p.split_ld, p.split_seg = out_split.data_ptr(), out_split.shape[-1], out_split.shape[-1] // nt
+        p.split_kind = int(nt == 2)
     meta = None
     if _lib.profiler is not None:
         pix = float(N) * H * W * hm
@@ -319,14 +367,29 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
     _lib.call("mq_conv_gemm", C.byref(p), _stream(), meta=meta)
 
 
+def _split_terms_of(out_split: torch.Tensor) -> int:
+    """A multi-term output buffer is bf16 (three terms) or fp16 (two terms)."""
+    if out_split.dtype == torch.bfloat16:
+        nt = 3
+    elif out_split.dtype == torch.float16:
+        nt = 2
+    else:
+        raise TypeError(f"out_split: expected bf16 (bf16x3) or fp16 (f16x2), got {out_split.dtype}")
+    if not out_split.is_cuda or not out_split.is_contiguous():
+        raise ValueError("out_split: expected a contiguous CUDA tensor")
+    return nt
+
+
 # ---------------------------------------------------------------------------
 # element-wise / reduction entry points
 # ---------------------------------------------------------------------------
 def split_bf16(x: torch.Tensor, nterms: int) -> torch.Tensor:
+    """fp32 -> 16-bit operand terms along channels: 1 = bf16, 3 = bf16x3, 2 = f16x2 (fp16 tensor)."""
     _chk(x, torch.float32, "x")
     Cc = x.shape[-1]
     rows = x.numel() // Cc
-    out = torch.empty(*x.shape[:-1], nterms * Cc, dtype=torch.bfloat16, device=x.device)
+    out = torch.empty(*x.shape[:-1], nterms * Cc, dtype=torch.float16 if nterms == 2 else torch.bfloat16,
+                      device=x.device)
     _lib.call("mq_split_bf16", x.data_ptr(), out.data_ptr(), rows, Cc, nterms, _stream())
     return out
 
@@ -345,6 +408,8 @@ def convblock2d(x: torch.Tensor, B: int, T: int, Cc: int, dw: torch.Tensor, pw: 
     p.row_mask = _ptr(row_mask)
     p.fast_tanh = int(fast_tanh)
     p.out_f32, p.out_bf16, p.out_split = _ptr(out_f32), _ptr(out_bf16), _ptr(out_split)
+    if out_split is not None:
+        p.split_kind = int(_split_terms_of(out_split) == 2)
     if table is not None:
         _chk(table, torch.float32, "table")
         p.table, p.table_n, p.table_off, p.table_inv_h = table.data_ptr(), table.shape[0], int(table_off), float(table_inv_h)
@@ -376,6 +441,8 @@ def cbam_apply(o, gate, res, row_mask, B, T, Cc, sam_w, beta, gamma, *, out_f32=
     p.sam_w = _chk(sam_w, torch.float32, "sam_w").data_ptr()
     p.beta, p.gamma = float(beta), float(gamma)
     p.out_f32, p.out_bf16, p.out_split = _ptr(out_f32), _ptr(out_bf16), _ptr(out_split)
+    if out_split is not None:
+        p.split_kind = int(_split_terms_of(out_split) == 2)
     _lib.call("mq_cbam_apply", C.byref(p), _stream())
 
 

@@ -49,7 +49,7 @@ def _attach(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
 class PreEncoder(nn.Module):
     def __init__(self, mel_channels, channels, kernel_sizes, fsq_levels=[8, 8, 5, 5, 5], dropout=0.1,
                  refiner_base_channels=128, refiner_depth=3, refiner_hidden_proj_divisor=8,
-                 encoder_precision: str = "bf16x3"):
+                 encoder_precision: str = "f16x2"):
         super().__init__()
         self.cfg = PreEncoderConfig(int(mel_channels), tuple(channels), tuple(kernel_sizes), tuple(fsq_levels),
                                     int(refiner_base_channels), int(refiner_depth),

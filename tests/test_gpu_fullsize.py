@@ -16,7 +16,7 @@ from tests.helpers import index_report  # noqa: E402
 def full():
     import bench
     cfg = S.HIFISPEECH
-    model, sd = bench.build_model(cfg, "bf16x3", torch.device("cuda"))
+    model, sd = bench.build_model(cfg, "f16x2", torch.device("cuda"))
     B, T = 256, 1024
     mel = synth_mels(B, T, cfg.mel_channels, seed=1)
     lengths = torch.randint(256, T + 1, (B,), generator=torch.Generator().manual_seed(3))

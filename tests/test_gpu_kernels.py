@@ -140,6 +140,38 @@ def test_conv_gemm_bf16x3_is_fp32_grade(kind, N, H, W, Cin, Cout, tail):
     assert err < max(4 * err32, 2e-5 * scale), (err, err32)
 
 
+@pytest.mark.parametrize("kind,N,H,W,Cin,Cout,tail", [
+    ("linear", 2, 100, 1, 128, 512, ()),
+    ("same1d", 1, 257, 1, 512, 768, (5,)),
+    ("linear", 1, 64, 1, 32, 64, ()),
+])
+@pytest.mark.parametrize("wscale", [1.0, 1e-3, 300.0])
+def test_conv_gemm_f16x2_is_fp32_grade(kind, N, H, W, Cin, Cout, tail, wscale):
+    """Two fp16 terms per operand, three product segments: 22-bit operands at half the MMA work of
+    bf16x3.  Weights are pre-scaled by a power of two at pack time (tiny weights would otherwise push
+    the low term into fp16 subnormals) and the epilogue undoes it exactly."""
+    x = _rand(N, H, W, Cin, seed=8) * 3.0
+    w = _rand(Cout, Cin, *tail, seed=9) / (Cin * max(1, int(np.prod(tail)))) ** 0.5 * wscale
+    b = _rand(Cout, seed=10) * wscale
+    ref = _ref_conv(x.double(), w.double(), b.double(), kind)
+    pc = ops.pack_conv(w, b, kind, split="f16x2").to(DEV)
+    assert pc.wpack.dtype == torch.float16 and pc.nseg == 3
+    xs = ops.split_bf16(x.reshape(-1, Cin).to(DEV), 2)
+    assert xs.dtype == torch.float16
+    h = xs.cpu().float().reshape(-1, 2, Cin)
+    assert (h.sum(1) - x.reshape(-1, Cin)).abs().max().item() < 2e-6        # 22 bits of |x| <= 15
+    out = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
+    osp = torch.empty(N, H, W, 2 * Cout, dtype=torch.float16, device=DEV)
+    ops.conv_gemm(xs, pc, N, H, W, out_f32=out, out_split=osp)
+    err = (out.cpu().double() - ref).abs().max().item()
+    ref32 = _ref_conv(x, w, b, kind)
+    err32 = (ref32.double() - ref).abs().max().item()
+    scale = max(1e-30, ref.abs().max().item())
+    assert err < max(4 * err32, 2e-5 * scale), (err, err32, scale)
+    s2 = osp.cpu().float().reshape(N, H, W, 2, Cout).sum(dim=3)
+    assert (s2 - out.cpu()).abs().max().item() < 1e-6 * max(1.0, scale) + 2e-7   # 2-term split of the output
+
+
 def test_convblock2d_matches_reference_op():
     B, T, Cc = 2, 37, 96
     x = _rand(B, T, Cc, seed=11)

@@ -2,9 +2,9 @@
 oracle and the committed reference outputs (tests/golden/).
 
 Gates (BASELINE north_star):
-  * fp32 mode ("bf16x3" encoder): indices equal to the reference on every frame
-    whose float64 distance to an FSQ rounding boundary exceeds TAU; raw agreement
-    reported and required >= 99.5 %.
+  * fp32-grade modes ("f16x2" = two fp16 terms per operand, the default; "bf16x3" = three bf16
+    terms): indices equal to the reference on every frame whose float64 distance to an FSQ
+    rounding boundary exceeds TAU; raw agreement reported and required >= 99.5 %.
   * bf16 encoder mode: agreement rate reported, required >= 80 %.
   * reconstructed mels (bf16 operands, fp32 accumulate, bf16 activations):
     max-abs error <= MEL_ATOL + MEL_RTOL * max|ref|.
@@ -38,7 +38,7 @@ def _dump():
         json.dump(REPORT, f, indent=1)
 
 
-def _model(cfg, sd, precision="bf16x3"):
+def _model(cfg, sd, precision="f16x2"):
     m = PreEncoder(cfg.mel_channels, list(cfg.channels), list(cfg.kernel_sizes), fsq_levels=list(cfg.fsq_levels),
                    dropout=0.0, refiner_base_channels=cfg.refiner_base_channels, refiner_depth=cfg.refiner_depth,
                    refiner_hidden_proj_divisor=cfg.refiner_hidden_proj_divisor, encoder_precision=precision)
@@ -46,12 +46,13 @@ def _model(cfg, sd, precision="bf16x3"):
     return m.to("cuda").eval()
 
 
+@pytest.mark.parametrize("precision", ["f16x2", "bf16x3"])
 @pytest.mark.parametrize("name", ["tiny", "hifispeech", "hifimusic"])
-def test_encode_indices_vs_reference(name):
+def test_encode_indices_vs_reference(name, precision):
     cfg, sd, mel, lengths, fx = load_golden(name)
     T = mel.shape[1]
     mask = sequence_mask(T, lengths).unsqueeze(1)
-    model = _model(cfg, sd)
+    model = _model(cfg, sd, precision)
     idx, z = model.engine().encode(mel.cuda(), mask.cuda(), return_latents=True)
     ref_idx = torch.from_numpy(fx["indices"].astype(np.int64))
     ref_z = torch.from_numpy(fx["z"])
@@ -61,9 +62,9 @@ def test_encode_indices_vs_reference(name):
     rep["z_maxabs_vs_ref32"] = float((z.cpu() - ref_z).abs().max())
     rep["z_maxabs_vs_fp64"] = float((z.cpu().double() - z64).abs().max())
     rep["ref32_maxabs_vs_fp64"] = float((ref_z.double() - z64).abs().max())
-    REPORT[f"encode/{name}"] = rep
+    REPORT[f"encode/{name}/{precision}"] = rep
     _dump()
-    print(name, rep)
+    print(name, precision, rep)
     assert rep["safe_mismatch"] == 0, rep
     assert rep["agree"] >= 0.995, rep
     # latents (unit std) within Z_ATOL of float64; the reference's own fp32 error is reported beside it
