@@ -116,6 +116,11 @@ typedef struct mq_conv_params {
    * fetched once per CTA tile as a (16*msub + 2) x 10 pixel halo and the nine taps are nine
    * shifted tensor-core descriptors into it (9x less L2->SM activation traffic). */
   int halo;
+  /* pair != 0: CTA-pair main loop (tcgen05 cta_group::2, M = 256) for single-source 3x3 / pad-1
+   * convolutions and for the fused upsample-concat mode (bh == 16, bw == 8, nseg == 1): the two
+   * CTAs of a cluster each stage the halo of their own msub sub-tiles and half of every weight
+   * tile, halving weight traffic per pixel (L2->SM and shared-memory reads).  Excludes halo. */
+  int pair;
 } mq_conv_params;
 
 int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream);

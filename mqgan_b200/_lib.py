@@ -51,6 +51,7 @@ class ConvParams(C.Structure):
         ("op_f16", C.c_int), ("split_kind", C.c_int),
         ("acc_scale", C.c_float),
         ("halo", C.c_int),
+        ("pair", C.c_int),
     ]
 
 

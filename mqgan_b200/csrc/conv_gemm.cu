@@ -47,6 +47,9 @@ struct ConvArgs {
   int tap_dh_odd[MQ_MAX_TAPS];
   int stages;
   int halo_nA, halo_nB, halo_slot_bytes, halo_tx_bytes;   // halo-tile variant (conv_halo_kernel)
+  int tile_rows;                  // rows of H one tile covers: bh * msub (x2 for a CTA pair)
+  int pair_boxb_off, pair_tx0, pair_tx1;   // conv_pair_kernel: byte offset of the second skip box, A bytes per chunk of group 0 / 1
+  int pair_bgrp;                  // taps per weight-ring slot (one barrier round trip and one commit per slot)
   int debug;                      // bench-only bottleneck probes (MQ_CONV_DEBUG): 1 no epilogue math/stores, 2 no MMA, 4 no TMA
   uint32_t a_tx_bytes, b_tile_bytes;
   // epilogue
@@ -80,7 +83,7 @@ __device__ __forceinline__ void decode_tile(const ConvArgs& a, int tile, int& n_
   int t2 = tm / a.tiles_w;
   int th = t2 % a.tiles_h;
   n_idx = t2 / a.tiles_h;
-  h0 = th * a.bh * a.msub;
+  h0 = th * a.tile_rows;
   w0 = tw * a.bw;
   n0 = tn * a.bn;
 }
@@ -259,9 +262,12 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
 }
 
 // The epilogue role (warps 4..11), shared by both main-loop variants.
+// (tile0, tstep): this CTA's tile sequence; hoff: row offset of this CTA inside the tile (CTA pairs);
+// tempty_addr: shared::cluster address of the accumulator-drained barriers (the leader's for a pair).
 template <bool kFast, bool kLean>
 __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_base, uint64_t* tfull_bar,
-                                             uint64_t* tempty_bar, float* bias_s, int warp, int lane) {
+                                             uint32_t tempty_addr, float* bias_s, int warp, int lane,
+                                             int tile0, int tstep, int hoff) {
   // Warp w may only read TMEM lanes [32*(w%4), +32); warps w and w+4 share a lane quarter and
   // split the 32-column chunks of the accumulator between them.
   const int q = warp & 3;
@@ -271,9 +277,10 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
   const int lw = r - lh * a.bw;
   const int et = threadIdx.x - 128;
   int it = 0;
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+  for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
     int n_idx, h0, w0, n0, par;
     decode_tile(a, tile, n_idx, h0, w0, n0, par);
+    h0 += hoff;
     const int hmul = a.up_mode ? 2 : 1;
     const int Hout = a.H * hmul;
     const uint32_t buf = it % a.nbuf;
@@ -318,7 +325,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
     // all TMEM reads of this buffer are complete (tcgen05.wait::ld above)
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    if (lane == 0) mbar_arrive_cluster(tempty_addr + buf * 8);
   }
 }
 
@@ -460,7 +467,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
-    run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, tempty_bar, bias_s, warp, lane);
+    run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, smem_u32(tempty_bar), bias_s, warp, lane,
+                               blockIdx.x, gridDim.x, 0);
   }
 
   tc_fence_before();
@@ -544,13 +552,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         decode_tile(a, tile, n_idx, h0, w0, n0, par);
         for (int kc = 0; kc < a.kchunks; ++kc) {
           mbar_wait(&emptyA[sa], pa ^ 1);
-          mbar_expect_tx(&fullA[sa], a.halo_tx_bytes);
-          tma_load_4d(&map_a, &fullA[sa], smem_a + sa * a.halo_slot_bytes, kc * kBlockK, w0 - 1, h0 - 1, n_idx);
+          if (a.debug & 4) {
+            mbar_arrive(&fullA[sa]);
+          } else {
+            mbar_expect_tx(&fullA[sa], a.halo_tx_bytes);
+            tma_load_4d(&map_a, &fullA[sa], smem_a + sa * a.halo_slot_bytes, kc * kBlockK, w0 - 1, h0 - 1, n_idx);
+          }
           if (++sa == nA) { sa = 0; pa ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&emptyB[sb], pb ^ 1);
-            mbar_expect_tx(&fullB[sb], a.b_tile_bytes);
-            tma_load_2d(&map_b, &fullB[sb], smem_b + sb * a.b_tile_bytes, (tap * a.kchunks + kc) * kBlockK, n0);
+            if (a.debug & 4) {
+              mbar_arrive(&fullB[sb]);
+            } else {
+              mbar_expect_tx(&fullB[sb], a.b_tile_bytes);
+              tma_load_2d(&map_b, &fullB[sb], smem_b + sb * a.b_tile_bytes, (tap * a.kchunks + kc) * kBlockK, n0);
+            }
             if (++sb == nB) { sb = 0; pb ^= 1; }
           }
         }
@@ -575,7 +591,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
             tc_fence_after();
             const uint64_t db = umma_desc_sw128(smem_u32(smem_b + sb * a.b_tile_bytes));
             const int ty = tap / 3, tx = tap - ty * 3;          // 1 + dh, 1 + dw
-            for (int sub = 0; sub < a.msub; ++sub) {
+            for (int sub = 0; sub < ((a.debug & 2) ? 0 : a.msub); ++sub) {
               const uint32_t start = a_base + static_cast<uint32_t>(((sub * kHaloSubRows + ty) * kHaloW + tx) * 128);
               const uint64_t da = umma_desc_sw128_sbo(start, kHaloW * 128);
 #pragma unroll
@@ -592,7 +608,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
   } else if (warp >= 4) {
-    run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, tempty_bar, bias_s, warp, lane);
+    run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, smem_u32(tempty_bar), bias_s, warp, lane,
+                               blockIdx.x, gridDim.x, 0);
   }
 
   tc_fence_before();
@@ -600,6 +617,192 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CTA-pair halo kernel (cta_group::2) for the refiner's 3x3 convolutions, plain and fused
+// nearest-upsample + concat.
+//
+// Every refiner layer is limited by L2->SM operand traffic before it is limited by the tensor pipe
+// (the LTS cap is ~43 B/clk/SM; the single-CTA kernels need 34-49).  Two CTAs on the two SMs of a
+// TPC run one M = 256 MMA: each stages the halo of its own msub sub-tiles (16 rows x 8 columns each,
+// stacked along H, rank 1 below rank 0) and only HALF of every weight tile (bn/2 rows), so weight
+// traffic per pixel halves in L2->SM and in shared-memory reads.  The leader (rank 0) issues the
+// MMAs; TMA loads of both CTAs count on the leader's full barriers (cp.async.bulk.tensor
+// .cta_group::2); tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs; the
+// epilogue warps of both CTAs arrive on the leader's "accumulator drained" barrier.
+//
+// K loop = chunk-major over up to two operand groups:
+//   group 0: `in` (for the fused up-conv: the LOW-resolution tensor), one (R+2) x 10 halo per
+//            64-channel chunk (R = 16*msub), taps [0, 9) or [0, up_taps) as shifted descriptors;
+//   group 1 (fused up-conv only): the skip tensor viewed as (C, W, parity, H, N).  An output tile has
+//            row parity p and rows 2i+p; tap dh = 0 reads skip parity p rows i (box A, origin i0), taps
+//            dh = -1 / +1 read parity 1-p rows i-1+p / i+p (box B, origin i0-1+p, row offsets 0 / 1).
+// ---------------------------------------------------------------------------
+constexpr int kPairMaxA = 4, kPairMaxB = 16;
+
+template <bool kFast, bool kLean>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
+                 const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_a2, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int nA = a.halo_nA, nB = a.halo_nB;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + nA * a.halo_slot_bytes;
+  uint8_t* tail = smem_b + nB * a.pair_bgrp * a.b_tile_bytes;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(tail);        // used in the leader only
+  uint64_t* emptyA = fullA + kPairMaxA;                       // per CTA (multicast commit)
+  uint64_t* fullB = emptyA + kPairMaxA;                       // leader only
+  uint64_t* emptyB = fullB + kPairMaxB;                       // per CTA
+  uint64_t* tfull_bar = emptyB + kPairMaxB;                   // per CTA (multicast commit)
+  uint64_t* tempty_bar = tfull_bar + 2;                       // leader only, both CTAs' epilogues arrive
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_s + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (a.up_mode) tma_prefetch_desc(&map_a2);
+    for (int i = 0; i < nA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < nB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * (kEpiThreads / 32)); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_ptr_s, kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();          // both CTAs' barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int tile0 = blockIdx.x >> 1, tstep = gridDim.x >> 1;
+  const int R = kHaloSubRows * a.msub;          // rows of this CTA's share of a tile
+  const int hoff = static_cast<int>(rank) * R;
+  const int ntap0 = a.up_mode ? a.up_taps : 9;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const int brow_half = static_cast<int>(rank) * (a.bn >> 1);
+      for (int tile = tile0; tile < a.num_tiles; tile += tstep) {
+        int n_idx, h0, w0, n0, par;
+        decode_tile(a, tile, n_idx, h0, w0, n0, par);
+        const int hc = h0 + hoff;
+        const int brow = n0 + par * a.cout_pad + brow_half;
+        for (int grp = 0; grp < (a.up_mode ? 2 : 1); ++grp) {
+          const int nch = grp ? a.kchunks2 : a.kchunks;
+          const int t0 = grp ? a.up_taps : 0, t1 = grp ? a.taps : ntap0;
+          const int kbase = grp ? a.up_taps * a.kchunks : 0;
+          for (int kc = 0; kc < nch; ++kc) {
+            mbar_wait(&emptyA[sa], pa ^ 1);
+            const uint32_t fa = smem_u32(&fullA[sa]) & kPeerBitMask;
+            uint8_t* dst = smem_a + sa * a.halo_slot_bytes;
+            if (a.debug & 4) {
+              if (rank == 0) mbar_arrive(&fullA[sa]);
+            } else if (rank == 0) {
+              mbar_expect_tx(&fullA[sa], 2u * static_cast<uint32_t>(grp ? a.pair_tx1 : a.pair_tx0));
+            }
+            if (a.debug & 4) {
+            } else if (!grp) {
+              tma_load_4d_2cta(&map_a, fa, dst, kc * kBlockK, w0 - 1, hc - 1, n_idx);
+            } else {
+              tma_load_5d_2cta(&map_a2, fa, dst, kc * kBlockK, w0 - 1, par, hc, n_idx);
+              tma_load_5d_2cta(&map_a2, fa, dst + a.pair_boxb_off, kc * kBlockK, w0 - 1, par ^ 1, hc - 1 + par, n_idx);
+            }
+            if (++sa == nA) { sa = 0; pa ^= 1; }
+            for (int tap = t0; tap < t1; tap += a.pair_bgrp) {
+              mbar_wait(&emptyB[sb], pb ^ 1);
+              if (a.debug & 4) {
+                if (rank == 0) mbar_arrive(&fullB[sb]);
+              } else {
+                if (rank == 0) mbar_expect_tx(&fullB[sb], 2u * a.b_tile_bytes * a.pair_bgrp);
+                const uint32_t fb = smem_u32(&fullB[sb]) & kPeerBitMask;
+                for (int j = 0; j < a.pair_bgrp; ++j)
+                  tma_load_2d_2cta(&map_b, fb, smem_b + (sb * a.pair_bgrp + j) * a.b_tile_bytes,
+                                   (kbase + (tap + j - t0) * nch + kc) * kBlockK, brow);
+              }
+              if (++sb == nB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = a.op_f16 ? umma_idesc_f16(2 * kTileM, a.bn) : umma_idesc_bf16(2 * kTileM, a.bn);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
+        const int par = (tile / a.tiles_n) % a.par_tiles;
+        const uint32_t buf = it % a.nbuf;
+        mbar_wait(&tempty_bar[buf], ((it / a.nbuf) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kAccStride;
+        uint32_t acc = 0;
+        for (int grp = 0; grp < (a.up_mode ? 2 : 1); ++grp) {
+          const int nch = grp ? a.kchunks2 : a.kchunks;
+          const int t0 = grp ? a.up_taps : 0, t1 = grp ? a.taps : ntap0;
+          for (int kc = 0; kc < nch; ++kc) {
+            mbar_wait(&fullA[sa], pa);
+            const uint32_t a_base = smem_u32(smem_a + sa * a.halo_slot_bytes);
+            for (int tg = t0; tg < t1; tg += a.pair_bgrp) {
+              mbar_wait(&fullB[sb], pb);
+              tc_fence_after();
+              for (int j = 0; j < a.pair_bgrp; ++j) {
+                const int tap = tg + j;
+                // byte offset of this tap's shifted view inside the halo slot
+                const int tx = a.tap_dw[tap] + 1;
+                uint32_t toff;
+                if (!grp) {
+                  const int ty = ((a.up_mode && par) ? a.tap_dh_odd[tap] : a.tap_dh[tap]) + 1;
+                  toff = static_cast<uint32_t>((ty * kHaloW + tx) * 128);
+                } else {
+                  const int dh = a.tap_dh[tap];
+                  toff = static_cast<uint32_t>((dh != 0 ? a.pair_boxb_off : 0) + ((dh == 1 ? kHaloW : 0) + tx) * 128);
+                }
+                const uint64_t db = umma_desc_sw128(smem_u32(smem_b + (sb * a.pair_bgrp + j) * a.b_tile_bytes));
+                for (int sub = 0; sub < ((a.debug & 2) ? 0 : a.msub); ++sub) {
+                  const uint64_t da = umma_desc_sw128_sbo(a_base + toff + static_cast<uint32_t>(sub * kHaloSubRows * kHaloW * 128),
+                                                          kHaloW * 128);
+#pragma unroll
+                  for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    umma_bf16_2cta(d_tmem + sub * a.bn, da + 2 * k, db + 2 * k, idesc, acc | static_cast<uint32_t>(k));
+                  }
+                }
+                acc = 1;
+              }
+              umma_commit_2cta(&emptyB[sb]);
+              if (++sb == nB) { sb = 0; pb ^= 1; }
+            }
+            umma_commit_2cta(&emptyA[sa]);
+            if (++sa == nA) { sa = 0; pa ^= 1; }
+          }
+        }
+        umma_commit_2cta(&tfull_bar[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, smem_u32(tempty_bar) & kPeerBitMask, bias_s, warp, lane,
+                               tile0, tstep, hoff);
+  }
+
+  // the leader's barriers receive arrivals from the peer until its last tile: leave together
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
   }
 }
 
@@ -669,7 +872,9 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.msub = p->msub > 0 ? p->msub : 1;
   MQ_REQUIRE(a.msub * p->bn <= kTmemCols && a.msub <= 4, "mq_conv_gemm: msub=%d * bn=%d exceeds %d TMEM columns", a.msub, p->bn, kTmemCols);
   a.nbuf = a.msub * p->bn <= kAccStride ? 2 : 1;   // one accumulator buffer when the tile needs more than 256 columns
-  a.tiles_h = (p->H + p->bh * a.msub - 1) / (p->bh * a.msub);
+  const bool pair = p->pair != 0;
+  a.tile_rows = p->bh * a.msub * (pair ? 2 : 1);
+  a.tiles_h = (p->H + a.tile_rows - 1) / a.tile_rows;
   a.tiles_w = (p->W + p->bw - 1) / p->bw;
   a.tiles_n = p->cout_pad / p->bn;
   a.up_mode = up ? 1 : 0;
@@ -691,8 +896,24 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     for (int t = 0; t < 9; ++t)
       MQ_REQUIRE(p->tap_dh[t] == t / 3 - 1 && p->tap_dw[t] == t % 3 - 1, "mq_conv_gemm: halo mode needs the standard 3x3 tap order");
   }
+  if (pair) {
+    MQ_REQUIRE(!halo && p->nseg == 1 && p->bw == 8 && p->bh == kHaloSubRows && p->bn % 32 == 0,
+               "mq_conv_gemm: pair mode needs nseg == 1, a 16x8 sub-tile and bn a multiple of 32");
+    if (!up) {
+      MQ_REQUIRE(p->taps == 9, "mq_conv_gemm: pair mode needs a 3x3 convolution");
+      for (int t = 0; t < 9; ++t)
+        MQ_REQUIRE(p->tap_dh[t] == t / 3 - 1 && p->tap_dw[t] == t % 3 - 1, "mq_conv_gemm: pair mode needs the standard 3x3 tap order");
+    } else {
+      for (int t = 0; t < p->taps; ++t) {
+        MQ_REQUIRE(p->tap_dw[t] >= -1 && p->tap_dw[t] <= 1 && p->tap_dh[t] >= -1 && p->tap_dh[t] <= 1,
+                   "mq_conv_gemm: pair mode taps must stay inside a 1-pixel halo");
+        if (t < p->up_taps)
+          MQ_REQUIRE(p->tap_dh_odd[t] >= -1 && p->tap_dh_odd[t] <= 1, "mq_conv_gemm: pair mode taps must stay inside a 1-pixel halo");
+      }
+    }
+  }
   a.a_tx_bytes = static_cast<uint32_t>(p->bh * p->bw * kBlockK * 2);
-  a.b_tile_bytes = static_cast<uint32_t>(p->bn * kBlockK * 2);
+  a.b_tile_bytes = static_cast<uint32_t>((pair ? p->bn / 2 : p->bn) * kBlockK * 2);
   const int a_stage_bytes = a.msub * kATileBytes;
   int stages = (kSmemBudget - 1024 - 4096) / (a_stage_bytes + static_cast<int>(a.b_tile_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
@@ -724,7 +945,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
                              static_cast<cuuint64_t>(p->W) * p->in_ld * 2,
                              static_cast<cuuint64_t>(p->H) * p->W * p->in_ld * 2};
     cuuint32_t box[4] = {kBlockK, static_cast<cuuint32_t>(p->bw), static_cast<cuuint32_t>(p->bh), 1};
-    if (halo) {                       // one (16*msub + 2) x 10 pixel halo box per channel chunk
+    if (halo || pair) {               // one (16*msub + 2) x 10 pixel halo box per channel chunk
       box[1] = kHaloW;
       box[2] = static_cast<cuuint32_t>(kHaloSubRows * a.msub + 2);
     }
@@ -741,7 +962,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
                             : static_cast<cuuint64_t>(p->taps) * p->nseg * p->kchunks * kBlockK;
     cuuint64_t dims[2] = {K, static_cast<cuuint64_t>(p->cout_pad) * (up ? 2 : 1)};
     cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(p->bn)};
+    cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(pair ? p->bn / 2 : p->bn)};   // a pair CTA stages half the rows
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&map_b, op_dt, 2, const_cast<void*>(p->wpack), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -757,6 +978,10 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     const cuuint64_t rowb = static_cast<cuuint64_t>(p->W) * p->in2_ld * 2;
     cuuint64_t strides[4] = {static_cast<cuuint64_t>(p->in2_ld) * 2, rowb, 2 * rowb, 2 * rowb * p->H};
     cuuint32_t box[5] = {kBlockK, static_cast<cuuint32_t>(p->bw), 1, static_cast<cuuint32_t>(p->bh), 1};
+    if (pair) {                       // one-parity halo boxes of 16*msub + 1 half-rows x 10 pixels
+      box[1] = kHaloW;
+      box[3] = static_cast<cuuint32_t>(kHaloSubRows * a.msub + 1);
+    }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&map_a2, op_dt, 5, const_cast<void*>(p->in2), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -784,7 +1009,42 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     a.halo_nA = nA; a.halo_nB = nB;
     smem = 1024 + nA * a.halo_slot_bytes + nB * static_cast<int>(a.b_tile_bytes) + tail_bytes;
   }
-  const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+  int grid = a.num_tiles < sms ? a.num_tiles : sms;
+  if (pair) {
+    const int R = kHaloSubRows * a.msub;
+    a.pair_tx0 = (R + 2) * kHaloW * 128;
+    const int box1 = (R + 1) * kHaloW * 128;
+    a.pair_tx1 = 2 * box1;
+    a.pair_boxb_off = (box1 + 1023) / 1024 * 1024;
+    int slot = a.pair_tx0;
+    if (up && a.pair_boxb_off + box1 > slot) slot = a.pair_boxb_off + box1;
+    a.halo_slot_bytes = (slot + 1023) / 1024 * 1024;
+    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 4) * 8 + 16 + 2 * 256 * 4;
+    const int budget = kSmemBudget - 1024 - tail_bytes - 256;
+    // weight ring: slots of pair_bgrp taps (3 = one filter row; every tap count on this path is a
+    // multiple of 3) -> one full/empty barrier round trip and one multicast commit per slot
+    int bgrp = 3;
+    {
+      const char* g = getenv("MQ_PAIR_BGRP");
+      if (g && (atoi(g) == 1 || atoi(g) == 3)) bgrp = atoi(g);
+    }
+    if (p->taps % 3 != 0 || (up && p->up_taps % 3 != 0)) bgrp = 1;
+    int nA = 0, nB = 0;
+    for (;;) {
+      const int bslot = bgrp * static_cast<int>(a.b_tile_bytes);
+      nA = (a.kchunks + a.kchunks2 >= 3) ? 3 : 2;
+      while (nA > 2 && budget - nA * a.halo_slot_bytes < 2 * bslot) --nA;
+      nB = (budget - nA * a.halo_slot_bytes) / bslot;
+      if (nB >= 2 || bgrp == 1) break;
+      bgrp = 1;
+    }
+    if (nB > kPairMaxB) nB = kPairMaxB;
+    MQ_REQUIRE(nB >= 2, "mq_conv_gemm: pair mode does not fit shared memory (msub=%d bn=%d)", a.msub, p->bn);
+    a.halo_nA = nA; a.halo_nB = nB; a.pair_bgrp = bgrp;
+    smem = 1024 + nA * a.halo_slot_bytes + nB * bgrp * static_cast<int>(a.b_tile_bytes) + tail_bytes;
+    const int pairs = sms / 2;
+    grid = 2 * (a.num_tiles < pairs ? a.num_tiles : pairs);
+  }
   const bool lean = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->out_split == nullptr &&
                     p->cout % 32 == 0 && (p->res_mode == 0 || p->res_is_bf16) && a.acc_scale == 1.0f;
 #define MQ_LAUNCH_CONV(FAST, LEAN)                                                                          \
@@ -797,7 +1057,18 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     MQ_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
     conv_halo_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);                        \
   } while (0)
-  if (halo) {
+#define MQ_LAUNCH_PAIR(FAST, LEAN)                                                                          \
+  do {                                                                                                      \
+    MQ_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    conv_pair_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, map_a2, a);                \
+  } while (0)
+  if (pair) {
+    if (p->fast_tanh) {
+      if (lean) MQ_LAUNCH_PAIR(true, true); else MQ_LAUNCH_PAIR(true, false);
+    } else {
+      if (lean) MQ_LAUNCH_PAIR(false, true); else MQ_LAUNCH_PAIR(false, false);
+    }
+  } else if (halo) {
     if (p->fast_tanh) {
       if (lean) MQ_LAUNCH_HALO(true, true); else MQ_LAUNCH_HALO(true, false);
     } else {
@@ -810,6 +1081,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   }
 #undef MQ_LAUNCH_CONV
 #undef MQ_LAUNCH_HALO
+#undef MQ_LAUNCH_PAIR
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

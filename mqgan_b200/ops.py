@@ -19,6 +19,8 @@ from ._lib import ConvParams, Cb2dParams, CbamApplyParams, FsqParams
 
 BLOCK_K = 64
 HALO_DEFAULT = os.environ.get("MQ_HALO", "1") != "0"   # halo-tile main loop for 3x3 convs
+PAIR_DEFAULT = os.environ.get("MQ_PAIR", "1") != "0"   # CTA-pair (cta_group::2) main loop for the refiner's 3x3 convs
+PAIR_MIN_BN = int(os.environ.get("MQ_PAIR_MIN_BN", "128"))
 
 
 def _stream() -> int:
@@ -272,6 +274,21 @@ def choose_msub(bn: int, N: int, H: int, W: int, bh: int, bw: int, up: bool = Fa
     return m
 
 
+def choose_msub_pair(bn: int, N: int, H: int, W: int, up: bool) -> int:
+    """Sub-tiles per CTA of a CTA pair (a pair tile is 2*msub sub-tiles of 16 rows x 8 columns).
+    msub*bn <= 256 keeps two TMEM accumulator buffers so the epilogue overlaps the next main loop."""
+    override = os.environ.get("MQ_MSUB_PAIR")
+    m = int(override) if override else (4 if bn <= 64 else (2 if bn <= 128 else 1))
+    if up:
+        m = min(m, 2)             # the two skip-parity boxes of msub = 4 do not fit shared memory twice
+    while m > 1 and m * bn > 512:
+        m //= 2
+    tiles_w = math.ceil(W / 8)
+    while m > 1 and (H < 32 * m or N * math.ceil(H / (32 * m)) * tiles_w < 2 * 74):
+        m //= 2
+    return m
+
+
 def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
               row_mask: Optional[torch.Tensor] = None, mask_pre=False, mask_post=False,
               act=False, beta=1.0, gamma=0.5, fast_tanh=True,
@@ -280,7 +297,7 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
               out_bf16: Optional[torch.Tensor] = None, bf16_coff=0,
               out_split: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None,
               msub: Optional[int] = None, tag: str = "", x2: Optional[torch.Tensor] = None,
-              halo: Optional[bool] = None) -> None:
+              halo: Optional[bool] = None, pair: Optional[bool] = None) -> None:
     """Launch mq_conv_gemm.  x: bf16 (fp16 for an "f16x2" weight) (N*H*W, in_ld) channel-last (any
     leading shape).  x2: skip tensor (N, 2H, W, C2) for a ``pack_upconv`` weight; outputs / masks then
     have 2H rows.  out_split: bf16 (.., 3C) or fp16 (.., 2C) multi-term output for the next split GEMM."""
@@ -313,9 +330,22 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         for i in range(pc.taps):
             p.tap_dh_odd[i] = pc.tap_dh_odd[i]
         hm = 2
+    conv3 = pc.taps == 9 and pc.nseg == 1 and not pc.up_taps
+    if pair is None:
+        # measured (tools/conv_bench.py): the CTA-pair loop wins on the wide plain 3x3 layers (bn > 128);
+        # narrow layers are epilogue-bound and the fused up-conv needs deeper rings than fit
+        pair = (PAIR_DEFAULT and conv3 and pc.bn > PAIR_MIN_BN and W >= 8 and H >= 32 and tile is None
+                and halo is not True and pc.bn % 32 == 0)
     if halo is None:
-        halo = HALO_DEFAULT and pc.taps == 9 and pc.nseg == 1 and not pc.up_taps and W >= 8 and tile is None
-    if halo:
+        halo = HALO_DEFAULT and conv3 and W >= 8 and tile is None and not pair
+    if pair and halo:
+        raise ValueError("pair and halo main loops are exclusive")
+    p.pair = int(bool(pair))
+    if pair:
+        bh, bw = 16, 8
+        if msub is None:
+            msub = choose_msub_pair(pc.bn, N, H, W, bool(pc.up_taps))
+    elif halo:
         bh, bw = 16, 8
     else:
         bh, bw = tile if tile is not None else choose_tile(H, W)

@@ -386,17 +386,23 @@ def test_conv_gemm_multi_subtile(kind, N, H, W, Cin, Cout, tail, msub):
     pc = ops.pack_conv(w.float(), b, kind, split=False).to(DEV)
     out = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
     ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, fast_tanh=False,
-                  out_f32=out, msub=msub)
+                  out_f32=out, msub=msub, pair=False)
     err = (out.cpu().double() - ref).abs().max().item()
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
 
 
-@pytest.mark.parametrize("N,Hl,W,Cx,Cs,Cout,msub", [
-    (2, 8, 48, 128, 64, 64, None),
-    (1, 11, 36, 96, 96, 96, 1),          # odd half-rows, channel counts that are not multiples of 64
-    (2, 20, 144, 256, 128, 128, 2),
+@pytest.mark.parametrize("N,Hl,W,Cx,Cs,Cout,msub,pair", [
+    (2, 8, 48, 128, 64, 64, None, False),
+    (1, 11, 36, 96, 96, 96, 1, False),          # odd half-rows, channel counts that are not multiples of 64
+    (2, 20, 144, 256, 128, 128, 2, False),
+    # CTA-pair main loop (cta_group::2): x halo + two skip-parity boxes per chunk
+    (2, 32, 48, 128, 64, 64, 1, True),
+    (1, 35, 36, 96, 96, 96, 1, True),           # ragged rows / columns, bn = 96 (48 weight rows per CTA)
+    (2, 72, 144, 256, 128, 128, 2, True),       # two sub-tiles per CTA, last pair tile half empty
+    (1, 64, 144, 512, 256, 256, None, True),    # ups.0.conv1 shape, automatic msub
+    (2, 8, 24, 64, 64, 64, 1, True),            # image smaller than one pair tile
 ])
-def test_conv_gemm_fused_upsample_concat(N, Hl, W, Cx, Cs, Cout, msub):
+def test_conv_gemm_fused_upsample_concat(N, Hl, W, Cx, Cs, Cout, msub, pair):
     """UpBlock: conv3x3(mask(cat[nearest_up(x), skip])) without materialising the concat."""
     H = 2 * Hl
     x = _rand(N, Hl, W, Cx, seed=70).to(torch.bfloat16)
@@ -416,14 +422,14 @@ def test_conv_gemm_fused_upsample_concat(N, Hl, W, Cx, Cs, Cout, msub):
     sd = skip.to(DEV)
     ops.zero_rows(sd, mask_new.to(DEV), mask_old.to(DEV))
     out = torch.empty(N, H, W, Cout, dtype=torch.bfloat16, device=DEV)
-    ops.conv_gemm(x.to(DEV), pc, N, Hl, W, x2=sd, act=True, fast_tanh=False, out_bf16=out, msub=msub)
+    ops.conv_gemm(x.to(DEV), pc, N, Hl, W, x2=sd, act=True, fast_tanh=False, out_bf16=out, msub=msub, pair=pair)
     err = (out.cpu().double() - ref).abs().max().item()
     # pre-summed tap weights are rounded to bf16 once more; output is bf16
     assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
     # masked-output variant with fp32 output for a tighter check of the indexing
     o32 = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
     ops.conv_gemm(x.to(DEV), pc, N, Hl, W, x2=sd, act=True, fast_tanh=False, row_mask=mask_new.to(DEV),
-                  mask_post=True, out_f32=o32, msub=msub)
+                  mask_post=True, out_f32=o32, msub=msub, pair=pair)
     ref_m = ref.masked_fill(mask_new.bool()[:, :, None, None], 0.0)
     assert (o32.cpu().double() - ref_m).abs().max().item() < 6e-3 * max(1.0, ref.abs().max().item())
 
@@ -453,7 +459,7 @@ def test_conv_halo_mode_matches_tap_mode(N, H, W, Cin, Cout, msub):
     for halo in (True, False):
         o = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
         ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, fast_tanh=False,
-                      res=res.to(DEV), res_mode=2, out_f32=o, msub=msub, halo=halo)
+                      res=res.to(DEV), res_mode=2, out_f32=o, msub=msub, halo=halo, pair=False)
         outs[halo] = o.cpu()
     err = (outs[True].double() - ref).abs().max().item()
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
@@ -461,6 +467,47 @@ def test_conv_halo_mode_matches_tap_mode(N, H, W, Cin, Cout, msub):
     assert (outs[True] - outs[False]).abs().max().item() < 1e-4
     ob = torch.empty(N, H, W, Cout, dtype=torch.bfloat16, device=DEV)
     ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, out_bf16=ob, halo=True,
-                  msub=msub)
+                  msub=msub, pair=False)
     ref2 = O.aptx(_ref_conv(x.double(), w.double(), b.double(), "conv2d3"), 1.0, 0.5).masked_fill(mask.bool()[:, :, None, None], 0.0)
     assert (ob.cpu().double() - ref2).abs().max().item() < 2e-2 * max(1.0, ref2.abs().max().item())
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,msub", [
+    (2, 128, 144, 64, 64, 4),        # narrow layer: 4 sub-tiles per CTA, 8 per pair
+    (1, 70, 36, 128, 128, 2),        # H not a multiple of the pair tile; W = 36 -> ragged last column tile
+    (2, 32, 144, 256, 256, 1),       # exactly one pair tile of rows
+    (1, 40, 72, 64, 512, 2),         # two N tiles, single TMEM accumulator buffer (msub*bn = 512)
+    (1, 33, 20, 96, 192, 1),         # Cin padded to 128, bn = 192 (96 weight rows per CTA)
+    (1, 64, 40, 96, 96, 2),          # hifimusic width: bn = 96 (48 weight rows per CTA)
+    (3, 128, 144, 192, 64, None),    # automatic msub
+    (1, 20, 16, 64, 64, 1),          # image smaller than one pair tile: the peer CTA works on padding only
+    (4, 128, 144, 512, 512, None),   # mid.conv shape: many pair tiles per cluster (ring wrap-around)
+])
+def test_conv_pair_mode_matches_tap_mode(N, H, W, Cin, Cout, msub):
+    """CTA-pair main loop (tcgen05 cta_group::2, M = 256, half a weight tile per CTA) against the
+    float64 convolution and against the single-CTA tap-shifted main loop."""
+    x = _rand(N, H, W, Cin, seed=91).to(torch.bfloat16)
+    w = (_rand(Cout, Cin, 3, 3, seed=92) / (9 * Cin) ** 0.5).to(torch.bfloat16)
+    b = _rand(Cout, seed=93)
+    res = _rand(N, H, W, Cout, seed=94).to(torch.bfloat16)
+    mask = torch.zeros(N, H, dtype=torch.uint8)
+    mask[0, H // 3:] = 1
+    ref = (O.aptx(_ref_conv(x.double(), w.double(), b.double(), "conv2d3"), 1.0, 0.5) + res.double())
+    ref = ref.masked_fill(mask.bool()[:, :, None, None], 0.0)
+    pc = ops.pack_conv(w.float(), b, "conv2d3", split=False).to(DEV)
+    outs = {}
+    for pair in (True, False):
+        o = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
+        ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, fast_tanh=False,
+                      res=res.to(DEV), res_mode=2, out_f32=o, msub=msub if pair else None, pair=pair, halo=False)
+        outs[pair] = o.cpu()
+    err = (outs[True].double() - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+    assert (outs[True] - outs[False]).abs().max().item() < 1e-4      # fp32 reordering differences only
+    # lean bf16 epilogue, run twice: persistent ring state must not leak between launches
+    ref2 = O.aptx(_ref_conv(x.double(), w.double(), b.double(), "conv2d3"), 1.0, 0.5).masked_fill(mask.bool()[:, :, None, None], 0.0)
+    for _ in range(2):
+        ob = torch.zeros(N, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+        ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, out_bf16=ob, pair=True,
+                      msub=msub)
+        assert (ob.cpu().double() - ref2).abs().max().item() < 2e-2 * max(1.0, ref2.abs().max().item())

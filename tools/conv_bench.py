@@ -1,39 +1,74 @@
-"""Micro-benchmark of mq_conv_gemm on the refiner layer shapes (bottleneck probes).
-Usage: python tools/conv_bench.py [B] ; env MQ_CONV_DEBUG / MQ_MSUB / MQ_CONV_STAGES select variants."""
-import os, sys
+"""Micro-benchmark of mq_conv_gemm on the refiner layer shapes, one line per (layer, main loop, msub).
+Usage: python tools/conv_bench.py [B] [filter]
+Main loops: halo = single-CTA halo tile, pair = CTA pair (cta_group::2), tap = tap-shifted (fused up-conv only).
+Env MQ_CONV_DEBUG / MQ_CONV_STAGES select bottleneck probes of the single-CTA kernels."""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mqgan_b200 import ops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-SHAPES = [  # name, H, W, Cin, Cout
+FILT = sys.argv[2] if len(sys.argv) > 2 else ""
+# name, H (output rows), W, Cin (or (Cx, Cs) for the fused up-conv), Cout
+SHAPES = [
     ("pre.conv2 64->64 L0", 1024, 144, 64, 64),
     ("down0.conv1 64->128 L1", 512, 144, 64, 128),
     ("down0.conv2 128->128 L1", 512, 144, 128, 128),
+    ("down1.conv1 128->256 L2", 256, 144, 128, 256),
     ("down1.conv2 256->256 L2", 256, 144, 256, 256),
-    ("up1.conv1 384->128 L1", 512, 144, 384, 128),
-    ("up2.conv1 192->64 L0", 1024, 144, 192, 64),
     ("mid.conv1 512->512 L3", 128, 144, 512, 512),
+    ("up0.conv1 512+256->256 L2", 256, 144, (512, 256), 256),
+    ("up1.conv1 256+128->128 L1", 512, 144, (256, 128), 128),
+    ("up2.conv1 128+64->64 L0", 1024, 144, (128, 64), 64),
 ]
 dev = "cuda"
-for name, H, W, Cin, Cout in SHAPES:
-    x = torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16)
-    w = torch.randn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5
-    pc = ops.pack_conv(w, torch.zeros(Cout), "conv2d3", False).to(dev)
-    y = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
-    mask = torch.zeros(B, H, dtype=torch.uint8, device=dev)
-    def run():
-        ops.conv_gemm(x, pc, B, H, W, act=True, row_mask=mask, mask_post=True, out_bf16=y)
+
+
+def bench(fn, n=10):
     for _ in range(3):
-        run()
+        fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    n = 10
     for _ in range(n):
-        run()
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    fl = 2.0 * B * H * W * Cout * Cin * 9
-    print(f"{name:28s} {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  msub={ops.choose_msub(pc.bn, B, H, W, *ops.choose_tile(H, W))}", flush=True)
+    return e0.elapsed_time(e1) / n
+
+
+for name, H, W, Cin, Cout in SHAPES:
+    if FILT and FILT not in name:
+        continue
+    up = isinstance(Cin, tuple)
+    mask = torch.zeros(B, H, dtype=torch.uint8, device=dev)
+    y = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    if up:
+        Cx, Cs = Cin
+        x = torch.randn(B, H // 2, W, Cx, device=dev).to(torch.bfloat16)
+        skip = torch.randn(B, H, W, Cs, device=dev).to(torch.bfloat16)
+        w = torch.randn(Cout, Cx + Cs, 3, 3) / (9 * (Cx + Cs)) ** 0.5
+        pc = ops.pack_upconv(w, torch.zeros(Cout), Cx, Cs).to(dev)
+        fl = 2.0 * B * H * W * Cout * (Cx + Cs) * 9
+        variants = [("tap", None)] + [("pair", m) for m in (1, 2) if m * pc.bn <= 512]
+
+        def run(mode, m):
+            ops.conv_gemm(x, pc, B, H // 2, W, x2=skip, act=True, out_bf16=y, msub=m, pair=(mode == "pair"))
+    else:
+        x = torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16)
+        w = torch.randn(Cout, Cin, 3, 3) / (9 * Cin) ** 0.5
+        pc = ops.pack_conv(w, torch.zeros(Cout), "conv2d3", False).to(dev)
+        fl = 2.0 * B * H * W * Cout * Cin * 9
+        variants = [("halo", None)] + [("pair", m) for m in (1, 2, 4) if m * pc.bn <= 512]
+
+        def run(mode, m):
+            ops.conv_gemm(x, pc, B, H, W, act=True, row_mask=mask, mask_post=True, out_bf16=y, msub=m,
+                          pair=(mode == "pair"), halo=(mode == "halo"))
+    for mode, m in variants:
+        try:
+            ms = bench(lambda: run(mode, m))
+            print(f"{name:28s} {mode:5s} msub={str(m):5s} {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s", flush=True)
+        except Exception as e:  # noqa: BLE001 - report and continue with the next variant
+            print(f"{name:28s} {mode:5s} msub={str(m):5s} FAILED: {e}", flush=True)
