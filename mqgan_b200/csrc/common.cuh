@@ -192,6 +192,36 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// The same descriptor split into 32-bit halves: only the low word (start address, LBO) changes
+// between MMAs of one main loop, so the issue loop advances a 32-bit value and keeps the high word
+// (SBO, version, swizzle mode) constant.  Shared-memory addresses stay below 2^18, so adding tap /
+// sub-tile / K-step offsets (in 16-byte units) never carries out of the 14-bit address field.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
+  return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t umma_desc_make(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+// One lane of a fully active warp (the tcgen05 issue sites are warp-uniform code guarded by this, so
+// descriptors live in uniform registers and ptxas emits no per-lane waterfall loop around UTCHMMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // kind::f16 instruction descriptor: C=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16
 // [10,13)=1, both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {

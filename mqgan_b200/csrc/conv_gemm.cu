@@ -50,7 +50,7 @@ struct ConvArgs {
   int tile_rows;                  // rows of H one tile covers: bh * msub (x2 for a CTA pair)
   int pair_boxb_off, pair_tx0, pair_tx1;   // conv_pair_kernel: byte offset of the second skip box, A bytes per chunk of group 0 / 1
   int pair_bgrp;                  // taps per weight-ring slot (one barrier round trip and one commit per slot)
-  int debug;                      // bench-only bottleneck probes (MQ_CONV_DEBUG): 1 no epilogue math/stores, 2 no MMA, 4 no TMA
+  int debug;                      // bench-only bottleneck probes (MQ_CONV_DEBUG): 1 no epilogue math/stores, 2 no MMA, 4 no TMA, 8 no stores
   uint32_t a_tx_bytes, b_tile_bytes;
   // epilogue
   const float* bias;
@@ -250,6 +250,7 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
     for (int j = 0; j < 32; ++j) x[j] += rr[j];
   }
   __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
+  if ((a.debug & 8) && x[0] != 1234.5678f) return;      // probe: math without the global stores
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     uint4 u;
@@ -433,9 +434,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the loop (warp-uniform control flow and descriptors); one elected lane
+    // issues.  Per MMA the loop costs two 32-bit adds: narrow tiles (N <= 128, <= 64 clocks per MMA)
+    // are otherwise bound by this thread's issue rate, not by the tensor pipe.
+    {
       const uint32_t idesc = a.op_f16 ? umma_idesc_f16(kTileM, a.bn) : umma_idesc_bf16(kTileM, a.bn);
+      constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+      const int msub = (a.debug & 2) ? 0 : a.msub;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -447,22 +453,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * a.b_tile_bytes));
-          for (int sub = 0; sub < ((a.debug & 2) ? 0 : a.msub); ++sub) {
-            const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * a_stage_bytes + sub * kATileBytes));
+          const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + stage * a.b_tile_bytes));
+          const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + stage * a_stage_bytes));
+          const uint32_t acc0 = kb != 0 ? 1u : 0u;
+          if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 field
-              umma_bf16(d_tmem + sub * a.bn, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int sub = 0; sub < 4; ++sub) {
+              if (sub < msub) {
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 field
+                  umma_bf16(d_tmem + sub * a.bn, umma_desc_make(a_lo + sub * (kATileBytes >> 4) + 2 * k, hi),
+                            umma_desc_make(b_lo + 2 * k, hi), idesc, k != 0 ? 1u : acc0);
+                }
+              }
             }
+            umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[buf]);         // accumulator ready for the epilogue
+        if (elect_one_sync()) umma_commit(&tfull_bar[buf]);   // accumulator ready for the epilogue
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -573,8 +588,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp walks the loop, one elected lane issues (see conv_gemm_kernel)
+    {
       const uint32_t idesc = a.op_f16 ? umma_idesc_f16(kTileM, a.bn) : umma_idesc_bf16(kTileM, a.bn);
+      constexpr uint32_t hi_a = umma_desc_hi_sw128(kHaloW * 128), hi_b = umma_desc_hi_sw128(1024);
+      constexpr uint32_t kSubStep = (kHaloSubRows * kHaloW * 128) >> 4;      // one sub-tile down the halo, 16-byte units
+      const int msub = (a.debug & 2) ? 0 : a.msub;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -585,26 +604,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         const uint32_t d_tmem = tmem_base + buf * kAccStride;
         for (int kc = 0; kc < a.kchunks; ++kc) {
           mbar_wait(&fullA[sa], pa);
-          const uint32_t a_base = smem_u32(smem_a + sa * a.halo_slot_bytes);
+          const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + sa * a.halo_slot_bytes));
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&fullB[sb], pb);
             tc_fence_after();
-            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + sb * a.b_tile_bytes));
-            const int ty = tap / 3, tx = tap - ty * 3;          // 1 + dh, 1 + dw
-            for (int sub = 0; sub < ((a.debug & 2) ? 0 : a.msub); ++sub) {
-              const uint32_t start = a_base + static_cast<uint32_t>(((sub * kHaloSubRows + ty) * kHaloW + tx) * 128);
-              const uint64_t da = umma_desc_sw128_sbo(start, kHaloW * 128);
+            const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + sb * a.b_tile_bytes));
+            const uint32_t a_tap = a_lo + (((tap / 3) * kHaloW + (tap % 3)) * 128 >> 4);   // shifted view of the halo
+            const uint32_t acc0 = (kc | tap) != 0 ? 1u : 0u;
+            if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                umma_bf16(d_tmem + sub * a.bn, da + 2 * k, db + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              for (int sub = 0; sub < 4; ++sub) {
+                if (sub < msub) {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                    umma_bf16(d_tmem + sub * a.bn, umma_desc_make(a_tap + sub * kSubStep + 2 * k, hi_a),
+                              umma_desc_make(b_lo + 2 * k, hi_b), idesc, k != 0 ? 1u : acc0);
+                }
+              }
+              umma_commit(&emptyB[sb]);
             }
-            umma_commit(&emptyB[sb]);
+            __syncwarp();
             if (++sb == nB) { sb = 0; pb ^= 1; }
           }
-          umma_commit(&emptyA[sa]);
+          if (elect_one_sync()) umma_commit(&emptyA[sa]);
+          __syncwarp();
           if (++sa == nA) { sa = 0; pa ^= 1; }
         }
-        umma_commit(&tfull_bar[buf]);
+        if (elect_one_sync()) umma_commit(&tfull_bar[buf]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -738,8 +766,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {       // the leader's warp walks the loop, one elected lane issues for both CTAs
       const uint32_t idesc = a.op_f16 ? umma_idesc_f16(2 * kTileM, a.bn) : umma_idesc_bf16(2 * kTileM, a.bn);
+      constexpr uint32_t hi_a = umma_desc_hi_sw128(kHaloW * 128), hi_b = umma_desc_hi_sw128(1024);
+      constexpr uint32_t kSubStep = (kHaloSubRows * kHaloW * 128) >> 4;
+      const int msub = (a.debug & 2) ? 0 : a.msub;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -755,41 +786,50 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
           const int t0 = grp ? a.up_taps : 0, t1 = grp ? a.taps : ntap0;
           for (int kc = 0; kc < nch; ++kc) {
             mbar_wait(&fullA[sa], pa);
-            const uint32_t a_base = smem_u32(smem_a + sa * a.halo_slot_bytes);
+            const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + sa * a.halo_slot_bytes));
             for (int tg = t0; tg < t1; tg += a.pair_bgrp) {
               mbar_wait(&fullB[sb], pb);
               tc_fence_after();
+              const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + sb * a.pair_bgrp * a.b_tile_bytes));
               for (int j = 0; j < a.pair_bgrp; ++j) {
                 const int tap = tg + j;
-                // byte offset of this tap's shifted view inside the halo slot
+                // offset (16-byte units) of this tap's shifted view inside the halo slot
                 const int tx = a.tap_dw[tap] + 1;
                 uint32_t toff;
                 if (!grp) {
                   const int ty = ((a.up_mode && par) ? a.tap_dh_odd[tap] : a.tap_dh[tap]) + 1;
-                  toff = static_cast<uint32_t>((ty * kHaloW + tx) * 128);
+                  toff = static_cast<uint32_t>((ty * kHaloW + tx) * 8);
                 } else {
                   const int dh = a.tap_dh[tap];
-                  toff = static_cast<uint32_t>((dh != 0 ? a.pair_boxb_off : 0) + ((dh == 1 ? kHaloW : 0) + tx) * 128);
+                  toff = static_cast<uint32_t>(((dh != 0 ? a.pair_boxb_off : 0) >> 4) + ((dh == 1 ? kHaloW : 0) + tx) * 8);
                 }
-                const uint64_t db = umma_desc_sw128(smem_u32(smem_b + (sb * a.pair_bgrp + j) * a.b_tile_bytes));
-                for (int sub = 0; sub < ((a.debug & 2) ? 0 : a.msub); ++sub) {
-                  const uint64_t da = umma_desc_sw128_sbo(a_base + toff + static_cast<uint32_t>(sub * kHaloSubRows * kHaloW * 128),
-                                                          kHaloW * 128);
+                const uint32_t a_tap = a_lo + toff;
+                const uint32_t b_tap = b_lo + j * (a.b_tile_bytes >> 4);
+                if (elect_one_sync()) {
 #pragma unroll
-                  for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    umma_bf16_2cta(d_tmem + sub * a.bn, da + 2 * k, db + 2 * k, idesc, acc | static_cast<uint32_t>(k));
+                  for (int sub = 0; sub < 4; ++sub) {
+                    if (sub < msub) {
+#pragma unroll
+                      for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_bf16_2cta(d_tmem + sub * a.bn, umma_desc_make(a_tap + sub * kSubStep + 2 * k, hi_a),
+                                       umma_desc_make(b_tap + 2 * k, hi_b), idesc, k != 0 ? 1u : acc);
+                    }
                   }
                 }
+                __syncwarp();
                 acc = 1;
               }
-              umma_commit_2cta(&emptyB[sb]);
+              if (elect_one_sync()) umma_commit_2cta(&emptyB[sb]);
+              __syncwarp();
               if (++sb == nB) { sb = 0; pb ^= 1; }
             }
-            umma_commit_2cta(&emptyA[sa]);
+            if (elect_one_sync()) umma_commit_2cta(&emptyA[sa]);
+            __syncwarp();
             if (++sa == nA) { sa = 0; pa ^= 1; }
           }
         }
-        umma_commit_2cta(&tfull_bar[buf]);
+        if (elect_one_sync()) umma_commit_2cta(&tfull_bar[buf]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -20,7 +20,7 @@ from ._lib import ConvParams, Cb2dParams, CbamApplyParams, FsqParams
 BLOCK_K = 64
 HALO_DEFAULT = os.environ.get("MQ_HALO", "1") != "0"   # halo-tile main loop for 3x3 convs
 PAIR_DEFAULT = os.environ.get("MQ_PAIR", "1") != "0"   # CTA-pair (cta_group::2) main loop for the refiner's 3x3 convs
-PAIR_MIN_BN = int(os.environ.get("MQ_PAIR_MIN_BN", "128"))
+PAIR_MIN_BN = int(os.environ.get("MQ_PAIR_MIN_BN", "0"))
 
 
 def _stream() -> int:
@@ -332,10 +332,10 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         hm = 2
     conv3 = pc.taps == 9 and pc.nseg == 1 and not pc.up_taps
     if pair is None:
-        # measured (tools/conv_bench.py): the CTA-pair loop wins on the wide plain 3x3 layers (bn > 128);
-        # narrow layers are epilogue-bound and the fused up-conv needs deeper rings than fit
-        pair = (PAIR_DEFAULT and conv3 and pc.bn > PAIR_MIN_BN and W >= 8 and H >= 32 and tile is None
-                and halo is not True and pc.bn % 32 == 0)
+        # measured (tools/conv_bench.py, profiles/conv_bench_r01_*.log): the CTA-pair loop beats the
+        # single-CTA halo / tap loops on every refiner layer shape, plain and fused up-conv
+        pair = (PAIR_DEFAULT and (conv3 or bool(pc.up_taps)) and pc.bn > PAIR_MIN_BN and W >= 8 and H >= 32
+                and tile is None and halo is not True and pc.bn % 32 == 0)
     if halo is None:
         halo = HALO_DEFAULT and conv3 and W >= 8 and tile is None and not pair
     if pair and halo:
