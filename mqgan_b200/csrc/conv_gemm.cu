@@ -33,6 +33,7 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // TMEM columns per accumulator buffer
 constexpr int kATileBytes = kTileM * kBlockK * 2;   // 16 KiB
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kBiasSmemFloats = 1024;       // the whole (padded) bias vector is staged in shared memory once per CTA
 
 struct ConvArgs {
   int N, H, W;
@@ -277,27 +278,39 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
   const int lh = r / a.bw;
   const int lw = r - lh * a.bw;
   const int et = threadIdx.x - 128;
+  // The bias vector is staged once per CTA, and the row masks of tile i+1 are fetched while tile i is
+  // processed: no global-load latency and no CTA-wide barrier sit between "accumulator ready" and the
+  // first tcgen05.ld of a tile (short tiles of narrow layers were paying ~1 us per tile for both).
+  for (int j = et; j < a.cout_pad; j += kEpiThreads)
+    bias_s[j] = (a.bias != nullptr && j < a.cout) ? a.bias[j] : 0.0f;
+  named_bar_sync(1, kEpiThreads);
+  const int hmul = a.up_mode ? 2 : 1;
+  const int Hout = a.H * hmul;
+  auto fetch_masks = [&](int tile, uint8_t (&m)[4]) {
+    int n_idx, h0, w0, n0, par;
+    decode_tile(a, tile, n_idx, h0, w0, n0, par);
+    h0 += hoff;
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      const int h = h0 + sub * a.bh + lh;
+      m[sub] = 0;
+      if (sub < a.msub && r < a.bh * a.bw && h < a.H)
+        m[sub] = a.row_mask[static_cast<int64_t>(n_idx) * Hout + h * hmul + par];
+    }
+  };
+  uint8_t mnext[4] = {0, 0, 0, 0};
+  if (a.row_mask != nullptr && tile0 < a.num_tiles) fetch_masks(tile0, mnext);
   int it = 0;
   for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
     int n_idx, h0, w0, n0, par;
     decode_tile(a, tile, n_idx, h0, w0, n0, par);
     h0 += hoff;
-    const int hmul = a.up_mode ? 2 : 1;
-    const int Hout = a.H * hmul;
     const uint32_t buf = it % a.nbuf;
-    float* bs = bias_s + buf * 256;
-    for (int j = et; j < a.bn; j += kEpiThreads)
-      bs[j] = (a.bias != nullptr && n0 + j < a.cout) ? a.bias[n0 + j] : 0.0f;
-    // row masks of every sub-tile, fetched before the accumulator wait so the latency overlaps it
-    bool mflag[4];
+    const float* bs = bias_s + n0;
+    uint32_t mbits = 0;                       // bit sub = "this thread's row of sub-tile sub is padded"
 #pragma unroll
-    for (int sub = 0; sub < 4; ++sub) {
-      const int h = h0 + sub * a.bh + lh;
-      mflag[sub] = false;
-      if (sub < a.msub && a.row_mask != nullptr && r < a.bh * a.bw && h < a.H)
-        mflag[sub] = a.row_mask[static_cast<int64_t>(n_idx) * Hout + h * hmul + par] != 0;
-    }
-    named_bar_sync(1, kEpiThreads);
+    for (int sub = 0; sub < 4; ++sub) mbits |= (mnext[sub] != 0 ? 1u : 0u) << sub;
+    if (a.row_mask != nullptr && tile + tstep < a.num_tiles) fetch_masks(tile + tstep, mnext);
 
     mbar_wait(&tfull_bar[buf], (it / a.nbuf) & 1);
     tc_fence_after();
@@ -306,7 +319,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
       const int h = h0 + sub * a.bh + lh, w = w0 + lw;
       const bool valid = (r < a.bh * a.bw) && (h < a.H) && (w < a.W);
       const int64_t pix = (static_cast<int64_t>(n_idx) * Hout + h * hmul + par) * a.W + w;
-      const bool masked = mflag[sub];
+      const bool masked = (mbits >> sub) & 1u;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride + sub * a.bn;
 #pragma unroll 1
       for (int c = half * 32; c < a.bn; c += 64) {
@@ -869,7 +882,7 @@ static EncodeTiledFn get_encode_fn() {
 
 static int conv_smem_bytes(int stages, int a_stage_bytes, int b_tile_bytes) {
   return 1024 /*alignment slack*/ + stages * (a_stage_bytes + b_tile_bytes) +
-         (2 * kMaxStages + 4) * 8 + 16 + 2 * 256 * 4;
+         (2 * kMaxStages + 4) * 8 + 16 + kBiasSmemFloats * 4;
 }
 
 }  // namespace mq
@@ -883,6 +896,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   MQ_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "mq_conv_gemm: bad N/H/W %d %d %d", p->N, p->H, p->W);
   MQ_REQUIRE(p->bn >= 32 && p->bn <= 256 && p->bn % 32 == 0, "mq_conv_gemm: bn=%d must be a multiple of 32 in [32,256]", p->bn);
   MQ_REQUIRE(p->cout > 0 && p->cout_pad >= p->cout && p->cout_pad % p->bn == 0, "mq_conv_gemm: cout=%d cout_pad=%d bn=%d", p->cout, p->cout_pad, p->bn);
+  MQ_REQUIRE(p->cout_pad <= kBiasSmemFloats, "mq_conv_gemm: cout_pad=%d exceeds %d", p->cout_pad, kBiasSmemFloats);
   MQ_REQUIRE(p->taps >= 1 && p->taps <= MQ_MAX_TAPS, "mq_conv_gemm: taps=%d", p->taps);
   const bool up = p->in2 != nullptr;
   if (up) {
@@ -955,7 +969,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.a_tx_bytes = static_cast<uint32_t>(p->bh * p->bw * kBlockK * 2);
   a.b_tile_bytes = static_cast<uint32_t>((pair ? p->bn / 2 : p->bn) * kBlockK * 2);
   const int a_stage_bytes = a.msub * kATileBytes;
-  int stages = (kSmemBudget - 1024 - 4096) / (a_stage_bytes + static_cast<int>(a.b_tile_bytes));
+  int stages = (kSmemBudget - 1024 - 6144) / (a_stage_bytes + static_cast<int>(a.b_tile_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
   MQ_REQUIRE(stages >= 2, "mq_conv_gemm: not enough shared memory for 2 stages");
   a.stages = stages;
@@ -1039,7 +1053,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     const int halo_px = (kHaloSubRows * a.msub + 2) * kHaloW;
     a.halo_tx_bytes = halo_px * 128;
     a.halo_slot_bytes = (a.halo_tx_bytes + 1023) / 1024 * 1024;
-    const int tail_bytes = (2 * kHaloMaxA + 2 * kHaloMaxB + 4) * 8 + 16 + 2 * 256 * 4;
+    const int tail_bytes = (2 * kHaloMaxA + 2 * kHaloMaxB + 4) * 8 + 16 + kBiasSmemFloats * 4;
     const int budget = kSmemBudget - 1024 - tail_bytes - 256;
     int nA = a.kchunks >= 3 ? 3 : 2;
     while (nA > 2 && budget - nA * a.halo_slot_bytes < 4 * static_cast<int>(a.b_tile_bytes)) --nA;
@@ -1059,7 +1073,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     int slot = a.pair_tx0;
     if (up && a.pair_boxb_off + box1 > slot) slot = a.pair_boxb_off + box1;
     a.halo_slot_bytes = (slot + 1023) / 1024 * 1024;
-    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 4) * 8 + 16 + 2 * 256 * 4;
+    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 4) * 8 + 16 + kBiasSmemFloats * 4;
     const int budget = kSmemBudget - 1024 - tail_bytes - 256;
     // weight ring: slots of pair_bgrp taps (3 = one filter row; every tap count on this path is a
     // multiple of 3) -> one full/empty barrier round trip and one multicast commit per slot
