@@ -207,6 +207,42 @@ int mq_qin_fsq(const float* y, int64_t rows, int C, const float* w, const float*
 int mq_fsq_quantize(const float* z, int64_t rows, const mq_fsq_params* fsq, int64_t* idx,
                     float* codes_out, mq_stream_t stream);
 
+/* ---- nearest-codeword lookup: distance GEMM + argmin + gather (BASELINE configs[3]) ---------- */
+/*
+ * idx[i] = argmin_k ||z_i - c_k||^2 (ties -> lowest k), codes_out[i] = c_idx[i], dist_out[i] =
+ * ||c||^2 - 2 z.c at the minimum (i.e. the squared distance minus ||z_i||^2).  The (n x k) distance
+ * matrix is never materialised: z.c^T is a tcgen05 GEMM (128 latents x 256 codes per accumulator),
+ * the ||c||^2 bias, the argmin and the gather run in its epilogue.
+ *
+ * The reference's quantiser is FSQ (quantizer.py:109-181, restated exactly by mq_fsq_quantize); it
+ * has no learned codebook.  Its implicit codebook (quantizer.py:101-104) is one valid `codebook`
+ * here, and the two agree except on exact ties; any other (k, d <= 64) fp32 codebook works too.
+ *
+ * cb_img / c2 / acc_scale come from the one-time host-side packing (mqgan_b200/ops.py:pack_codebook):
+ *   cb_img  [k_pad / (256*slices)][nterm][256][128 B] ready-made 128-byte-swizzled shared-memory
+ *           images of the codebook operand, slices = 4 / ks codes side by side per row,
+ *           ks = K-steps of 16 per code = 1, 2 or 4 (>= ceil(d / 16)); nterm = 1 (bf16) or 2 (fp16 h0, h1);
+ *   c2      [k_pad] fp32 ||c_k||^2, +inf on the padding codes;
+ *   acc_scale = 1 / (power-of-two pre-scale applied to the f16x2 codebook terms), 0 means 1.
+ * mode 0: bf16 operands, one product (index agreement with fp32 is reported, not exact);
+ * mode 1: "f16x2", three fp16 products of 2-term splits (22-bit operands): fp32-grade argmin.
+ */
+typedef struct mq_vq_params {
+  const float* z;          /* (n, d) fp32 latents, read once */
+  int64_t n;
+  int d;                   /* 1..64 */
+  const void* cb_img;
+  const float* c2;
+  const float* codebook;   /* (k, d) fp32, gathered into codes_out */
+  int k, k_pad;
+  int mode;
+  float acc_scale;
+  int64_t* idx;            /* (n) */
+  float* codes_out;        /* (n, d) or NULL */
+  float* dist_out;         /* (n) or NULL */
+} mq_vq_params;
+int mq_vq_nearest(const mq_vq_params* p, mq_stream_t stream);
+
 /* ---- K8: indices_to_codes + q_out_proj as a table gather (quantizer.py:183-205,
  *          preencoder.py:464-466) -------------------------------------------- */
 /* table (n_codes, C) fp32 = q_out_proj(implicit_codebook); idx (rows) int64;

@@ -81,6 +81,15 @@ class CbamApplyParams(C.Structure):
     ]
 
 
+class VqParams(C.Structure):
+    _fields_ = [
+        ("z", C.c_void_p), ("n", C.c_int64), ("d", C.c_int),
+        ("cb_img", C.c_void_p), ("c2", C.c_void_p), ("codebook", C.c_void_p),
+        ("k", C.c_int), ("k_pad", C.c_int), ("mode", C.c_int), ("acc_scale", C.c_float),
+        ("idx", C.c_void_p), ("codes_out", C.c_void_p), ("dist_out", C.c_void_p),
+    ]
+
+
 class FsqParams(C.Structure):
     _fields_ = [
         ("D", C.c_int),
@@ -106,6 +115,7 @@ SIGNATURES = {
     "mq_qin_fsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                              C.POINTER(FsqParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_fsq_quantize": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(FsqParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mq_vq_nearest": (C.c_int, [C.POINTER(VqParams), C.c_void_p]),
     "mq_code_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_refiner_masks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

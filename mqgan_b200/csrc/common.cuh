@@ -83,6 +83,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tile mode, completion on an mbarrier
 // ---------------------------------------------------------------------------

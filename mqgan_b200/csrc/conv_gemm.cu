@@ -70,10 +70,6 @@ struct ConvArgs {
   float acc_scale;                // accumulator scale applied before the bias (undoes the f16x2 weight scale)
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 __device__ __forceinline__ void decode_tile(const ConvArgs& a, int tile, int& n_idx, int& h0,
                                             int& w0, int& n0, int& par) {
   int tn = tile % a.tiles_n;

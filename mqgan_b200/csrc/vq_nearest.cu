@@ -1,0 +1,390 @@
+// Nearest-codeword lookup: distance contraction + argmin + codeword gather in one kernel
+// (BASELINE.json configs[3]; north_star "VQ distance step").
+//
+//   idx[i] = argmin_k ||z_i - c_k||^2 = argmin_k ( ||c_k||^2 - 2 z_i . c_k ),  ties -> lowest k
+//   codes_out[i] = c_idx[i]
+//
+// The reference's own quantiser is FSQ (quantizer.py:109-181): it has no learned codebook, and its
+// implicit codebook (quantizer.py:101-104) is searched by rounding, which mq_fsq_quantize restates
+// exactly.  This kernel is the generic form the benchmark config asks for: any (K, D <= 64) fp32
+// codebook.  The (N x K) distance matrix never exists in memory:
+//
+//   * z . c^T is a tcgen05 GEMM: M = 128 latents per CTA tile (TMEM lanes), N = 256 codes per
+//     accumulator (TMEM columns, two buffers), fp32 accumulate.  "f16x2" mode runs three fp16
+//     products of 2-term operand splits (22-bit operands, like the encoder GEMMs) so that the argmin
+//     equals the fp32/fp64 one except at float ties; "bf16" mode is one product (agreement reported).
+//   * Latents are converted in the kernel (fp32 global -> fp16/bf16 terms -> 128-byte-swizzled
+//     K-major shared-memory tiles), so z is read from HBM exactly once, as fp32.
+//   * The codebook is packed once (mq "pack" step on the host) as ready-made shared-memory images of
+//     [256 codes][64 K] tiles and streamed with cp.async.bulk through a ring.  A code occupies
+//     ks = ceil(D/16) K-steps; when ks < 4 one 128-byte row carries 4/ks codes side by side ("slices")
+//     and the latent tile repeats z in every slice, so narrow codebooks (D = 4, 5) move no padding.
+//   * Epilogue (thread = latent row, warps w and w+4 alternate 32-column chunks): score =
+//     fma(acc, -2*scale, ||c||^2) with ||c||^2 staged in shared memory, a min tree per chunk, and an
+//     index rescan only when the chunk improves the running best (about ln K times per row).
+//     Strict '<' in ascending k keeps the lowest index on ties.
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mqgan_b200.h"
+#include "common.cuh"
+
+namespace mq {
+
+constexpr int kVqThreads = 384;            // warp 0 codebook producer, warp 1 MMA, warps 2-3 latent converters, 4-11 epilogue
+constexpr int kVqEpiThreads = 256;
+constexpr int kVqCvtThreads = 64;
+constexpr int kVqTileM = 128;
+constexpr int kVqTileN = 256;
+constexpr int kVqImgBytes = kVqTileN * 128;        // one codebook operand image: 256 rows x 128 B
+constexpr int kVqATileBytes = kVqTileM * 128;      // one latent operand tile: 128 rows x 128 B
+constexpr int kVqStages = 4;
+constexpr int kVqMaxC2 = 8192;                     // ||c||^2 entries staged in shared memory
+
+struct VqArgs {
+  const float* z;
+  long long n;
+  int d;
+  const uint8_t* cb_img;          // [tiles][nterm][256][128 B] pre-swizzled shared-memory images
+  const float* c2;                // [k_pad]; +inf on padding codes
+  const float* codebook;          // (k, d) fp32, for the gather
+  int k, k_pad;
+  int ks, slices, nterm;          // K-steps per code, codes per 128-byte row, operand terms
+  int units, tiles;               // 256-code accumulator blocks; codebook images per term
+  long long row_tiles;
+  float score_scale;              // -2 / codebook pre-scale
+  int op_f16;
+  long long* idx;
+  float* codes_out;
+  float* dist_out;
+};
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kVqThreads, 1) vq_nearest_kernel(const VqArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_b = smem;                                          // [kVqStages][32 KB]
+  uint8_t* smem_a = smem_b + kVqStages * kVqImgBytes;              // [2 buffers][nterm][16 KB]
+  float* c2_s = reinterpret_cast<float*>(smem_a + 2 * 2 * kVqATileBytes);   // [min(k_pad, kVqMaxC2)]
+  float* comb_best = c2_s + kVqMaxC2;                              // [128] second half's running best
+  int* comb_idx = reinterpret_cast<int*>(comb_best + kVqTileM);    // [128]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(comb_idx + kVqTileM);
+  uint64_t* empty_bar = full_bar + kVqStages;
+  uint64_t* afull_bar = empty_bar + kVqStages;     // [2]
+  uint64_t* aempty_bar = afull_bar + 2;            // [2]
+  uint64_t* tfull_bar = aempty_bar + 2;            // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kVqStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&afull_bar[b], kVqCvtThreads);
+      mbar_init(&aempty_bar[b], 1);
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], kVqEpiThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int a_buf_bytes = a.nterm * kVqATileBytes;
+
+  if (warp == 0) {
+    // ===================== codebook producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long rt = blockIdx.x; rt < a.row_tiles; rt += gridDim.x) {
+        for (int t = 0; t < a.tiles; ++t) {
+          // f16x2: the low term g1 first (it feeds the small product h0*g1), then g0
+          for (int j = a.nterm - 1; j >= 0; --j) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], kVqImgBytes);
+            bulk_load(smem_b + stage * kVqImgBytes,
+                      a.cb_img + (static_cast<size_t>(t) * a.nterm + j) * kVqImgBytes, kVqImgBytes, &full_bar[stage]);
+            if (++stage == kVqStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t idesc = a.op_f16 ? umma_idesc_f16(kVqTileM, kVqTileN) : umma_idesc_bf16(kVqTileM, kVqTileN);
+    constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int ab = 0;
+    uint32_t aphase = 0;
+    int uit = 0;                                    // accumulator blocks issued so far (TMEM buffer ring)
+    for (long long rt = blockIdx.x; rt < a.row_tiles; rt += gridDim.x) {
+      mbar_wait(&afull_bar[ab], aphase);
+      tc_fence_after();
+      const uint32_t a0_lo = umma_desc_lo(smem_u32(smem_a + ab * a_buf_bytes));          // h0 (or the bf16 tile)
+      const uint32_t a1_lo = a0_lo + (kVqATileBytes >> 4);                               // h1
+      for (int t = 0; t < a.tiles; ++t) {
+        // stages of this codebook tile: f16x2 -> g1 then g0; bf16 -> one
+        const int s_lo = stage;                      // g1 (f16x2) or the only image
+        mbar_wait(&full_bar[stage], phase);
+        int s_hi = stage;
+        if (a.nterm == 2) {
+          int st = stage + 1;
+          uint32_t ph = phase;
+          if (st == kVqStages) { st = 0; ph ^= 1; }
+          mbar_wait(&full_bar[st], ph);
+          s_hi = st;                                  // g0
+        }
+        tc_fence_after();
+        const uint32_t g1_lo = umma_desc_lo(smem_u32(smem_b + s_lo * kVqImgBytes));
+        const uint32_t g0_lo = umma_desc_lo(smem_u32(smem_b + s_hi * kVqImgBytes));
+        for (int s = 0; s < a.slices; ++s, ++uit) {
+          const uint32_t buf = uit & 1;
+          mbar_wait(&tempty_bar[buf], ((uit >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kVqTileN;
+          const uint32_t koff = static_cast<uint32_t>(s * a.ks * 2);      // 32 bytes per K-step, in 16-byte units
+          if (elect_one_sync()) {
+            if (a.nterm == 2) {
+              // small products first: h0*g1, h1*g0, then h0*g0
+              for (int k = 0; k < a.ks; ++k)
+                umma_bf16(d_tmem, umma_desc_make(a0_lo + koff + 2 * k, hi), umma_desc_make(g1_lo + koff + 2 * k, hi),
+                          idesc, k != 0 ? 1u : 0u);
+              for (int k = 0; k < a.ks; ++k)
+                umma_bf16(d_tmem, umma_desc_make(a1_lo + koff + 2 * k, hi), umma_desc_make(g0_lo + koff + 2 * k, hi),
+                          idesc, 1u);
+              for (int k = 0; k < a.ks; ++k)
+                umma_bf16(d_tmem, umma_desc_make(a0_lo + koff + 2 * k, hi), umma_desc_make(g0_lo + koff + 2 * k, hi),
+                          idesc, 1u);
+            } else {
+              for (int k = 0; k < a.ks; ++k)
+                umma_bf16(d_tmem, umma_desc_make(a0_lo + koff + 2 * k, hi), umma_desc_make(g0_lo + koff + 2 * k, hi),
+                          idesc, k != 0 ? 1u : 0u);
+            }
+            umma_commit(&tfull_bar[buf]);
+          }
+          __syncwarp();
+        }
+        // both images of the tile are free once every slice's MMAs retired
+        for (int j = 0; j < a.nterm; ++j) {
+          if (elect_one_sync()) umma_commit(&empty_bar[stage]);
+          __syncwarp();
+          if (++stage == kVqStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (elect_one_sync()) umma_commit(&aempty_bar[ab]);
+      __syncwarp();
+      if (++ab == 2) { ab = 0; aphase ^= 1; }
+    }
+  } else if (warp < 4) {
+    // ===================== latent converters: fp32 rows -> swizzled 16-bit operand tiles =====================
+    const int ct = threadIdx.x - 64;               // 0..63
+    int ab = 0;
+    uint32_t aphase = 0;
+    const int slice_cols = 16 * a.ks;
+    for (long long rt = blockIdx.x; rt < a.row_tiles; rt += gridDim.x) {
+      mbar_wait(&aempty_bar[ab], aphase ^ 1);
+      uint8_t* abuf = smem_a + ab * a_buf_bytes;
+      for (int rr = ct; rr < kVqTileM; rr += kVqCvtThreads) {
+        const long long row = rt * kVqTileM + rr;
+        const float* zr = a.z + row * a.d;
+        // the whole row is fetched before any conversion starts (one global-latency exposure per row,
+        // 128-bit loads when the row pitch allows), zero beyond d and beyond n
+        float xr[64];
+        const bool live = row < a.n;
+        if ((a.d & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && i < a.d) f = __ldg(reinterpret_cast<const float4*>(zr + i));
+            xr[i] = f.x; xr[i + 1] = f.y; xr[i + 2] = f.z; xr[i + 3] = f.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) xr[i] = (live && i < a.d) ? __ldg(zr + i) : 0.0f;
+        }
+        // one slice worth of terms (slice_cols <= 64 columns), then replicated into every slice
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {                       // 16-byte chunks (8 columns) of one slice
+          if (c8 * 8 < slice_cols) {
+            uint32_t w0[4], w1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = xr[c8 * 8 + 2 * e], x1 = xr[c8 * 8 + 2 * e + 1];
+              if (a.op_f16) {
+                uint16_t t0[3], t1[3];
+                split_terms(x0, 1, t0);
+                split_terms(x1, 1, t1);
+                w0[e] = static_cast<uint32_t>(t0[0]) | (static_cast<uint32_t>(t1[0]) << 16);
+                w1[e] = static_cast<uint32_t>(t0[1]) | (static_cast<uint32_t>(t1[1]) << 16);
+              } else {
+                w0[e] = pack_bf16x2(x0, x1);
+                w1[e] = 0;
+              }
+            }
+            for (int s = 0; s < a.slices; ++s) {
+              const int chunk = s * (slice_cols / 8) + c8;                  // 16-byte chunk index in the 128-byte row
+              const uint32_t off = static_cast<uint32_t>(rr * 128 + ((chunk ^ (rr & 7)) << 4));
+              *reinterpret_cast<uint4*>(abuf + off) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+              if (a.nterm == 2)
+                *reinterpret_cast<uint4*>(abuf + kVqATileBytes + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();                     // generic-proxy writes -> visible to the tensor core's async proxy
+      mbar_arrive(&afull_bar[ab]);
+      if (++ab == 2) { ab = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue: scores, running argmin, gather =====================
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const int et = threadIdx.x - 128;
+    const bool c2_in_smem = a.k_pad <= kVqMaxC2;
+    if (c2_in_smem)
+      for (int j = et; j < a.k_pad; j += kVqEpiThreads) c2_s[j] = a.c2[j];
+    named_bar_sync(1, kVqEpiThreads);
+    int uit = 0;
+    for (long long rt = blockIdx.x; rt < a.row_tiles; rt += gridDim.x) {
+      float best = INFINITY;
+      int bidx = 0x7fffffff;
+      for (int u = 0; u < a.units; ++u, ++uit) {
+        const uint32_t buf = uit & 1;
+        mbar_wait(&tfull_bar[buf], (uit >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kVqTileN;
+        // two 32-column chunks per tcgen05.wait::ld (the TMEM read latency is paid once per pair), and
+        // four partial minima per chunk instead of one 32-long dependent chain
+#pragma unroll 1
+        for (int cp = 0; cp < 2; ++cp) {
+          uint32_t v[2][32];
+          __syncwarp();
+          tmem_ld_32x32(t_row + half * 32 + 128 * cp, v[0]);
+          tmem_ld_32x32(t_row + half * 32 + 128 * cp + 64, v[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = half * 32 + 128 * cp + 64 * h;
+            const int k0 = u * kVqTileN + c;
+            float sc[32];
+            if (c2_in_smem) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 cc = *reinterpret_cast<const float4*>(c2_s + k0 + 4 * g);
+                sc[4 * g] = fmaf(__uint_as_float(v[h][4 * g]), a.score_scale, cc.x);
+                sc[4 * g + 1] = fmaf(__uint_as_float(v[h][4 * g + 1]), a.score_scale, cc.y);
+                sc[4 * g + 2] = fmaf(__uint_as_float(v[h][4 * g + 2]), a.score_scale, cc.z);
+                sc[4 * g + 3] = fmaf(__uint_as_float(v[h][4 * g + 3]), a.score_scale, cc.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sc[j] = fmaf(__uint_as_float(v[h][j]), a.score_scale, __ldg(a.c2 + k0 + j));
+            }
+            float m4[4] = {sc[0], sc[1], sc[2], sc[3]};
+#pragma unroll
+            for (int j = 4; j < 32; ++j) m4[j & 3] = fminf(m4[j & 3], sc[j]);
+            const float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
+            if (m < best) {                            // rare after the first blocks: ~ln K improvements per row
+              best = m;
+              int jj = 31;
+#pragma unroll
+              for (int j = 30; j >= 0; --j) jj = (sc[j] == m) ? j : jj;     // first (lowest) column attaining the min
+              bidx = k0 + jj;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      }
+      // combine the two column halves of each row (lexicographic on (score, index)), write, gather
+      if (half == 1) {
+        comb_best[r] = best;
+        comb_idx[r] = bidx;
+      }
+      named_bar_sync(1, kVqEpiThreads);
+      if (half == 0) {
+        const float ob = comb_best[r];
+        const int oi = comb_idx[r];
+        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        const long long row = rt * kVqTileM + r;
+        if (row < a.n) {
+          a.idx[row] = bidx;
+          if (a.dist_out != nullptr) a.dist_out[row] = best;
+          if (a.codes_out != nullptr && bidx < a.k) {
+            const float* src = a.codebook + static_cast<long long>(bidx) * a.d;
+            float* dst = a.codes_out + row * a.d;
+            for (int i = 0; i < a.d; ++i) dst[i] = src[i];
+          }
+        }
+      }
+      named_bar_sync(1, kVqEpiThreads);   // comb_* reusable for the next row tile
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace mq
+
+using namespace mq;
+
+extern "C" int mq_vq_nearest(const mq_vq_params* p, mq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MQ_REQUIRE(p != nullptr, "mq_vq_nearest: null params");
+  MQ_REQUIRE(p->z && p->cb_img && p->c2 && p->codebook && p->idx, "mq_vq_nearest: null pointer argument");
+  MQ_REQUIRE(p->n > 0 && p->d >= 1 && p->d <= 64, "mq_vq_nearest: n=%lld d=%d (1 <= d <= 64)", (long long)p->n, p->d);
+  MQ_REQUIRE(p->k >= 1 && p->k_pad >= p->k, "mq_vq_nearest: k=%d k_pad=%d", p->k, p->k_pad);
+  MQ_REQUIRE(p->mode == 0 || p->mode == 1, "mq_vq_nearest: mode=%d (0 = bf16, 1 = f16x2)", p->mode);
+  MQ_REQUIRE((reinterpret_cast<uintptr_t>(p->cb_img) & 15) == 0, "mq_vq_nearest: cb_img must be 16-byte aligned");
+  VqArgs a;
+  memset(&a, 0, sizeof(a));
+  a.z = p->z; a.n = p->n; a.d = p->d;
+  a.cb_img = reinterpret_cast<const uint8_t*>(p->cb_img);
+  a.c2 = p->c2; a.codebook = p->codebook; a.k = p->k; a.k_pad = p->k_pad;
+  const int ks_raw = (p->d + 15) / 16;
+  a.ks = ks_raw <= 1 ? 1 : (ks_raw == 2 ? 2 : 4);
+  a.slices = 4 / a.ks;
+  a.nterm = p->mode == 1 ? 2 : 1;
+  a.op_f16 = p->mode == 1;
+  MQ_REQUIRE(p->k_pad % (kVqTileN * a.slices) == 0, "mq_vq_nearest: k_pad=%d must be a multiple of %d for d=%d",
+             p->k_pad, kVqTileN * a.slices, p->d);
+  a.units = p->k_pad / kVqTileN;
+  a.tiles = a.units / a.slices;
+  a.row_tiles = (p->n + kVqTileM - 1) / kVqTileM;
+  a.score_scale = -2.0f * (p->acc_scale != 0.0f ? p->acc_scale : 1.0f);
+  a.idx = reinterpret_cast<long long*>(p->idx); a.codes_out = p->codes_out; a.dist_out = p->dist_out;
+
+  int dev = 0, sms = 0;
+  MQ_CUDA_OK(cudaGetDevice(&dev));
+  MQ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int smem = 1024 + kVqStages * kVqImgBytes + 2 * 2 * kVqATileBytes + kVqMaxC2 * 4 + kVqTileM * 8 +
+                   (2 * kVqStages + 8) * 8 + 64;
+  MQ_CUDA_OK(cudaFuncSetAttribute(vq_nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = static_cast<int>(a.row_tiles < sms ? a.row_tiles : sms);
+  vq_nearest_kernel<<<grid, kVqThreads, smem, stream>>>(a);
+  MQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvParams, Cb2dParams, CbamApplyParams, FsqParams
+from ._lib import ConvParams, Cb2dParams, CbamApplyParams, FsqParams, VqParams
 
 BLOCK_K = 64
 HALO_DEFAULT = os.environ.get("MQ_HALO", "1") != "0"   # halo-tile main loop for 3x3 convs
@@ -516,6 +516,96 @@ def fsq_quantize(z: torch.Tensor, fsq: FsqParams, want_codes=False):
     codes = torch.empty_like(z) if want_codes else None
     _lib.call("mq_fsq_quantize", z.data_ptr(), rows, C.byref(fsq), idx.data_ptr(), _ptr(codes), _stream())
     return (idx, codes) if want_codes else idx
+
+
+@dataclass
+class PackedCodebook:
+    """Codebook operand of mq_vq_nearest, packed once (host side)."""
+    cb_img: torch.Tensor       # uint8 shared-memory images [tiles][nterm][256][128]
+    c2: torch.Tensor           # fp32 [k_pad], +inf on padding codes
+    codebook: torch.Tensor     # fp32 (k, d)
+    k: int
+    k_pad: int
+    d: int
+    mode: int                  # 0 = bf16, 1 = f16x2
+    acc_scale: float
+
+    def to(self, device):
+        self.cb_img, self.c2, self.codebook = self.cb_img.to(device), self.c2.to(device), self.codebook.to(device)
+        return self
+
+
+def pack_codebook(codebook: torch.Tensor, precision: str = "f16x2") -> PackedCodebook:
+    """Pack a (K, D <= 64) fp32 codebook for mq_vq_nearest: 16-bit operand terms laid out as the
+    128-byte-swizzled [256 codes][64 K] shared-memory tiles the tensor core reads (slices = 4/ks codes side
+    by side per 128-byte row when D <= 32), plus ||c||^2 in fp32 (computed in float64)."""
+    if precision not in ("f16x2", "bf16"):
+        raise ValueError("precision must be 'f16x2' or 'bf16'")
+    cb = codebook.detach().float().cpu().contiguous()
+    K, D = cb.shape
+    if not 1 <= D <= 64:
+        raise ValueError("codebook width must be in [1, 64]")
+    ks = 1 if D <= 16 else (2 if D <= 32 else 4)
+    slices = 4 // ks
+    per_tile = 256 * slices
+    k_pad = (K + per_tile - 1) // per_tile * per_tile
+    tiles = k_pad // per_tile
+    acc_scale = 1.0
+    if precision == "f16x2":
+        cmax = float(cb.abs().max())
+        e = 0 if cmax == 0.0 else 13 - math.floor(math.log2(cmax))
+        e = max(-24, min(24, e))
+        terms = list(split2_f16(cb * (2.0 ** e)))                 # g0, g1
+        acc_scale = 2.0 ** (-e)
+        dt = torch.float16
+    else:
+        terms = [cb.to(torch.bfloat16)]
+        dt = torch.bfloat16
+    dense = torch.zeros(tiles, len(terms), 256, 64, dtype=dt)          # [tile][term][row n][K column]
+    code = torch.arange(k_pad)
+    t, rem = code // per_tile, code % per_tile
+    s, n = rem // 256, rem % 256                                       # code = (tile*slices + slice)*256 + row
+    valid = code < K
+    for j, tj in enumerate(terms):
+        for i in range(D):
+            dense[t[valid], j, n[valid], (s[valid] * 16 * ks + i)] = tj[code[valid], i]
+    # 128-byte swizzle of a 1024-byte-aligned tile: 16-byte chunk c of row n lives at chunk c ^ (n & 7)
+    chunks = dense.view(tiles, len(terms), 256, 8, 8)
+    rows = torch.arange(256)
+    src = (torch.arange(8)[None, :] ^ (rows[:, None] & 7))              # image chunk p holds data chunk p ^ (n&7)
+    img = torch.gather(chunks, 3, src[None, None, :, :, None].expand(tiles, len(terms), 256, 8, 8))
+    c2 = torch.full((k_pad,), float("inf"), dtype=torch.float32)
+    c2[:K] = (cb.double() ** 2).sum(1).float()
+    return PackedCodebook(img.contiguous().view(torch.uint8).reshape(-1), c2, cb, K, k_pad, D,
+                          1 if precision == "f16x2" else 0, acc_scale)
+
+
+def vq_nearest(z: torch.Tensor, pc: PackedCodebook, want_codes: bool = True, want_dist: bool = False):
+    """Nearest codeword of every row of z (n, d) fp32: returns idx (n,) int64 [, codes (n, d)] [, dist (n,)]."""
+    _chk(z, torch.float32, "z")
+    if z.dim() != 2 or z.shape[1] != pc.d:
+        raise ValueError(f"z must be (n, {pc.d})")
+    n = z.shape[0]
+    idx = torch.empty(n, dtype=torch.int64, device=z.device)
+    codes = torch.empty(n, pc.d, dtype=torch.float32, device=z.device) if want_codes else None
+    dist = torch.empty(n, dtype=torch.float32, device=z.device) if want_dist else None
+    p = VqParams()
+    p.z, p.n, p.d = z.data_ptr(), n, pc.d
+    p.cb_img = _chk(pc.cb_img, torch.uint8, "cb_img").data_ptr()
+    p.c2 = _chk(pc.c2, torch.float32, "c2").data_ptr()
+    p.codebook = _chk(pc.codebook, torch.float32, "codebook").data_ptr()
+    p.k, p.k_pad, p.mode, p.acc_scale = pc.k, pc.k_pad, pc.mode, float(pc.acc_scale)
+    p.idx, p.codes_out, p.dist_out = idx.data_ptr(), _ptr(codes), _ptr(dist)
+    meta = None
+    if _lib.profiler is not None:
+        meta = {"tag": f"vq k={pc.k} d={pc.d}", "flops": 2.0 * n * pc.k * pc.d}
+    _lib.call("mq_vq_nearest", C.byref(p), _stream(), meta=meta)
+    out = [idx]
+    if want_codes:
+        out.append(codes)
+    if want_dist:
+        out.append(dist)
+    return out[0] if len(out) == 1 else tuple(out)
 
 
 def code_gather(idx: torch.Tensor, table: torch.Tensor, *, bf16=True, f32=False, bad: Optional[torch.Tensor] = None):

@@ -511,3 +511,82 @@ def test_conv_pair_mode_matches_tap_mode(N, H, W, Cin, Cout, msub):
         ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True, out_bf16=ob, pair=True,
                       msub=msub)
         assert (ob.cpu().double() - ref2).abs().max().item() < 2e-2 * max(1.0, ref2.abs().max().item())
+
+
+# ---------------------------------------------------------------------------
+# nearest-codeword lookup (BASELINE configs[3]): distance GEMM + argmin + gather
+# ---------------------------------------------------------------------------
+def _vq_ref(z, cb):
+    """float64 argmin of ||z - c||^2 (lowest index on ties) and the gap to the runner-up."""
+    d = torch.cdist(z.double(), cb.double()) ** 2
+    best2 = torch.topk(d, 2, dim=1, largest=False)
+    idx = torch.argmin(d, dim=1)          # first occurrence = lowest index
+    return idx, best2.values[:, 1] - best2.values[:, 0], d
+
+
+@pytest.mark.parametrize("levels", [[8, 8, 4, 4], [8, 8, 8, 4, 4], [8, 5, 5, 5]])
+def test_vq_nearest_equals_reference_fsq_on_implicit_codebook(levels):
+    """On FSQ's implicit codebook (quantizer.py:101-104) the generic nearest-codeword kernel must give
+    the reference quantiser's index (quantizer.py:128-140,177-181) wherever the latent is not within
+    1e-4 of a rounding boundary, and gather exactly the reference's codes."""
+    D, K = len(levels), int(np.prod(levels))
+    codebook = O.fsq_indices_to_codes(torch.arange(K), levels)                     # (K, D), the implicit codebook
+    z = _rand(20000, D, seed=40) * 1.5
+    codes_ref, idx_ref = O.fsq_quantize(z, levels)
+    lv, basis, half_l, offset, shift, half_w = O.fsq_constants(levels)
+    y = (((z + shift).tanh() * half_l - offset) / half_w).contiguous()             # bounded latent in code units
+    margin = O.fsq_round_margin(z, levels)
+    pc = ops.pack_codebook(codebook, "f16x2").to(DEV)
+    assert pc.k == K and pc.k_pad % 256 == 0
+    idx, codes = ops.vq_nearest(y.to(DEV), pc, want_codes=True)
+    neq = idx.cpu() != idx_ref
+    assert int((neq & (margin > 1e-4)).sum()) == 0, int(neq.sum())
+    assert float(neq.float().mean()) < 1e-3
+    assert torch.equal(codes.cpu(), codebook[idx.cpu()])                          # gather is exact
+    assert torch.equal(codes.cpu()[~neq], codes_ref[~neq])
+
+
+@pytest.mark.parametrize("n,K,D", [
+    (5000, 1024, 64),      # one row tile is ragged (5000 = 39*128 + 8)
+    (3000, 1000, 64),      # K not a multiple of the 256-code accumulator block: padding codes carry +inf
+    (2048, 8192, 64),      # 32 accumulator blocks per row tile: ||c||^2 exactly fills its shared-memory stage
+    (1500, 700, 20),       # two K-steps per code, two codes per 128-byte row
+    (1500, 3000, 40),      # D padded to 64
+    (4097, 512, 4),        # four codes per row
+    (100, 300, 1),
+])
+def test_vq_nearest_generic_codebook(n, K, D):
+    z = _rand(n, D, seed=41)
+    cb = _rand(K, D, seed=42)
+    ref_idx, gap, d64 = _vq_ref(z, cb)
+    scale = float(d64.min(dim=1).values.mean()) + 1.0
+    pc = ops.pack_codebook(cb, "f16x2").to(DEV)
+    idx, codes, dist = ops.vq_nearest(z.to(DEV), pc, want_codes=True, want_dist=True)
+    idx = idx.cpu()
+    neq = idx != ref_idx
+    # fp32-grade: disagreement only where the float64 runner-up is within 1e-5 (relative) of the winner
+    assert int((neq & (gap > 1e-5 * scale)).sum()) == 0, (int(neq.sum()), float(gap[neq].max()) if neq.any() else 0)
+    assert int(idx.min()) >= 0 and int(idx.max()) < K
+    assert torch.equal(codes.cpu(), cb[idx])
+    # dist_out = ||c||^2 - 2 z.c at the minimum
+    ref_d = (d64.gather(1, idx[:, None]).squeeze(1) - (z.double() ** 2).sum(1))
+    assert (dist.cpu().double() - ref_d).abs().max().item() < 1e-4 * scale
+    # bf16 mode: agreement rate is reported, not exact
+    pcb = ops.pack_codebook(cb, "bf16").to(DEV)
+    ib = ops.vq_nearest(z.to(DEV), pcb, want_codes=False).cpu()
+    agree = float((ib == ref_idx).float().mean())
+    print(f"vq bf16 agreement n={n} K={K} D={D}: {agree:.4f}")
+    if D >= 20:
+        assert agree > 0.80
+
+
+def test_vq_nearest_ties_pick_lowest_index():
+    D = 8
+    base = _rand(300, D, seed=43)
+    cb = torch.cat([base, base, base[:100]])          # every code appears 2-3 times
+    z = base[torch.randint(0, 300, (1000,), generator=torch.Generator().manual_seed(44))] + 0.01 * _rand(1000, D, seed=45)
+    pc = ops.pack_codebook(cb, "f16x2").to(DEV)
+    idx = ops.vq_nearest(z.to(DEV), pc, want_codes=False).cpu()
+    ref_idx, _, _ = _vq_ref(z, cb)
+    assert int(idx.max()) < 300                         # duplicates at k + 300 / k + 600 never win
+    assert float((idx == ref_idx).float().mean()) > 0.999

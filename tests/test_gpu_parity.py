@@ -140,13 +140,13 @@ def test_batch_invariance_and_determinism():
     assert torch.equal(a[1:3], b)
     assert torch.equal(a, model.encode(mel.cuda(), mask.cuda()))
     eng = model.engine()
-    old = eng.max_chunk_frames
-    eng.max_chunk_frames = T            # one utterance per chunk
+    old = eng.max_chunk_frames, eng.max_chunk_frames_enc
+    eng.max_chunk_frames = eng.max_chunk_frames_enc = T            # one utterance per chunk
     try:
         assert torch.equal(a, model.encode(mel.cuda(), mask.cuda()))
         d1 = model.decode(a, mask.cuda())
     finally:
-        eng.max_chunk_frames = old
+        eng.max_chunk_frames, eng.max_chunk_frames_enc = old
     d2 = model.decode(a, mask.cuda())
     assert torch.equal(d1, d2)
 
