@@ -121,6 +121,12 @@ typedef struct mq_conv_params {
    * CTAs of a cluster each stage the halo of their own msub sub-tiles and half of every weight
    * tile, halving weight traffic per pixel (L2->SM and shared-memory reads).  Excludes halo. */
   int pair;
+  /* out_pool != NULL: the epilogue also writes AvgPool2d((2,1)) of the bf16 output, filled with zero
+   * where either source row is padded (preencoder.py:111-114 with the max-pooled mask :63-65, :96):
+   * (N, H/2, W, pool_ld) bf16, channel c at c (no offset).  Needs the bf16-only epilogue (out_bf16,
+   * cout % 32 == 0, no fp32/split output), bw == 8, bh even, H even; not with in2. */
+  void* out_pool;
+  int pool_ld;
 } mq_conv_params;
 
 int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream);

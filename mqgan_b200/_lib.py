@@ -52,6 +52,7 @@ class ConvParams(C.Structure):
         ("acc_scale", C.c_float),
         ("halo", C.c_int),
         ("pair", C.c_int),
+        ("out_pool", C.c_void_p), ("pool_ld", C.c_int),
     ]
 
 

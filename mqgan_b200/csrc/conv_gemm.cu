@@ -64,6 +64,8 @@ struct ConvArgs {
   int f32_ld, f32_coff;
   __nv_bfloat16* out_bf16;
   int bf16_ld, bf16_coff;
+  __nv_bfloat16* out_pool;        // optional fused AvgPool2d((2,1)) of the bf16 output: (N, H/2, W, pool_ld)
+  int pool_ld;
   uint16_t* out_split;
   int split_ld, split_seg, split_kind;
   int op_f16;                     // operands are fp16 (f16x2 mode) instead of bf16
@@ -204,7 +206,7 @@ __device__ __forceinline__ void epilogue_generic(const ConvArgs& a, const uint32
 // epilogue-issue bound, ncu profiles/ncu_conv_small_r01).
 template <bool kFast>
 __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t (&v)[32], const float* bs,
-                                              int64_t pix, int co0, bool masked) {
+                                              int64_t pix, int co0, bool masked, bool valid, int64_t pix_pool) {
   float x[32];
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
@@ -215,7 +217,8 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
     x[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b4.w;
   }
   float rr[32];
-  if (a.res_mode != 0) {
+  const bool has_res = a.res_mode != 0 && valid;       // rows / columns outside the image have no residual to read
+  if (has_res) {
     const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.res_ld + a.res_coff + co0;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -242,20 +245,45 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = 0.0f;
   }
-  if (a.res_mode == 2) {
+  if (has_res && a.res_mode == 2) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] += rr[j];
   }
-  __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
-  if ((a.debug & 8) && x[0] != 1234.5678f) return;      // probe: math without the global stores
+  uint32_t u[16];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint4 u;
-    u.x = zero_post ? 0u : pack_bf16x2(x[8 * g], x[8 * g + 1]);
-    u.y = zero_post ? 0u : pack_bf16x2(x[8 * g + 2], x[8 * g + 3]);
-    u.z = zero_post ? 0u : pack_bf16x2(x[8 * g + 4], x[8 * g + 5]);
-    u.w = zero_post ? 0u : pack_bf16x2(x[8 * g + 6], x[8 * g + 7]);
-    *reinterpret_cast<uint4*>(op + 8 * g) = u;
+  for (int j = 0; j < 16; ++j) u[j] = zero_post ? 0u : pack_bf16x2(x[2 * j], x[2 * j + 1]);
+  if ((a.debug & 8) && x[0] != 1234.5678f) valid = false;   // probe: math without the global stores
+  if (valid) {
+    __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(op + 8 * g) = make_uint4(u[4 * g], u[4 * g + 1], u[4 * g + 2], u[4 * g + 3]);
+  }
+  if (a.out_pool != nullptr) {
+    // Fused AvgPool2d((2,1)) + pooled-mask fill (preencoder.py:111-114, :63-65, :96): with 8-pixel-wide
+    // sub-tiles the two rows of a pooling pair sit 8 lanes apart.  The bf16-rounded outputs are
+    // averaged (what a separate pass over the stored tensor computes, bit for bit), the pooled row is
+    // padded when either source row is (max-pool of the mask), and the even row's lane writes it.
+    const unsigned lane = threadIdx.x & 31u;
+    const bool pm = (__shfl_xor_sync(0xffffffffu, static_cast<int>(masked), 8) != 0) || masked;
+    uint32_t r[16];
+    const __nv_bfloat162 half2 = __floats2bfloat162_rn(0.5f, 0.5f);
+    const bool pz = pm && a.mask_post;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      // bf16 add (one rounding, the sum of two bf16 is exact in fp32) then an exact halving ==
+      // rn_bf16(0.5f * (a + b)) of the separate pass, at two packed instructions per word
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, u[j], 8);
+      const __nv_bfloat162 s2 = __hmul2(__hadd2(*reinterpret_cast<const __nv_bfloat162*>(&u[j]),
+                                                *reinterpret_cast<const __nv_bfloat162*>(&o)), half2);
+      r[j] = pz ? 0u : *reinterpret_cast<const uint32_t*>(&s2);
+    }
+    if (valid && (lane & 8u) == 0u) {
+      __nv_bfloat16* pp = a.out_pool + pix_pool * a.pool_ld + co0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(pp + 8 * g) = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+    }
   }
 }
 
@@ -315,6 +343,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
       const int h = h0 + sub * a.bh + lh, w = w0 + lw;
       const bool valid = (r < a.bh * a.bw) && (h < a.H) && (w < a.W);
       const int64_t pix = (static_cast<int64_t>(n_idx) * Hout + h * hmul + par) * a.W + w;
+      const int64_t pix_pool = (static_cast<int64_t>(n_idx) * (a.H >> 1) + (h >> 1)) * a.W + w;
       const bool masked = (mbits >> sub) & 1u;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride + sub * a.bn;
 #pragma unroll 1
@@ -326,7 +355,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
         const int co0 = n0 + c;
         if (a.debug & 1) continue;
         if (kLean) {
-          if (valid) epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked);
+          epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked, valid, pix_pool);
         } else {
           if (valid && co0 < a.cout) epilogue_generic<kFast>(a, v, bs + c, pix, co0, masked);
         }
@@ -982,6 +1011,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.out_f32 = p->out_f32; a.f32_ld = p->f32_ld; a.f32_coff = p->f32_coff;
   a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16); a.bf16_ld = p->bf16_ld; a.bf16_coff = p->bf16_coff;
   a.out_split = reinterpret_cast<uint16_t*>(p->out_split); a.split_ld = p->split_ld; a.split_seg = p->split_seg;
+  a.out_pool = reinterpret_cast<__nv_bfloat16*>(p->out_pool); a.pool_ld = p->pool_ld;
   a.split_kind = p->split_kind; a.op_f16 = p->op_f16;
   a.acc_scale = p->acc_scale != 0.0f ? p->acc_scale : 1.0f;
   const CUtensorMapDataType op_dt = p->op_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -1097,6 +1127,10 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   }
   const bool lean = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->out_split == nullptr &&
                     p->cout % 32 == 0 && (p->res_mode == 0 || p->res_is_bf16) && a.acc_scale == 1.0f;
+  if (p->out_pool != nullptr)
+    MQ_REQUIRE(lean && !up && p->bw == 8 && p->bh % 2 == 0 && p->H % 2 == 0 && p->pool_ld % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(p->out_pool) & 15) == 0,
+               "mq_conv_gemm: out_pool needs the bf16-only epilogue, an 8-pixel-wide sub-tile with an even number of rows, even H");
 #define MQ_LAUNCH_CONV(FAST, LEAN)                                                                          \
   do {                                                                                                      \
     MQ_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \

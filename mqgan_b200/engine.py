@@ -124,7 +124,7 @@ class _CB2D:
 class PreEncoderEngine:
     def __init__(self, cfg: PreEncoderConfig, state_dict: Dict[str, torch.Tensor], device="cuda",
                  encoder_precision: str = "f16x2", max_chunk_frames: int = 32768, cb2d_table: bool = True,
-                 fuse_upcat: bool = True, max_chunk_frames_enc: int = 262144):
+                 fuse_upcat: bool = True, max_chunk_frames_enc: int = 262144, fuse_pool: bool = True):
         if encoder_precision not in ("f16x2", "bf16x3", "bf16"):
             raise ValueError("encoder_precision must be 'f16x2', 'bf16x3' or 'bf16'")
         self.cfg = cfg
@@ -216,6 +216,7 @@ class PreEncoderEngine:
         self.ref_mid = cb("refiner.mid")
         self.ref_ups = [cb(f"refiner.ups.{i}.conv") for i in range(d)]
         self.fuse_upcat = bool(fuse_upcat)
+        self.fuse_pool = bool(fuse_pool)       # DownBlock's AvgPool2d written by the producing conv's epilogue
         for i in range(d):          # fused nearest-upsample + concat variant of ups[i].conv1
             pfx = f"refiner.ups.{i}.conv.conv1"
             self.ref_ups[i]["conv1_up"] = pack_upconv(w[pfx + ".weight"], w[pfx + ".bias"], chs[d - i], chs[d - i - 1]).to(dev)
@@ -318,12 +319,17 @@ class PreEncoderEngine:
         out = torch.empty(B, T, self.cfg.mel_channels, dtype=torch.float32, device=self.device)
         hid = torch.empty(B, T, self.cfg.c0, dtype=torch.float32, device=self.device) if return_hidden else None
         recon = torch.empty_like(out) if return_recon else None
+        bad = torch.zeros(1, dtype=torch.int32, device=self.device)      # out-of-range index flag, read once below
         for b0, b1 in self._chunks(B, T):
-            h, R = self._decode_chunk(idx[b0:b1], None if m8 is None else m8[b0:b1], out[b0:b1], return_hidden, taps)
+            h, R = self._decode_chunk(idx[b0:b1], None if m8 is None else m8[b0:b1], out[b0:b1], return_hidden, taps,
+                                      bad)
             if return_hidden:
                 hid[b0:b1] = h
             if return_recon:
                 recon[b0:b1] = R.view(b1 - b0, T, -1)[..., : self.cfg.mel_channels]
+        # one host sync per decode call (not per chunk: a sync drains the launch queue and idles the GPU)
+        if int(bad.item()) != 0:
+            raise IndexError("decode: index outside [0, codebook_size)")
         res = [out]
         if return_hidden:
             res.append(hid.permute(0, 2, 1))          # reference layout (B, C0, T), preencoder.py:480
@@ -331,11 +337,10 @@ class PreEncoderEngine:
             res.append(recon)
         return res[0] if len(res) == 1 else tuple(res)
 
-    def _decode_chunk(self, idx, m8, out, want_hidden, taps):
+    def _decode_chunk(self, idx, m8, out, want_hidden, taps, bad):
         cfg, dev = self.cfg, self.device
         B, T = idx.shape
         rows = B * T
-        bad = torch.zeros(1, dtype=torch.int32, device=dev)
         x, _ = ops.code_gather(idx.reshape(rows), self.code_table, bad=bad)                # preencoder.py:464-466
         for i, blk in enumerate(self.dec):                                                  # :476-477
             cout = blk["cout"]
@@ -364,8 +369,6 @@ class PreEncoderEngine:
         if taps is not None:
             taps["refiner_in"] = R
         self._refiner(R, m8, B, T, out, taps)                                               # :496-499
-        if int(bad.item()) != 0:
-            raise IndexError("decode: index outside [0, codebook_size)")
         return (dec_out.view(B, T, cfg.c0).float() if want_hidden else None), R
 
     def _refiner(self, R, m8, B, T, out, taps):
@@ -376,7 +379,9 @@ class PreEncoderEngine:
         T8, down, up = ops.refiner_masks(m8, B, T, d, dev)
         H = [T8 >> l for l in range(d + 1)]
 
-        def convblock(x, blk, l, mask, cin, cout, first=True, tag=""):
+        def convblock(x, blk, l, mask, cin, cout, first=True, tag="", pool=False):
+            """ConvBlock (preencoder.py:86-102).  pool=True also returns AvgPool2d((2,1)) of the output,
+            filled by the max-pooled mask, written by conv2's epilogue (DownBlock, :111-114)."""
             if first:
                 t = torch.empty(B, H[l], F, cout, dtype=torch.bfloat16, device=dev)
                 ops.conv_gemm(x, blk["conv1"], B, H[l], F, act=True, out_bf16=t, tag=tag + ".conv1")   # preencoder.py:97
@@ -384,18 +389,27 @@ class PreEncoderEngine:
                 t = x
             y = torch.empty(B, H[l], F, cout, dtype=torch.bfloat16, device=dev)
             match = first and cin == cout
+            # needs the 8-pixel-wide sub-tiles of the halo / CTA-pair main loops
+            fused_pool = (pool and self.fuse_pool and F >= 8 and cout % 32 == 0
+                          and (ops.HALO_DEFAULT or (ops.PAIR_DEFAULT and H[l] >= 32)))
+            yp = torch.empty(B, H[l] // 2, F, cout, dtype=torch.bfloat16, device=dev) if fused_pool else None
             ops.conv_gemm(t, blk["conv2"], B, H[l], F, act=True, row_mask=mask, mask_post=True,
-                          res=x if match else None, res_mode=2 if match else 0, out_bf16=y,
+                          res=x if match else None, res_mode=2 if match else 0, out_bf16=y, out_pool=yp,
                           tag=tag + ".conv2")                                               # :98-101
-            return y
+            if pool and not fused_pool:
+                yp = ops.avgpool_mask(y, down[l + 1], B, H[l], F, cout)
+            return (y, yp) if pool else y
 
         s1 = ops.refiner_stem(R, m8, B, T, T8, F, chs[0], self.stem_w, self.stem_b, True)   # :172-175, :97
-        x = convblock(s1, self.ref_pre, 0, down[0], 1, chs[0], first=False, tag="ref.pre")
+        x, p = convblock(s1, self.ref_pre, 0, down[0], 1, chs[0], first=False, tag="ref.pre", pool=True)
         skips = []
         for i in range(d):                                                                  # :179-181
             skips.append(x)
-            p = ops.avgpool_mask(x, down[i + 1], B, H[i], F, chs[i])
-            x = convblock(p, self.ref_downs[i], i + 1, down[i + 1], chs[i], chs[i + 1], tag=f"ref.down{i}")
+            if i + 1 < d:
+                x, p = convblock(p, self.ref_downs[i], i + 1, down[i + 1], chs[i], chs[i + 1], tag=f"ref.down{i}",
+                                 pool=True)
+            else:
+                x = convblock(p, self.ref_downs[i], i + 1, down[i + 1], chs[i], chs[i + 1], tag=f"ref.down{i}")
             if taps is not None:
                 taps[f"refiner.downs.{i}"] = x
         x = convblock(x, self.ref_mid, d, down[d], chs[d], chs[d], tag="ref.mid")                          # :184

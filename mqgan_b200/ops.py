@@ -297,7 +297,8 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
               out_bf16: Optional[torch.Tensor] = None, bf16_coff=0,
               out_split: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None,
               msub: Optional[int] = None, tag: str = "", x2: Optional[torch.Tensor] = None,
-              halo: Optional[bool] = None, pair: Optional[bool] = None) -> None:
+              halo: Optional[bool] = None, pair: Optional[bool] = None,
+              out_pool: Optional[torch.Tensor] = None) -> None:
     """Launch mq_conv_gemm.  x: bf16 (fp16 for an "f16x2" weight) (N*H*W, in_ld) channel-last (any
     leading shape).  x2: skip tensor (N, 2H, W, C2) for a ``pack_upconv`` weight; outputs / masks then
     have 2H rows.  out_split: bf16 (.., 3C) or fp16 (.., 2C) multi-term output for the next split GEMM."""
@@ -379,6 +380,11 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
     if out_bf16 is not None:
         _chk(out_bf16, torch.bfloat16, "out_bf16")
         p.out_bf16, p.bf16_ld, p.bf16_coff = out_bf16.data_ptr(), out_bf16.shape[-1], bf16_coff
+    if out_pool is not None:
+        _chk(out_pool, torch.bfloat16, "out_pool")
+        if H % 2 or out_pool.numel() != N * (H // 2) * W * out_pool.shape[-1]:
+            raise ValueError("out_pool must be (N, H/2, W, C) with H even")
+        p.out_pool, p.pool_ld = out_pool.data_ptr(), out_pool.shape[-1]
     if out_split is not None:
         nt = _split_terms_of(out_split)
         if out_split.shape[-1] % nt:

@@ -590,3 +590,37 @@ def test_vq_nearest_ties_pick_lowest_index():
     ref_idx, _, _ = _vq_ref(z, cb)
     assert int(idx.max()) < 300                         # duplicates at k + 300 / k + 600 never win
     assert float((idx == ref_idx).float().mean()) > 0.999
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,pair", [
+    (2, 64, 144, 64, 64, True),          # pre.conv2-like: 4 sub-tiles per CTA
+    (1, 70, 36, 128, 128, True),         # ragged rows (70 = 2*32 + 6) and columns
+    (2, 32, 144, 256, 256, True),
+    (1, 22, 20, 64, 128, False),         # single-CTA halo loop
+])
+def test_conv_epilogue_fused_avgpool_equals_separate_pass(N, H, W, Cin, Cout, pair):
+    """DownBlock's AvgPool2d((2,1)) + pooled-mask fill written by the producing conv's epilogue must
+    equal mq_avgpool_mask applied to the stored bf16 output bit for bit (preencoder.py:111-114)."""
+    x = _rand(N, H, W, Cin, seed=101).to(torch.bfloat16)
+    w = (_rand(Cout, Cin, 3, 3, seed=102) / (9 * Cin) ** 0.5).to(torch.bfloat16)
+    b = _rand(Cout, seed=103)
+    res = _rand(N, H, W, Cout, seed=104).to(torch.bfloat16) if Cin == Cout else None
+    mask = torch.zeros(N, H, dtype=torch.uint8)
+    mask[0, H // 2 + 1:] = 1                                   # odd boundary: one pooling pair is half padded
+    mask_pool = (mask.view(N, H // 2, 2).max(dim=2).values).contiguous()
+    pc = ops.pack_conv(w.float(), b, "conv2d3", split=False).to(DEV)
+    y = torch.empty(N, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    yp = torch.full((N, H // 2, W, Cout), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True,
+                  res=None if res is None else res.to(DEV), res_mode=0 if res is None else 2,
+                  out_bf16=y, out_pool=yp, pair=pair, halo=not pair)
+    y2 = torch.empty_like(y)
+    ops.conv_gemm(x.to(DEV), pc, N, H, W, row_mask=mask.to(DEV), mask_post=True, act=True,
+                  res=None if res is None else res.to(DEV), res_mode=0 if res is None else 2,
+                  out_bf16=y2, pair=pair, halo=not pair)
+    assert torch.equal(y, y2)                                   # the pooled output does not disturb the main one
+    ref = ops.avgpool_mask(y2, mask_pool.to(DEV), N, H, W, Cout)
+    assert torch.equal(yp, ref)
+    # and against the float64 definition
+    r64 = y2.cpu().double().view(N, H // 2, 2, W, Cout).mean(dim=2).masked_fill(mask_pool.bool()[:, :, None, None], 0.0)
+    assert (yp.cpu().double() - r64).abs().max().item() < 1e-2 * max(1.0, r64.abs().max().item())
