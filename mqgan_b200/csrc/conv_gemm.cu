@@ -30,7 +30,7 @@ constexpr int kThreads = 384;               // WG0: producer, MMA issuer (+2 idl
 constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;             // TMEM columns per accumulator buffer
+constexpr int kMaxAccBufs = 4;              // TMEM accumulator stages: 512 / (msub * bn) columns each, at most 4
 constexpr int kATileBytes = kTileM * kBlockK * 2;   // 16 KiB
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBiasSmemFloats = 1024;       // the whole (padded) bias vector is staged in shared memory once per CTA
@@ -40,7 +40,8 @@ struct ConvArgs {
   int tiles_h, tiles_w, tiles_n, num_tiles;
   int bh, bw, bn, cout;
   int msub;                       // 128-pixel sub-tiles per CTA tile (share one B tile)
-  int nbuf;                       // TMEM accumulator buffers: 2 if msub*bn <= 256, else 1 (msub*bn <= 512)
+  int nbuf;                       // TMEM accumulator stages: min(4, 512 / acc_stride)
+  int acc_stride;                 // TMEM columns per accumulator stage: msub * bn rounded up to 32
   int taps, nseg, kchunks;
   int tap_dh[MQ_MAX_TAPS], tap_dw[MQ_MAX_TAPS], a_coff[MQ_MAX_SEGS];
   // fused nearest-upsample + concat (UpBlock): output rows 2*H, tiles carry a row parity
@@ -345,7 +346,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
       const int64_t pix = (static_cast<int64_t>(n_idx) * Hout + h * hmul + par) * a.W + w;
       const int64_t pix_pool = (static_cast<int64_t>(n_idx) * (a.H >> 1) + (h >> 1)) * a.W + w;
       const bool masked = (mbits >> sub) & 1u;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride + sub * a.bn;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * a.acc_stride + sub * a.bn;
 #pragma unroll 1
       for (int c = half * 32; c < a.bn; c += 64) {
         uint32_t v[32];
@@ -386,8 +387,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + kMaxAccBufs;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAccBufs);
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [2][256]
 
   const int warp = threadIdx.x >> 5;
@@ -401,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kMaxAccBufs; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], kEpiThreads / 32);     // one arrive per epilogue warp
     }
@@ -487,7 +488,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
         const uint32_t buf = it % a.nbuf;
         mbar_wait(&tempty_bar[buf], ((it / a.nbuf) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kAccStride;
+        const uint32_t d_tmem = tmem_base + buf * a.acc_stride;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -573,8 +574,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
   uint64_t* fullB = emptyA + kHaloMaxA;
   uint64_t* emptyB = fullB + kHaloMaxB;
   uint64_t* tfull_bar = emptyB + kHaloMaxB;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + kMaxAccBufs;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAccBufs);
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_s + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -584,7 +585,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     tma_prefetch_desc(&map_b);
     for (int i = 0; i < nA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiThreads / 32); }
+    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiThreads / 32); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -639,7 +640,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         const uint32_t buf = it % a.nbuf;
         mbar_wait(&tempty_bar[buf], ((it / a.nbuf) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kAccStride;
+        const uint32_t d_tmem = tmem_base + buf * a.acc_stride;
         for (int kc = 0; kc < a.kchunks; ++kc) {
           mbar_wait(&fullA[sa], pa);
           const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + sa * a.halo_slot_bytes));
@@ -725,8 +726,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
   uint64_t* fullB = emptyA + kPairMaxA;                       // leader only
   uint64_t* emptyB = fullB + kPairMaxB;                       // per CTA
   uint64_t* tfull_bar = emptyB + kPairMaxB;                   // per CTA (multicast commit)
-  uint64_t* tempty_bar = tfull_bar + 2;                       // leader only, both CTAs' epilogues arrive
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + kMaxAccBufs;                       // leader only, both CTAs' epilogues arrive
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAccBufs);
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_s + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -738,7 +739,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
     if (a.up_mode) tma_prefetch_desc(&map_a2);
     for (int i = 0; i < nA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * (kEpiThreads / 32)); }
+    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * (kEpiThreads / 32)); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -817,7 +818,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
         const uint32_t buf = it % a.nbuf;
         mbar_wait(&tempty_bar[buf], ((it / a.nbuf) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kAccStride;
+        const uint32_t d_tmem = tmem_base + buf * a.acc_stride;
         uint32_t acc = 0;
         for (int grp = 0; grp < (a.up_mode ? 2 : 1); ++grp) {
           const int nch = grp ? a.kchunks2 : a.kchunks;
@@ -907,7 +908,7 @@ static EncodeTiledFn get_encode_fn() {
 
 static int conv_smem_bytes(int stages, int a_stage_bytes, int b_tile_bytes) {
   return 1024 /*alignment slack*/ + stages * (a_stage_bytes + b_tile_bytes) +
-         (2 * kMaxStages + 4) * 8 + 16 + kBiasSmemFloats * 4;
+         (2 * kMaxStages + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4;
 }
 
 }  // namespace mq
@@ -950,7 +951,13 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.bh = p->bh; a.bw = p->bw; a.bn = p->bn; a.cout = p->cout;
   a.msub = p->msub > 0 ? p->msub : 1;
   MQ_REQUIRE(a.msub * p->bn <= kTmemCols && a.msub <= 4, "mq_conv_gemm: msub=%d * bn=%d exceeds %d TMEM columns", a.msub, p->bn, kTmemCols);
-  a.nbuf = a.msub * p->bn <= kAccStride ? 2 : 1;   // one accumulator buffer when the tile needs more than 256 columns
+  a.acc_stride = (a.msub * p->bn + 31) / 32 * 32;
+  a.nbuf = kTmemCols / a.acc_stride;               // 1 (msub*bn > 256), 2, or up to 4 stages for small tiles
+  if (a.nbuf > kMaxAccBufs) a.nbuf = kMaxAccBufs;
+  {
+    const char* nb = getenv("MQ_CONV_NBUF");
+    if (nb && atoi(nb) >= 1 && atoi(nb) < a.nbuf) a.nbuf = atoi(nb);
+  }
   const bool pair = p->pair != 0;
   a.tile_rows = p->bh * a.msub * (pair ? 2 : 1);
   a.tiles_h = (p->H + a.tile_rows - 1) / a.tile_rows;
@@ -1079,7 +1086,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     const int halo_px = (kHaloSubRows * a.msub + 2) * kHaloW;
     a.halo_tx_bytes = halo_px * 128;
     a.halo_slot_bytes = (a.halo_tx_bytes + 1023) / 1024 * 1024;
-    const int tail_bytes = (2 * kHaloMaxA + 2 * kHaloMaxB + 4) * 8 + 16 + kBiasSmemFloats * 4;
+    const int tail_bytes = (2 * kHaloMaxA + 2 * kHaloMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4;
     const int budget = kSmemBudget - 1024 - tail_bytes - 256;
     int nA = a.kchunks >= 3 ? 3 : 2;
     while (nA > 2 && budget - nA * a.halo_slot_bytes < 4 * static_cast<int>(a.b_tile_bytes)) --nA;
@@ -1099,7 +1106,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     int slot = a.pair_tx0;
     if (up && a.pair_boxb_off + box1 > slot) slot = a.pair_boxb_off + box1;
     a.halo_slot_bytes = (slot + 1023) / 1024 * 1024;
-    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 4) * 8 + 16 + kBiasSmemFloats * 4;
+    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4;
     const int budget = kSmemBudget - 1024 - tail_bytes - 256;
     // weight ring: slots of pair_bgrp taps (3 = one filter row; every tap count on this path is a
     // multiple of 3) -> one full/empty barrier round trip and one multicast commit per slot
