@@ -35,7 +35,7 @@ WORKLOADS = {
     "tiny_8x256": ("TINY", 8, 256, "f16x2"),
 }
 DEFAULT_WORKLOAD = "hifispeech_256x1024_fp32idx"
-CPU_SAMPLE = (2, 1024)       # utterances x frames timed on the host cores (bounded sample)
+CPU_SAMPLE = (6, 1024)       # utterances x frames timed on the host cores (bounded sample, ~10 s)
 
 
 def load_peaks():

@@ -179,3 +179,49 @@ def test_hifispeech_longer_ragged_batch_vs_oracle():
     _dump()
     print(REPORT["decode/hifispeech_4x200"])
     assert err <= MEL_ATOL + MEL_RTOL * scale
+
+
+@pytest.mark.parametrize("B,T,lengths", [
+    (1, 1, [1]),                    # a single frame: every conv sees only padding around it
+    (1, 5, [5]),                    # T < 8: the refiner pads to one 8-row block
+    (2, 9, [9, 3]),                 # T % 8 == 1
+    (3, 33, [33, 1, 17]),           # one-frame utterance inside a batch
+    (2, 40, [40, 0]),               # an empty utterance (all padding) in the batch
+    (1, 700, [700]),                # B = 1, many pair tiles along T
+])
+def test_edge_shapes_vs_oracle(B, T, lengths):
+    """Ragged / tiny / empty inputs through the public API against the CPU oracle (tiny config)."""
+    cfg, sd, _, _, _ = load_golden("tiny")
+    lengths = torch.tensor(lengths)
+    mel = synth_mels(B, T, cfg.mel_channels, seed=11)
+    pad = torch.arange(T)[None, :] >= lengths[:, None]
+    mel = mel.masked_fill(pad.unsqueeze(-1), 0.0)
+    mask = pad.unsqueeze(1)
+    w = O.effective_weights(sd)
+    z32 = O.encode_latents(w, cfg, mel, mask, folded=True)
+    ref_idx = O.fsq_quantize(z32, cfg.fsq_levels)[1]
+    z64 = O.encode_latents(sd, cfg, mel, mask, dtype=torch.float64)
+    margin = O.fsq_round_margin(z64, cfg.fsq_levels)
+    model = _model(cfg, sd)
+    idx = model.encode(mel.cuda(), mask.cuda())
+    assert tuple(idx.shape) == (B, T)
+    rep = index_report(idx, ref_idx, margin, TAU)
+    assert rep["safe_mismatch"] == 0, rep
+    ref = O.decode(w, cfg, ref_idx, mask, folded=True)
+    out = model.decode(ref_idx.cuda(), mask.cuda()).cpu()
+    assert out.shape == ref.shape
+    err, scale = float((out - ref).abs().max()), float(ref.abs().max())
+    assert err <= MEL_ATOL + MEL_RTOL * scale, (err, scale)
+    assert bool(torch.isfinite(out).all())
+
+
+def test_decode_rejects_out_of_range_indices():
+    """bos/eos ids (codebook_size + 1/2, preencoder.py:340-341) are outside the FSQ range: the reference
+    silently produces garbage digits; this path raises instead."""
+    cfg, sd, mel, lengths, fx = load_golden("tiny")
+    model = _model(cfg, sd)
+    idx = torch.zeros(1, 16, dtype=torch.int64)
+    idx[0, 3] = cfg.codebook_size + 1
+    with pytest.raises((IndexError, RuntimeError)):
+        model.decode(idx.cuda(), None)
+    model.decode(torch.zeros(1, 16, dtype=torch.int64).cuda(), None)      # the engine is still usable afterwards
