@@ -298,6 +298,36 @@ int mq_refiner_tail(const float* taps, int ldp, const uint8_t* mask, int B, int 
                     float bias, const float* reproj_t, int M, const float* r, float* out,
                     mq_stream_t stream);
 
+/* ---- f3: log-mel front-end (convert_spectrograms.py:14-35) ------------------ */
+/*
+ * out[b, f, m] = log(max(sum_k fb[k, m] * |STFT(wav_b)[f, k]|, clip)): torchaudio
+ * MelSpectrogram(n_fft, win_length, hop_length, f_min, f_max, n_mels, power=1) with its defaults
+ * (hann window, center=True, pad_mode="reflect", onesided, htk mel scale, norm=None) followed by
+ * log(clamp(min=1e-5)), laid out (frames, n_mels) as convert_spectrograms.py:35 returns it.
+ * wav (B, wav_ld) fp32 with lengths[b] valid samples; utterance b has 1 + lengths[b] / hop frames
+ * (0 if lengths[b] <= n_fft/2, which torch.stft rejects); rows beyond that up to out_frames are zero.
+ * Host-prepared tables (mqgan_b200/melspec.py): window [n_fft] (hann(win_length) centred in n_fft),
+ * twiddle [n_fft/2][2] = (cos, -sin)(2 pi t / n_fft), and the mel filterbank in sparse row form:
+ * mel bin m sums fb_w[fb_off[m] + i] * |S[fb_start[m] + i]| for i < fb_count[m].
+ */
+typedef struct mq_melspec_params {
+  const float* wav;
+  int64_t wav_ld;
+  const int64_t* lengths;   /* device, [B] */
+  int B;
+  int n_fft, hop, n_mels, n_freqs;
+  const float* window;
+  const float* twiddle;
+  const int* fb_start;
+  const int* fb_count;
+  const int* fb_off;
+  const float* fb_w;
+  float clip;
+  float* out;               /* (B, out_frames, n_mels) fp32 */
+  int64_t out_frames;
+} mq_melspec_params;
+int mq_log_mel(const mq_melspec_params* p, mq_stream_t stream);
+
 /* ---- sequence mask (preencoder.py:15-24) ----------------------------------- */
 int mq_sequence_mask(const int64_t* lengths, int B, int T, uint8_t* mask, mq_stream_t stream);
 

@@ -91,6 +91,16 @@ class VqParams(C.Structure):
     ]
 
 
+class MelspecParams(C.Structure):
+    _fields_ = [
+        ("wav", C.c_void_p), ("wav_ld", C.c_int64), ("lengths", C.c_void_p), ("B", C.c_int),
+        ("n_fft", C.c_int), ("hop", C.c_int), ("n_mels", C.c_int), ("n_freqs", C.c_int),
+        ("window", C.c_void_p), ("twiddle", C.c_void_p),
+        ("fb_start", C.c_void_p), ("fb_count", C.c_void_p), ("fb_off", C.c_void_p), ("fb_w", C.c_void_p),
+        ("clip", C.c_float), ("out", C.c_void_p), ("out_frames", C.c_int64),
+    ]
+
+
 class FsqParams(C.Structure):
     _fields_ = [
         ("D", C.c_int),
@@ -117,6 +127,7 @@ SIGNATURES = {
                              C.POINTER(FsqParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_fsq_quantize": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(FsqParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_vq_nearest": (C.c_int, [C.POINTER(VqParams), C.c_void_p]),
+    "mq_log_mel": (C.c_int, [C.POINTER(MelspecParams), C.c_void_p]),
     "mq_code_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_refiner_masks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

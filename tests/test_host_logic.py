@@ -222,3 +222,28 @@ def test_sequence_mask_matches_reference_definition():
     m = sequence_mask(5, lengths)
     assert m.tolist() == [[False, False, False, True, True], [True] * 5, [False] * 5]
     assert torch.equal(m, O.sequence_mask(5, lengths))
+
+
+def test_convert_spectrograms_host_logic(tmp_path):
+    """Host side of the mel front-end CLI (convert_spectrograms.py:73-90, :111-120): config validation,
+    task discovery, chunking; and the extractor refuses a CPU device (no fallback)."""
+    from mqgan_b200 import convert_spectrograms as cs
+    cfg = {"io": {"input_folder": str(tmp_path / "in"), "output_folder": str(tmp_path / "out"),
+                  "audio_extensions": [".wav", ".flac"]},
+           "spectrogram": {"sampling_rate": 44100, "filter_length": 2048, "hop_length": 512, "win_length": 2048,
+                           "n_mel_channels": 128, "mel_fmin": 0.0, "mel_fmax": 22050.0}}
+    cs.validate_config(cfg)
+    bad = {"io": cfg["io"], "spectrogram": {k: v for k, v in cfg["spectrogram"].items() if k != "hop_length"}}
+    with pytest.raises(ValueError, match="hop_length"):
+        cs.validate_config(bad)
+    with pytest.raises(ValueError, match="io"):
+        cs.validate_config({"spectrogram": cfg["spectrogram"]})
+    os.makedirs(tmp_path / "in" / "spk", exist_ok=True)
+    for n in ("a.wav", "b.FLAC", "c.txt"):
+        (tmp_path / "in" / "spk" / n).write_bytes(b"")
+    tasks = cs.collect_tasks(cfg)
+    assert sorted(os.path.basename(t[0]) for t in tasks) == ["a.wav", "b.FLAC"]
+    assert all(t[1] == os.path.join(cfg["io"]["output_folder"], "spk") for t in tasks)
+    assert cs.chunkify(list(range(7)), 3) == [[0, 1, 2], [3, 4], [5, 6]]
+    with pytest.raises(ValueError, match="CUDA"):
+        cs.TorchMelSpectrogramExtractor(cfg["spectrogram"], device="cpu")
