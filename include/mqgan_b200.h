@@ -307,7 +307,7 @@ int mq_refiner_tail(const float* taps, int ldp, const uint8_t* mask, int B, int 
  * wav (B, wav_ld) fp32 with lengths[b] valid samples; utterance b has 1 + lengths[b] / hop frames
  * (0 if lengths[b] <= n_fft/2, which torch.stft rejects); rows beyond that up to out_frames are zero.
  * Host-prepared tables (mqgan_b200/melspec.py): window [n_fft] (hann(win_length) centred in n_fft),
- * twiddle [n_fft/2][2] = (cos, -sin)(2 pi t / n_fft), and the mel filterbank in sparse row form:
+ * twiddle [n_fft][2] = (cos, -sin)(2 pi t / n_fft), and the mel filterbank in sparse row form:
  * mel bin m sums fb_w[fb_off[m] + i] * |S[fb_start[m] + i]| for i < fb_count[m].
  */
 typedef struct mq_melspec_params {

@@ -81,13 +81,38 @@ __global__ void __launch_bounds__(kMelThreads) log_mel_kernel(const MelArgs a) {
   float2* in = buf0;
   float2* out = buf1;
   const int half = N >> 1;
-  for (int s = 0; s < a.log2n; ++s) {
-    const int Ns = 1 << s;
-    const int tstep = half >> s;                      // twiddle table stride: exp(-2 pi i k / (2 Ns)) = table[k * (N/2) / Ns]
+  // Stockham autosort: radix-4 passes (sub-transform size Ns = 1, 4, 16, ...) and one radix-2 pass when
+  // log2(n_fft) is odd.  Pass (Ns, R): thread j combines in[j + r N/R], twiddled by exp(-2 pi i k r / (R Ns))
+  // with k = j mod Ns (twiddle[t] = exp(-2 pi i t / N), t < N), and writes out[(j - k) R + k + r Ns].
+  int Ns = 1;
+  for (; Ns * 4 <= N; Ns *= 4) {
+    const int quarter = N >> 2;
+    const int tstep = quarter / Ns;                   // k r / (4 Ns) = (k r tstep) / N
+    for (int j = tid; j < quarter; j += kMelThreads) {
+      const int k = j & (Ns - 1);
+      const float2 v0 = in[j];
+      const float2 v1 = cmul(in[j + quarter], __ldg(a.twiddle + k * tstep));
+      const float2 v2 = cmul(in[j + 2 * quarter], __ldg(a.twiddle + 2 * k * tstep));
+      const float2 v3 = cmul(in[j + 3 * quarter], __ldg(a.twiddle + 3 * k * tstep));
+      const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y), a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+      const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+      const float2 a3 = make_float2(v1.y - v3.y, v3.x - v1.x);          // (v1 - v3) * (-i)
+      const int j0 = ((j - k) << 2) + k;
+      out[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+      out[j0 + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
+      out[j0 + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+      out[j0 + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+    }
+    __syncthreads();
+    float2* tmp = in;
+    in = out;
+    out = tmp;
+  }
+  if (Ns < N) {                                       // one radix-2 pass left (Ns == N/2)
     for (int j = tid; j < half; j += kMelThreads) {
       const int k = j & (Ns - 1);
       const float2 v0 = in[j];
-      const float2 t = cmul(in[j + half], __ldg(a.twiddle + k * tstep));
+      const float2 t = cmul(in[j + half], __ldg(a.twiddle + k * (half / Ns)));
       const int j0 = ((j - k) << 1) + k;
       out[j0] = make_float2(v0.x + t.x, v0.y + t.y);
       out[j0 + Ns] = make_float2(v0.x - t.x, v0.y - t.y);

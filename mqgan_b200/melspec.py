@@ -61,7 +61,7 @@ class LogMelExtractor:
         self.clip = float(clip_val)
         dev = self.device
         self.window = torch.from_numpy(_hann_padded(self.win, self.n_fft).astype(np.float32)).to(dev)
-        t = np.arange(self.n_fft // 2, dtype=np.float64) * (2.0 * math.pi / self.n_fft)
+        t = np.arange(self.n_fft, dtype=np.float64) * (2.0 * math.pi / self.n_fft)
         self.twiddle = torch.from_numpy(np.stack([np.cos(t), -np.sin(t)], axis=1).astype(np.float32)).contiguous().to(dev)
         fb = _mel_fbanks(self.n_freqs, float(spec["mel_fmin"]), float(spec["mel_fmax"]), self.n_mels, self.sr).astype(np.float32)
         start, count, off, w = [], [], [], []
