@@ -320,13 +320,19 @@ class PreEncoderEngine:
         hid = torch.empty(B, T, self.cfg.c0, dtype=torch.float32, device=self.device) if return_hidden else None
         recon = torch.empty_like(out) if return_recon else None
         bad = torch.zeros(1, dtype=torch.int32, device=self.device)      # out-of-range index flag, read once below
-        for b0, b1 in self._chunks(B, T):
-            h, R = self._decode_chunk(idx[b0:b1], None if m8 is None else m8[b0:b1], out[b0:b1], return_hidden, taps,
-                                      bad)
+        # The 1-D decoder (live set ~10 KB per frame) runs in the large encoder-size chunks; only the
+        # refiner (~0.2 MB per frame) is cut into the small ones.
+        for c0, c1 in self._chunks(B, T, self.max_chunk_frames_enc):
+            mc = None if m8 is None else m8[c0:c1]
+            h, R = self._decode_1d(idx[c0:c1], mc, return_hidden, taps, bad)
             if return_hidden:
-                hid[b0:b1] = h
+                hid[c0:c1] = h
             if return_recon:
-                recon[b0:b1] = R.view(b1 - b0, T, -1)[..., : self.cfg.mel_channels]
+                recon[c0:c1] = R.view(c1 - c0, T, -1)[..., : self.cfg.mel_channels]
+            Rv = R.view(c1 - c0, T, -1)
+            for b0, b1 in self._chunks(c1 - c0, T):
+                self._refiner(Rv[b0:b1].reshape((b1 - b0) * T, -1), None if mc is None else mc[b0:b1], b1 - b0, T,
+                              out[c0 + b0:c0 + b1], taps)                                    # :496-499
         # one host sync per decode call (not per chunk: a sync drains the launch queue and idles the GPU)
         if int(bad.item()) != 0:
             raise IndexError("decode: index outside [0, codebook_size)")
@@ -337,7 +343,9 @@ class PreEncoderEngine:
             res.append(recon)
         return res[0] if len(res) == 1 else tuple(res)
 
-    def _decode_chunk(self, idx, m8, out, want_hidden, taps, bad):
+    def _decode_1d(self, idx, m8, want_hidden, taps, bad):
+        """code gather -> causal decoder blocks -> post -> out_proj / hidden_proj: returns (decoder_out | None,
+        R = cat[x_recon, hidden] (rows, F) fp32), preencoder.py:464-492."""
         cfg, dev = self.cfg, self.device
         B, T = idx.shape
         rows = B * T
@@ -368,7 +376,6 @@ class PreEncoderEngine:
         ops.conv_gemm(dec_out, self.hidden_proj, B, T, 1, out_f32=R, f32_coff=M, tag="dec.hidden_proj")            # :490-492
         if taps is not None:
             taps["refiner_in"] = R
-        self._refiner(R, m8, B, T, out, taps)                                               # :496-499
         return (dec_out.view(B, T, cfg.c0).float() if want_hidden else None), R
 
     def _refiner(self, R, m8, B, T, out, taps):
