@@ -113,6 +113,9 @@ SPLIT_KIND = {"bf16x3": 0, "f16x2": 1}
 
 def choose_bn(cout: int) -> Tuple[int, int]:
     """N tile (multiple of 32, <= 256) and padded cout."""
+    cap = int(os.environ.get("MQ_BN_CAP", "256"))          # experiment knob: narrower N tiles
+    if cap < 256 and cout > cap and cout % cap == 0:
+        return cap, cout
     if cout <= 256:
         bn = (cout + 31) // 32 * 32
         return bn, bn

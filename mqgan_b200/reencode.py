@@ -18,6 +18,7 @@ from __future__ import annotations
 import os
 import queue
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -48,9 +49,30 @@ def shard_indices(n_batches: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_batches, world))
 
 
+IO_THREADS = int(os.environ.get("MQ_IO_THREADS", "4"))    # file reads / writes inside one batch run concurrently
+_io_pool: Optional[ThreadPoolExecutor] = None
+
+
+def _pool() -> ThreadPoolExecutor:
+    global _io_pool
+    if _io_pool is None:
+        _io_pool = ThreadPoolExecutor(max_workers=max(1, IO_THREADS), thread_name_prefix="mq_io")
+    return _io_pool
+
+
+def sort_batches_by_length(files: Sequence[str]) -> List[str]:
+    """Optional (``--sort_by_length``): order files by frame count so that batches are nearly rectangular
+    (less padding).  NOT the reference's batch composition: batch composition influences the encoder
+    through padding, so this can change indices; off by default."""
+    def n_frames(p):
+        return int(np.load(p, mmap_mode="r").shape[0])
+    lens = list(_pool().map(n_frames, files))
+    return [f for _, f in sorted(zip(lens, files), key=lambda t: (t[0], t[1]))]
+
+
 def load_and_pad(paths: Sequence[str]) -> Tuple[torch.Tensor, List[int]]:
     """np.load each file, zero-pad to the longest, stack, float32 (reencode_spectrograms.py:49-62)."""
-    specs = [np.load(p) for p in paths]
+    specs = list(_pool().map(np.load, paths)) if len(paths) > 1 and IO_THREADS > 1 else [np.load(p) for p in paths]
     lengths = [int(s.shape[0]) for s in specs]
     max_len = max(lengths)
     n_mels = specs[0].shape[1]
@@ -66,15 +88,22 @@ def save_outputs(reencoded: torch.Tensor, lengths: Sequence[int], paths: Sequenc
                  output_dir: str) -> None:
     """Trim to the original length and save under the mirrored path (:69-81)."""
     arr = reencoded.numpy() if not reencoded.is_cuda else reencoded.cpu().numpy()
-    for i, p in enumerate(paths):
-        out_path = os.path.join(output_dir, os.path.relpath(p, input_dir))
+
+    def save_one(i):
+        out_path = os.path.join(output_dir, os.path.relpath(paths[i], input_dir))
         os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
         np.save(out_path, np.ascontiguousarray(arr[i, : lengths[i], :], dtype=np.float32))
+
+    if len(paths) > 1 and IO_THREADS > 1:
+        list(_pool().map(save_one, range(len(paths))))
+    else:
+        for i in range(len(paths)):
+            save_one(i)
 
 
 def reencode_tree(run_batch: Callable[[torch.Tensor, List[int]], torch.Tensor], input_dir: str, output_dir: str,
                   batch_size: int, rank: int = 0, world: int = 1, progress: bool = True,
-                  prefetch: int = 2) -> Tuple[int, int]:
+                  prefetch: int = 2, sort_by_length: bool = False) -> Tuple[int, int]:
     """Process this worker's share of the tree.  ``run_batch(batch (B,T,M) float32 CPU, lengths)``
     returns the re-encoded (B,T,M) tensor (any device).  Returns (files done, batches failed)."""
     files = list_npy_files(input_dir)
@@ -83,6 +112,8 @@ def reencode_tree(run_batch: Callable[[torch.Tensor, List[int]], torch.Tensor], 
         return 0, 0
     if rank == 0:
         print(f"Found {len(files)} spectrogram files to process.")
+    if sort_by_length:
+        files = sort_batches_by_length(files)
     batches = make_batches(files, batch_size)
     mine = shard_indices(len(batches), rank, world)
 
@@ -177,7 +208,7 @@ def finish_distributed(done: int, failed: int, backend: Optional[str] = None) ->
 
 
 def _worker(rank: int, world: int, make_model: Callable[[str], object], input_dir: str, output_dir: str,
-            batch_size: int, ret) -> None:
+            batch_size: int, ret, sort_by_length: bool = False) -> None:
     torch.cuda.set_device(rank)
     model = make_model(f"cuda:{rank}")
 
@@ -185,17 +216,19 @@ def _worker(rank: int, world: int, make_model: Callable[[str], object], input_di
         idx = model.encode(batch, lengths=lengths)
         return model.decode(idx, lengths=lengths)
 
-    ret[rank] = reencode_tree(run, input_dir, output_dir, batch_size, rank, world, progress=(rank == 0))
+    ret[rank] = reencode_tree(run, input_dir, output_dir, batch_size, rank, world, progress=(rank == 0),
+                              sort_by_length=sort_by_length)
 
 
 def run_multi_gpu(make_model: Callable[[str], object], input_dir: str, output_dir: str, batch_size: int,
-                  gpus: int) -> Tuple[int, int]:
+                  gpus: int, sort_by_length: bool = False) -> Tuple[int, int]:
     """One worker process per GPU (``--gpus N``); each builds its own model copy."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
         ret = mgr.dict()
-        procs = [ctx.Process(target=_worker, args=(r, gpus, make_model, input_dir, output_dir, batch_size, ret))
+        procs = [ctx.Process(target=_worker, args=(r, gpus, make_model, input_dir, output_dir, batch_size, ret,
+                                                   sort_by_length))
                  for r in range(gpus)]
         for p in procs:
             p.start()

@@ -20,12 +20,12 @@ def _make_model(model_path, device):
     return ScriptedPreEncoder(model_path, device=device)
 
 
-def reencode_spectrograms(model_path, input_dir, output_dir, device, batch_size, gpus=1):
+def reencode_spectrograms(model_path, input_dir, output_dir, device, batch_size, gpus=1, sort_by_length=False):
     print(f"Loading model from: {model_path}")
     rank, world, local = R.dist_env()
     if gpus > 1 and world == 1:
         done, failed = R.run_multi_gpu(functools.partial(_make_model, model_path), input_dir, output_dir,
-                                       batch_size, gpus)
+                                       batch_size, gpus, sort_by_length)
     else:
         if world > 1 and torch.device(device).type == "cuda":
             device = f"cuda:{local}"
@@ -41,7 +41,8 @@ def reencode_spectrograms(model_path, input_dir, output_dir, device, batch_size,
             idx = model.encode(batch, lengths=lengths)
             return model.decode(idx, lengths=lengths)
 
-        done, failed = R.reencode_tree(run, input_dir, output_dir, batch_size, rank, world)
+        done, failed = R.reencode_tree(run, input_dir, output_dir, batch_size, rank, world,
+                                        sort_by_length=sort_by_length)
         done, failed = R.finish_distributed(done, failed)
     if rank == 0:
         print("\nProcessing complete.")
@@ -63,10 +64,13 @@ def main():
                              'reference; this build only runs on "cuda" and says so otherwise.')
     parser.add_argument('--batch_size', type=int, default=32,
                         help='Number of spectrograms to process in a single batch. Defaults to 32.')
+    parser.add_argument('--sort_by_length', action='store_true',
+                        help='(added) batch files of similar length together (less padding, faster). Changes the '
+                             'batch composition, which the encoder is sensitive to through padding: off by default.')
     parser.add_argument('--gpus', type=int, default=1,
                         help='(added) shard batches over this many GPUs of one box. Defaults to 1.')
     args = parser.parse_args()
-    reencode_spectrograms(args.model, args.input_dir, args.output_dir, args.device, args.batch_size, args.gpus)
+    reencode_spectrograms(args.model, args.input_dir, args.output_dir, args.device, args.batch_size, args.gpus, args.sort_by_length)
 
 
 if __name__ == '__main__':

@@ -45,12 +45,13 @@ def _make_model(checkpoint_path, config, device):
     return _CheckpointModel(checkpoint_path, config, device)
 
 
-def reencode_spectrograms(checkpoint_path, config, input_dir, output_dir, device, batch_size, gpus=1):
+def reencode_spectrograms(checkpoint_path, config, input_dir, output_dir, device, batch_size, gpus=1,
+                          sort_by_length=False):
     print(f"Loading model from checkpoint: {checkpoint_path}")
     rank, world, local = R.dist_env()
     if gpus > 1 and world == 1:
         done, failed = R.run_multi_gpu(functools.partial(_make_model, checkpoint_path, config), input_dir,
-                                       output_dir, batch_size, gpus)
+                                       output_dir, batch_size, gpus, sort_by_length)
     else:
         if world > 1 and torch.device(device).type == "cuda":
             device = f"cuda:{local}"
@@ -65,7 +66,8 @@ def reencode_spectrograms(checkpoint_path, config, input_dir, output_dir, device
         def run(batch, lengths):
             return model.decode(model.encode(batch, lengths), lengths)
 
-        done, failed = R.reencode_tree(run, input_dir, output_dir, batch_size, rank, world)
+        done, failed = R.reencode_tree(run, input_dir, output_dir, batch_size, rank, world,
+                                        sort_by_length=sort_by_length)
         done, failed = R.finish_distributed(done, failed)
     if rank == 0:
         print("\nProcessing complete.")
@@ -87,6 +89,9 @@ def main():
                         help='Device to use for inference (e.g., "cpu", "cuda"). This build only runs on "cuda".')
     parser.add_argument('--batch_size', type=int, default=32,
                         help='Number of spectrograms to process in a single batch. Defaults to 32.')
+    parser.add_argument('--sort_by_length', action='store_true',
+                        help='(added) batch files of similar length together (less padding, faster). Changes the '
+                             'batch composition, which the encoder is sensitive to through padding: off by default.')
     parser.add_argument('--gpus', type=int, default=1, help='(added) shard batches over this many GPUs.')
     args = parser.parse_args()
     try:

@@ -247,3 +247,35 @@ def test_convert_spectrograms_host_logic(tmp_path):
     assert cs.chunkify(list(range(7)), 3) == [[0, 1, 2], [3, 4], [5, 6]]
     with pytest.raises(ValueError, match="CUDA"):
         cs.TorchMelSpectrogramExtractor(cfg["spectrogram"], device="cpu")
+
+
+def test_sort_by_length_is_optional_and_io_pool_preserves_results(tmp_path):
+    """--sort_by_length regroups files (less padding) but every file is still processed exactly once and saved
+    under its mirrored path; without the flag the reference's os.walk batch composition is untouched.  The
+    threaded loads / saves give byte-identical files."""
+    rng = np.random.default_rng(5)
+    src, dst1, dst2 = str(tmp_path / "in"), str(tmp_path / "o1"), str(tmp_path / "o2")
+    lens = {}
+    for i in range(11):
+        d = os.path.join(src, f"s{i % 3}")
+        os.makedirs(d, exist_ok=True)
+        T = int(rng.integers(3, 40))
+        lens[f"u{i}.npy"] = T
+        np.save(os.path.join(d, f"u{i}.npy"), rng.standard_normal((T, 6)).astype(np.float32))
+    seen = []
+
+    def run(batch, lengths):
+        seen.append(list(lengths))
+        return batch * 2.0
+
+    assert R.reencode_tree(run, src, dst1, 4, progress=False) == (11, 0)
+    unsorted_batches = [list(b) for b in seen]
+    seen.clear()
+    assert R.reencode_tree(run, src, dst2, 4, progress=False, sort_by_length=True) == (11, 0)
+    flat = [l for b in seen for l in b]
+    assert flat == sorted(flat) and sorted(flat) == sorted(lens.values())
+    assert [l for b in unsorted_batches for l in b] != flat            # the default order is the walk order
+    for p in R.list_npy_files(src):
+        rel = os.path.relpath(p, src)
+        a, b = np.load(os.path.join(dst1, rel)), np.load(os.path.join(dst2, rel))
+        assert a.shape == (lens[os.path.basename(p)], 6) and np.array_equal(a, b) and np.array_equal(a, np.load(p) * 2.0)

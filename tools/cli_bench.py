@@ -1,0 +1,59 @@
+"""End-to-end benchmark of the re-encode CLI path INCLUDING .npy file I/O ("report
+separately an end-to-end CLI number including .npy I/O"): writes N synthetic log-mel files, runs
+mqgan_b200.reencode.reencode_tree with the hifispeech model (reader / writer threads, pinned staging)
+at the CLI's batch size, and reports files/s and frames/s of wall-clock time.
+Usage: python tools/cli_bench.py [n_files] [batch_size] [dir]"""
+import json
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import bench
+from mqgan_b200 import reencode as R, spec as S
+from mqgan_b200.preencoder import sequence_mask
+
+n_files = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+batch_size = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+SORT = os.environ.get("MQ_SORT", "0") == "1"
+root = sys.argv[3] if len(sys.argv) > 3 else tempfile.mkdtemp(prefix="mq_cli_bench_")
+cfg = S.HIFISPEECH
+src, dst = os.path.join(root, "in"), os.path.join(root, "out")
+rng = np.random.default_rng(0)
+frames = 0
+t0 = time.perf_counter()
+for i in range(n_files):
+    d = os.path.join(src, f"spk{i % 16:02d}")
+    os.makedirs(d, exist_ok=True)
+    T = int(rng.integers(300, 1100))
+    frames += T
+    np.save(os.path.join(d, f"u{i:05d}.npy"), (rng.standard_normal((T, cfg.mel_channels)) * 2 - 4).astype(np.float32))
+t_write = time.perf_counter() - t0
+dev = torch.device("cuda", 0)
+model, _ = bench.build_model(cfg, "f16x2", dev)
+
+
+def run(batch, lengths):
+    lt = torch.tensor(lengths, dtype=torch.long, device=dev)
+    mask = sequence_mask(batch.shape[1], lt).unsqueeze(1)
+    x = batch.to(dev, non_blocking=True)
+    with torch.no_grad():
+        return model.decode(model.encode(x, mask), mask)
+
+
+for warm in range(2):                       # first pass warms the page cache, allocator and weight packing
+    shutil.rmtree(dst, ignore_errors=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    done, failed = R.reencode_tree(run, src, dst, batch_size, progress=False, sort_by_length=SORT)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+print(json.dumps({"tool": "cli_bench", "files": n_files, "batch_size": batch_size, "frames": frames, "done": done,
+                  "failed": failed, "sort_by_length": SORT, "io_threads": R.IO_THREADS, "seconds": dt, "files_per_s": done / dt, "frames_per_s": frames / dt,
+                  "input_gb": frames * cfg.mel_channels * 4 / 1e9, "setup_write_s": t_write,
+                  "note": "wall clock of reencode_tree: np.load + pad + H2D + encode + decode + D2H + trim + np.save"}))
+shutil.rmtree(root, ignore_errors=True)
