@@ -279,10 +279,16 @@ def main():
     total_ms = sum(r[3] for r in table)
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {
-        "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv, all %d launches of one step)" % conv_launches,
+        "bound": "tensor",
+        "kernel": "mq_conv_gemm (tcgen05 implicit-GEMM conv: conv_pair_kernel cta_group::2 for the refiner's 3x3 layers, "
+                  "conv_gemm_kernel for 1-D / 1x1 layers; all %d launches of one step)" % conv_launches,
         "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " bf16 sustained",
-        "traffic": None,
+        # DRAM bytes of ONE launch of the dominant layer shape from the committed ncu --set full capture
+        # (profiles/ncu_conv_pair_mid_r01.csv: dram__bytes_read.sum + dram__bytes_write.sum of conv_pair_kernel on
+        # refiner mid.conv1, 32 utterances x 128 x 144 x 512 ch); its algorithmic bytes are 2 x 604 MB + 4.7 MB weights
+        "traffic": 1174064896 if cfg_name == "HIFISPEECH" else None,
+        "traffic_algorithmic_bytes": 1212678144 if cfg_name == "HIFISPEECH" else None,
         "issued_mma_tflops": conv_mma / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
         "share_of_step": conv_ms / total_ms if total_ms > 0 else None,
         "flops_per_launch_avg": conv_flops / max(conv_launches, 1),
