@@ -119,7 +119,10 @@ typedef struct mq_conv_params {
   /* pair != 0: CTA-pair main loop (tcgen05 cta_group::2, M = 256) for single-source 3x3 / pad-1
    * convolutions and for the fused upsample-concat mode (bh == 16, bw == 8, nseg == 1): the two
    * CTAs of a cluster each stage the halo of their own msub sub-tiles and half of every weight
-   * tile, halving weight traffic per pixel (L2->SM and shared-memory reads).  Excludes halo. */
+   * tile, halving weight traffic per pixel (L2->SM and shared-memory reads).  Excludes halo.
+   * With W == 1 (1-D convolutions / linears; bh == 128, bw == 1, msub == 1, consecutive row taps, any
+   * nseg) the row-halo variant runs: one (128 + taps - 1)-row activation fetch per channel chunk, taps
+   * as descriptors shifted by whole rows. */
   int pair;
   /* out_pool != NULL: the epilogue also writes AvgPool2d((2,1)) of the bf16 output, filled with zero
    * where either source row is padded (preencoder.py:111-114 with the max-pooled mask :63-65, :96):

@@ -886,6 +886,163 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
 }
 
 // ---------------------------------------------------------------------------
+// CTA-pair kernel for the 1-D convolutions and linears (W == 1: encoder / decoder blocks, projections).
+//
+// Same pairing as conv_pair_kernel (M = 256 across two CTAs, half a weight tile per CTA, leader issues),
+// with a ROW halo: per (segment, 64-channel chunk) a CTA loads the 128*msub + taps - 1 consecutive rows
+// its sub-tiles need ONCE, and tap j is the descriptor shifted by j rows (rows are 128 bytes, so a
+// shift is 8 sixteen-byte units; the 128-byte swizzle depends on absolute address bits, so unaligned
+// starts need no base offset).  The tap-shifted kernel above re-fetches the activation tile for every
+// tap (k = 3..7 times the L2->SM traffic).  K order = (segment, chunk, tap): segment-major like the
+// packed weights, so the f16x2 / bf16x3 "small products first" accumulation order is unchanged.
+// Weight ring slots hold up to three taps (ragged last group) to amortise the barrier round trip.
+// ---------------------------------------------------------------------------
+constexpr int kPair1dGroup = 3;
+
+template <bool kFast, bool kLean>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_pair1d_kernel(const __grid_constant__ CUtensorMap map_a,
+                   const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int nA = a.halo_nA, nB = a.halo_nB;
+  const int bslot = kPair1dGroup * static_cast<int>(a.b_tile_bytes);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + nA * a.halo_slot_bytes;
+  uint8_t* tail = smem_b + nB * bslot;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(tail);        // leader only
+  uint64_t* emptyA = fullA + kPairMaxA;                       // per CTA (multicast commit)
+  uint64_t* fullB = emptyA + kPairMaxA;                       // leader only
+  uint64_t* emptyB = fullB + kPairMaxB;                       // per CTA
+  uint64_t* tfull_bar = emptyB + kPairMaxB;                   // per CTA (multicast commit)
+  uint64_t* tempty_bar = tfull_bar + kMaxAccBufs;             // leader only, both CTAs' epilogues arrive
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAccBufs);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_s + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < nA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < nB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * (kEpiThreads / 32)); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_ptr_s, kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int tile0 = blockIdx.x >> 1, tstep = gridDim.x >> 1;
+  const int R = kTileM * a.msub;                // rows of this CTA's share of a tile
+  const int hoff = static_cast<int>(rank) * R;
+  const int dh0 = a.tap_dh[0];                  // taps are consecutive row offsets dh0, dh0 + 1, ...
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const int brow_half = static_cast<int>(rank) * (a.bn >> 1);
+      for (int tile = tile0; tile < a.num_tiles; tile += tstep) {
+        int n_idx, h0, w0, n0, par;
+        decode_tile(a, tile, n_idx, h0, w0, n0, par);
+        const int hc = h0 + hoff;
+        for (int seg = 0; seg < a.nseg; ++seg) {
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait(&emptyA[sa], pa ^ 1);
+            if (rank == 0) mbar_expect_tx(&fullA[sa], 2u * static_cast<uint32_t>(a.pair_tx0));
+            tma_load_4d_2cta(&map_a, smem_u32(&fullA[sa]) & kPeerBitMask, smem_a + sa * a.halo_slot_bytes,
+                             a.a_coff[seg] + kc * kBlockK, 0, hc + dh0, n_idx);
+            if (++sa == nA) { sa = 0; pa ^= 1; }
+            for (int tap = 0; tap < a.taps; tap += kPair1dGroup) {
+              const int g = min(kPair1dGroup, a.taps - tap);
+              mbar_wait(&emptyB[sb], pb ^ 1);
+              if (rank == 0) mbar_expect_tx(&fullB[sb], 2u * a.b_tile_bytes * g);
+              const uint32_t fb = smem_u32(&fullB[sb]) & kPeerBitMask;
+              for (int j = 0; j < g; ++j)
+                tma_load_2d_2cta(&map_b, fb, smem_b + sb * bslot + j * a.b_tile_bytes,
+                                 ((seg * a.taps + tap + j) * a.kchunks + kc) * kBlockK, n0 + brow_half);
+              if (++sb == nB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = a.op_f16 ? umma_idesc_f16(2 * kTileM, a.bn) : umma_idesc_bf16(2 * kTileM, a.bn);
+      constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+      constexpr uint32_t kSubStep = kATileBytes >> 4;           // 128 rows of 128 bytes, 16-byte units
+      const int msub = a.msub;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
+        const uint32_t buf = it % a.nbuf;
+        mbar_wait(&tempty_bar[buf], ((it / a.nbuf) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * a.acc_stride;
+        uint32_t acc = 0;
+        for (int seg = 0; seg < a.nseg; ++seg) {
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait(&fullA[sa], pa);
+            const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + sa * a.halo_slot_bytes));
+            for (int tap = 0; tap < a.taps; tap += kPair1dGroup) {
+              const int g = min(kPair1dGroup, a.taps - tap);
+              mbar_wait(&fullB[sb], pb);
+              tc_fence_after();
+              const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + sb * bslot));
+              for (int j = 0; j < g; ++j) {
+                const uint32_t a_tap = a_lo + static_cast<uint32_t>((tap + j) * 8);     // j rows down the halo
+                const uint32_t b_tap = b_lo + j * (a.b_tile_bytes >> 4);
+                if (elect_one_sync()) {
+#pragma unroll
+                  for (int sub = 0; sub < 4; ++sub) {
+                    if (sub < msub) {
+#pragma unroll
+                      for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_bf16_2cta(d_tmem + sub * a.bn, umma_desc_make(a_tap + sub * kSubStep + 2 * k, hi),
+                                       umma_desc_make(b_tap + 2 * k, hi), idesc, k != 0 ? 1u : acc);
+                    }
+                  }
+                }
+                __syncwarp();
+                acc = 1;
+              }
+              if (elect_one_sync()) umma_commit_2cta(&emptyB[sb]);
+              __syncwarp();
+              if (++sb == nB) { sb = 0; pb ^= 1; }
+            }
+            if (elect_one_sync()) umma_commit_2cta(&emptyA[sa]);
+            __syncwarp();
+            if (++sa == nA) { sa = 0; pa ^= 1; }
+          }
+        }
+        if (elect_one_sync()) umma_commit_2cta(&tfull_bar[buf]);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, smem_u32(tempty_bar) & kPeerBitMask, bias_s, warp, lane,
+                               tile0, tstep, hoff);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -982,7 +1139,13 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     for (int t = 0; t < 9; ++t)
       MQ_REQUIRE(p->tap_dh[t] == t / 3 - 1 && p->tap_dw[t] == t % 3 - 1, "mq_conv_gemm: halo mode needs the standard 3x3 tap order");
   }
-  if (pair) {
+  const bool pair1d = pair && p->W == 1;          // row-halo variant for 1-D convolutions / linears
+  if (pair1d) {
+    MQ_REQUIRE(!halo && !up && p->bw == 1 && p->bh == kTileM && a.msub == 1 && p->bn % 32 == 0,
+               "mq_conv_gemm: 1-D pair mode needs a 128x1 sub-tile, msub == 1, bn a multiple of 32 and no in2");
+    for (int t = 0; t < p->taps; ++t)
+      MQ_REQUIRE(p->tap_dw[t] == 0 && p->tap_dh[t] == p->tap_dh[0] + t, "mq_conv_gemm: 1-D pair mode needs consecutive row taps");
+  } else if (pair) {
     MQ_REQUIRE(!halo && p->nseg == 1 && p->bw == 8 && p->bh == kHaloSubRows && p->bn % 32 == 0,
                "mq_conv_gemm: pair mode needs nseg == 1, a 16x8 sub-tile and bn a multiple of 32");
     if (!up) {
@@ -1032,7 +1195,10 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
                              static_cast<cuuint64_t>(p->W) * p->in_ld * 2,
                              static_cast<cuuint64_t>(p->H) * p->W * p->in_ld * 2};
     cuuint32_t box[4] = {kBlockK, static_cast<cuuint32_t>(p->bw), static_cast<cuuint32_t>(p->bh), 1};
-    if (halo || pair) {               // one (16*msub + 2) x 10 pixel halo box per channel chunk
+    if (pair1d) {                     // one (128*msub + taps - 1)-row halo per channel chunk
+      box[1] = 1;
+      box[2] = static_cast<cuuint32_t>(kTileM * a.msub + p->taps - 1);
+    } else if (halo || pair) {        // one (16*msub + 2) x 10 pixel halo box per channel chunk
       box[1] = kHaloW;
       box[2] = static_cast<cuuint32_t>(kHaloSubRows * a.msub + 2);
     }
@@ -1097,7 +1263,21 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     smem = 1024 + nA * a.halo_slot_bytes + nB * static_cast<int>(a.b_tile_bytes) + tail_bytes;
   }
   int grid = a.num_tiles < sms ? a.num_tiles : sms;
-  if (pair) {
+  if (pair1d) {
+    a.pair_tx0 = (kTileM * a.msub + p->taps - 1) * 128;
+    a.halo_slot_bytes = (a.pair_tx0 + 1023) / 1024 * 1024;
+    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4;
+    const int budget = kSmemBudget - 1024 - tail_bytes - 256;
+    const int bslot = kPair1dGroup * static_cast<int>(a.b_tile_bytes);
+    int nA = (a.nseg * a.kchunks >= 3) ? 3 : 2;
+    int nB = (budget - nA * a.halo_slot_bytes) / bslot;
+    if (nB > kPairMaxB) nB = kPairMaxB;
+    MQ_REQUIRE(nB >= 2, "mq_conv_gemm: 1-D pair mode does not fit shared memory (bn=%d)", p->bn);
+    a.halo_nA = nA; a.halo_nB = nB;
+    smem = 1024 + nA * a.halo_slot_bytes + nB * bslot + tail_bytes;
+    const int pairs = sms / 2;
+    grid = 2 * (a.num_tiles < pairs ? a.num_tiles : pairs);
+  } else if (pair) {
     const int R = kHaloSubRows * a.msub;
     a.pair_tx0 = (R + 2) * kHaloW * 128;
     const int box1 = (R + 1) * kHaloW * 128;
@@ -1153,7 +1333,18 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     MQ_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
     conv_pair_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, map_a2, a);                \
   } while (0)
-  if (pair) {
+#define MQ_LAUNCH_PAIR1D(FAST, LEAN)                                                                        \
+  do {                                                                                                      \
+    MQ_CUDA_OK(cudaFuncSetAttribute(conv_pair1d_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    conv_pair1d_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);                      \
+  } while (0)
+  if (pair1d) {
+    if (p->fast_tanh) {
+      if (lean) MQ_LAUNCH_PAIR1D(true, true); else MQ_LAUNCH_PAIR1D(true, false);
+    } else {
+      if (lean) MQ_LAUNCH_PAIR1D(false, true); else MQ_LAUNCH_PAIR1D(false, false);
+    }
+  } else if (pair) {
     if (p->fast_tanh) {
       if (lean) MQ_LAUNCH_PAIR(true, true); else MQ_LAUNCH_PAIR(true, false);
     } else {
@@ -1173,6 +1364,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
 #undef MQ_LAUNCH_CONV
 #undef MQ_LAUNCH_HALO
 #undef MQ_LAUNCH_PAIR
+#undef MQ_LAUNCH_PAIR1D
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -21,6 +21,8 @@ BLOCK_K = 64
 HALO_DEFAULT = os.environ.get("MQ_HALO", "1") != "0"   # halo-tile main loop for 3x3 convs
 PAIR_DEFAULT = os.environ.get("MQ_PAIR", "1") != "0"   # CTA-pair (cta_group::2) main loop for the refiner's 3x3 convs
 PAIR_MIN_BN = int(os.environ.get("MQ_PAIR_MIN_BN", "0"))
+PAIR_1D = os.environ.get("MQ_PAIR_1D", "1") != "0"     # row-halo CTA-pair loop for 1-D convolutions
+PAIR_1D_MIN_BN = int(os.environ.get("MQ_PAIR_1D_MIN_BN", "128"))
 
 
 def _stream() -> int:
@@ -335,6 +337,20 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
             p.tap_dh_odd[i] = pc.tap_dh_odd[i]
         hm = 2
     conv3 = pc.taps == 9 and pc.nseg == 1 and not pc.up_taps
+    conv1d = (W == 1 and not pc.up_taps and all(d == 0 for d in pc.tap_dw[:pc.taps])
+              and all(pc.tap_dh[i] == pc.tap_dh[0] + i for i in range(pc.taps)))
+    if pair is None and conv1d:
+        # row-halo CTA-pair loop for the wide 1-D layers (encoder / decoder blocks): measured against the
+        # tap-shifted loop in tools/conv_bench.py
+        pair = (PAIR_DEFAULT and PAIR_1D and pc.bn >= PAIR_1D_MIN_BN and pc.bn % 32 == 0 and H >= 256
+                and tile is None and halo is not True and (msub is None or msub == 1))
+    if pair and conv1d:
+        if halo:
+            raise ValueError("pair and halo main loops are exclusive")
+        p.pair, p.halo = 1, 0
+        halo = False
+        tile = (128, 1)
+        msub = 1
     if pair is None:
         # measured (tools/conv_bench.py, profiles/conv_bench_r01_*.log): the CTA-pair loop beats the
         # single-CTA halo / tap loops on every refiner layer shape, plain and fused up-conv
@@ -345,7 +361,9 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
     if pair and halo:
         raise ValueError("pair and halo main loops are exclusive")
     p.pair = int(bool(pair))
-    if pair:
+    if pair and conv1d:
+        bh, bw = tile
+    elif pair:
         bh, bw = 16, 8
         if msub is None:
             msub = choose_msub_pair(pc.bn, N, H, W, bool(pc.up_taps))

@@ -624,3 +624,51 @@ def test_conv_epilogue_fused_avgpool_equals_separate_pass(N, H, W, Cin, Cout, pa
     # and against the float64 definition
     r64 = y2.cpu().double().view(N, H // 2, 2, W, Cout).mean(dim=2).masked_fill(mask_pool.bool()[:, :, None, None], 0.0)
     assert (yp.cpu().double() - r64).abs().max().item() < 1e-2 * max(1.0, r64.abs().max().item())
+
+
+@pytest.mark.parametrize("kind,N,H,Cin,Cout,tail,mode", [
+    ("same1d", 2, 1000, 512, 512, (3,), "bf16"),       # 3 taps = one weight-ring slot; H not a multiple of 256
+    ("same1d", 1, 700, 512, 768, (5,), "f16x2"),       # 5 taps = ragged slot groups (3 + 2), three N tiles, 3 segments
+    ("causal1d", 2, 512, 768, 512, (7,), "bf16"),      # 7 taps (3 + 3 + 1), left halo only
+    ("causal1d", 1, 300, 512, 384, (5,), "bf16"),      # bn = 192 (96 weight rows per CTA), one ragged pair tile
+    ("linear", 3, 256, 128, 512, (), "f16x2"),         # a single tap
+    ("same1d", 1, 1024, 384, 512, (3,), "bf16x3"),     # six segments
+])
+def test_conv_pair_1d_matches_tap_mode(kind, N, H, Cin, Cout, tail, mode):
+    """Row-halo CTA-pair loop for 1-D convolutions against float64 and the single-CTA tap-shifted loop."""
+    x = _rand(N, H, 1, Cin, seed=111)
+    w = _rand(Cout, Cin, *tail, seed=112) / (Cin * max(1, int(np.prod(tail)))) ** 0.5
+    b = _rand(Cout, seed=113)
+    res = _rand(N, H, 1, Cout, seed=114)
+    mask = torch.zeros(N, H, dtype=torch.uint8)
+    mask[0, H // 2:] = 1
+    m = mask.bool()[:, :, None, None]
+    if mode == "bf16":
+        xq, wq = x.to(torch.bfloat16), w.to(torch.bfloat16)
+        xin = xq.to(DEV)
+        ref_in, ref_w = xq.double(), wq.double()
+        tol = 2e-4
+    else:
+        xin = ops.split_bf16(x.reshape(-1, Cin).to(DEV), ops.SPLIT_TERMS[mode])
+        ref_in, ref_w = x.double(), w.double()
+        tol = 3e-5
+    acc = _ref_conv(ref_in, ref_w, b.double(), kind)
+    ref = O.aptx((acc + res.double()).masked_fill(m, 0.0), 0.9, 0.6)          # ResidualBlock1D tail (attentions.py:545-549)
+    pc = ops.pack_conv(w if mode != "bf16" else wq.float(), b, kind, split=mode).to(DEV)
+    outs = {}
+    for pair in (True, False):
+        o32 = torch.empty(N, H, 1, Cout, dtype=torch.float32, device=DEV)
+        ops.conv_gemm(xin, pc, N, H, 1, row_mask=mask.to(DEV), mask_pre=True, act=True, beta=0.9, gamma=0.6,
+                      fast_tanh=False, res=res.to(DEV), res_mode=1, out_f32=o32, pair=pair)
+        outs[pair] = o32.cpu()
+    scale = max(1.0, ref.abs().max().item())
+    assert (outs[True].double() - ref).abs().max().item() < tol * scale
+    assert (outs[True] - outs[False]).abs().max().item() < tol * scale
+    if mode == "bf16":               # lean bf16 epilogue with a bf16 residual, run twice (ring state across launches)
+        rb = res.to(torch.bfloat16)
+        ref2 = O.aptx((acc + rb.double()).masked_fill(m, 0.0), 0.9, 0.6)
+        for _ in range(2):
+            ob = torch.zeros(N, H, 1, Cout, dtype=torch.bfloat16, device=DEV)
+            ops.conv_gemm(xin, pc, N, H, 1, row_mask=mask.to(DEV), mask_pre=True, act=True, beta=0.9, gamma=0.6,
+                          res=rb.to(DEV), res_mode=1, out_bf16=ob, pair=True)
+            assert (ob.cpu().double() - ref2).abs().max().item() < 2e-2 * max(1.0, ref2.abs().max().item())
