@@ -331,6 +331,34 @@ typedef struct mq_melspec_params {
 } mq_melspec_params;
 int mq_log_mel(const mq_melspec_params* p, mq_stream_t stream);
 
+/* ---- f4 (training step): weight gradient of the convolutions on tcgen05 ------ */
+/*
+ * dw[s][tap][co][ci] = sum over the pixels of K-split s of  dy[n,h,w,co] * x[n, h+tap_dh[tap], w+tap_dw[tap], ci]
+ * (zero outside the image): the weight gradient autograd produces for F.conv2d preencoder.py:97-98,
+ * F.conv1d attentions.py:471-474, 532-541 and F.linear preencoder.py:433,486,490 inside
+ * train.py:380-501 (loss.backward()).  dy (N,H,W,dy_ld) and x (N,H,W,x_ld) are bf16 channel-last; the
+ * contraction over pixels runs on tcgen05 with both operands MN-major (no transposes), fp32 accumulate.
+ * The caller sums the `split` partial tensors (deterministic; no atomics).  bh*bw must be 64: the pixel
+ * box of one K block (8x8 for images, 64x1 for sequences).  mq_conv_wgrad_split() returns the split the
+ * kernel wants for a problem (fills 148 SMs); any split >= 1 is valid.
+ * The data gradient needs no kernel of its own: it is mq_conv_gemm on dy with the taps mirrored and the
+ * weight transposed (mqgan_b200/training.py:dgrad_pack).
+ */
+typedef struct mq_wgrad_params {
+  const void* dy; int dy_ld;
+  const void* x;  int x_ld;
+  int N, H, W;
+  int cout, cin;
+  int taps;
+  int tap_dh[MQ_MAX_TAPS];
+  int tap_dw[MQ_MAX_TAPS];
+  int bh, bw;
+  int split;
+  float* dw;       /* [split][taps][cout][cin] fp32 */
+} mq_wgrad_params;
+int mq_conv_wgrad_split(const mq_wgrad_params* p);
+int mq_conv_wgrad(const mq_wgrad_params* p, mq_stream_t stream);
+
 /* ---- sequence mask (preencoder.py:15-24) ----------------------------------- */
 int mq_sequence_mask(const int64_t* lengths, int B, int T, uint8_t* mask, mq_stream_t stream);
 

@@ -101,6 +101,21 @@ class MelspecParams(C.Structure):
     ]
 
 
+class WgradParams(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("dy_ld", C.c_int),
+        ("x", C.c_void_p), ("x_ld", C.c_int),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("cout", C.c_int), ("cin", C.c_int),
+        ("taps", C.c_int),
+        ("tap_dh", C.c_int * MQ_MAX_TAPS),
+        ("tap_dw", C.c_int * MQ_MAX_TAPS),
+        ("bh", C.c_int), ("bw", C.c_int),
+        ("split", C.c_int),
+        ("dw", C.c_void_p),
+    ]
+
+
 class FsqParams(C.Structure):
     _fields_ = [
         ("D", C.c_int),
@@ -127,6 +142,8 @@ SIGNATURES = {
                              C.POINTER(FsqParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_fsq_quantize": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(FsqParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_vq_nearest": (C.c_int, [C.POINTER(VqParams), C.c_void_p]),
+    "mq_conv_wgrad_split": (C.c_int, [C.POINTER(WgradParams)]),
+    "mq_conv_wgrad": (C.c_int, [C.POINTER(WgradParams), C.c_void_p]),
     "mq_log_mel": (C.c_int, [C.POINTER(MelspecParams), C.c_void_p]),
     "mq_code_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

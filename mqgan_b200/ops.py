@@ -131,7 +131,7 @@ def choose_bn(cout: int) -> Tuple[int, int]:
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, split=False,
-              in_seg_stride: Optional[int] = None) -> PackedConv:
+              in_seg_stride: Optional[int] = None, on_device: bool = False) -> PackedConv:
     """Pack a folded conv/linear weight for mq_conv_gemm.
 
     kind: "linear" (Cout, Cin) | "same1d" / "causal1d" (Cout, Cin, k) | "conv2d3" (Cout, Cin, 3, 3).
@@ -140,21 +140,27 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, spl
     segments h0*g1, h1*g0, h0*g0 of 2-term fp16 splits (activation [h0 | h1]; weights pre-scaled by a
     power of two so the low term stays in fp16's normal range, undone by ``acc_scale``).  The term
     stride of the activation is ``in_seg_stride`` (default Cin).  K order is (segment, tap, channel
-    chunk), matching the kernel.
+    chunk), matching the kernel.  ``on_device``: pack where the weight lives (the training step re-packs
+    the folded weights every iteration); otherwise on the host, once at load.  "anticausal1d" (taps at
+    rows 0 .. k-1) is the data gradient of a causal convolution.
     """
     mode = split_mode(split)
-    w = weight.detach().float().cpu()
+    w = weight.detach().float()
+    if not on_device:
+        w = w.cpu()
     if kind == "linear":
         cout, cin = w.shape
         wt = w.reshape(cout, cin, 1)
         dh, dw = [0], [0]
-    elif kind in ("same1d", "causal1d"):
+    elif kind in ("same1d", "causal1d", "anticausal1d"):
         cout, cin, k = w.shape
         wt = w
         if kind == "same1d":
             if k % 2 != 1:
                 raise ValueError("same-padded conv1d needs an odd kernel")
             dh = [j - (k - 1) // 2 for j in range(k)]
+        elif kind == "anticausal1d":
+            dh = list(range(k))
         else:
             dh = [j - (k - 1) for j in range(k)]
         dw = [0] * k
@@ -195,11 +201,12 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, spl
         seg_w = [wt.to(torch.bfloat16)]
         a_coff = [0]
     nseg = len(seg_w)
-    wp = torch.zeros(cout_pad, nseg, taps, cpad, dtype=torch.float16 if mode == "f16x2" else torch.bfloat16)
+    wp = torch.zeros(cout_pad, nseg, taps, cpad, dtype=torch.float16 if mode == "f16x2" else torch.bfloat16,
+                     device=w.device)
     for s, ws in enumerate(seg_w):
         wp[:cout, s, :, :cin] = ws.permute(0, 2, 1)      # (cout, taps, cin)
     wp = wp.reshape(cout_pad, nseg * taps * cpad).contiguous()
-    b = None if bias is None else bias.detach().float().cpu().contiguous()
+    b = None if bias is None else bias.detach().float().to(w.device).contiguous()
     return PackedConv(wp, b, cin, cout, cout_pad, bn, taps, nseg, kchunks, dh, dw,
                       a_coff + [0] * (_lib.MQ_MAX_SEGS - len(a_coff)), mode != "bf16", mode=mode,
                       acc_scale=acc_scale)
@@ -435,6 +442,74 @@ def _split_terms_of(out_split: torch.Tensor) -> int:
     if not out_split.is_cuda or not out_split.is_contiguous():
         raise ValueError("out_split: expected a contiguous CUDA tensor")
     return nt
+
+
+# ---------------------------------------------------------------------------
+# training step: data and weight gradients of the convolutions
+# ---------------------------------------------------------------------------
+DGRAD_KIND = {"linear": "linear", "same1d": "same1d", "causal1d": "anticausal1d", "conv2d3": "conv2d3"}
+
+
+def dgrad_weight(weight: torch.Tensor, kind: str) -> Tuple[torch.Tensor, str]:
+    """The convolution whose forward pass is the data gradient of ``conv(x, weight)``: taps mirrored,
+    in/out channels swapped.  dx = conv(dy, w'), w'[ci, co, j'] = w[co, ci, k-1-j']; a causal
+    convolution (taps at rows -(k-1) .. 0, attentions.py:471-474) turns anti-causal (rows 0 .. k-1)."""
+    if kind == "linear":
+        return weight.t().contiguous(), "linear"
+    if kind in ("same1d", "causal1d"):
+        return weight.flip(2).transpose(0, 1).contiguous(), DGRAD_KIND[kind]
+    if kind == "conv2d3":
+        return weight.flip(2, 3).transpose(0, 1).contiguous(), "conv2d3"
+    raise ValueError(kind)
+
+
+def conv_taps(kind: str, wshape) -> Tuple[List[int], List[int]]:
+    """(tap_dh, tap_dw) of a convolution kind in the weight's own tap order (as pack_conv)."""
+    if kind == "linear":
+        return [0], [0]
+    if kind == "same1d":
+        k = wshape[2]
+        return [j - (k - 1) // 2 for j in range(k)], [0] * k
+    if kind == "causal1d":
+        k = wshape[2]
+        return [j - (k - 1) for j in range(k)], [0] * k
+    if kind == "conv2d3":
+        return [i - 1 for i in range(3) for _ in range(3)], [j - 1 for _ in range(3) for j in range(3)]
+    raise ValueError(kind)
+
+
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, N: int, H: int, W: int, cout: int, cin: int,
+               tap_dh: Sequence[int], tap_dw: Sequence[int], *, split: Optional[int] = None,
+               tag: str = "") -> torch.Tensor:
+    """Launch mq_conv_wgrad: dy bf16 (N,H,W,>=cout), x bf16 (N,H,W,>=cin) channel-last ->
+    fp32 (taps, cout, cin) = sum over pixels of dy[p, co] * x[p + tap, ci]."""
+    _chk(dy, torch.bfloat16, "dy")
+    _chk(x, torch.bfloat16, "x")
+    p = _lib.WgradParams()
+    p.dy, p.dy_ld = dy.data_ptr(), dy.shape[-1]
+    p.x, p.x_ld = x.data_ptr(), x.shape[-1]
+    if dy.numel() != N * H * W * p.dy_ld or x.numel() != N * H * W * p.x_ld:
+        raise ValueError("dy / x must hold N*H*W pixels")
+    p.N, p.H, p.W = N, H, W
+    p.cout, p.cin = cout, cin
+    taps = len(tap_dh)
+    p.taps = taps
+    for i in range(taps):
+        p.tap_dh[i] = tap_dh[i]
+        p.tap_dw[i] = tap_dw[i]
+    p.bh, p.bw = (64, 1) if W == 1 else (8, 8)
+    p.split = 1
+    if split is None:
+        split = _lib.lib().mq_conv_wgrad_split(C.byref(p))
+    p.split = max(1, int(split))
+    part = torch.empty(p.split, taps, cout, cin, dtype=torch.float32, device=dy.device)
+    p.dw = part.data_ptr()
+    meta = None
+    if _lib.profiler is not None:
+        fl = 2.0 * N * H * W * cout * cin * taps
+        meta = {"tag": tag, "flops": fl, "mma_flops": fl}
+    _lib.call("mq_conv_wgrad", C.byref(p), _stream(), meta=meta)
+    return part[0] if p.split == 1 else part.sum(dim=0)
 
 
 # ---------------------------------------------------------------------------
