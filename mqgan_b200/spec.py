@@ -224,3 +224,108 @@ def flops_per_frame(cfg: PreEncoderConfig) -> Dict[str, float]:
     ref += 2.0 * 9 * chs[0] * F
     ref += 2.0 * F * cfg.mel_channels
     return {"encode": enc, "decode_1d": dec, "refiner": ref, "total": enc + dec + ref}
+
+
+# ----------------------------------------------------------------------------
+# training step: discriminators and the reference's training hyper-parameters
+# ----------------------------------------------------------------------------
+@dataclass(frozen=True)
+class PatchDiscConfig:
+    """MelSpectrogramPatchDiscriminator2D (discriminators.py:70-190): ``len(hidden_channels)`` strided,
+    spectrally-normalised Conv2d layers over the (mel, time) plane plus a stride-1 logits conv, LeakyReLU(0.2)
+    after every conv, a masked squeeze-excite (reduction 8) in front of the last one."""
+    mel_channels: int
+    hidden_channels: Tuple[int, ...]
+    kernels: Tuple[Tuple[int, int], ...]     # (kh, kw) per conv, len(hidden_channels) + 1
+    strides: Tuple[Tuple[int, int], ...]     # (sh, sw) per conv; the logits conv always runs at stride 1
+
+    def __post_init__(self):
+        if len(self.kernels) != len(self.hidden_channels) + 1 or len(self.strides) != len(self.kernels):
+            raise ValueError("kernel_sizes / strides must have len(hidden_channels) + 1 entries")
+
+    @staticmethod
+    def from_patch_yaml(mel_channels: int, d: dict) -> "PatchDiscConfig":
+        """``discriminator_patch`` section of a reference model_config*.yaml (train.py:290-296)."""
+        return PatchDiscConfig(int(mel_channels), tuple(d["hidden_channels"]),
+                               tuple((int(k), int(k)) for k in d["kernel_sizes"]),
+                               tuple((int(s[0]), int(s[1])) for s in d["strides"]))
+
+    def conv_shapes(self) -> List[Shape]:
+        cin, out = 1, []
+        for c, (kh, kw) in zip(tuple(self.hidden_channels) + (1,), self.kernels):
+            out.append((c, cin, kh, kw))
+            cin = c
+        return out
+
+    def layer_stride(self, i: int) -> Tuple[int, int]:
+        return self.strides[i] if i < len(self.kernels) - 1 else (1, 1)
+
+    @property
+    def feature_layers(self) -> Tuple[bool, ...]:
+        """Which conv outputs feature matching uses (discriminators.py:108-112)."""
+        n = len(self.kernels)
+        return tuple(not (i in (0, 1) or i == n - 1) for i in range(n))
+
+
+@dataclass(frozen=True)
+class MultiBinConfig:
+    """MultiBinDiscriminator (discriminators.py:260-312): ``n_bins`` equal mel bands, one patch
+    discriminator each with (3, k) kernels, no stride on the first ``n_no_strides`` layers, then (1, 2)."""
+    mel_channels: int
+    n_bins: int
+    hidden_channels: Tuple[int, ...]
+    kernel_sizes: Tuple[int, ...]
+    n_no_strides: int = 2
+
+    @staticmethod
+    def from_yaml(mel_channels: int, d: dict) -> "MultiBinConfig":
+        return MultiBinConfig(int(mel_channels), int(d["n_bins"]), tuple(d["hidden_channels"]),
+                              tuple(int(k) for k in d["kernel_sizes"]), int(d.get("n_no_strides", 2)))
+
+    @property
+    def bin_config(self) -> PatchDiscConfig:
+        n = len(self.kernel_sizes)
+        return PatchDiscConfig(self.mel_channels // self.n_bins, tuple(self.hidden_channels),
+                               tuple((3, int(k)) for k in self.kernel_sizes),
+                               tuple((1, 1) if i < self.n_no_strides else (1, 2) for i in range(n)))
+
+
+def patch_disc_param_spec(dc: PatchDiscConfig, prefix: str = "") -> List[Tuple[str, Shape]]:
+    """(state-dict key, shape) of one patch discriminator: legacy ``spectral_norm`` keeps ``weight_orig``
+    as the parameter and ``weight_u`` / ``weight_v`` as buffers."""
+    s: List[Tuple[str, Shape]] = []
+    for i, w in enumerate(dc.conv_shapes()):
+        p = f"{prefix}convs.{i}"
+        s += [(p + ".bias", (w[0],)), (p + ".weight_orig", w), (p + ".weight_u", (w[0],)),
+              (p + ".weight_v", (w[1] * w[2] * w[3],))]
+    c = dc.hidden_channels[-1]
+    r = max(1, c // 8)
+    s += [(prefix + "se_block.fc1.weight", (r, c)), (prefix + "se_block.fc1.bias", (r,)),
+          (prefix + "se_block.fc2.weight", (c, r)), (prefix + "se_block.fc2.bias", (c,))]
+    return s
+
+
+def multibin_param_spec(mc: MultiBinConfig) -> List[Tuple[str, Shape]]:
+    s: List[Tuple[str, Shape]] = []
+    for b in range(mc.n_bins):
+        s += patch_disc_param_spec(mc.bin_config, f"discriminators.{b}.")
+    return s
+
+
+def is_disc_buffer(key: str) -> bool:
+    return key.endswith(".weight_u") or key.endswith(".weight_v")
+
+
+# training hyper-parameters of configs/model_config_hifispeech.yaml:31-48 (``training`` section)
+TRAIN_DEFAULTS = {
+    "lr": 1e-4, "beta1": 0.9, "beta2": 0.999, "lr_d_factor": 1.15, "d_beta1": 0.5, "d_beta2": 0.999,
+    "warmup_steps": 1000, "discriminator_train_start_epoch": 8, "use_fm_loss": False,
+    "loss_weights": {"fm_lambda": 0.25, "Gloss_lambda": 15.0, "recon_lambda": 15.0},
+}
+HIFISPEECH_PATCH_D = PatchDiscConfig(128, (256, 256, 384, 512, 512), ((5, 5), (5, 5), (5, 5), (3, 3), (3, 3), (3, 3)),
+                                     ((1, 2), (2, 2), (2, 2), (2, 1), (2, 1), (2, 1)))
+HIFISPEECH_MULTIBIN_D = MultiBinConfig(128, 8, (128, 128, 256, 256, 384), (7, 5, 3, 3, 3, 3), 2)
+# small discriminators of the same topology for the TINY generator
+TINY_PATCH_D = PatchDiscConfig(32, (16, 16, 32), ((5, 5), (5, 5), (3, 3), (3, 3)), ((1, 2), (2, 2), (2, 1), (1, 1)))
+TINY_MULTIBIN_D = MultiBinConfig(32, 2, (16, 16, 32), (7, 5, 3, 3), 2)
+TINY_TRAIN = dict(TRAIN_DEFAULTS, warmup_steps=4)

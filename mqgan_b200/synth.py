@@ -112,3 +112,27 @@ def recalibrate_q_in_proj(sd: Dict[str, torch.Tensor], latents: torch.Tensor,
     sd["q_in_proj.weight"] = w
     sd["q_in_proj.bias"] = b
     return w, b
+
+
+def synth_disc_state_dict(spec, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded state-dict for a discriminator from ``spec.patch_disc_param_spec`` / ``multibin_param_spec``:
+    conv weights ~ N(0, 0.02) as discriminators.py:193-198 initialises them, small non-zero biases (the
+    reference's zeros would leave the bias path untested), unit-norm spectral-norm vectors u and v, and
+    PyTorch-default uniform squeeze-excite linears."""
+    sd: Dict[str, torch.Tensor] = {}
+    shapes = dict(spec)
+    for key, shape in spec:
+        g = _gen("disc." + key, seed)
+        if key.endswith(".weight_orig"):
+            t = torch.randn(shape, generator=g) * 0.02
+        elif key.endswith(".weight_u") or key.endswith(".weight_v"):
+            t = torch.randn(shape, generator=g)
+            t = t / t.norm().clamp_min(1e-12)
+        elif key.endswith(".bias") and (key[: -len(".bias")] + ".weight_orig") in shapes:
+            t = torch.randn(shape, generator=g) * 0.01
+        else:
+            wshape = shapes[key[: -len(".bias")] + ".weight"] if key.endswith(".bias") else shape
+            bound = 1.0 / math.sqrt(max(wshape[1], 1))
+            t = (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
+        sd[key] = t
+    return sd
