@@ -359,6 +359,23 @@ typedef struct mq_wgrad_params {
 int mq_conv_wgrad_split(const mq_wgrad_params* p);
 int mq_conv_wgrad(const mq_wgrad_params* p, mq_stream_t stream);
 
+/* ---- f4 (training step): ConvBlock2D point-wise stage, forward and backward ---- */
+/*
+ * y[p] = bout + sum_k wout[k] * aptx(wpw[k]*s[p] + bpw[k]; 1, .5) at valid rows, bout at padded rows
+ * (preencoder.py:288-295 after the masked depth-wise conv :286-287), for s (rows, C) fp32 with one
+ * row_mask byte per row; parameters are DEVICE arrays [C] (bout: [1]) because they change every step.
+ * mq_cb2d_backward returns ds (rows, C) = dL/ds and per-block partial sums part[blocks][3][C] of
+ * (dL/dwpw, dL/dbpw, dL/dwout), blocks = mq_cb2d_grad_blocks(rows, C); dL/dbout = sum(dy) is the caller's.
+ * The (B, C, C, T) expansion autograd would keep alive in the reference (train.py:380-501 -> backward of
+ * preencoder.py:288-295) never exists.
+ */
+int mq_cb2d_point_forward(const float* s, const uint8_t* row_mask, int64_t rows, int C, const float* wpw,
+                          const float* bpw, const float* wout, const float* bout, float* y, mq_stream_t stream);
+int mq_cb2d_grad_blocks(int64_t rows, int C);
+int mq_cb2d_backward(const float* s, const float* dy, const uint8_t* row_mask, int64_t rows, int C,
+                     const float* wpw, const float* bpw, const float* wout, float* ds, float* part,
+                     mq_stream_t stream);
+
 /* ---- sequence mask (preencoder.py:15-24) ----------------------------------- */
 int mq_sequence_mask(const int64_t* lengths, int B, int T, uint8_t* mask, mq_stream_t stream);
 

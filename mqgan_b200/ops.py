@@ -512,6 +512,36 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, N: int, H: int, W: int, cout: 
     return part[0] if p.split == 1 else part.sum(dim=0)
 
 
+def cb2d_point_forward(s: torch.Tensor, wpw, bpw, wout, bout, row_mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """s (B, T, C) fp32 (masked depth-wise output) -> y (B, T, C): mq_cb2d_point_forward."""
+    _chk(s, torch.float32, "s")
+    Cc = s.shape[-1]
+    rows = s.numel() // Cc
+    prm = [_chk(t.detach().contiguous(), torch.float32, n) for t, n in ((wpw, "wpw"), (bpw, "bpw"), (wout, "wout"), (bout, "bout"))]
+    if row_mask is not None:
+        _chk(row_mask, torch.uint8, "row_mask")
+    y = torch.empty_like(s)
+    _lib.call("mq_cb2d_point_forward", s.data_ptr(), _ptr(row_mask), rows, Cc, prm[0].data_ptr(), prm[1].data_ptr(),
+              prm[2].data_ptr(), prm[3].data_ptr(), y.data_ptr(), _stream())
+    return y
+
+
+def cb2d_point_backward(s: torch.Tensor, dy: torch.Tensor, wpw, bpw, wout, row_mask: Optional[torch.Tensor]):
+    """-> (ds, dwpw, dbpw, dwout, dbout) for y = cb2d_point_forward(s, ...): mq_cb2d_backward (two launches)."""
+    _chk(s, torch.float32, "s")
+    _chk(dy, torch.float32, "dy")
+    Cc = s.shape[-1]
+    rows = s.numel() // Cc
+    prm = [_chk(t.detach().contiguous(), torch.float32, n) for t, n in ((wpw, "wpw"), (bpw, "bpw"), (wout, "wout"))]
+    nb = _lib.lib().mq_cb2d_grad_blocks(rows, Cc)
+    ds = torch.empty_like(s)
+    part = torch.empty(nb, 3, Cc, dtype=torch.float32, device=s.device)
+    _lib.call("mq_cb2d_backward", s.data_ptr(), dy.data_ptr(), _ptr(row_mask), rows, Cc, prm[0].data_ptr(),
+              prm[1].data_ptr(), prm[2].data_ptr(), ds.data_ptr(), part.data_ptr(), _stream())
+    g = part.sum(dim=0)
+    return ds, g[0], g[1], g[2], dy.sum().reshape(1)
+
+
 # ---------------------------------------------------------------------------
 # element-wise / reduction entry points
 # ---------------------------------------------------------------------------

@@ -1,0 +1,597 @@
+"""Training step of the PreEncoder on B200s (BASELINE configs[4]).
+
+Mirrors one iteration of the reference's loop - ``Trainer._train_epoch`` body (train.py:521-529):
+generator forward (preencoder.py:363-418), ``_train_discriminator`` (:380-412), ``_train_generator``
+(:414-501) - with the same losses (losses.py), discriminators (discriminators.py, legacy spectral norm),
+Adam + warm-up (train.py:312-329) and gradient clipping, as data-parallel replicas: one process per GPU,
+gradients averaged with NCCL all-reduces that are launched per bucket from autograd hooks while the
+backward pass is still running (the reference has no multi-GPU training to be compatible with).
+
+What runs where in this build (round 1 of the training variant):
+  * every wide convolution / linear of the generator - forward, data gradient and weight gradient - runs
+    in libmqgan_b200.so on tcgen05 (``mq_conv_gemm`` forward and, on the mirrored weight, data gradient;
+    ``mq_conv_wgrad`` weight gradient): bf16 operands, fp32 accumulate, fp32 activations between layers.
+    That is 99.7 % of the generator's FLOPs.
+  * ConvBlock2D `pre` / `post` run in ``mq_cb2d_point_forward`` and ``mq_cb2d_backward`` so the
+    (B, C, C, T) expansion of preencoder.py:288-295 never exists in memory, forward or backward.
+  * the remaining element-wise / reduction work (APTx, masks, CBAM, pooling, FSQ straight-through, the
+    1-channel stem / tail convolutions, the 4-wide quantiser projections), the discriminators (strided
+    Conv2d: cuDNN) and Adam are PyTorch ops under autograd for now; DESIGN.md 3.7 lists them as the next
+    kernels.
+There is no CPU path: tensors must live on a CUDA device and the shared library must be present.
+
+Dropout: the reference hard-wires p = 0.1 into parts of the generator regardless of its ``dropout``
+argument (preencoder.py:109, 121, 233).  This step implements ``dropout = 0`` only (what the parity
+fixtures pin); a non-zero ``dropout_p`` raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .spec import (MultiBinConfig, PatchDiscConfig, PreEncoderConfig, is_disc_buffer, multibin_param_spec,
+                   patch_disc_param_spec)
+
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------
+# convolutions on the tcgen05 kernels, differentiable
+# ----------------------------------------------------------------------------
+def _weight_from_taps(dw: Tensor, kind: str) -> Tensor:
+    """(taps, cout, cin) -> the weight's own shape."""
+    if kind == "linear":
+        return dw[0]
+    if kind in ("same1d", "causal1d"):
+        return dw.permute(1, 2, 0)
+    return dw.permute(1, 2, 0).reshape(dw.shape[1], dw.shape[2], 3, 3)
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = conv(x, w) + b on channel-last x (N, H, W, Cin); kind as ops.pack_conv."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, kind: str, tag: str):
+        N, H, W, cin = x.shape
+        cout = weight.shape[0]
+        xb = x.contiguous().to(torch.bfloat16)
+        pc = ops.pack_conv(weight, bias, kind, on_device=True)
+        out = torch.empty(N, H, W, cout, dtype=torch.float32, device=x.device)
+        ops.conv_gemm(xb, pc, N, H, W, out_f32=out, tag=tag)
+        ctx.save_for_backward(xb, weight)
+        ctx.kind, ctx.tag, ctx.has_bias = kind, tag, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight = ctx.saved_tensors
+        N, H, W, cin = xb.shape
+        cout = weight.shape[0]
+        dyb = dy.contiguous().to(torch.bfloat16)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wd, kd = ops.dgrad_weight(weight, ctx.kind)
+            dx = torch.empty(N, H, W, cin, dtype=torch.float32, device=dy.device)
+            ops.conv_gemm(dyb, ops.pack_conv(wd, None, kd, on_device=True), N, H, W, out_f32=dx, tag=ctx.tag + ".dgrad")
+        if ctx.needs_input_grad[1]:
+            dh, dwt = ops.conv_taps(ctx.kind, weight.shape)
+            dw = _weight_from_taps(ops.conv_wgrad(dyb, xb, N, H, W, cout, cin, dh, dwt, tag=ctx.tag + ".wgrad"), ctx.kind)
+            dw = dw.reshape(weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=(0, 1, 2))
+        return dx, dw, db, None, None
+
+
+def conv(x: Tensor, weight: Tensor, bias: Optional[Tensor], kind: str, tag: str = "") -> Tensor:
+    """Channel-last convolution / linear through the tcgen05 kernels.  x: (N, H, W, Cin) fp32."""
+    if not x.is_cuda:
+        raise RuntimeError("mqgan_b200.training runs on CUDA (B200) only - there is no CPU fallback")
+    if kind == "linear" and weight.dim() == 3:
+        weight = weight[:, :, 0]                                  # a 1x1 Conv1d (ResidualBlock1D.residual)
+    cout, cin = weight.shape[0], weight.shape[1]
+    pad_i, pad_o = (-cin) % 8, (-cout) % 8                        # TMA needs 16-byte channel pitches
+    if pad_i or pad_o:
+        x = F.pad(x, (0, pad_i)) if pad_i else x
+        weight = F.pad(weight, (0, 0) * (weight.dim() - 2) + (0, pad_i, 0, pad_o))
+        bias = F.pad(bias, (0, pad_o)) if (bias is not None and pad_o) else bias
+    y = _ConvFn.apply(x, weight, bias, kind, tag)
+    return y[..., :cout] if pad_o else y
+
+
+def aptx(x: Tensor, beta, gamma) -> Tensor:
+    """(1 + tanh(beta x)) * gamma * x (attentions.py:34-35)."""
+    return (1 + torch.tanh(beta * x)) * gamma * x
+
+
+# ----------------------------------------------------------------------------
+# ConvBlock2D `pre` / `post` (preencoder.py:277-301), never expanding to (B, C, C, T)
+# ----------------------------------------------------------------------------
+class _Cb2dPointFn(torch.autograd.Function):
+    """y[p] = sum_k wout_k * aptx(wpw_k * s[p] + bpw_k; 1, .5) + bout over valid rows, bout at padded rows."""
+
+    @staticmethod
+    def forward(ctx, s, wpw, bpw, wout, bout, row_mask):
+        B, T, Cc = s.shape
+        y = ops.cb2d_point_forward(s, wpw, bpw, wout, bout, row_mask)
+        ctx.save_for_backward(s, wpw, bpw, wout, row_mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, wpw, bpw, wout, row_mask = ctx.saved_tensors
+        ds, dwpw, dbpw, dwout, dbout = ops.cb2d_point_backward(s, dy.contiguous(), wpw, bpw, wout, row_mask)
+        return ds, dwpw, dbpw, dwout, dbout, None
+
+
+def convblock2d(x: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], prefix: str, native: bool = True) -> Tensor:
+    """x (B, T, C) -> (B, T, C).  The 5x5 depth-wise conv over the (channel, time) plane is a 25-tap torch
+    conv2d; the C-fold point-wise expansion + APTx + contraction is one fused kernel each way."""
+    B, T, Cc = x.shape
+    img = x.permute(0, 2, 1).unsqueeze(1)                                             # (B,1,C,T) view
+    s = F.conv2d(img, w[prefix + ".dw.weight"], w[prefix + ".dw.bias"], padding=2)   # :286
+    s = s.squeeze(1).permute(0, 2, 1).masked_fill(mask_bt.unsqueeze(-1), 0.0)        # (B,T,C) :287
+    wpw = w[prefix + ".pw.weight"].reshape(Cc)
+    bpw = w[prefix + ".pw.bias"].reshape(Cc)
+    wout = w[prefix + ".conv_out.weight"].reshape(Cc)
+    bout = w[prefix + ".conv_out.bias"].reshape(1)
+    if native:
+        return _Cb2dPointFn.apply(s.contiguous(), wpw, bpw, wout, bout, mask_bt.to(torch.uint8).contiguous())
+    # plain-torch form of the same arithmetic (memory-hungry; kept as the on-device cross-check)
+    u = (s.unsqueeze(-1) * wpw + bpw).masked_fill(mask_bt[:, :, None, None], 0.0)    # (B,T,C,K) :288-292
+    return (aptx(u, 1.0, 0.5) * wout).sum(dim=-1) + bout                             # :293-295
+
+
+# ----------------------------------------------------------------------------
+# generator, training mode (channel-last)
+# ----------------------------------------------------------------------------
+def effective_weights(params: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """Fold both weight-norm flavours differentiably (w = g v / ||v||)."""
+    out: Dict[str, Tensor] = {}
+    for k, t in params.items():
+        if k.endswith(".parametrizations.weight.original1"):
+            base = k[: -len(".parametrizations.weight.original1")]
+            out[base + ".weight"] = torch._weight_norm(t, params[base + ".parametrizations.weight.original0"], 0)
+        elif k.endswith(".weight_v"):
+            base = k[: -len(".weight_v")]
+            out[base + ".weight"] = torch._weight_norm(t, params[base + ".weight_g"], 0)
+        elif k.endswith("original0") or k.endswith(".weight_g"):
+            continue
+        else:
+            out[k] = t
+    return out
+
+
+def _cbam(o: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], prefix: str) -> Tensor:
+    """CBAM1D with the reference's effective masking (attentions.py:248-273, 322-365, 411)."""
+    mx = o.max(dim=1).values                                               # over ALL t
+    valid = (~mask_bt).to(o.dtype).unsqueeze(-1)
+    av = (o * valid).sum(dim=1) / valid.sum(dim=1).clamp(min=1.0)
+    p = prefix + ".channel_attention.mlp."
+
+    def mlp(v):
+        return F.linear(F.relu(F.linear(v, w[p + "0.weight"], w[p + "0.bias"])), w[p + "2.weight"], w[p + "2.bias"])
+
+    o1 = torch.sigmoid(mlp(mx) + mlp(av)).unsqueeze(1) * o
+    pooled = torch.stack((o1.max(dim=2).values, o1.mean(dim=2)), dim=1)   # (B,2,T)
+    logits = F.conv1d(pooled, w[prefix + ".spatial_attention.conv.weight"], None, padding=3)
+    return torch.sigmoid(logits).permute(0, 2, 1) * o1 + o
+
+
+def _residual_block(x: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], prefix: str, causal: bool) -> Tensor:
+    """ResidualBlock1D.forward (attentions.py:525-551), x (B, T, C)."""
+    B, T, _ = x.shape
+    beta, gamma = w[prefix + ".relu.beta"], w[prefix + ".relu.gamma"]
+    kind = "causal1d" if causal else "same1d"
+    m = mask_bt.unsqueeze(-1)
+    x4 = x.reshape(B, T, 1, -1)
+    if (prefix + ".residual.weight") in w:
+        r = conv(x4, w[prefix + ".residual.weight"], w[prefix + ".residual.bias"], "linear", prefix + ".res").reshape(B, T, -1)
+    else:
+        r = x
+    o = conv(x4, w[prefix + ".conv1.weight"], w[prefix + ".conv1.bias"], kind, prefix + ".conv1").reshape(B, T, -1)
+    o = aptx(o.masked_fill(m, 0.0), beta, gamma)
+    o = conv(o.reshape(B, T, 1, -1), w[prefix + ".conv2.weight"], w[prefix + ".conv2.bias"], kind, prefix + ".conv2").reshape(B, T, -1)
+    if not causal:
+        o = _cbam(o, mask_bt, w, prefix + ".cbam")
+    return aptx((o + r).masked_fill(m, 0.0), beta, gamma)
+
+
+def _conv2d_small(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """3x3 convolution with one input or one output channel (refiner stem / tail: 0.05 % of the FLOPs), cuDNN."""
+    return F.conv2d(x.permute(0, 3, 1, 2), weight, bias, padding=1).permute(0, 2, 3, 1)
+
+
+def _refiner_convblock(x: Tensor, m4: Tensor, w: Dict[str, Tensor], prefix: str) -> Tensor:
+    """ConvBlock.forward (preencoder.py:95-102), x (B, T', F, C), m4 (B, T', 1, 1)."""
+    x = x.masked_fill(m4, 0.0)
+    w1, w2 = w[prefix + ".conv1.weight"], w[prefix + ".conv2.weight"]
+    if w1.shape[1] % 8:
+        y = _conv2d_small(x, w1, w[prefix + ".conv1.bias"])
+    else:
+        y = conv(x, w1, w[prefix + ".conv1.bias"], "conv2d3", prefix + ".conv1")
+    y = aptx(y, 1.0, 0.5)
+    y = aptx(conv(y, w2, w[prefix + ".conv2.bias"], "conv2d3", prefix + ".conv2"), 1.0, 0.5)
+    if w1.shape[0] == w1.shape[1]:
+        y = y + x
+    return y.masked_fill(m4, 0.0)
+
+
+def _refiner(r_in: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], depth: int) -> Tensor:
+    """UNetRefiner.forward (preencoder.py:169-202).  r_in (B, T, F) -> residual (B, T, mel)."""
+    B, T, Fw = r_in.shape
+    mult = 1 << depth
+    pad = (mult - T % mult) % mult
+    x = F.pad(r_in, (0, 0, 0, pad)).unsqueeze(-1)                                  # (B, T8, F, 1)
+    m = F.pad(mask_bt, (0, pad), value=True)
+    cur = m
+    x = _refiner_convblock(x, cur[:, :, None, None], w, "refiner.pre")
+    skips: List[Tensor] = []
+    for i in range(depth):
+        skips.append(x)
+        Bq, Tq, Fq, Cq = x.shape
+        x = x.reshape(Bq, Tq // 2, 2, Fq, Cq).mean(dim=2)                           # AvgPool2d((2,1)) :112
+        cur = cur.reshape(B, -1, 2).any(dim=2)                                      # max-pooled mask :65
+        x = _refiner_convblock(x, cur[:, :, None, None], w, f"refiner.downs.{i}.conv")
+    x = _refiner_convblock(x, cur[:, :, None, None], w, "refiner.mid")
+    for i in range(depth):
+        x = torch.cat([x.repeat_interleave(2, dim=1), skips.pop()], dim=-1)         # Upsample((2,1)) + cat :124-129
+        cur = cur.repeat_interleave(2, dim=1)
+        x = _refiner_convblock(x, cur[:, :, None, None], w, f"refiner.ups.{i}.conv")
+    out = _conv2d_small(x.masked_fill(cur[:, :, None, None], 0.0), w["refiner.post.weight"], w["refiner.post.bias"])
+    out = out.squeeze(-1)[:, :T, :].masked_fill(mask_bt.unsqueeze(-1), 0.0)         # :192-198
+    return conv(out.reshape(B, T, 1, Fw), w["refiner.reproj.weight"], None, "linear", "refiner.reproj").reshape(B, T, -1)
+
+
+def fsq_quantize_ste(z: Tensor, levels: Sequence[int]) -> Tensor:
+    """FSQ.quantize in training mode, noise_dropout = 0 (quantizer.py:109-114, 128-140): fp32, straight-through round."""
+    lv = torch.tensor(list(levels), dtype=torch.int32, device=z.device)
+    half_l = ((lv - 1) * (1 + 1e-3) / 2).to(z.dtype)
+    offset = torch.where(lv % 2 == 0, 0.5, 0.0).to(z.dtype)
+    shift = (offset / half_l).atanh()
+    bounded = (z + shift).tanh() * half_l - offset
+    return (bounded + (bounded.round() - bounded).detach()) / (lv // 2)
+
+
+def generator_forward(params: Dict[str, Tensor], cfg: PreEncoderConfig, mel: Tensor, lengths: Tensor,
+                      native_cb2d: bool = True) -> Tuple[Tensor, Tensor]:
+    """PreEncoder.forward (preencoder.py:363-418), dropout 0 -> (x_recon, x_post), both (B, T, mel)."""
+    w = effective_weights(params)
+    B, T, n_mels = mel.shape
+    mask_bt = torch.arange(T, device=mel.device)[None, :] >= lengths.to(mel.device)[:, None]
+    x = conv(mel.reshape(B, T, 1, n_mels), w["proj.weight"], w["proj.bias"], "linear", "proj").reshape(B, T, -1)
+    x = convblock2d(x, mask_bt, w, "pre", native_cb2d)
+    for i in range(len(cfg.encoder_layers)):
+        x = _residual_block(x, mask_bt, w, f"encoder_blocks.{i}", causal=False)
+    z = F.linear(x, w["q_in_proj.weight"], w["q_in_proj.bias"])
+    codes = fsq_quantize_ste(z.float(), cfg.fsq_levels)
+    dec = F.linear(codes, w["q_out_proj.weight"], w["q_out_proj.bias"])
+    for i in range(len(cfg.decoder_layers)):
+        dec = _residual_block(dec, mask_bt, w, f"decoder_blocks.{i}", causal=True)
+    xr = convblock2d(dec, mask_bt, w, "post", native_cb2d)
+    x_recon = conv(xr.reshape(B, T, 1, -1), w["out_proj.weight"], w["out_proj.bias"], "linear", "out_proj").reshape(B, T, -1)
+    hid = conv(dec.reshape(B, T, 1, -1), w["hidden_proj.weight"], w["hidden_proj.bias"], "linear", "hidden_proj").reshape(B, T, -1)
+    r_in = torch.cat([x_recon, hid], dim=2).detach()                               # :411-413
+    return x_recon, x_recon + _refiner(r_in, mask_bt, w, cfg.refiner_depth)
+
+
+# ----------------------------------------------------------------------------
+# discriminators (discriminators.py), legacy spectral norm
+# ----------------------------------------------------------------------------
+def _spectral_weight(sd: Dict[str, Tensor], prefix: str, training: bool) -> Tensor:
+    """torch.nn.utils.spectral_norm: one in-place power iteration of (u, v) per training-mode forward, none
+    in eval; w = w_orig / (u . W v)."""
+    w_orig = sd[prefix + ".weight_orig"]
+    u, v = sd[prefix + ".weight_u"], sd[prefix + ".weight_v"]
+    wm = w_orig.reshape(w_orig.shape[0], -1)
+    if training:
+        with torch.no_grad():
+            v.copy_(F.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12))
+            u.copy_(F.normalize(torch.mv(wm, v), dim=0, eps=1e-12))
+        u, v = u.clone(), v.clone()
+    return w_orig / torch.dot(u, torch.mv(wm, v))
+
+
+def patch_discriminator(sd: Dict[str, Tensor], dc: PatchDiscConfig, x: Tensor, lengths: Tensor, training: bool,
+                        prefix: str = "", autocast_bf16: bool = False):
+    """MelSpectrogramPatchDiscriminator2D.forward (discriminators.py:208-257): x (B, T, F) ->
+    (logits (B,1,H,W), valid-patch mask, [(feature, padded mask)])."""
+    B, T, Fm = x.shape
+    n = len(dc.kernels)
+    pad_mask = (torch.arange(T, device=x.device)[None, :] >= lengths.to(x.device)[:, None])[:, None, None, :].expand(-1, 1, Fm, -1)
+    out = x.transpose(1, 2).unsqueeze(1)
+    feats = []
+    for i in range(n):
+        if i == n - 1:                                                              # masked squeeze-excite :10-67, :231-232
+            valid = ~pad_mask
+            denom = valid.sum(dim=(2, 3)).clamp(min=1)
+            sq = (out * valid).reshape(B, out.shape[1], -1).sum(dim=2) / denom
+            h = F.relu(F.linear(sq, sd[prefix + "se_block.fc1.weight"], sd[prefix + "se_block.fc1.bias"]))
+            ex = torch.sigmoid(F.linear(h, sd[prefix + "se_block.fc2.weight"], sd[prefix + "se_block.fc2.bias"]))
+            out = out * ex.reshape(B, -1, 1, 1)
+        kh, kw = dc.kernels[i]
+        sh, sw = dc.layer_stride(i)
+        wgt = _spectral_weight(sd, f"{prefix}convs.{i}", training)
+        # channels_last on purpose: in NCHW / bf16 cuDNN's heuristic sends the data gradient of the (1, 2)-strided
+        # 256 -> 384 multi-bin layer to dgrad2d_grouped_direct_kernel - 9.1 ms per call instead of 0.27 ms, 2/3 of the
+        # whole step (tools/disc_conv_probe.py, profiles/disc_conv_probe_r01.log)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast_bf16):
+            y = F.conv2d(out.contiguous(memory_format=torch.channels_last), wgt.contiguous(memory_format=torch.channels_last),
+                         sd[f"{prefix}convs.{i}.bias"], stride=(sh, sw), padding=((kh - 1) // 2, (kw - 1) // 2))
+        out = F.leaky_relu(y.float(), 0.2)
+        if sh > 1 or sw > 1:
+            pad_mask = F.max_pool2d(pad_mask.float(), kernel_size=(sh, sw), stride=(sh, sw), ceil_mode=True).bool()
+        out = out.masked_fill(pad_mask, 0.0)
+        if dc.feature_layers[i]:
+            feats.append((out, pad_mask))
+    return out, ~pad_mask, feats
+
+
+def multibin_discriminator(sd: Dict[str, Tensor], mc: MultiBinConfig, x: Tensor, lengths: Tensor, training: bool,
+                           autocast_bf16: bool = False):
+    """MultiBinDiscriminator.forward (discriminators.py:292-312)."""
+    outs, masks, feats = [], [], []
+    for b, sub in enumerate(torch.split(x, x.size(-1) // mc.n_bins, dim=-1)):
+        o, m, f = patch_discriminator(sd, mc.bin_config, sub, lengths, training, f"discriminators.{b}.", autocast_bf16)
+        outs.append(o); masks.append(m); feats.append(f)
+    return outs, masks, feats
+
+
+# ----------------------------------------------------------------------------
+# losses (losses.py, train.py:38-45)
+# ----------------------------------------------------------------------------
+def masked_mse(pred: Tensor, target: float, mask: Tensor) -> Tensor:
+    """LSGANLoss._masked_mse (losses.py:21-35), mask True = valid; no host sync: an empty mask gives 0."""
+    m = mask.to(pred.dtype)
+    valid = m.sum()
+    return torch.where(valid > 0, (((pred - target) ** 2) * m).sum() / valid.clamp(min=1), pred.new_zeros(()))
+
+
+def masked_mel_loss(x: Tensor, y: Tensor, lengths: Tensor, group_size: int) -> Tensor:
+    """MaskedMelLoss("mse", group_size) (losses.py:148-182)."""
+    B, T, Cc = x.shape
+    G = Cc // group_size
+    pad = (torch.arange(T, device=x.device)[None, :] >= lengths.to(x.device)[:, None])[:, :, None].expand(B, T, Cc)
+    pad = pad.reshape(B, T, G, group_size)
+    per = ((x - y) ** 2).reshape(B, T, G, group_size).masked_fill(pad, 0.0)
+    return (per.sum(dim=[0, 1, 3]) / ((~pad).to(x.dtype).sum(dim=[0, 1, 3]) + 1e-12)).mean()
+
+
+def masked_mae(pred: Tensor, target: Tensor, mask: Tensor, eps: float = 1e-8) -> Tensor:
+    """train.py:38-45, mask True = padded."""
+    mask = mask.expand_as(pred)
+    return (pred - target).abs().masked_fill(mask, 0.0).sum() / ((~mask).sum() + eps)
+
+
+class LeCam:
+    """EMA anchors of LSGANLoss (losses.py:17-20, 37-79).  Under data parallelism the batch means are
+    averaged over the replicas before they enter the EMA, so every replica carries the same anchors."""
+
+    def __init__(self, device, decay: float = 0.99, group=None):
+        self.decay, self.group = decay, group
+        self.ema = torch.zeros(2, device=device)          # [real, fake]
+        self.initialized = False
+
+    def d_loss(self, real: Tensor, fake: Tensor, real_mask: Tensor, fake_mask: Tensor) -> Tensor:
+        """LSGANLoss.discriminator_loss (losses.py:81-107): the EMA moves first, then LeCam reads it."""
+        loss = 0.5 * (masked_mse(real, 1.0, real_mask) + masked_mse(fake, 0.0, fake_mask))
+        rm, fm = real_mask.to(real.dtype), fake_mask.to(fake.dtype)
+        means = torch.stack(((real * rm).sum() / rm.sum().clamp(min=1), (fake * fm).sum() / fm.sum().clamp(min=1))).detach()
+        if self.group is not None or (torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1):
+            torch.distributed.all_reduce(means, group=self.group)
+            means = means / torch.distributed.get_world_size(self.group)
+        if not self.initialized:
+            self.ema, self.initialized = means.clone(), True
+        else:
+            self.ema = self.ema * self.decay + (1 - self.decay) * means
+        term_r = (((real - self.ema[1]).clamp(min=0) * rm) ** 2).sum() / rm.sum().clamp(min=1)
+        term_f = (((self.ema[0] - fake).clamp(min=0) * fm) ** 2).sum() / fm.sum().clamp(min=1)
+        return loss + term_r + term_f
+
+
+# ----------------------------------------------------------------------------
+# gradient all-reduce, bucketed and overlapped with the backward pass
+# ----------------------------------------------------------------------------
+class GradBucketReducer:
+    """Flat gradient buckets whose all-reduce (average) starts as soon as the last gradient of the bucket
+    has been accumulated, while autograd is still producing the others (NCCL runs on its own stream).
+
+    Parameters keep ``.grad`` as VIEWS into the bucket, so nothing is copied either way; ``zero()`` clears
+    the buckets instead of ``optimizer.zero_grad()``.  Buckets are filled in reverse registration order
+    (gradients arrive roughly last-layer-first).  With world size 1 (or no process group) it only provides
+    the flat buffers.  Parameters that receive no gradient in a step (hidden_proj, preencoder.py:411-413)
+    would stall their bucket, so ``finish()`` launches whatever has not been launched."""
+
+    def __init__(self, params: Sequence[Tensor], bucket_bytes: int = 25 << 20, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = torch.distributed.get_world_size(group) if torch.distributed.is_initialized() else 1
+        self.buckets: List[Tensor] = []
+        self._bucket_of: Dict[int, int] = {}
+        self._pending: List[int] = []
+        self._count: List[int] = []
+        self._launched: List[bool] = []
+        self._handles = []
+        cur: List[Tensor] = []
+        size = 0
+        groups: List[List[Tensor]] = []
+        for p in reversed(self.params):
+            if cur and (size + p.numel()) * 4 > bucket_bytes:
+                groups.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += p.numel()
+        if cur:
+            groups.append(cur)
+        for bi, g in enumerate(groups):
+            flat = torch.zeros(sum(p.numel() for p in g), dtype=torch.float32, device=g[0].device)
+            off = 0
+            for p in g:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._bucket_of[id(p)] = bi
+                if self.world > 1:
+                    p.register_post_accumulate_grad_hook(self._hook)
+            self.buckets.append(flat)
+            self._count.append(len(g))
+        self.zero()
+
+    def zero(self):
+        for b in self.buckets:
+            b.zero_()
+        self._pending = list(self._count)
+        self._launched = [False] * len(self.buckets)
+        self._handles = []
+
+    def _launch(self, bi: int):
+        self._launched[bi] = True
+        self._handles.append(torch.distributed.all_reduce(self.buckets[bi], group=self.group, async_op=True))
+
+    def _hook(self, p: Tensor):
+        bi = self._bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and not self._launched[bi]:
+            self._launch(bi)
+
+    def finish(self):
+        """Wait for every bucket's all-reduce and turn the sums into averages."""
+        if self.world <= 1:
+            return
+        for bi in range(len(self.buckets)):
+            if not self._launched[bi]:
+                self._launch(bi)
+        for h in self._handles:
+            h.wait()
+        for b in self.buckets:
+            b.div_(self.world)
+
+
+# ----------------------------------------------------------------------------
+# the step
+# ----------------------------------------------------------------------------
+class TrainStep:
+    """One replica of the reference's training iteration.
+
+    ``g_sd`` / ``pd_sd`` / ``mb_sd``: state-dicts with the reference's key names (generator; patch and
+    multi-bin discriminators incl. the spectral-norm ``weight_u`` / ``weight_v`` buffers).  ``tcfg``: the
+    ``training`` section of a reference model_config*.yaml.  Call ``step(real, lengths)`` per batch; it returns
+    the dict of losses the reference logs (train.py:494-500, plus ``loss_d``)."""
+
+    def __init__(self, cfg: PreEncoderConfig, pd_cfg: PatchDiscConfig, mb_cfg: MultiBinConfig, g_sd, pd_sd, mb_sd,
+                 tcfg: dict, device, dropout_p: float = 0.0, d_autocast_bf16: bool = False, native_cb2d: bool = True,
+                 group=None):
+        if dropout_p != 0.0:
+            raise NotImplementedError("mqgan_b200.training implements dropout = 0 only (see module docstring)")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("mqgan_b200.training runs on CUDA (B200) only - there is no CPU fallback")
+        ops._lib.lib()                                    # fail now if the extension is missing
+        self.cfg, self.pd_cfg, self.mb_cfg, self.tcfg = cfg, pd_cfg, mb_cfg, tcfg
+        self.device, self.group = dev, group
+        self.d_autocast_bf16, self.native_cb2d = d_autocast_bf16, native_cb2d
+        self.g = {k: v.detach().clone().float().to(dev).requires_grad_(True) for k, v in g_sd.items()}
+        self.pd = {k: v.detach().clone().float().to(dev) for k, v in pd_sd.items()}
+        self.mb = {k: v.detach().clone().float().to(dev) for k, v in mb_sd.items()}
+        for sd in (self.pd, self.mb):
+            for k, v in sd.items():
+                if not is_disc_buffer(k):
+                    v.requires_grad_(True)
+        self.d_training = True
+        self.lecam = LeCam(dev, group=group)
+        t = tcfg
+        fused = True
+        self.opt_g = torch.optim.Adam(list(self.g.values()), lr=t["lr"], betas=(t["beta1"], t["beta2"]), fused=fused)
+        self.opt_d = torch.optim.Adam(self.d_params(), lr=t["lr"] * t["lr_d_factor"], betas=(t["d_beta1"], t["d_beta2"]),
+                                      fused=fused)
+        self.sched_g = torch.optim.lr_scheduler.LambdaLR(self.opt_g, lambda s: min((s + 1) / t["warmup_steps"], 1.0))
+        self.red_g = GradBucketReducer(list(self.g.values()), group=group)
+        self.red_d = GradBucketReducer(self.d_params(), group=group)
+
+    def d_params(self) -> List[Tensor]:
+        return [v for sd in (self.pd, self.mb) for v in sd.values() if v.requires_grad]
+
+    def start_epoch(self):
+        """train.py:504-506: the discriminators go back to training mode (power iteration on) each epoch."""
+        self.d_training = True
+
+    def generator_state_dict(self) -> Dict[str, Tensor]:
+        return {k: v.detach() for k, v in self.g.items()}
+
+    def step(self, real: Tensor, lengths: Tensor, gan: bool = True, use_fm: Optional[bool] = None) -> Dict[str, Tensor]:
+        """train.py:521-529 for one batch.  ``gan``: epoch >= discriminator_train_start_epoch.  Losses are
+        returned as 0-d device tensors (one host read at the caller's discretion)."""
+        t = self.tcfg
+        clip = t.get("clip_grad_norm", 1.0)
+        lw = t["loss_weights"]
+        use_fm = t.get("use_fm_loss", False) if use_fm is None else use_fm
+        real = real.to(self.device, non_blocking=True)
+        lengths = lengths.to(self.device, non_blocking=True)
+        ac = self.d_autocast_bf16
+        recon_pre, recon_post = generator_forward(self.g, self.cfg, real, lengths, self.native_cb2d)
+        out: Dict[str, Tensor] = {"loss_d": real.new_zeros(())}
+        if gan:                                                                     # _train_discriminator
+            self.red_d.zero()
+            fake = recon_post.detach()
+            rl, rm, _ = patch_discriminator(self.pd, self.pd_cfg, real, lengths, self.d_training, autocast_bf16=ac)
+            fl, fm, _ = patch_discriminator(self.pd, self.pd_cfg, fake, lengths, self.d_training, autocast_bf16=ac)
+            loss_d = self.lecam.d_loss(rl, fl, rm, fm)
+            rl2, rm2, _ = multibin_discriminator(self.mb, self.mb_cfg, real, lengths, self.d_training, ac)
+            fl2, fm2, _ = multibin_discriminator(self.mb, self.mb_cfg, fake, lengths, self.d_training, ac)
+            loss_d = loss_d + sum(self.lecam.d_loss(r, f, rm2[0], fm2[0]) for r, f in zip(rl2, fl2)) / len(rl2)
+            loss_d.backward()
+            self.red_d.finish()
+            if clip:
+                torch.nn.utils.clip_grad_norm_(self.d_params(), clip)
+            self.opt_d.step()
+            out["loss_d"] = loss_d.detach()
+        # _train_generator
+        self.red_g.zero()
+        self.d_training = False                                                     # train.py:417-418
+        d_all = self.d_params_all()
+        for p in d_all:                                                             # D is only a loss here: skip its weight gradients
+            p.requires_grad_(False)
+        try:
+            mel = lambda a, g: masked_mel_loss(a, real, lengths, g)
+            loss_recon_pre = mel(recon_pre, 1) + 0.25 * mel(recon_pre, 16)
+            loss_recon_post = mel(recon_post, 1) + 0.25 * mel(recon_post, 16)
+            loss_gan = real.new_zeros(())
+            loss_fm = real.new_zeros(())
+            gl_lambda = fm_lambda = 0.0
+            if gan:
+                gl, gm, gf = patch_discriminator(self.pd, self.pd_cfg, recon_post, lengths, False, autocast_bf16=ac)
+                gl2, gm2, gf2 = multibin_discriminator(self.mb, self.mb_cfg, recon_post, lengths, False, ac)
+                loss_gan = 0.5 * (masked_mse(gl, 1.0, gm) + sum(masked_mse(g, 1.0, gm2[0]) for g in gl2) / len(gl2))
+                gl_lambda, fm_lambda = lw["Gloss_lambda"], lw["fm_lambda"]
+                if use_fm:                                                          # train.py:454-476
+                    with torch.no_grad():
+                        _, _, rf = patch_discriminator(self.pd, self.pd_cfg, real, lengths, False, autocast_bf16=ac)
+                        _, _, rf2 = multibin_discriminator(self.mb, self.mb_cfg, real, lengths, False, ac)
+                    fm_d1 = sum(masked_mae(ff, r, m) for (r, m), (ff, _) in zip(rf, gf)) / max(len(rf), 1)
+                    fm_mbd = real.new_zeros(())
+                    for rfe, gfe in zip(rf2, gf2):                                  # the reference's running division :466-472
+                        for (r, m), (ff, _) in zip(rfe, gfe):
+                            fm_mbd = fm_mbd + masked_mae(ff, r, m)
+                        if len(rfe) > 0:
+                            fm_mbd = fm_mbd / len(rfe)
+                    loss_fm = 0.5 * (fm_d1 + fm_mbd / max(len(gf2), 1))
+            total = (loss_recon_pre * lw.get("recon_lambda_pre", 1.0) + loss_recon_post * lw.get("recon_lambda_post", 2.0)
+                     + loss_gan * gl_lambda + loss_fm * fm_lambda)
+            total.backward()
+        finally:
+            for p in d_all:
+                p.requires_grad_(True)
+        self.red_g.finish()
+        if clip:
+            torch.nn.utils.clip_grad_norm_(list(self.g.values()), clip)
+        self.opt_g.step()
+        self.sched_g.step()
+        out.update(loss_g_total=total.detach(), loss_recon_pre=loss_recon_pre.detach(),
+                   loss_recon_post=loss_recon_post.detach(), loss_gan=loss_gan.detach(), loss_fm=loss_fm.detach())
+        self.last_recon = (recon_pre.detach(), recon_post.detach())
+        return out
+
+    def d_params_all(self) -> List[Tensor]:
+        return [v for sd in (self.pd, self.mb) for k, v in sd.items() if not is_disc_buffer(k)]

@@ -67,6 +67,14 @@ def main():
     pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=3)
     mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=4)
 
+    # with default init every frame quantises to one code (all codes 0 -> q_out_proj sees no gradient);
+    # recalibrate q_in_proj on the reference's own latents so the codes vary.  Stored in the fixture.
+    from oracle.make_golden import build_reference_model, reference_latents
+    from mqgan_b200.synth import recalibrate_q_in_proj
+    import preencoder as ref_pre
+    z0, _ = reference_latents(build_reference_model(ref_pre, cfg, g_sd), synth_mels(4, 96, cfg.mel_channels, seed=100), None)
+    recalibrate_q_in_proj(g_sd, z0)
+
     gen = T_.MVQGenerator(cfg.mel_channels, list(cfg.channels), list(cfg.kernel_sizes), fsq_levels=list(cfg.fsq_levels),
                           dropout=0.0, refiner_base_channels=cfg.refiner_base_channels, refiner_depth=cfg.refiner_depth,
                           refiner_hidden_proj_divisor=cfg.refiner_hidden_proj_divisor)
@@ -158,6 +166,7 @@ def main():
               f"u diff {float((st.pd['convs.1.weight_u'] - dsd_now['pd:convs.1.weight_u']).abs().max()):.3e}")
 
     out["B"], out["T"] = np.array(B), np.array(T)
+    out["qin_w"], out["qin_b"] = g_sd["q_in_proj.weight"].numpy(), g_sd["q_in_proj.bias"].numpy()
     out["g_keys"] = np.array(list(g_sd))
     out["d_keys"] = np.array(["pd:" + k for k in pd_sd] + ["mb:" + k for k in mb_sd])
     path = os.path.join(REPO, "tests", "golden", "train_tiny.npz")

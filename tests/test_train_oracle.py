@@ -16,6 +16,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tra
 def tiny_train_state():
     cfg, pdc, mbc = S.TINY, S.TINY_PATCH_D, S.TINY_MULTIBIN_D
     g_sd = synth_state_dict(cfg, seed=3)
+    fx = np.load(GOLDEN)
+    g_sd["q_in_proj.weight"] = torch.from_numpy(fx["qin_w"]).clone()      # calibrated on the reference's latents
+    g_sd["q_in_proj.bias"] = torch.from_numpy(fx["qin_b"]).clone()
     pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=3)
     mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=4)
     return cfg, pdc, mbc, g_sd, pd_sd, mb_sd

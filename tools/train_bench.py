@@ -1,0 +1,264 @@
+"""Training-step benchmark (BASELINE configs[4]: hifispeech PreEncoder, fwd + bwd + discriminators, gradient
+all-reduce over NVLink at N B200s).  One "step" is one iteration of the reference's loop (train.py:521-529):
+generator forward, discriminator step, generator step, both Adam updates.
+
+    python tools/train_bench.py [--steps K --warmup W --batch 16 --frames 256 --layers out.md]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/train_bench.py --gpus N ...
+    python tools/train_bench.py --impl reference      # the CPU oracle port of the same step, bounded sample
+
+Prints one JSON line (same keys as bench.py).  ``value`` = mel frames trained per second over all ranks with
+the batch resident in HBM; ``e2e`` = the same through TrainStep.step() from pinned host buffers with the H2D
+copy and a D2H read of the logged losses inside the timed region.  ``roofline`` is the aggregate of the
+library's tcgen05 launches (forward, data-gradient and weight-gradient convolutions) measured with CUDA events
+in one instrumented step; ``native_share_of_step`` says how much of the step they are - the rest is PyTorch
+element-wise work, cuDNN discriminators and Adam (mqgan_b200/training.py docstring).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from mqgan_b200 import spec as S
+from mqgan_b200.synth import synth_disc_state_dict, synth_mels, synth_state_dict
+
+METRIC = "mel frames/sec trained (G fwd+bwd, D step, G step, Adam)"
+
+
+def train_flops_per_frame(cfg, pdc, mbc, frames):
+    """Algorithmic FLOPs of one iteration per mel frame: generator forward + data and weight gradients
+    (3x forward; the refiner's first conv and hidden_proj need no data gradient - negligible), discriminators:
+    3 forward passes (real, fake, fake-for-G), weight+data gradients for the two D-step passes, data gradient
+    for the G-step pass."""
+    g = S.flops_per_frame(cfg)["total"]
+
+    def disc(dc, mel):
+        fl, h, w = 0.0, mel, frames
+        for i, (co, ci, kh, kw) in enumerate(dc.conv_shapes()):
+            sh, sw = dc.layer_stride(i)
+            h, w = -(-h // sh), -(-w // sw)
+            fl += 2.0 * co * ci * kh * kw * h * w
+        return fl / frames
+    d = disc(pdc, pdc.mel_channels) + mbc.n_bins * disc(mbc.bin_config, mbc.mel_channels // mbc.n_bins)
+    return {"generator_fwd": g, "disc_fwd": d, "step": 3.0 * g + d * (3 + 2 * 2 + 1)}
+
+
+def clocks_sampler(stop, out):
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("LOCAL_RANK", "0")))
+        out["max"] = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not stop.is_set():
+            out["mhz"].append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for bit, n in names.items():
+                if r & bit:
+                    out["reasons"].add(n)
+            time.sleep(0.05)
+    except Exception as e:                                          # pragma: no cover
+        out["error"] = repr(e)
+
+
+def run_reference(args):
+    """The CPU oracle port of the step on a bounded sample (the Python reference cannot travel to the GPU box)."""
+    from oracle import train_oracle as TO
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg, pdc, mbc = S.HIFISPEECH, S.HIFISPEECH_PATCH_D, S.HIFISPEECH_MULTIBIN_D
+    B, T = args.ref_batch, args.ref_frames
+    st = TO.TrainState(cfg, synth_state_dict(cfg, 0), synth_disc_state_dict(S.patch_disc_param_spec(pdc), 1),
+                       synth_disc_state_dict(S.multibin_param_spec(mbc), 2),
+                       TO.patch_cfg([k[0] for k in pdc.kernels], pdc.strides),
+                       TO.multibin_cfg(mbc.kernel_sizes, mbc.n_bins, mbc.n_no_strides), dict(S.TRAIN_DEFAULTS))
+    real = synth_mels(B, T, cfg.mel_channels, seed=7)
+    lens = torch.full((B,), T, dtype=torch.long)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        TO.train_iteration(st, real, lens, gan=True, use_fm=False)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    v = B * T / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "hifispeech_train_16x256", "sample": f"{B}x{T} frames per step on host CPU", "device": "cpu"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{B} utterances x {T} frames, oracle/train_oracle.py, torch {torch.__version__} CPU"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ref_batch", type=int, default=1)
+    ap.add_argument("--ref_frames", type=int, default=64)
+    ap.add_argument("--d_fp32", action="store_true", help="discriminator convs in fp32 instead of bf16 autocast")
+    ap.add_argument("--torch_cb2d", action="store_true", help="ConvBlock2D through plain torch ops (cross-check)")
+    ap.add_argument("--layers", default=None, help="write the per-kernel table of one instrumented step here")
+    ap.add_argument("--cpu_baseline", action="store_true", help="also time the CPU oracle port on a bounded sample")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+    import torch.distributed as dist
+    from mqgan_b200 import _lib
+    from mqgan_b200 import training as TR
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, pdc, mbc = S.HIFISPEECH, S.HIFISPEECH_PATCH_D, S.HIFISPEECH_MULTIBIN_D
+    B, T = args.batch, args.frames
+    ts = TR.TrainStep(cfg, pdc, mbc, synth_state_dict(cfg, 0), synth_disc_state_dict(S.patch_disc_param_spec(pdc), 1),
+                      synth_disc_state_dict(S.multibin_param_spec(mbc), 2), dict(S.TRAIN_DEFAULTS), dev,
+                      d_autocast_bf16=not args.d_fp32, native_cb2d=not args.torch_cb2d)
+    nbuf = 4
+    host = [synth_mels(B, T, cfg.mel_channels, seed=100 * rank + i).pin_memory() for i in range(nbuf)]
+    lens_h = torch.full((B,), T, dtype=torch.long).pin_memory()
+    resident = [h.to(dev) for h in host]
+    lens_d = lens_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    losses = {}
+
+    def step_resident(i):
+        ts.step(resident[i % nbuf], lens_d)
+
+    def step_e2e(i):
+        o = ts.step(host[i % nbuf], lens_h)
+        vals = torch.stack([o[k] for k in ("loss_d", "loss_g_total", "loss_recon_pre", "loss_recon_post", "loss_gan", "loss_fm")])
+        losses["last"] = vals.cpu().tolist()                        # D2H read of the logged losses
+
+    for i in range(args.warmup):
+        step_resident(i)
+    n0 = _lib.launch_count
+    clk = {"mhz": [], "reasons": set()}
+    stop = threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(stop, clk), daemon=True)
+    th.start()
+    ms = timed(step_resident, args.steps)
+    launches = (_lib.launch_count - n0) // args.steps
+    ms_e2e = timed(step_e2e, args.steps)
+    stop.set()
+    th.join(timeout=1.0)
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    # one instrumented step: CUDA events around every library launch on the launching stream
+    _lib.profiler = _lib.LaunchProfiler()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    step_resident(0)
+    e1.record()
+    rows = _lib.profiler.summary()
+    _lib.profiler = None
+    step_ms_prof = e0.elapsed_time(e1)
+    conv_ms = sum(r[3] for r in rows if r[0] in ("mq_conv_gemm", "mq_conv_wgrad"))
+    conv_fl = sum(r[4] for r in rows if r[0] in ("mq_conv_gemm", "mq_conv_wgrad"))
+    lib_ms = sum(r[3] for r in rows)
+    by_kind = {}
+    for name, tag, n, tms, fl, _ in rows:
+        kind = "wgrad" if name == "mq_conv_wgrad" else ("dgrad" if tag.endswith(".dgrad") else ("fwd" if name == "mq_conv_gemm" else name))
+        a = by_kind.setdefault(kind, [0, 0.0, 0.0])
+        a[0] += n; a[1] += tms; a[2] += fl
+    if args.layers and rank == 0:
+        with open(args.layers, "w") as f:
+            f.write(f"# library launches of one training step, hifispeech {B}x{T}, CUDA events on the launching stream\n\n")
+            f.write("| entry point | layer | launches | ms | algorithmic TFLOP/s |\n|---|---|---|---|---|\n")
+            for name, tag, n, tms, fl, _ in sorted(rows, key=lambda r: -r[3]):
+                f.write(f"| {name} | {tag} | {n} | {tms:.3f} | {fl / tms / 1e9 if fl else 0:.1f} |\n")
+            f.write(f"\nlibrary total {lib_ms:.2f} ms of a {step_ms_prof:.2f} ms instrumented step ({ms:.2f} ms uninstrumented)\n")
+            for k, a in by_kind.items():
+                f.write(f"\n{k}: {a[0]} launches, {a[1]:.3f} ms, {a[2] / a[1] / 1e9 if a[2] else 0:.1f} TFLOP/s")
+            f.write("\n")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_dense_tflops_sustained", 1402.6))) if isinstance(peaks, dict) else 1402.6
+    fl = train_flops_per_frame(cfg, pdc, mbc, T)
+    frames = B * T * world
+    if rank == 0:
+        mhz = sorted(clk["mhz"])
+        line = {
+            "metric": METRIC, "value": frames / ms * 1e3, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"hifispeech_train_{B}x{T}", "model": "hifispeech", "batch_per_gpu": B, "frames": T,
+                       "precision": "generator conv operands bf16 (fwd, dgrad, wgrad), fp32 accumulate and activations; "
+                                    + ("discriminator convs fp32" if args.d_fp32 else "discriminator convs bf16 autocast (train.py:523)"),
+                       "weights": "random-init (seed 0/1/2)", "dropout": 0.0,
+                       "l2": "activations saved for backward exceed L2 (GBs per step)",
+                       "parallelism": f"data-parallel replicas x{world}, bucketed NCCL gradient all-reduce overlapped with backward"
+                       if world > 1 else "single replica"},
+            "e2e": {"value": frames / ms_e2e * 1e3, "unit": "frames/s", "h2d_bytes_per_step": host[0].numel() * 4 + lens_h.numel() * 8,
+                    "d2h_bytes_per_step": 6 * 4, "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "clocks": {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": clk.get("max"), "samples": len(mhz),
+                       "reasons": sorted(clk["reasons"])},
+            "roofline": {"bound": "tensor", "kernel": "conv_gemm / conv_pair / conv_wgrad kernels (tcgen05), all launches of one step",
+                         "achieved": conv_fl / conv_ms / 1e9 if conv_ms else None, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (conv_fl / conv_ms / 1e9 / peak) if conv_ms else None, "peak_source": "measured bf16 sustained",
+                         "traffic": None, "share_of_step": conv_ms / step_ms_prof,
+                         "by_kind": {k: {"launches": a[0], "ms": a[1], "tflops": a[2] / a[1] / 1e9 if a[2] else None} for k, a in by_kind.items()}},
+            "native_share_of_step": lib_ms / step_ms_prof,
+            "step_tflops_algorithmic": fl["step"] * B * T / ms / 1e9,
+            "flops_per_frame": fl, "peak_mem_gib": peak_mem, "losses_last": losses.get("last"),
+        }
+        if args.cpu_baseline:
+            from oracle import train_oracle as TO
+            torch.set_num_threads(os.cpu_count() or 1)
+            st = TO.TrainState(cfg, synth_state_dict(cfg, 0), synth_disc_state_dict(S.patch_disc_param_spec(pdc), 1),
+                               synth_disc_state_dict(S.multibin_param_spec(mbc), 2),
+                               TO.patch_cfg([k[0] for k in pdc.kernels], pdc.strides),
+                               TO.multibin_cfg(mbc.kernel_sizes, mbc.n_bins, mbc.n_no_strides), dict(S.TRAIN_DEFAULTS))
+            rb, rt = args.ref_batch, args.ref_frames
+            real = synth_mels(rb, rt, cfg.mel_channels, seed=7)
+            t0 = time.perf_counter()
+            TO.train_iteration(st, real, torch.full((rb,), rt, dtype=torch.long), gan=True, use_fm=False)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": rb * rt / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"one iteration on {rb} x {rt} frames, oracle/train_oracle.py ({dt:.1f} s)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
