@@ -376,6 +376,18 @@ int mq_cb2d_backward(const float* s, const float* dy, const uint8_t* row_mask, i
                      const float* wpw, const float* bpw, const float* wout, float* ds, float* part,
                      mq_stream_t stream);
 
+/* ---- f4 (training step): fused activation passes of the refiner's ConvBlock ----- */
+/*
+ * u (pixels, C) fp32 convolution output; bf16 everywhere else; row_mask[pixel / pix_per_row] != 0 = padded row.
+ * forward:  out = padded ? 0 : (1 + tanh(beta u)) gamma u [+ res]        (preencoder.py:97-101, attentions.py:34-35)
+ * backward: du = padded ? 0 : dy * d aptx/du (u),  dres (optional) = padded ? 0 : dy
+ * i.e. what autograd runs for APTx -> (+x) -> masked_fill in train.py:400/484's backward.  C % 8 == 0.
+ */
+int mq_act_forward(const float* u, const void* res_bf16, const uint8_t* row_mask, int64_t pixels, int C,
+                   int pix_per_row, float beta, float gamma, void* out_bf16, mq_stream_t stream);
+int mq_act_backward(const void* dy_bf16, const float* u, const uint8_t* row_mask, int64_t pixels, int C,
+                    int pix_per_row, float beta, float gamma, void* du_bf16, void* dres_bf16, mq_stream_t stream);
+
 /* ---- sequence mask (preencoder.py:15-24) ----------------------------------- */
 int mq_sequence_mask(const int64_t* lengths, int B, int T, uint8_t* mask, mq_stream_t stream);
 

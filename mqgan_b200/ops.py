@@ -512,6 +512,42 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, N: int, H: int, W: int, cout: 
     return part[0] if p.split == 1 else part.sum(dim=0)
 
 
+def act_forward(u: torch.Tensor, res: Optional[torch.Tensor], row_mask: Optional[torch.Tensor], pix_per_row: int,
+                beta: float = 1.0, gamma: float = 0.5) -> torch.Tensor:
+    """u (.., C) fp32 conv output -> bf16 aptx(u) [+ res], zero at padded rows: mq_act_forward."""
+    _chk(u, torch.float32, "u")
+    Cc = u.shape[-1]
+    pixels = u.numel() // Cc
+    if res is not None:
+        _chk(res, torch.bfloat16, "res")
+        if res.numel() != u.numel():
+            raise ValueError("res must have the shape of u")
+    if row_mask is not None:
+        _chk(row_mask, torch.uint8, "row_mask")
+        if row_mask.numel() * pix_per_row != pixels:
+            raise ValueError("row_mask must have one entry per row of pix_per_row pixels")
+    out = torch.empty(u.shape, dtype=torch.bfloat16, device=u.device)
+    _lib.call("mq_act_forward", u.data_ptr(), _ptr(res), _ptr(row_mask), pixels, Cc, pix_per_row, float(beta), float(gamma),
+              out.data_ptr(), _stream())
+    return out
+
+
+def act_backward(dy: torch.Tensor, u: torch.Tensor, row_mask: Optional[torch.Tensor], pix_per_row: int,
+                 beta: float = 1.0, gamma: float = 0.5, want_res: bool = False):
+    """-> (du, dres or None), both bf16: mq_act_backward."""
+    _chk(dy, torch.bfloat16, "dy")
+    _chk(u, torch.float32, "u")
+    if dy.numel() != u.numel():
+        raise ValueError("dy must have the shape of u")
+    Cc = u.shape[-1]
+    pixels = u.numel() // Cc
+    du = torch.empty(u.shape, dtype=torch.bfloat16, device=u.device)
+    dres = torch.empty_like(du) if want_res else None
+    _lib.call("mq_act_backward", dy.data_ptr(), u.data_ptr(), _ptr(row_mask), pixels, Cc, pix_per_row, float(beta),
+              float(gamma), du.data_ptr(), _ptr(dres), _stream())
+    return du, dres
+
+
 def cb2d_point_forward(s: torch.Tensor, wpw, bpw, wout, bout, row_mask: Optional[torch.Tensor]) -> torch.Tensor:
     """s (B, T, C) fp32 (masked depth-wise output) -> y (B, T, C): mq_cb2d_point_forward."""
     _chk(s, torch.float32, "s")

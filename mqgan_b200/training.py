@@ -63,7 +63,7 @@ class _ConvFn(torch.autograd.Function):
         out = torch.empty(N, H, W, cout, dtype=torch.float32, device=x.device)
         ops.conv_gemm(xb, pc, N, H, W, out_f32=out, tag=tag)
         ctx.save_for_backward(xb, weight)
-        ctx.kind, ctx.tag, ctx.has_bias = kind, tag, bias is not None
+        ctx.kind, ctx.tag, ctx.has_bias, ctx.x_dtype = kind, tag, bias is not None, x.dtype
         return out
 
     @staticmethod
@@ -77,6 +77,7 @@ class _ConvFn(torch.autograd.Function):
             wd, kd = ops.dgrad_weight(weight, ctx.kind)
             dx = torch.empty(N, H, W, cin, dtype=torch.float32, device=dy.device)
             ops.conv_gemm(dyb, ops.pack_conv(wd, None, kd, on_device=True), N, H, W, out_f32=dx, tag=ctx.tag + ".dgrad")
+            dx = dx.to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
             dh, dwt = ops.conv_taps(ctx.kind, weight.shape)
             dw = _weight_from_taps(ops.conv_wgrad(dyb, xb, N, H, W, cout, cin, dh, dwt, tag=ctx.tag + ".wgrad"), ctx.kind)
@@ -92,14 +93,10 @@ def conv(x: Tensor, weight: Tensor, bias: Optional[Tensor], kind: str, tag: str 
         raise RuntimeError("mqgan_b200.training runs on CUDA (B200) only - there is no CPU fallback")
     if kind == "linear" and weight.dim() == 3:
         weight = weight[:, :, 0]                                  # a 1x1 Conv1d (ResidualBlock1D.residual)
-    cout, cin = weight.shape[0], weight.shape[1]
-    pad_i, pad_o = (-cin) % 8, (-cout) % 8                        # TMA needs 16-byte channel pitches
-    if pad_i or pad_o:
-        x = F.pad(x, (0, pad_i)) if pad_i else x
-        weight = F.pad(weight, (0, 0) * (weight.dim() - 2) + (0, pad_i, 0, pad_o))
-        bias = F.pad(bias, (0, pad_o)) if (bias is not None and pad_o) else bias
+    cout = weight.shape[0]
+    x, weight, bias = _pad_channels(x, weight, bias)              # TMA needs 16-byte channel pitches
     y = _ConvFn.apply(x, weight, bias, kind, tag)
-    return y[..., :cout] if pad_o else y
+    return y[..., :cout] if weight.shape[0] != cout else y
 
 
 def aptx(x: Tensor, beta, gamma) -> Tensor:
@@ -200,48 +197,98 @@ def _residual_block(x: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], prefix: st
     return aptx((o + r).masked_fill(m, 0.0), beta, gamma)
 
 
-def _conv2d_small(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
-    """3x3 convolution with one input or one output channel (refiner stem / tail: 0.05 % of the FLOPs), cuDNN."""
-    return F.conv2d(x.permute(0, 3, 1, 2), weight, bias, padding=1).permute(0, 2, 3, 1)
+def _pad_channels(x: Tensor, weight: Tensor, bias: Optional[Tensor]):
+    """Zero-pad Cin / Cout to multiples of 8 (16-byte TMA channel pitches); differentiable."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    pad_i, pad_o = (-cin) % 8, (-cout) % 8
+    if pad_i:
+        x = F.pad(x, (0, pad_i))
+    if pad_i or pad_o:
+        weight = F.pad(weight, (0, 0) * (weight.dim() - 2) + (0, pad_i, 0, pad_o))
+    if pad_o and bias is not None:
+        bias = F.pad(bias, (0, pad_o))
+    return x, weight, bias
 
 
-def _refiner_convblock(x: Tensor, m4: Tensor, w: Dict[str, Tensor], prefix: str) -> Tensor:
-    """ConvBlock.forward (preencoder.py:95-102), x (B, T', F, C), m4 (B, T', 1, 1)."""
-    x = x.masked_fill(m4, 0.0)
-    w1, w2 = w[prefix + ".conv1.weight"], w[prefix + ".conv2.weight"]
-    if w1.shape[1] % 8:
-        y = _conv2d_small(x, w1, w[prefix + ".conv1.bias"])
-    else:
-        y = conv(x, w1, w[prefix + ".conv1.bias"], "conv2d3", prefix + ".conv1")
-    y = aptx(y, 1.0, 0.5)
-    y = aptx(conv(y, w2, w[prefix + ".conv2.bias"], "conv2d3", prefix + ".conv2"), 1.0, 0.5)
-    if w1.shape[0] == w1.shape[1]:
-        y = y + x
-    return y.masked_fill(m4, 0.0)
+class _RefConvBlockFn(torch.autograd.Function):
+    """ConvBlock.forward (preencoder.py:95-102) on a bf16 channel-last image whose padded rows are already zero:
+    conv3x3 -> APTx -> conv3x3 -> APTx -> (+x) -> mask, as four library launches forward (two tcgen05 convs,
+    two fused activation passes) and eight backward (two activation-gradient passes, two data-gradient and
+    two weight-gradient convs, bias reductions in torch).  Saves the two fp32 pre-activations."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, mask8, residual: bool, tag: str):
+        N, H, W, cin = x.shape
+        c1 = w1.shape[0]
+        u1 = torch.empty(N, H, W, c1, dtype=torch.float32, device=x.device)
+        ops.conv_gemm(x, ops.pack_conv(w1, b1, "conv2d3", on_device=True), N, H, W, out_f32=u1, tag=tag + ".conv1")
+        a1 = ops.act_forward(u1, None, None, W)
+        u2 = torch.empty(N, H, W, w2.shape[0], dtype=torch.float32, device=x.device)
+        ops.conv_gemm(a1, ops.pack_conv(w2, b2, "conv2d3", on_device=True), N, H, W, out_f32=u2, tag=tag + ".conv2")
+        y = ops.act_forward(u2, x if residual else None, mask8, W)
+        ctx.save_for_backward(x, u1, a1, u2, w1, w2, mask8)
+        ctx.residual, ctx.tag = residual, tag
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, u1, a1, u2, w1, w2, mask8 = ctx.saved_tensors
+        N, H, W, cin = x.shape
+        c1, c2 = w1.shape[0], w2.shape[0]
+        tag = ctx.tag
+        dh, dwt = ops.conv_taps("conv2d3", w1.shape)
+        du2, dres = ops.act_backward(dy.contiguous(), u2, mask8, W, want_res=ctx.residual)
+        dw2 = _weight_from_taps(ops.conv_wgrad(du2, a1, N, H, W, c2, c1, dh, dwt, tag=tag + ".conv2.wgrad"), "conv2d3")
+        db2 = du2.sum(dim=(0, 1, 2), dtype=torch.float32)
+        wd, kd = ops.dgrad_weight(w2, "conv2d3")
+        da1 = torch.empty(N, H, W, c1, dtype=torch.bfloat16, device=dy.device)
+        ops.conv_gemm(du2, ops.pack_conv(wd, None, kd, on_device=True), N, H, W, out_bf16=da1, tag=tag + ".conv2.dgrad")
+        du1, _ = ops.act_backward(da1, u1, None, W)
+        dw1 = _weight_from_taps(ops.conv_wgrad(du1, x, N, H, W, c1, cin, dh, dwt, tag=tag + ".conv1.wgrad"), "conv2d3")
+        db1 = du1.sum(dim=(0, 1, 2), dtype=torch.float32)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wd, kd = ops.dgrad_weight(w1, "conv2d3")
+            dx = torch.empty(N, H, W, cin, dtype=torch.bfloat16, device=dy.device)
+            # the epilogue adds the skip path's gradient and re-applies the entry mask (x = x.masked_fill(mask) :96)
+            ops.conv_gemm(du1, ops.pack_conv(wd, None, kd, on_device=True), N, H, W, out_bf16=dx, tag=tag + ".conv1.dgrad",
+                          row_mask=mask8, mask_pre=True, res=dres, res_mode=1 if dres is not None else 0)
+        return dx, dw1, db1, dw2, db2, None, None, None
+
+
+def _refiner_convblock(x: Tensor, mask_rows: Tensor, w: Dict[str, Tensor], prefix: str) -> Tensor:
+    """x (B, T', F, C) bf16, zero at padded rows; mask_rows (B, T') bool."""
+    w1, b1 = w[prefix + ".conv1.weight"], w[prefix + ".conv1.bias"]
+    w2, b2 = w[prefix + ".conv2.weight"], w[prefix + ".conv2.bias"]
+    residual = w1.shape[0] == w1.shape[1]
+    x, w1, b1 = _pad_channels(x, w1, b1)
+    return _RefConvBlockFn.apply(x.contiguous(), w1, b1, w2, b2, mask_rows.to(torch.uint8).contiguous(), residual, prefix)
 
 
 def _refiner(r_in: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], depth: int) -> Tensor:
-    """UNetRefiner.forward (preencoder.py:169-202).  r_in (B, T, F) -> residual (B, T, mel)."""
+    """UNetRefiner.forward (preencoder.py:169-202).  r_in (B, T, F) -> residual (B, T, mel).  Activations are
+    bf16 between the blocks (fp32 accumulate and pre-activations inside them)."""
     B, T, Fw = r_in.shape
     mult = 1 << depth
     pad = (mult - T % mult) % mult
-    x = F.pad(r_in, (0, 0, 0, pad)).unsqueeze(-1)                                  # (B, T8, F, 1)
-    m = F.pad(mask_bt, (0, pad), value=True)
-    cur = m
-    x = _refiner_convblock(x, cur[:, :, None, None], w, "refiner.pre")
+    cur = F.pad(mask_bt, (0, pad), value=True)                                      # pad_to_pow2_4d :29-47
+    x = F.pad(r_in, (0, 0, 0, pad)).masked_fill(cur.unsqueeze(-1), 0.0).unsqueeze(-1).to(torch.bfloat16)   # (B,T8,F,1)
+    x = _refiner_convblock(x, cur, w, "refiner.pre")
     skips: List[Tensor] = []
     for i in range(depth):
         skips.append(x)
         Bq, Tq, Fq, Cq = x.shape
-        x = x.reshape(Bq, Tq // 2, 2, Fq, Cq).mean(dim=2)                           # AvgPool2d((2,1)) :112
         cur = cur.reshape(B, -1, 2).any(dim=2)                                      # max-pooled mask :65
-        x = _refiner_convblock(x, cur[:, :, None, None], w, f"refiner.downs.{i}.conv")
-    x = _refiner_convblock(x, cur[:, :, None, None], w, "refiner.mid")
+        x = x.reshape(Bq, Tq // 2, 2, Fq, Cq).mean(dim=2).masked_fill(cur[:, :, None, None], 0.0)   # AvgPool2d((2,1)) :112, entry mask :96
+        x = _refiner_convblock(x, cur, w, f"refiner.downs.{i}.conv")
+    x = _refiner_convblock(x, cur, w, "refiner.mid")
     for i in range(depth):
-        x = torch.cat([x.repeat_interleave(2, dim=1), skips.pop()], dim=-1)         # Upsample((2,1)) + cat :124-129
-        cur = cur.repeat_interleave(2, dim=1)
-        x = _refiner_convblock(x, cur[:, :, None, None], w, f"refiner.ups.{i}.conv")
-    out = _conv2d_small(x.masked_fill(cur[:, :, None, None], 0.0), w["refiner.post.weight"], w["refiner.post.bias"])
+        cur = cur.repeat_interleave(2, dim=1)                                       # nearest-upsampled mask :70
+        # Upsample((2,1)) + cat :124-129; the up-sampled mask can cover a valid row of the skip tensor (odd lengths),
+        # which ConvBlock's entry mask (:96) zeroes
+        x = torch.cat([x.repeat_interleave(2, dim=1), skips.pop()], dim=-1).masked_fill(cur[:, :, None, None], 0.0)
+        x = _refiner_convblock(x, cur, w, f"refiner.ups.{i}.conv")
+    out = conv(x, w["refiner.post.weight"], w["refiner.post.bias"], "conv2d3", "refiner.post")   # x is masked already (:191)
     out = out.squeeze(-1)[:, :T, :].masked_fill(mask_bt.unsqueeze(-1), 0.0)         # :192-198
     return conv(out.reshape(B, T, 1, Fw), w["refiner.reproj.weight"], None, "linear", "refiner.reproj").reshape(B, T, -1)
 

@@ -230,3 +230,30 @@ def test_train_step_needs_cuda_and_zero_dropout():
         TR.TrainStep(S.TINY, S.TINY_PATCH_D, S.TINY_MULTIBIN_D, {}, {}, {}, dict(S.TINY_TRAIN), "cpu")
     with pytest.raises(NotImplementedError):
         TR.TrainStep(S.TINY, S.TINY_PATCH_D, S.TINY_MULTIBIN_D, {}, {}, {}, dict(S.TINY_TRAIN), DEV, dropout_p=0.1)
+
+
+@pytest.mark.parametrize("C,residual", [(64, True), (128, False)])
+def test_act_forward_backward_match_float64(C, residual):
+    """mq_act_forward / mq_act_backward (APTx [+ residual] + row mask, bf16 in/out) against float64 autograd."""
+    N, H, W = 2, 9, 20
+    u = _rand(N, H, W, C, seed=61) * 2
+    res = _rand(N, H, W, C, seed=62).to(torch.bfloat16)
+    dy = _rand(N, H, W, C, seed=63).to(torch.bfloat16)
+    mask = torch.zeros(N, H, dtype=torch.bool)
+    mask[1, 5:] = True
+    ud = u.double().requires_grad_(True)
+    rd = res.double().requires_grad_(True)
+    y_ref = ((1 + torch.tanh(ud)) * 0.5 * ud + (rd if residual else 0.0)).masked_fill(mask[:, :, None, None], 0.0)
+    y_ref.backward(dy.double())
+    m8 = mask.to(torch.uint8).to(DEV)
+    y = ops.act_forward(u.to(DEV), res.to(DEV) if residual else None, m8, W)
+    du, dres = ops.act_backward(dy.to(DEV), u.to(DEV), m8, W, want_res=residual)
+    torch.cuda.synchronize()
+    assert y.dtype == torch.bfloat16 and du.dtype == torch.bfloat16
+    # outputs are rounded to bf16 once: half an ulp = 2^-9 relative
+    assert float((y.cpu().double() - y_ref.detach()).abs().max()) <= 2.0 ** -8 * float(y_ref.abs().max())
+    assert float((du.cpu().double() - ud.grad).abs().max()) <= 2.0 ** -8 * float(ud.grad.abs().max())
+    if residual:
+        assert torch.equal(dres.cpu().double(), rd.grad)          # dy passed through (exact) or zeroed
+    else:
+        assert dres is None
