@@ -388,6 +388,13 @@ int mq_act_forward(const float* u, const void* res_bf16, const uint8_t* row_mask
 int mq_act_backward(const void* dy_bf16, const float* u, const uint8_t* row_mask, int64_t pixels, int C,
                     int pix_per_row, float beta, float gamma, void* du_bf16, void* dres_bf16, mq_stream_t stream);
 
+/* Discriminator activation (discriminators.py:234, 247): out = pix_mask[pixel] ? 0 : LeakyReLU_slope(u) over a
+ * channels-last (pixels, C) tensor, u fp32 or bf16 (cuDNN's autocast output), out / dy / du bf16; one pass each way. */
+int mq_leaky_mask_forward(const void* u, int u_is_bf16, const uint8_t* pix_mask, int64_t pixels, int C, float slope,
+                          void* out_bf16, mq_stream_t stream);
+int mq_leaky_mask_backward(const void* dy_bf16, const void* u, int u_is_bf16, const uint8_t* pix_mask, int64_t pixels,
+                           int C, float slope, void* du_bf16, mq_stream_t stream);
+
 /* ---- sequence mask (preencoder.py:15-24) ----------------------------------- */
 int mq_sequence_mask(const int64_t* lengths, int B, int T, uint8_t* mask, mq_stream_t stream);
 

@@ -153,6 +153,9 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p]),
     "mq_act_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mq_leaky_mask_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "mq_leaky_mask_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_float,
+                                         C.c_void_p, C.c_void_p]),
     "mq_log_mel": (C.c_int, [C.POINTER(MelspecParams), C.c_void_p]),
     "mq_code_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

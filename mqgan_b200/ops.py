@@ -548,6 +548,44 @@ def act_backward(dy: torch.Tensor, u: torch.Tensor, row_mask: Optional[torch.Ten
     return du, dres
 
 
+def _chk_cl(t: torch.Tensor, name: str) -> torch.Tensor:
+    """A (B, C, H, W) tensor stored channels-last (the discriminators' cuDNN layout)."""
+    if not t.is_cuda or t.dim() != 4 or not t.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError(f"{name}: expected a channels_last (B, C, H, W) CUDA tensor")
+    if t.shape[1] % 8:
+        raise ValueError(f"{name}: channel count must be a multiple of 8")
+    return t
+
+
+def leaky_mask_forward(y: torch.Tensor, pix_mask: torch.Tensor, slope: float = 0.2) -> torch.Tensor:
+    """y (B, C, H, W) channels_last fp32 / bf16; pix_mask (B, H, W) uint8 (1 = padded) -> bf16
+    LeakyReLU(y) with padded pixels zeroed (discriminators.py:234, 247): mq_leaky_mask_forward."""
+    _chk_cl(y, "y")
+    if y.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("y must be fp32 or bf16")
+    _chk(pix_mask, torch.uint8, "pix_mask")
+    B, Cc, H, W = y.shape
+    if pix_mask.numel() != B * H * W:
+        raise ValueError("pix_mask must have one entry per pixel")
+    out = torch.empty_like(y, dtype=torch.bfloat16)
+    _lib.call("mq_leaky_mask_forward", y.data_ptr(), int(y.dtype == torch.bfloat16), pix_mask.data_ptr(), B * H * W, Cc,
+              float(slope), out.data_ptr(), _stream())
+    return out
+
+
+def leaky_mask_backward(dout: torch.Tensor, y: torch.Tensor, pix_mask: torch.Tensor, slope: float = 0.2) -> torch.Tensor:
+    """Gradient of leaky_mask_forward w.r.t. y (bf16, y's layout): mq_leaky_mask_backward."""
+    _chk_cl(y, "y")
+    _chk_cl(dout, "dout")
+    if dout.dtype != torch.bfloat16:
+        raise TypeError("dout must be bf16")
+    B, Cc, H, W = y.shape
+    du = torch.empty_like(y, dtype=torch.bfloat16)
+    _lib.call("mq_leaky_mask_backward", dout.data_ptr(), y.data_ptr(), int(y.dtype == torch.bfloat16), pix_mask.data_ptr(),
+              B * H * W, Cc, float(slope), du.data_ptr(), _stream())
+    return du
+
+
 def cb2d_point_forward(s: torch.Tensor, wpw, bpw, wout, bout, row_mask: Optional[torch.Tensor]) -> torch.Tensor:
     """s (B, T, C) fp32 (masked depth-wise output) -> y (B, T, C): mq_cb2d_point_forward."""
     _chk(s, torch.float32, "s")

@@ -293,14 +293,26 @@ def _refiner(r_in: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], depth: int) ->
     return conv(out.reshape(B, T, 1, Fw), w["refiner.reproj.weight"], None, "linear", "refiner.reproj").reshape(B, T, -1)
 
 
+_FSQ_CONST: Dict[tuple, tuple] = {}
+
+
+def _fsq_constants(levels: Sequence[int], device) -> tuple:
+    """(half_l, offset, shift, half_width) of quantizer.py:109-114, 132 as device tensors, built once per device (a
+    host-to-device copy is illegal inside a CUDA-graph capture)."""
+    key = (tuple(levels), str(device))
+    if key not in _FSQ_CONST:
+        lv = torch.tensor(list(levels), dtype=torch.int32, device=device)
+        half_l = ((lv - 1) * (1 + 1e-3) / 2).float()
+        offset = torch.where(lv % 2 == 0, 0.5, 0.0).float()
+        _FSQ_CONST[key] = (half_l, offset, (offset / half_l).atanh(), (lv // 2).float())
+    return _FSQ_CONST[key]
+
+
 def fsq_quantize_ste(z: Tensor, levels: Sequence[int]) -> Tensor:
     """FSQ.quantize in training mode, noise_dropout = 0 (quantizer.py:109-114, 128-140): fp32, straight-through round."""
-    lv = torch.tensor(list(levels), dtype=torch.int32, device=z.device)
-    half_l = ((lv - 1) * (1 + 1e-3) / 2).to(z.dtype)
-    offset = torch.where(lv % 2 == 0, 0.5, 0.0).to(z.dtype)
-    shift = (offset / half_l).atanh()
+    half_l, offset, shift, half_w = _fsq_constants(levels, z.device)
     bounded = (z + shift).tanh() * half_l - offset
-    return (bounded + (bounded.round() - bounded).detach()) / (lv // 2)
+    return (bounded + (bounded.round() - bounded).detach()) / half_w
 
 
 def generator_forward(params: Dict[str, Tensor], cfg: PreEncoderConfig, mel: Tensor, lengths: Tensor,
@@ -342,39 +354,65 @@ def _spectral_weight(sd: Dict[str, Tensor], prefix: str, training: bool) -> Tens
     return w_orig / torch.dot(u, torch.mv(wm, v))
 
 
+class _LeakyMaskFn(torch.autograd.Function):
+    """LeakyReLU(0.2) + zero the padded patches (discriminators.py:234, 247) in one pass each way, bf16 out."""
+
+    @staticmethod
+    def forward(ctx, y, pix_mask):
+        ctx.save_for_backward(y, pix_mask)
+        return ops.leaky_mask_forward(y, pix_mask, 0.2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, pix_mask = ctx.saved_tensors
+        du = ops.leaky_mask_backward(dout.contiguous(memory_format=torch.channels_last), y, pix_mask, 0.2)
+        return du.to(y.dtype), None
+
+
 def patch_discriminator(sd: Dict[str, Tensor], dc: PatchDiscConfig, x: Tensor, lengths: Tensor, training: bool,
                         prefix: str = "", autocast_bf16: bool = False):
     """MelSpectrogramPatchDiscriminator2D.forward (discriminators.py:208-257): x (B, T, F) ->
-    (logits (B,1,H,W), valid-patch mask, [(feature, padded mask)])."""
+    (logits (B,1,H,W), valid-patch mask, [(feature, padded mask)]).
+
+    ``autocast_bf16`` is the reference's CUDA training precision (train.py:523: convs under bf16 autocast, the
+    activations after them bf16): feature maps stay bf16 and channels_last from layer to layer, and the
+    LeakyReLU + patch mask after each conv is one library pass.  Otherwise everything is fp32 (parity mode)."""
     B, T, Fm = x.shape
     n = len(dc.kernels)
     pad_mask = (torch.arange(T, device=x.device)[None, :] >= lengths.to(x.device)[:, None])[:, None, None, :].expand(-1, 1, Fm, -1)
     out = x.transpose(1, 2).unsqueeze(1)
+    if autocast_bf16:
+        out = out.to(torch.bfloat16)
     feats = []
     for i in range(n):
         if i == n - 1:                                                              # masked squeeze-excite :10-67, :231-232
             valid = ~pad_mask
             denom = valid.sum(dim=(2, 3)).clamp(min=1)
-            sq = (out * valid).reshape(B, out.shape[1], -1).sum(dim=2) / denom
+            sq = (out.float() * valid).sum(dim=(2, 3)) / denom
             h = F.relu(F.linear(sq, sd[prefix + "se_block.fc1.weight"], sd[prefix + "se_block.fc1.bias"]))
             ex = torch.sigmoid(F.linear(h, sd[prefix + "se_block.fc2.weight"], sd[prefix + "se_block.fc2.bias"]))
-            out = out * ex.reshape(B, -1, 1, 1)
+            out = (out * ex.reshape(B, -1, 1, 1)).to(out.dtype)
         kh, kw = dc.kernels[i]
         sh, sw = dc.layer_stride(i)
         wgt = _spectral_weight(sd, f"{prefix}convs.{i}", training)
+        bias = sd[f"{prefix}convs.{i}.bias"]
+        if autocast_bf16:
+            wgt, bias = wgt.to(torch.bfloat16), bias.to(torch.bfloat16)
         # channels_last on purpose: in NCHW / bf16 cuDNN's heuristic sends the data gradient of the (1, 2)-strided
         # 256 -> 384 multi-bin layer to dgrad2d_grouped_direct_kernel - 9.1 ms per call instead of 0.27 ms, 2/3 of the
         # whole step (tools/disc_conv_probe.py, profiles/disc_conv_probe_r01.log)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast_bf16):
-            y = F.conv2d(out.contiguous(memory_format=torch.channels_last), wgt.contiguous(memory_format=torch.channels_last),
-                         sd[f"{prefix}convs.{i}.bias"], stride=(sh, sw), padding=((kh - 1) // 2, (kw - 1) // 2))
-        out = F.leaky_relu(y.float(), 0.2)
+        y = F.conv2d(out.contiguous(memory_format=torch.channels_last), wgt.contiguous(memory_format=torch.channels_last),
+                     bias, stride=(sh, sw), padding=((kh - 1) // 2, (kw - 1) // 2))
         if sh > 1 or sw > 1:
             pad_mask = F.max_pool2d(pad_mask.float(), kernel_size=(sh, sw), stride=(sh, sw), ceil_mode=True).bool()
-        out = out.masked_fill(pad_mask, 0.0)
+        if autocast_bf16 and y.shape[1] % 8 == 0:
+            out = _LeakyMaskFn.apply(y.contiguous(memory_format=torch.channels_last),
+                                     pad_mask.reshape(B, y.shape[2], y.shape[3]).to(torch.uint8).contiguous())
+        else:
+            out = F.leaky_relu(y, 0.2).masked_fill(pad_mask, 0.0)
         if dc.feature_layers[i]:
             feats.append((out, pad_mask))
-    return out, ~pad_mask, feats
+    return out.float(), ~pad_mask, feats
 
 
 def multibin_discriminator(sd: Dict[str, Tensor], mc: MultiBinConfig, x: Tensor, lengths: Tensor, training: bool,
@@ -430,10 +468,11 @@ class LeCam:
         if self.group is not None or (torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1):
             torch.distributed.all_reduce(means, group=self.group)
             means = means / torch.distributed.get_world_size(self.group)
-        if not self.initialized:
-            self.ema, self.initialized = means.clone(), True
+        if not self.initialized:                          # in place: the buffer's address is baked into a captured CUDA graph
+            self.ema.copy_(means)
+            self.initialized = True
         else:
-            self.ema = self.ema * self.decay + (1 - self.decay) * means
+            self.ema.mul_(self.decay).add_(means, alpha=1 - self.decay)
         term_r = (((real - self.ema[1]).clamp(min=0) * rm) ** 2).sum() / rm.sum().clamp(min=1)
         term_f = (((self.ema[0] - fake).clamp(min=0) * fm) ** 2).sum() / fm.sum().clamp(min=1)
         return loss + term_r + term_f
@@ -549,11 +588,17 @@ class TrainStep:
         self.d_training = True
         self.lecam = LeCam(dev, group=group)
         t = tcfg
-        fused = True
-        self.opt_g = torch.optim.Adam(list(self.g.values()), lr=t["lr"], betas=(t["beta1"], t["beta2"]), fused=fused)
-        self.opt_d = torch.optim.Adam(self.d_params(), lr=t["lr"] * t["lr_d_factor"], betas=(t["d_beta1"], t["d_beta2"]),
-                                      fused=fused)
-        self.sched_g = torch.optim.lr_scheduler.LambdaLR(self.opt_g, lambda s: min((s + 1) / t["warmup_steps"], 1.0))
+        # learning rates live in device tensors and Adam is capturable, so the whole step can be replayed from a CUDA
+        # graph (capture()); the warm-up schedule (train.py:326-329, LambdaLR) is applied to the tensor before each step
+        self.lr_g = torch.tensor(float(t["lr"]), device=dev)
+        self.lr_d = torch.tensor(float(t["lr"] * t["lr_d_factor"]), device=dev)
+        self.opt_g = torch.optim.Adam(list(self.g.values()), lr=self.lr_g, betas=(t["beta1"], t["beta2"]), fused=True,
+                                      capturable=True)
+        self.opt_d = torch.optim.Adam(self.d_params(), lr=self.lr_d, betas=(t["d_beta1"], t["d_beta2"]), fused=True,
+                                      capturable=True)
+        self.g_steps = 0
+        self._graphs: Dict[tuple, tuple] = {}
+        _fsq_constants(cfg.fsq_levels, dev)
         self.red_g = GradBucketReducer(list(self.g.values()), group=group)
         self.red_d = GradBucketReducer(self.d_params(), group=group)
 
@@ -567,9 +612,56 @@ class TrainStep:
     def generator_state_dict(self) -> Dict[str, Tensor]:
         return {k: v.detach() for k, v in self.g.items()}
 
+    def current_lr_g(self) -> float:
+        """LambdaLR(min((step + 1) / warmup_steps, 1)) of train.py:326-329 for the step about to run."""
+        t = self.tcfg
+        return float(t["lr"]) * min((self.g_steps + 1) / t["warmup_steps"], 1.0)
+
     def step(self, real: Tensor, lengths: Tensor, gan: bool = True, use_fm: Optional[bool] = None) -> Dict[str, Tensor]:
         """train.py:521-529 for one batch.  ``gan``: epoch >= discriminator_train_start_epoch.  Losses are
         returned as 0-d device tensors (one host read at the caller's discretion)."""
+        self.lr_g.fill_(self.current_lr_g())
+        out = self._step_body(real, lengths, gan, use_fm)
+        self.g_steps += 1
+        return out
+
+    def capture(self, real: Tensor, lengths: Tensor, gan: bool = True, use_fm: Optional[bool] = None, warmup: int = 3):
+        """Record the whole iteration for this batch shape into a CUDA graph (≈ 7 000 launches become one replay).
+        Runs ``warmup`` real iterations on a side stream first (they train: LeCam / spectral-norm state must be past
+        their first-call branches), then captures.  Use ``step_graphed`` afterwards."""
+        key = (tuple(real.shape), bool(gan), use_fm)
+        real = real.to(self.device)
+        lengths = lengths.to(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(real, lengths, gan, use_fm)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        s_real, s_len = real.clone(), lengths.clone()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = self._step_body(s_real, s_len, gan, use_fm)
+        self._graphs[key] = (graph, s_real, s_len, outs, self.last_recon)
+        return key
+
+    def step_graphed(self, real: Tensor, lengths: Tensor, gan: bool = True, use_fm: Optional[bool] = None) -> Dict[str, Tensor]:
+        """Replay the captured iteration on a new batch of the captured shape.  The returned loss tensors are the
+        graph's static outputs (overwritten by the next replay)."""
+        key = (tuple(real.shape), bool(gan), use_fm)
+        if key not in self._graphs:
+            raise KeyError(f"no CUDA graph captured for batch shape {tuple(real.shape)}; call capture() first")
+        graph, s_real, s_len, outs, recon = self._graphs[key]
+        s_real.copy_(real, non_blocking=True)
+        s_len.copy_(lengths, non_blocking=True)
+        self.lr_g.fill_(self.current_lr_g())
+        graph.replay()
+        self.g_steps += 1
+        self.last_recon = recon
+        return outs
+
+    def _step_body(self, real: Tensor, lengths: Tensor, gan: bool, use_fm: Optional[bool]) -> Dict[str, Tensor]:
         t = self.tcfg
         clip = t.get("clip_grad_norm", 1.0)
         lw = t["loss_weights"]
@@ -634,7 +726,6 @@ class TrainStep:
         if clip:
             torch.nn.utils.clip_grad_norm_(list(self.g.values()), clip)
         self.opt_g.step()
-        self.sched_g.step()
         out.update(loss_g_total=total.detach(), loss_recon_pre=loss_recon_pre.detach(),
                    loss_recon_post=loss_recon_post.detach(), loss_gan=loss_gan.detach(), loss_fm=loss_fm.detach())
         self.last_recon = (recon_pre.detach(), recon_post.detach())

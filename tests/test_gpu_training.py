@@ -257,3 +257,75 @@ def test_act_forward_backward_match_float64(C, residual):
         assert torch.equal(dres.cpu().double(), rd.grad)          # dy passed through (exact) or zeroed
     else:
         assert dres is None
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_leaky_mask_forward_backward(dtype):
+    """mq_leaky_mask_forward / backward on a channels_last feature map against the torch definition."""
+    B, Cc, H, W = 2, 24, 5, 7
+    y = _rand(B, Cc, H, W, seed=71).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    dout = _rand(B, Cc, H, W, seed=72).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    mask = torch.zeros(B, 1, H, W, dtype=torch.bool, device=DEV)
+    mask[1, :, :, 4:] = True
+    m8 = mask.reshape(B, H, W).to(torch.uint8).contiguous()
+    out = ops.leaky_mask_forward(y, m8)
+    du = ops.leaky_mask_backward(dout, y, m8)
+    ref = F.leaky_relu(y.float(), 0.2).masked_fill(mask, 0.0)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(out, ref.to(torch.bfloat16))
+    ref_du = (dout.float() * torch.where(y.float() > 0, 1.0, 0.2)).masked_fill(mask, 0.0)
+    assert torch.equal(du, ref_du.to(torch.bfloat16))
+
+
+def test_discriminator_bf16_mode_tracks_fp32_mode():
+    """The reference-precision (bf16 autocast) discriminator path - channels_last bf16 feature maps, fused
+    LeakyReLU + mask passes - against the fp32 path on the same weights: logits and input gradients."""
+    from mqgan_b200 import spec as S
+    from mqgan_b200 import training as TR
+    from mqgan_b200.synth import synth_disc_state_dict, synth_mels
+    dc = S.PatchDiscConfig(32, (16, 32, 64), ((5, 5), (5, 5), (3, 3), (3, 3)), ((1, 2), (2, 2), (2, 1), (1, 1)))
+    sd = {k: v.to(DEV) for k, v in synth_disc_state_dict(S.patch_disc_param_spec(dc), seed=9).items()}
+    lens = torch.tensor([40, 23], device=DEV)
+    with torch.no_grad():                          # settle the spectral-norm vectors (random u, v give a near-zero sigma)
+        for _ in range(20):
+            TR.patch_discriminator(sd, dc, synth_mels(2, 40, 32, seed=3).to(DEV), lens, training=True)
+    outs, grads = [], []
+    for fast in (False, True):
+        x = synth_mels(2, 40, 32, seed=3).to(DEV).requires_grad_(True)
+        logits, valid, feats = TR.patch_discriminator(sd, dc, x, lens, training=False, autocast_bf16=fast)
+        (logits * valid).pow(2).sum().backward()
+        outs.append(logits.detach())
+        grads.append(x.grad.detach())
+        assert len(feats) == 1
+    e_out = float((outs[0] - outs[1]).abs().max()) / float(outs[0].abs().max())
+    e_grad = float((grads[0] - grads[1]).norm() / grads[0].norm())
+    assert e_out < 3e-2, e_out                     # bf16 operands and bf16 feature maps through four layers
+    assert e_grad < 0.15, e_grad
+
+
+def test_graph_replayed_iterations_equal_eager_iterations():
+    """TrainStep.capture() + step_graphed(): the whole iteration replayed from one CUDA graph trains exactly like
+    the eager launches (same kernels, same order), including the warm-up learning-rate schedule fed through a
+    device tensor."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    fx, cfg, eager = _tiny_train_step()
+    _, _, graphed = _tiny_train_step()
+    B, T = int(fx["B"]), int(fx["T"])
+    batches = [_tiny_batch(s, B, T, cfg.mel_channels) for s in (1, 2, 3)]
+    for _ in range(3):
+        eager.step(*batches[0])
+    graphed.capture(batches[0][0], batches[0][1], warmup=3)
+    assert graphed.g_steps == eager.g_steps == 3
+    for real, lens in batches[1:]:
+        a = eager.step(real, lens)
+        b = graphed.step_graphed(real, lens)
+        for k in a:
+            assert abs(float(a[k]) - float(b[k])) <= 1e-5 * max(1.0, abs(float(a[k]))), k
+    assert graphed.g_steps == eager.g_steps == 5
+    assert float(graphed.lr_g) == float(eager.lr_g) > 0
+    for k in eager.g:
+        d = float((eager.g[k].detach() - graphed.g[k].detach()).abs().max())
+        assert d <= 1e-6 + 1e-4 * float(eager.g[k].detach().abs().max()), (k, d)
+    with pytest.raises(KeyError):
+        graphed.step_graphed(batches[0][0][:2], batches[0][1][:2])

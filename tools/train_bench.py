@@ -109,6 +109,7 @@ def main():
     ap.add_argument("--d_fp32", action="store_true", help="discriminator convs in fp32 instead of bf16 autocast")
     ap.add_argument("--torch_cb2d", action="store_true", help="ConvBlock2D through plain torch ops (cross-check)")
     ap.add_argument("--layers", default=None, help="write the per-kernel table of one instrumented step here")
+    ap.add_argument("--no_graph", action="store_true", help="eager launches instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu_baseline", action="store_true", help="also time the CPU oracle port on a bounded sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -156,11 +157,16 @@ def main():
 
     losses = {}
 
+    use_graph = not args.no_graph
+    if use_graph:
+        ts.capture(resident[0], lens_d)
+    run = ts.step_graphed if use_graph else ts.step
+
     def step_resident(i):
-        ts.step(resident[i % nbuf], lens_d)
+        run(resident[i % nbuf], lens_d)
 
     def step_e2e(i):
-        o = ts.step(host[i % nbuf], lens_h)
+        o = run(host[i % nbuf], lens_h)
         vals = torch.stack([o[k] for k in ("loss_d", "loss_g_total", "loss_recon_pre", "loss_recon_post", "loss_gan", "loss_fm")])
         losses["last"] = vals.cpu().tolist()                        # D2H read of the logged losses
 
@@ -173,6 +179,10 @@ def main():
     th.start()
     ms = timed(step_resident, args.steps)
     launches = (_lib.launch_count - n0) // args.steps
+    if use_graph:                                                   # replays do not pass through the binding: count one eager step
+        n1 = _lib.launch_count
+        ts.step(resident[0], lens_d)
+        launches = _lib.launch_count - n1
     ms_e2e = timed(step_e2e, args.steps)
     stop.set()
     th.join(timeout=1.0)
@@ -183,7 +193,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    step_resident(0)
+    ts.step(resident[0], lens_d)
     e1.record()
     rows = _lib.profiler.summary()
     _lib.profiler = None
@@ -224,6 +234,7 @@ def main():
                        "precision": "generator conv operands bf16 (fwd, dgrad, wgrad), fp32 accumulate and activations; "
                                     + ("discriminator convs fp32" if args.d_fp32 else "discriminator convs bf16 autocast (train.py:523)"),
                        "weights": "random-init (seed 0/1/2)", "dropout": 0.0,
+                       "launch": "whole iteration replayed from one CUDA graph" if use_graph else "eager launches",
                        "l2": "activations saved for backward exceed L2 (GBs per step)",
                        "parallelism": f"data-parallel replicas x{world}, bucketed NCCL gradient all-reduce overlapped with backward"
                        if world > 1 else "single replica"},
