@@ -268,7 +268,11 @@ def main():
                                     "sample": f"one iteration on {rb} x {rt} frames, oracle/train_oracle.py ({dt:.1f} s)"}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: tearing the communicator down under them hangs, so leave without it
+        sys.stdout.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":
