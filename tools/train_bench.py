@@ -11,7 +11,7 @@ Prints one JSON line (same keys as bench.py).  ``value`` = mel frames trained pe
 the batch resident in HBM; ``e2e`` = the same through TrainStep.step() from pinned host buffers with the H2D
 copy and a D2H read of the logged losses inside the timed region.  ``roofline`` is the aggregate of the
 library's tcgen05 launches (forward, data-gradient and weight-gradient convolutions) measured with CUDA events
-in one instrumented step; ``native_share_of_step`` says how much of the step they are - the rest is PyTorch
+in one instrumented (eager) step; ``native_share_of_step`` = library kernel time / timed step - the rest is PyTorch
 element-wise work, cuDNN discriminators and Adam (mqgan_b200/training.py docstring).
 """
 import argparse
@@ -246,9 +246,9 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "conv_gemm / conv_pair / conv_wgrad kernels (tcgen05), all launches of one step",
                          "achieved": conv_fl / conv_ms / 1e9 if conv_ms else None, "peak": peak, "unit": "TFLOP/s",
                          "frac": (conv_fl / conv_ms / 1e9 / peak) if conv_ms else None, "peak_source": "measured bf16 sustained",
-                         "traffic": None, "share_of_step": conv_ms / step_ms_prof,
+                         "traffic": None, "share_of_step": conv_ms / ms,
                          "by_kind": {k: {"launches": a[0], "ms": a[1], "tflops": a[2] / a[1] / 1e9 if a[2] else None} for k, a in by_kind.items()}},
-            "native_share_of_step": lib_ms / step_ms_prof,
+            "native_share_of_step": lib_ms / ms,
             "step_tflops_algorithmic": fl["step"] * B * T / ms / 1e9,
             "flops_per_frame": fl, "peak_mem_gib": peak_mem, "losses_last": losses.get("last"),
         }
