@@ -226,12 +226,18 @@ extern "C" int mq_conv_wgrad_split(const mq_wgrad_params* p) {
   const int bn = wg_choose_bn(p->cin);
   const long long tiles = static_cast<long long>(p->taps) * ((p->cout + kWgTileM - 1) / kWgTileM) * ((p->cin + bn - 1) / bn);
   const long long kblocks = static_cast<long long>(p->N) * ((p->H + p->bh - 1) / p->bh) * ((p->W + p->bw - 1) / p->bw);
-  // fill the machine (up to two CTAs' worth of work items per SM), at least 8 K blocks per CTA
-  long long split = (2LL * sms + tiles - 1) / tiles;
-  const long long max_split = kblocks / 8 > 0 ? kblocks / 8 : 1;
-  if (split > max_split) split = max_split;
-  if (split < 1) split = 1;
-  if (split > 64) split = 64;
+  // One CTA per SM is resident (197 KB of shared memory), so time ~ waves x (K blocks per CTA + fixed cost): pick the split
+  // that minimises it.  (The first version took ceil(2 * SMs / tiles): 360 CTAs = 2.4 waves on mid.conv1, a third of the
+  // last wave's SMs idle - profiles/ncu_conv_wgrad_mid_r01.csv.)
+  const long long fixed = 8;                               // prologue + epilogue in K-block units
+  long long split = 1, best_cost = -1;
+  for (long long sp = 1; sp <= 64; ++sp) {
+    const long long per = (kblocks + sp - 1) / sp;
+    if (sp > 1 && per < 16) break;
+    const long long waves = (tiles * sp + sms - 1) / sms;
+    const long long cost = waves * (per + fixed);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; split = sp; }
+  }
   return static_cast<int>(split);
 }
 
