@@ -380,13 +380,17 @@ int mq_cb2d_backward(const float* s, const float* dy, const uint8_t* row_mask, i
 /*
  * u (pixels, C) fp32 convolution output; bf16 everywhere else; row_mask[pixel / pix_per_row] != 0 = padded row.
  * forward:  out = padded ? 0 : (1 + tanh(beta u)) gamma u [+ res]        (preencoder.py:97-101, attentions.py:34-35)
- * backward: du = padded ? 0 : dy * d aptx/du (u),  dres (optional) = padded ? 0 : dy
+ * backward: du = padded ? 0 : dy * d aptx/du (u),  dres (optional) = padded ? 0 : dy,  dbias_part (optional) below
  * i.e. what autograd runs for APTx -> (+x) -> masked_fill in train.py:400/484's backward.  C % 8 == 0.
  */
 int mq_act_forward(const float* u, const void* res_bf16, const uint8_t* row_mask, int64_t pixels, int C,
                    int pix_per_row, float beta, float gamma, void* out_bf16, mq_stream_t stream);
 int mq_act_backward(const void* dy_bf16, const float* u, const uint8_t* row_mask, int64_t pixels, int C,
-                    int pix_per_row, float beta, float gamma, void* du_bf16, void* dres_bf16, mq_stream_t stream);
+                    int pix_per_row, float beta, float gamma, void* du_bf16, void* dres_bf16, float* dbias_part,
+                    mq_stream_t stream);
+/* dbias_part (optional): [mq_act_bias_blocks(pixels, C)][C] per-block column sums of du in fp32 - summed over blocks they
+ * are the bias gradient of the convolution that produced u.  mq_act_bias_blocks returns 0 when C does not allow it. */
+int mq_act_bias_blocks(int64_t pixels, int C);
 
 /* Discriminator activation (discriminators.py:234, 247): out = pix_mask[pixel] ? 0 : LeakyReLU_slope(u) over a
  * channels-last (pixels, C) tensor, u fp32 or bf16 (cuDNN's autocast output), out / dy / du bf16; one pass each way. */

@@ -533,8 +533,9 @@ def act_forward(u: torch.Tensor, res: Optional[torch.Tensor], row_mask: Optional
 
 
 def act_backward(dy: torch.Tensor, u: torch.Tensor, row_mask: Optional[torch.Tensor], pix_per_row: int,
-                 beta: float = 1.0, gamma: float = 0.5, want_res: bool = False):
-    """-> (du, dres or None), both bf16: mq_act_backward."""
+                 beta: float = 1.0, gamma: float = 0.5, want_res: bool = False, want_bias: bool = False):
+    """-> (du, dres or None[, dbias fp32 (C)]), du / dres bf16: mq_act_backward.  ``want_bias``: also the column sums of
+    du (the producing convolution's bias gradient), reduced in the same pass instead of re-reading du."""
     _chk(dy, torch.bfloat16, "dy")
     _chk(u, torch.float32, "u")
     if dy.numel() != u.numel():
@@ -543,8 +544,16 @@ def act_backward(dy: torch.Tensor, u: torch.Tensor, row_mask: Optional[torch.Ten
     pixels = u.numel() // Cc
     du = torch.empty(u.shape, dtype=torch.bfloat16, device=u.device)
     dres = torch.empty_like(du) if want_res else None
+    part = None
+    if want_bias:
+        nb = _lib.lib().mq_act_bias_blocks(pixels, Cc)
+        if nb > 0:
+            part = torch.empty(nb, Cc, dtype=torch.float32, device=u.device)
     _lib.call("mq_act_backward", dy.data_ptr(), u.data_ptr(), _ptr(row_mask), pixels, Cc, pix_per_row, float(beta),
-              float(gamma), du.data_ptr(), _ptr(dres), _stream())
+              float(gamma), du.data_ptr(), _ptr(dres), _ptr(part), _stream())
+    if want_bias:
+        db = part.sum(dim=0) if part is not None else du.reshape(-1, Cc).sum(dim=0, dtype=torch.float32)
+        return du, dres, db
     return du, dres
 
 

@@ -237,15 +237,13 @@ class _RefConvBlockFn(torch.autograd.Function):
         c1, c2 = w1.shape[0], w2.shape[0]
         tag = ctx.tag
         dh, dwt = ops.conv_taps("conv2d3", w1.shape)
-        du2, dres = ops.act_backward(dy.contiguous(), u2, mask8, W, want_res=ctx.residual)
+        du2, dres, db2 = ops.act_backward(dy.contiguous(), u2, mask8, W, want_res=ctx.residual, want_bias=True)
         dw2 = _weight_from_taps(ops.conv_wgrad(du2, a1, N, H, W, c2, c1, dh, dwt, tag=tag + ".conv2.wgrad"), "conv2d3")
-        db2 = du2.sum(dim=(0, 1, 2), dtype=torch.float32)
         wd, kd = ops.dgrad_weight(w2, "conv2d3")
         da1 = torch.empty(N, H, W, c1, dtype=torch.bfloat16, device=dy.device)
         ops.conv_gemm(du2, ops.pack_conv(wd, None, kd, on_device=True), N, H, W, out_bf16=da1, tag=tag + ".conv2.dgrad")
-        du1, _ = ops.act_backward(da1, u1, None, W)
+        du1, _, db1 = ops.act_backward(da1, u1, None, W, want_bias=True)
         dw1 = _weight_from_taps(ops.conv_wgrad(du1, x, N, H, W, c1, cin, dh, dwt, tag=tag + ".conv1.wgrad"), "conv2d3")
-        db1 = du1.sum(dim=(0, 1, 2), dtype=torch.float32)
         dx = None
         if ctx.needs_input_grad[0]:
             wd, kd = ops.dgrad_weight(w1, "conv2d3")
@@ -674,11 +672,23 @@ class TrainStep:
         if gan:                                                                     # _train_discriminator
             self.red_d.zero()
             fake = recon_post.detach()
-            rl, rm, _ = patch_discriminator(self.pd, self.pd_cfg, real, lengths, self.d_training, autocast_bf16=ac)
-            fl, fm, _ = patch_discriminator(self.pd, self.pd_cfg, fake, lengths, self.d_training, autocast_bf16=ac)
+            if self.d_training:
+                # two passes, as the reference makes them: in training mode each forward advances the spectral-norm
+                # power iteration (first iteration of an epoch only, train.py:417-418 vs :504-506)
+                rl, rm, _ = patch_discriminator(self.pd, self.pd_cfg, real, lengths, True, autocast_bf16=ac)
+                fl, fm, _ = patch_discriminator(self.pd, self.pd_cfg, fake, lengths, True, autocast_bf16=ac)
+                rl2, rm2, _ = multibin_discriminator(self.mb, self.mb_cfg, real, lengths, True, ac)
+                fl2, fm2, _ = multibin_discriminator(self.mb, self.mb_cfg, fake, lengths, True, ac)
+            else:
+                # eval-mode discriminators are per-sample functions: real and fake go through as one batch of 2B
+                nb = real.shape[0]
+                both, len2 = torch.cat([real, fake], dim=0), torch.cat([lengths, lengths], dim=0)
+                lg, mk, _ = patch_discriminator(self.pd, self.pd_cfg, both, len2, False, autocast_bf16=ac)
+                rl, fl, rm, fm = lg[:nb], lg[nb:], mk[:nb], mk[nb:]
+                lg2, mk2, _ = multibin_discriminator(self.mb, self.mb_cfg, both, len2, False, ac)
+                rl2, fl2 = [t_[:nb] for t_ in lg2], [t_[nb:] for t_ in lg2]
+                rm2, fm2 = [t_[:nb] for t_ in mk2], [t_[nb:] for t_ in mk2]
             loss_d = self.lecam.d_loss(rl, fl, rm, fm)
-            rl2, rm2, _ = multibin_discriminator(self.mb, self.mb_cfg, real, lengths, self.d_training, ac)
-            fl2, fm2, _ = multibin_discriminator(self.mb, self.mb_cfg, fake, lengths, self.d_training, ac)
             loss_d = loss_d + sum(self.lecam.d_loss(r, f, rm2[0], fm2[0]) for r, f in zip(rl2, fl2)) / len(rl2)
             loss_d.backward()
             self.red_d.finish()

@@ -247,8 +247,12 @@ def test_act_forward_backward_match_float64(C, residual):
     y_ref.backward(dy.double())
     m8 = mask.to(torch.uint8).to(DEV)
     y = ops.act_forward(u.to(DEV), res.to(DEV) if residual else None, m8, W)
-    du, dres = ops.act_backward(dy.to(DEV), u.to(DEV), m8, W, want_res=residual)
+    du, dres, db = ops.act_backward(dy.to(DEV), u.to(DEV), m8, W, want_res=residual, want_bias=True)
+    du_only, _ = ops.act_backward(dy.to(DEV), u.to(DEV), m8, W)
     torch.cuda.synchronize()
+    assert torch.equal(du, du_only)
+    ref_db = ud.grad.sum(dim=(0, 1, 2))
+    assert float((db.cpu().double() - ref_db).abs().max()) <= 1e-5 * max(1.0, float(ref_db.abs().max()))   # fp32 column sums
     assert y.dtype == torch.bfloat16 and du.dtype == torch.bfloat16
     # outputs are rounded to bf16 once: half an ulp = 2^-9 relative
     assert float((y.cpu().double() - y_ref.detach()).abs().max()) <= 2.0 ** -8 * float(y_ref.abs().max())
