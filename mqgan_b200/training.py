@@ -413,14 +413,38 @@ def patch_discriminator(sd: Dict[str, Tensor], dc: PatchDiscConfig, x: Tensor, l
     return out.float(), ~pad_mask, feats
 
 
+_SIDE_STREAMS: Dict[str, List["torch.cuda.Stream"]] = {}
+
+
+def _side_streams(device, n: int) -> List["torch.cuda.Stream"]:
+    key = str(device)
+    pool = _SIDE_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
 def multibin_discriminator(sd: Dict[str, Tensor], mc: MultiBinConfig, x: Tensor, lengths: Tensor, training: bool,
-                           autocast_bf16: bool = False):
-    """MultiBinDiscriminator.forward (discriminators.py:292-312)."""
-    outs, masks, feats = [], [], []
-    for b, sub in enumerate(torch.split(x, x.size(-1) // mc.n_bins, dim=-1)):
-        o, m, f = patch_discriminator(sd, mc.bin_config, sub, lengths, training, f"discriminators.{b}.", autocast_bf16)
-        outs.append(o); masks.append(m); feats.append(f)
-    return outs, masks, feats
+                           autocast_bf16: bool = False, concurrent: bool = True):
+    """MultiBinDiscriminator.forward (discriminators.py:292-312).  The bands are independent networks on 1/n_bins of
+    the mel axis, each too small to fill 148 SMs: with ``concurrent`` every band runs on its own CUDA stream (forked
+    from / joined to the caller's stream; autograd replays each band's backward on the same stream, and a CUDA-graph
+    capture records them as parallel branches)."""
+    subs = torch.split(x, x.size(-1) // mc.n_bins, dim=-1)
+    res = []
+    if concurrent and x.is_cuda and mc.n_bins > 1:
+        cur = torch.cuda.current_stream(x.device)
+        streams = _side_streams(x.device, mc.n_bins)
+        for b, sub in enumerate(subs):
+            streams[b].wait_stream(cur)
+            with torch.cuda.stream(streams[b]):
+                res.append(patch_discriminator(sd, mc.bin_config, sub, lengths, training, f"discriminators.{b}.", autocast_bf16))
+        for st in streams:
+            cur.wait_stream(st)
+    else:
+        for b, sub in enumerate(subs):
+            res.append(patch_discriminator(sd, mc.bin_config, sub, lengths, training, f"discriminators.{b}.", autocast_bf16))
+    return [r[0] for r in res], [r[1] for r in res], [r[2] for r in res]
 
 
 # ----------------------------------------------------------------------------
