@@ -224,6 +224,15 @@ def main():
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_dense_tflops_sustained", 1402.6))) if isinstance(peaks, dict) else 1402.6
     fl = train_flops_per_frame(cfg, pdc, mbc, T)
     frames = B * T * world
+    # replicas must hold identical weights after the timed iterations (different batches, averaged gradients)
+    chk = torch.stack([torch.stack([p.detach().double().sum() for p in ts.g.values()]).sum(),
+                       torch.stack([p.detach().double().sum() for p in ts.d_params_all()]).sum()])
+    in_sync = True
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
     if rank == 0:
         mhz = sorted(clk["mhz"])
         line = {
@@ -250,7 +259,8 @@ def main():
                          "by_kind": {k: {"launches": a[0], "ms": a[1], "tflops": a[2] / a[1] / 1e9 if a[2] else None} for k, a in by_kind.items()}},
             "native_share_of_step": lib_ms / ms,
             "step_tflops_algorithmic": fl["step"] * B * T / ms / 1e9,
-            "flops_per_frame": fl, "peak_mem_gib": peak_mem, "losses_last": losses.get("last"),
+            "flops_per_frame": fl, "peak_mem_gib": peak_mem, "replicas_in_sync": in_sync,
+            "param_checksums": chk.tolist(), "losses_last": losses.get("last"),
         }
         if args.cpu_baseline:
             from oracle import train_oracle as TO
