@@ -392,12 +392,14 @@ int mq_act_backward(const void* dy_bf16, const float* u, const uint8_t* row_mask
  * are the bias gradient of the convolution that produced u.  mq_act_bias_blocks returns 0 when C does not allow it. */
 int mq_act_bias_blocks(int64_t pixels, int C);
 
-/* Discriminator activation (discriminators.py:234, 247): out = pix_mask[pixel] ? 0 : LeakyReLU_slope(u) over a
- * channels-last (pixels, C) tensor, u fp32 or bf16 (cuDNN's autocast output), out / dy / du bf16; one pass each way. */
-int mq_leaky_mask_forward(const void* u, int u_is_bf16, const uint8_t* pix_mask, int64_t pixels, int C, float slope,
-                          void* out_bf16, mq_stream_t stream);
-int mq_leaky_mask_backward(const void* dy_bf16, const void* u, int u_is_bf16, const uint8_t* pix_mask, int64_t pixels,
-                           int C, float slope, void* du_bf16, mq_stream_t stream);
+/* Discriminator activation (discriminators.py:234, 247): out = pix_mask[pixel] ? 0 : LeakyReLU_slope(u + bias) over a
+ * channels-last (pixels, C) tensor, u fp32 or bf16 (cuDNN's autocast output, computed WITHOUT its bias), bias fp32 [C] or
+ * NULL, out / dy / du bf16; one pass each way.  dbias_part (optional): [mq_act_bias_blocks(pixels, C)][C] per-block column
+ * sums of du = the conv bias gradient, so neither cuDNN nor a reduction kernel has to re-read du for it. */
+int mq_leaky_mask_forward(const void* u, int u_is_bf16, const float* bias, const uint8_t* pix_mask, int64_t pixels, int C,
+                          float slope, void* out_bf16, mq_stream_t stream);
+int mq_leaky_mask_backward(const void* dy_bf16, const void* u, int u_is_bf16, const float* bias, const uint8_t* pix_mask,
+                           int64_t pixels, int C, float slope, void* du_bf16, float* dbias_part, mq_stream_t stream);
 
 /* ---- sequence mask (preencoder.py:15-24) ----------------------------------- */
 int mq_sequence_mask(const int64_t* lengths, int B, int T, uint8_t* mask, mq_stream_t stream);

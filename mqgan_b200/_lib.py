@@ -154,9 +154,10 @@ SIGNATURES = {
     "mq_act_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_act_bias_blocks": (C.c_int, [C.c_int64, C.c_int]),
-    "mq_leaky_mask_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
-    "mq_leaky_mask_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_float,
-                                         C.c_void_p, C.c_void_p]),
+    "mq_leaky_mask_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float,
+                                        C.c_void_p, C.c_void_p]),
+    "mq_leaky_mask_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                         C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_log_mel": (C.c_int, [C.POINTER(MelspecParams), C.c_void_p]),
     "mq_code_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

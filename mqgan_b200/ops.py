@@ -566,9 +566,10 @@ def _chk_cl(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
-def leaky_mask_forward(y: torch.Tensor, pix_mask: torch.Tensor, slope: float = 0.2) -> torch.Tensor:
-    """y (B, C, H, W) channels_last fp32 / bf16; pix_mask (B, H, W) uint8 (1 = padded) -> bf16
-    LeakyReLU(y) with padded pixels zeroed (discriminators.py:234, 247): mq_leaky_mask_forward."""
+def leaky_mask_forward(y: torch.Tensor, pix_mask: torch.Tensor, slope: float = 0.2,
+                       bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y (B, C, H, W) channels_last fp32 / bf16; pix_mask (B, H, W) uint8 (1 = padded); bias fp32 (C) or None -> bf16
+    LeakyReLU(y + bias) with padded pixels zeroed (discriminators.py:234, 247): mq_leaky_mask_forward."""
     _chk_cl(y, "y")
     if y.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("y must be fp32 or bf16")
@@ -576,22 +577,33 @@ def leaky_mask_forward(y: torch.Tensor, pix_mask: torch.Tensor, slope: float = 0
     B, Cc, H, W = y.shape
     if pix_mask.numel() != B * H * W:
         raise ValueError("pix_mask must have one entry per pixel")
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
     out = torch.empty_like(y, dtype=torch.bfloat16)
-    _lib.call("mq_leaky_mask_forward", y.data_ptr(), int(y.dtype == torch.bfloat16), pix_mask.data_ptr(), B * H * W, Cc,
-              float(slope), out.data_ptr(), _stream())
+    _lib.call("mq_leaky_mask_forward", y.data_ptr(), int(y.dtype == torch.bfloat16), _ptr(bias), pix_mask.data_ptr(),
+              B * H * W, Cc, float(slope), out.data_ptr(), _stream())
     return out
 
 
-def leaky_mask_backward(dout: torch.Tensor, y: torch.Tensor, pix_mask: torch.Tensor, slope: float = 0.2) -> torch.Tensor:
-    """Gradient of leaky_mask_forward w.r.t. y (bf16, y's layout): mq_leaky_mask_backward."""
+def leaky_mask_backward(dout: torch.Tensor, y: torch.Tensor, pix_mask: torch.Tensor, slope: float = 0.2,
+                        bias: Optional[torch.Tensor] = None, want_bias: bool = False):
+    """Gradient of leaky_mask_forward w.r.t. y (bf16, y's layout) [and w.r.t. bias, fp32 (C)]: mq_leaky_mask_backward."""
     _chk_cl(y, "y")
     _chk_cl(dout, "dout")
     if dout.dtype != torch.bfloat16:
         raise TypeError("dout must be bf16")
     B, Cc, H, W = y.shape
     du = torch.empty_like(y, dtype=torch.bfloat16)
-    _lib.call("mq_leaky_mask_backward", dout.data_ptr(), y.data_ptr(), int(y.dtype == torch.bfloat16), pix_mask.data_ptr(),
-              B * H * W, Cc, float(slope), du.data_ptr(), _stream())
+    part = None
+    if want_bias:
+        nb = _lib.lib().mq_act_bias_blocks(B * H * W, Cc)
+        if nb > 0:
+            part = torch.empty(nb, Cc, dtype=torch.float32, device=y.device)
+    _lib.call("mq_leaky_mask_backward", dout.data_ptr(), y.data_ptr(), int(y.dtype == torch.bfloat16), _ptr(bias),
+              pix_mask.data_ptr(), B * H * W, Cc, float(slope), du.data_ptr(), _ptr(part), _stream())
+    if want_bias:
+        db = part.sum(dim=0) if part is not None else du.float().sum(dim=(0, 2, 3))
+        return du, db
     return du
 
 

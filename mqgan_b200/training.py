@@ -353,18 +353,24 @@ def _spectral_weight(sd: Dict[str, Tensor], prefix: str, training: bool) -> Tens
 
 
 class _LeakyMaskFn(torch.autograd.Function):
-    """LeakyReLU(0.2) + zero the padded patches (discriminators.py:234, 247) in one pass each way, bf16 out."""
+    """LeakyReLU(0.2)(y + bias) with the padded patches zeroed (discriminators.py:234, 247) in one pass each way, bf16 out.
+    The convolution in front runs WITHOUT its bias: the add happens here, and the bias gradient is the column sum the
+    backward pass produces on the fly (cuDNN would re-read the whole gradient tensor for it)."""
 
     @staticmethod
-    def forward(ctx, y, pix_mask):
-        ctx.save_for_backward(y, pix_mask)
-        return ops.leaky_mask_forward(y, pix_mask, 0.2)
+    def forward(ctx, y, bias, pix_mask):
+        ctx.save_for_backward(y, bias, pix_mask)
+        return ops.leaky_mask_forward(y, pix_mask, 0.2, bias)
 
     @staticmethod
     def backward(ctx, dout):
-        y, pix_mask = ctx.saved_tensors
-        du = ops.leaky_mask_backward(dout.contiguous(memory_format=torch.channels_last), y, pix_mask, 0.2)
-        return du.to(y.dtype), None
+        y, bias, pix_mask = ctx.saved_tensors
+        dout = dout.contiguous(memory_format=torch.channels_last)
+        if ctx.needs_input_grad[1]:
+            du, db = ops.leaky_mask_backward(dout, y, pix_mask, 0.2, bias, want_bias=True)
+        else:                                                  # generator step: the discriminator is only a loss
+            du, db = ops.leaky_mask_backward(dout, y, pix_mask, 0.2, bias), None
+        return du.to(y.dtype), db, None
 
 
 def patch_discriminator(sd: Dict[str, Tensor], dc: PatchDiscConfig, x: Tensor, lengths: Tensor, training: bool,
@@ -399,12 +405,13 @@ def patch_discriminator(sd: Dict[str, Tensor], dc: PatchDiscConfig, x: Tensor, l
         # channels_last on purpose: in NCHW / bf16 cuDNN's heuristic sends the data gradient of the (1, 2)-strided
         # 256 -> 384 multi-bin layer to dgrad2d_grouped_direct_kernel - 9.1 ms per call instead of 0.27 ms, 2/3 of the
         # whole step (tools/disc_conv_probe.py, profiles/disc_conv_probe_r01.log)
+        fused = autocast_bf16 and wgt.shape[0] % 8 == 0                             # library activation pass (adds the bias itself)
         y = F.conv2d(out.contiguous(memory_format=torch.channels_last), wgt.contiguous(memory_format=torch.channels_last),
-                     bias, stride=(sh, sw), padding=((kh - 1) // 2, (kw - 1) // 2))
+                     None if fused else bias, stride=(sh, sw), padding=((kh - 1) // 2, (kw - 1) // 2))
         if sh > 1 or sw > 1:
             pad_mask = F.max_pool2d(pad_mask.float(), kernel_size=(sh, sw), stride=(sh, sw), ceil_mode=True).bool()
-        if autocast_bf16 and y.shape[1] % 8 == 0:
-            out = _LeakyMaskFn.apply(y.contiguous(memory_format=torch.channels_last),
+        if fused:
+            out = _LeakyMaskFn.apply(y.contiguous(memory_format=torch.channels_last), sd[f"{prefix}convs.{i}.bias"],
                                      pad_mask.reshape(B, y.shape[2], y.shape[3]).to(torch.uint8).contiguous())
         else:
             out = F.leaky_relu(y, 0.2).masked_fill(pad_mask, 0.0)

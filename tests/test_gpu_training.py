@@ -266,19 +266,25 @@ def test_act_forward_backward_match_float64(C, residual):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_leaky_mask_forward_backward(dtype):
     """mq_leaky_mask_forward / backward on a channels_last feature map against the torch definition."""
-    B, Cc, H, W = 2, 24, 5, 7
+    B, Cc, H, W = 2, 32, 5, 7                      # 256 % (C / 8) == 0: the fused bias gradient is available
     y = _rand(B, Cc, H, W, seed=71).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
     dout = _rand(B, Cc, H, W, seed=72).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
     mask = torch.zeros(B, 1, H, W, dtype=torch.bool, device=DEV)
     mask[1, :, :, 4:] = True
     m8 = mask.reshape(B, H, W).to(torch.uint8).contiguous()
-    out = ops.leaky_mask_forward(y, m8)
-    du = ops.leaky_mask_backward(dout, y, m8)
-    ref = F.leaky_relu(y.float(), 0.2).masked_fill(mask, 0.0)
-    assert out.dtype == torch.bfloat16 and out.is_contiguous(memory_format=torch.channels_last)
-    assert torch.equal(out, ref.to(torch.bfloat16))
-    ref_du = (dout.float() * torch.where(y.float() > 0, 1.0, 0.2)).masked_fill(mask, 0.0)
-    assert torch.equal(du, ref_du.to(torch.bfloat16))
+    bias = _rand(Cc, seed=73).to(DEV)
+    for b in (None, bias):
+        yb = y.float() if b is None else y.float() + b.reshape(1, -1, 1, 1)
+        out = ops.leaky_mask_forward(y, m8, 0.2, b)
+        du, db = ops.leaky_mask_backward(dout, y, m8, 0.2, b, want_bias=True)
+        ref = F.leaky_relu(yb, 0.2).masked_fill(mask, 0.0)
+        assert out.dtype == torch.bfloat16 and out.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(out, ref.to(torch.bfloat16))
+        ref_du = (dout.float() * torch.where(yb > 0, 1.0, 0.2)).masked_fill(mask, 0.0)
+        assert torch.equal(du, ref_du.to(torch.bfloat16))
+        assert torch.equal(du, ops.leaky_mask_backward(dout, y, m8, 0.2, b))
+        ref_db = ref_du.double().sum(dim=(0, 2, 3))
+        assert float((db.double() - ref_db).abs().max()) <= 1e-5 * max(1.0, float(ref_db.abs().max()))
 
 
 def test_discriminator_bf16_mode_tracks_fp32_mode():
