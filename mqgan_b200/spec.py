@@ -277,6 +277,14 @@ class MultiBinConfig:
     kernel_sizes: Tuple[int, ...]
     n_no_strides: int = 2
 
+    def __post_init__(self):
+        # discriminators.py:262-266
+        if self.mel_channels % self.n_bins:
+            raise ValueError("mel_channels must divide n_bins")
+        for h in self.hidden_channels:
+            if h % self.n_bins:
+                raise ValueError(f"hidden size {h} must divide n_bins")
+
     @staticmethod
     def from_yaml(mel_channels: int, d: dict) -> "MultiBinConfig":
         return MultiBinConfig(int(mel_channels), int(d["n_bins"]), tuple(d["hidden_channels"]),
@@ -329,3 +337,9 @@ HIFISPEECH_MULTIBIN_D = MultiBinConfig(128, 8, (128, 128, 256, 256, 384), (7, 5,
 TINY_PATCH_D = PatchDiscConfig(32, (16, 16, 32), ((5, 5), (5, 5), (3, 3), (3, 3)), ((1, 2), (2, 2), (2, 1), (1, 1)))
 TINY_MULTIBIN_D = MultiBinConfig(32, 2, (16, 16, 32), (7, 5, 3, 3), 2)
 TINY_TRAIN = dict(TRAIN_DEFAULTS, warmup_steps=4)
+# A second small training topology with hifimusic's block pattern (channel change in the middle encoder / decoder
+# block) and awkward widths: refiner channels 24/48/96/192 (not multiples of 64; 24 has no fused bias-gradient path),
+# refiner image width 54 (padded to 56 channels for reproj), three 16-bin bands.
+TINY_M = PreEncoderConfig(48, (48, 48, 64, 64), (3, 3, 5, 7), (8, 5, 5, 5), 24, 3, 8)
+TINY_M_PATCH_D = PatchDiscConfig(48, (16, 24, 32), ((5, 5), (5, 5), (3, 3), (3, 3)), ((1, 2), (2, 2), (2, 1), (1, 1)))
+TINY_M_MULTIBIN_D = MultiBinConfig(48, 3, (24, 24, 48), (7, 5, 3, 3), 2)

@@ -30,9 +30,10 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 REF = os.environ.get("MQGAN_REFERENCE", "/root/reference")
 
-FULL_GRADS = ["proj.weight", "pre.pw.parametrizations.weight.original0", "pre.dw.parametrizations.weight.original1",
+FULL_GRADS_ALL = ["proj.weight", "pre.pw.parametrizations.weight.original0", "pre.dw.parametrizations.weight.original1",
               "encoder_blocks.0.conv1.parametrizations.weight.original1", "encoder_blocks.2.relu.beta",
-              "encoder_blocks.1.cbam.spatial_attention.conv.weight", "q_in_proj.weight", "q_out_proj.weight",
+              "encoder_blocks.1.cbam.spatial_attention.conv.weight", "encoder_blocks.1.residual.weight",
+              "decoder_blocks.1.residual.weight", "q_in_proj.weight", "q_out_proj.weight",
               "decoder_blocks.2.conv2.weight_v", "decoder_blocks.0.conv1.weight_g", "out_proj.weight",
               "refiner.pre.conv2.parametrizations.weight.original1", "refiner.downs.0.conv.conv1.parametrizations.weight.original1",
               "refiner.ups.2.conv.conv1.parametrizations.weight.original0", "refiner.post.parametrizations.weight.original1",
@@ -54,18 +55,29 @@ def import_reference():
     return ref_train
 
 
+CASES = {
+    # fixture name: (generator config, patch D, multi-bin D, B, T, seed)
+    "train_tiny": ("TINY", "TINY_PATCH_D", "TINY_MULTIBIN_D", 4, 48, 3),
+    "train_tiny_m": ("TINY_M", "TINY_M_PATCH_D", "TINY_M_MULTIBIN_D", 3, 43, 5),     # T not a multiple of 8
+}
+
+
 def main():
+    T_ = import_reference()
+    for name, case in CASES.items():
+        run_case(T_, name, *case)
+
+
+def run_case(T_, name, cfg_name, pd_name, mb_name, B, T, seed):
     from mqgan_b200 import spec as S
     from mqgan_b200.synth import synth_state_dict, synth_mels, synth_lengths, synth_disc_state_dict
     from oracle import train_oracle as TO
 
-    T_ = import_reference()
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg, pdc, mbc, tcfg = S.TINY, S.TINY_PATCH_D, S.TINY_MULTIBIN_D, S.TINY_TRAIN
-    B, T = 4, 48
-    g_sd = synth_state_dict(cfg, seed=3)
-    pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=3)
-    mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=4)
+    cfg, pdc, mbc, tcfg = getattr(S, cfg_name), getattr(S, pd_name), getattr(S, mb_name), S.TINY_TRAIN
+    g_sd = synth_state_dict(cfg, seed=seed)
+    pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=seed)
+    mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=seed + 1)
 
     # with default init every frame quantises to one code (all codes 0 -> q_out_proj sees no gradient);
     # recalibrate q_in_proj on the reference's own latents so the codes vary.  Stored in the fixture.
@@ -137,8 +149,9 @@ def main():
         out[pre + "g_grad_norms"] = np.array([g_gn[k] for k in g_sd], np.float64)
         out[pre + "d_grad_keys"] = np.array([k for k, _ in d_named])
         out[pre + "d_grad_norms"] = np.array([d_gn[k] for k, _ in d_named], np.float64)
-        for k in FULL_GRADS:
-            out[pre + "gg:" + k] = g_named[k].grad.detach().numpy().copy()
+        for k in FULL_GRADS_ALL:
+            if k in g_named and g_named[k].grad is not None:
+                out[pre + "gg:" + k] = g_named[k].grad.detach().numpy().copy()
         for k, v in d_full.items():
             out[pre + "dg:" + k] = v.numpy()
         gsd_now = gen.state_dict()
@@ -165,11 +178,12 @@ def main():
         print(f"[step {step}] G param-sum diff max {np.abs(ps_o - out[pre + 'g_param_sums']).max():.3e}; "
               f"u diff {float((st.pd['convs.1.weight_u'] - dsd_now['pd:convs.1.weight_u']).abs().max()):.3e}")
 
-    out["B"], out["T"] = np.array(B), np.array(T)
+    out["B"], out["T"], out["seed"] = np.array(B), np.array(T), np.array(seed)
+    out["configs"] = np.array([cfg_name, pd_name, mb_name])
     out["qin_w"], out["qin_b"] = g_sd["q_in_proj.weight"].numpy(), g_sd["q_in_proj.bias"].numpy()
     out["g_keys"] = np.array(list(g_sd))
     out["d_keys"] = np.array(["pd:" + k for k in pd_sd] + ["mb:" + k for k in mb_sd])
-    path = os.path.join(REPO, "tests", "golden", "train_tiny.npz")
+    path = os.path.join(REPO, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 

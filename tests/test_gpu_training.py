@@ -150,19 +150,20 @@ def test_cb2d_point_forward_backward_match_float64_autograd(B, T, C):
 # ----------------------------------------------------------------------------
 # the whole training iteration against the reference's own Trainer step (tests/golden/train_tiny.npz)
 # ----------------------------------------------------------------------------
-def _tiny_train_step(native_cb2d=True):
+def _tiny_train_step(native_cb2d=True, name="train_tiny", **kw):
     import os
     from mqgan_b200 import spec as S
     from mqgan_b200 import training as TR
     from mqgan_b200.synth import synth_disc_state_dict, synth_state_dict
-    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_tiny.npz"))
-    cfg, pdc, mbc = S.TINY, S.TINY_PATCH_D, S.TINY_MULTIBIN_D
-    g_sd = synth_state_dict(cfg, seed=3)
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    cfg, pdc, mbc = (getattr(S, str(n)) for n in fx["configs"])
+    seed = int(fx["seed"])
+    g_sd = synth_state_dict(cfg, seed=seed)
     g_sd["q_in_proj.weight"] = torch.from_numpy(fx["qin_w"]).clone()
     g_sd["q_in_proj.bias"] = torch.from_numpy(fx["qin_b"]).clone()
-    pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=3)
-    mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=4)
-    ts = TR.TrainStep(cfg, pdc, mbc, g_sd, pd_sd, mb_sd, dict(S.TINY_TRAIN), DEV, native_cb2d=native_cb2d)
+    pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=seed)
+    mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=seed + 1)
+    ts = TR.TrainStep(cfg, pdc, mbc, g_sd, pd_sd, mb_sd, dict(S.TINY_TRAIN), DEV, native_cb2d=native_cb2d, **kw)
     return fx, cfg, ts
 
 
@@ -173,7 +174,8 @@ def _tiny_batch(step, B, T, n_mels):
     return real.masked_fill((torch.arange(T)[None, :] >= lens[:, None]).unsqueeze(-1), 0.0), lens
 
 
-def test_train_step_matches_reference_trainer_two_iterations():
+@pytest.mark.parametrize("name", ["train_tiny", "train_tiny_m"])
+def test_train_step_matches_reference_trainer_two_iterations(name):
     """Losses, reconstructions, gradients (as the step leaves them: clipped), updated weights, spectral-norm
     vectors and LeCam anchors after two consecutive iterations (the second with feature matching) against the
     UNMODIFIED reference run on the CPU in fp32.  The generator's convolutions run with bf16 operands here
@@ -181,7 +183,7 @@ def test_train_step_matches_reference_trainer_two_iterations():
     Measured on B200 (tools/train_parity.py, profiles/train_parity_r01.json) next to each bound."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    fx, cfg, ts = _tiny_train_step()
+    fx, cfg, ts = _tiny_train_step(name=name)
     B, T = int(fx["B"]), int(fx["T"])
     g_keys = [str(k) for k in fx["g_keys"]]
     names = ["loss_d", "loss_g_total", "loss_recon_pre", "loss_recon_post", "loss_gan", "loss_fm"]

@@ -10,17 +10,21 @@ from mqgan_b200 import spec as S
 from mqgan_b200.synth import synth_disc_state_dict, synth_lengths, synth_mels, synth_state_dict
 from oracle import train_oracle as TO
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_tiny.npz")
+import pytest
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIXTURES = ["train_tiny", "train_tiny_m"]
 
 
-def tiny_train_state():
-    cfg, pdc, mbc = S.TINY, S.TINY_PATCH_D, S.TINY_MULTIBIN_D
-    g_sd = synth_state_dict(cfg, seed=3)
-    fx = np.load(GOLDEN)
+def tiny_train_state(name="train_tiny"):
+    fx = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg, pdc, mbc = (getattr(S, str(n)) for n in fx["configs"])
+    seed = int(fx["seed"])
+    g_sd = synth_state_dict(cfg, seed=seed)
     g_sd["q_in_proj.weight"] = torch.from_numpy(fx["qin_w"]).clone()      # calibrated on the reference's latents
     g_sd["q_in_proj.bias"] = torch.from_numpy(fx["qin_b"]).clone()
-    pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=3)
-    mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=4)
+    pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=seed)
+    mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=seed + 1)
     return cfg, pdc, mbc, g_sd, pd_sd, mb_sd
 
 
@@ -30,9 +34,10 @@ def tiny_batch(step, B, T, n_mels):
     return real.masked_fill((torch.arange(T)[None, :] >= lens[:, None]).unsqueeze(-1), 0.0), lens
 
 
-def test_train_oracle_matches_reference_two_iterations():
-    fx = np.load(GOLDEN)
-    cfg, pdc, mbc, g_sd, pd_sd, mb_sd = tiny_train_state()
+@pytest.mark.parametrize("name", FIXTURES)
+def test_train_oracle_matches_reference_two_iterations(name):
+    fx = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg, pdc, mbc, g_sd, pd_sd, mb_sd = tiny_train_state(name)
     st = TO.TrainState(cfg, g_sd, pd_sd, mb_sd, TO.patch_cfg([k[0] for k in pdc.kernels], pdc.strides),
                        TO.multibin_cfg(mbc.kernel_sizes, mbc.n_bins, mbc.n_no_strides), dict(S.TINY_TRAIN))
     B, T = int(fx["B"]), int(fx["T"])

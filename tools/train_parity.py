@@ -17,13 +17,23 @@ from mqgan_b200.synth import synth_disc_state_dict, synth_lengths, synth_mels, s
 def main():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    fx = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "train_tiny.npz"))
-    cfg, pdc, mbc = S.TINY, S.TINY_PATCH_D, S.TINY_MULTIBIN_D
-    g_sd = synth_state_dict(cfg, seed=3)
+    rep = {}
+    for fixture in ("train_tiny", "train_tiny_m"):
+        rep.update(run_fixture(fixture))
+    print(json.dumps(rep, indent=1))
+    if len(sys.argv) > 1:
+        json.dump(rep, open(sys.argv[1], "w"), indent=1)
+
+
+def run_fixture(fixture):
+    fx = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", fixture + ".npz"))
+    cfg, pdc, mbc = (getattr(S, str(n)) for n in fx["configs"])
+    seed = int(fx["seed"])
+    g_sd = synth_state_dict(cfg, seed=seed)
     g_sd["q_in_proj.weight"] = torch.from_numpy(fx["qin_w"]).clone()
     g_sd["q_in_proj.bias"] = torch.from_numpy(fx["qin_b"]).clone()
-    pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=3)
-    mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=4)
+    pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=seed)
+    mb_sd = synth_disc_state_dict(S.multibin_param_spec(mbc), seed=seed + 1)
     rep = {}
     for native in (True, False):
         ts = TR.TrainStep(cfg, pdc, mbc, g_sd, pd_sd, mb_sd, dict(S.TINY_TRAIN), "cuda", native_cb2d=native)
@@ -76,10 +86,8 @@ def main():
             d_now = {**{"pd:" + k: v for k, v in ts.pd.items()}, **{"mb:" + k: v for k, v in ts.mb.items()}}
             dps = np.array([float(d_now[str(k)].detach().double().sum()) for k in fx["d_keys"]])
             r["d_param_sum_abs_err_max"] = float(np.abs(dps - fx[pre + "d_param_sums"]).max())
-            rep[f"{'native' if native else 'torch'}_cb2d_step{step}"] = r
-    print(json.dumps(rep, indent=1))
-    if len(sys.argv) > 1:
-        json.dump(rep, open(sys.argv[1], "w"), indent=1)
+            rep[f"{fixture}_{'native' if native else 'torch'}_cb2d_step{step}"] = r
+    return rep
 
 
 if __name__ == "__main__":
