@@ -665,7 +665,7 @@ class TrainStep:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.step(real, lengths, gan, use_fm)
+                self.last_losses = {k: v.clone() for k, v in self.step(real, lengths, gan, use_fm).items()}
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         s_real, s_len = real.clone(), lengths.clone()
