@@ -333,6 +333,10 @@ TRAIN_DEFAULTS = {
 HIFISPEECH_PATCH_D = PatchDiscConfig(128, (256, 256, 384, 512, 512), ((5, 5), (5, 5), (5, 5), (3, 3), (3, 3), (3, 3)),
                                      ((1, 2), (2, 2), (2, 2), (2, 1), (2, 1), (2, 1)))
 HIFISPEECH_MULTIBIN_D = MultiBinConfig(128, 8, (128, 128, 256, 256, 384), (7, 5, 3, 3, 3, 3), 2)
+# configs/model_config_hifimusic.yaml:22-31
+HIFIMUSIC_PATCH_D = PatchDiscConfig(160, (384, 384, 512, 512, 512), ((7, 7), (7, 7), (5, 5), (5, 5), (3, 3), (3, 3)),
+                                    ((1, 2), (2, 2), (2, 2), (2, 2), (2, 2), (2, 2)))
+HIFIMUSIC_MULTIBIN_D = MultiBinConfig(160, 8, (128, 256, 256, 256, 256), (7, 5, 5, 3, 3, 3), 2)
 # small discriminators of the same topology for the TINY generator
 TINY_PATCH_D = PatchDiscConfig(32, (16, 16, 32), ((5, 5), (5, 5), (3, 3), (3, 3)), ((1, 2), (2, 2), (2, 1), (1, 1)))
 TINY_MULTIBIN_D = MultiBinConfig(32, 2, (16, 16, 32), (7, 5, 3, 3), 2)

@@ -51,6 +51,21 @@ def _weight_from_taps(dw: Tensor, kind: str) -> Tensor:
     return dw.permute(1, 2, 0).reshape(dw.shape[1], dw.shape[2], 3, 3)
 
 
+def _dgrad_launch(dyb: Tensor, weight: Tensor, kind: str, N: int, H: int, W: int, out: Tensor, tag: str, **epi) -> None:
+    """dx = conv(dy, mirrored weight) into ``out`` (N, H, W, Cin), fp32 or bf16.  mq_conv_gemm takes at most 1024 output
+    channels per launch, and a data gradient's output channels are the layer's INPUT channels (1152 for hifimusic's
+    first up-block): wider ones are produced in channel slices."""
+    wd, kd = ops.dgrad_weight(weight, kind)
+    cin = wd.shape[0]
+    key = "out_bf16" if out.dtype == torch.bfloat16 else "out_f32"
+    off = "bf16_coff" if out.dtype == torch.bfloat16 else "f32_coff"
+    step = cin if cin <= 1024 else 768
+    for c0 in range(0, cin, step):
+        pc = ops.pack_conv(wd[c0:c0 + step], None, kd, on_device=True)
+        extra = {"res_coff": c0} if epi.get("res") is not None else {}
+        ops.conv_gemm(dyb, pc, N, H, W, tag=tag, **{key: out, off: c0}, **epi, **extra)
+
+
 class _ConvFn(torch.autograd.Function):
     """y = conv(x, w) + b on channel-last x (N, H, W, Cin); kind as ops.pack_conv."""
 
@@ -74,9 +89,8 @@ class _ConvFn(torch.autograd.Function):
         dyb = dy.contiguous().to(torch.bfloat16)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wd, kd = ops.dgrad_weight(weight, ctx.kind)
             dx = torch.empty(N, H, W, cin, dtype=torch.float32, device=dy.device)
-            ops.conv_gemm(dyb, ops.pack_conv(wd, None, kd, on_device=True), N, H, W, out_f32=dx, tag=ctx.tag + ".dgrad")
+            _dgrad_launch(dyb, weight, ctx.kind, N, H, W, dx, ctx.tag + ".dgrad")
             dx = dx.to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
             dh, dwt = ops.conv_taps(ctx.kind, weight.shape)
@@ -239,18 +253,16 @@ class _RefConvBlockFn(torch.autograd.Function):
         dh, dwt = ops.conv_taps("conv2d3", w1.shape)
         du2, dres, db2 = ops.act_backward(dy.contiguous(), u2, mask8, W, want_res=ctx.residual, want_bias=True)
         dw2 = _weight_from_taps(ops.conv_wgrad(du2, a1, N, H, W, c2, c1, dh, dwt, tag=tag + ".conv2.wgrad"), "conv2d3")
-        wd, kd = ops.dgrad_weight(w2, "conv2d3")
         da1 = torch.empty(N, H, W, c1, dtype=torch.bfloat16, device=dy.device)
-        ops.conv_gemm(du2, ops.pack_conv(wd, None, kd, on_device=True), N, H, W, out_bf16=da1, tag=tag + ".conv2.dgrad")
+        _dgrad_launch(du2, w2, "conv2d3", N, H, W, da1, tag + ".conv2.dgrad")
         du1, _, db1 = ops.act_backward(da1, u1, None, W, want_bias=True)
         dw1 = _weight_from_taps(ops.conv_wgrad(du1, x, N, H, W, c1, cin, dh, dwt, tag=tag + ".conv1.wgrad"), "conv2d3")
         dx = None
         if ctx.needs_input_grad[0]:
-            wd, kd = ops.dgrad_weight(w1, "conv2d3")
             dx = torch.empty(N, H, W, cin, dtype=torch.bfloat16, device=dy.device)
             # the epilogue adds the skip path's gradient and re-applies the entry mask (x = x.masked_fill(mask) :96)
-            ops.conv_gemm(du1, ops.pack_conv(wd, None, kd, on_device=True), N, H, W, out_bf16=dx, tag=tag + ".conv1.dgrad",
-                          row_mask=mask8, mask_pre=True, res=dres, res_mode=1 if dres is not None else 0)
+            _dgrad_launch(du1, w1, "conv2d3", N, H, W, dx, tag + ".conv1.dgrad", row_mask=mask8, mask_pre=True, res=dres,
+                          res_mode=1 if dres is not None else 0)
         return dx, dw1, db1, dw2, db2, None, None, None
 
 

@@ -341,3 +341,19 @@ def test_graph_replayed_iterations_equal_eager_iterations():
         assert d <= 1e-6 + 1e-4 * float(eager.g[k].detach().abs().max()), (k, d)
     with pytest.raises(KeyError):
         graphed.step_graphed(batches[0][0][:2], batches[0][1][:2])
+
+
+def test_dgrad_wider_than_one_launch_is_sliced():
+    """A data gradient with more than 1024 output channels (hifimusic's first up-block reads 768 + 384 = 1152 channels)
+    is produced in channel slices; against float64 autograd."""
+    from mqgan_b200 import training as TR
+    N, H, W, Cin, Cout = 1, 16, 24, 1152, 64
+    x = _rand(N, H, W, Cin, seed=81).to(torch.bfloat16)
+    w = (_rand(Cout, Cin, 3, 3, seed=82) / (9 * Cin) ** 0.5).to(torch.bfloat16)
+    dy = _rand(N, H, W, Cout, seed=83).to(torch.bfloat16)
+    gx, _ = _ref_grads(x, w, dy, "conv2d3")
+    for dt in (torch.float32, torch.bfloat16):
+        out = torch.empty(N, H, W, Cin, dtype=dt, device=DEV)
+        TR._dgrad_launch(dy.to(DEV), w.float().to(DEV), "conv2d3", N, H, W, out, "t")
+        tol = 2e-4 if dt == torch.float32 else 2.0 ** -7
+        assert float((out.cpu().double() - gx).abs().max()) < tol * max(1.0, float(gx.abs().max()))

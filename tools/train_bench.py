@@ -104,6 +104,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--model", default="hifispeech", choices=["hifispeech", "hifimusic"])
     ap.add_argument("--ref_batch", type=int, default=1)
     ap.add_argument("--ref_frames", type=int, default=64)
     ap.add_argument("--d_fp32", action="store_true", help="discriminator convs in fp32 instead of bf16 autocast")
@@ -126,7 +127,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg, pdc, mbc = S.HIFISPEECH, S.HIFISPEECH_PATCH_D, S.HIFISPEECH_MULTIBIN_D
+    cfg, pdc, mbc = ((S.HIFISPEECH, S.HIFISPEECH_PATCH_D, S.HIFISPEECH_MULTIBIN_D) if args.model == "hifispeech" else
+                     (S.HIFIMUSIC, S.HIFIMUSIC_PATCH_D, S.HIFIMUSIC_MULTIBIN_D))
     B, T = args.batch, args.frames
     ts = TR.TrainStep(cfg, pdc, mbc, synth_state_dict(cfg, 0), synth_disc_state_dict(S.patch_disc_param_spec(pdc), 1),
                       synth_disc_state_dict(S.multibin_param_spec(mbc), 2), dict(S.TRAIN_DEFAULTS), dev,
@@ -239,7 +241,7 @@ def main():
             "metric": METRIC, "value": frames / ms * 1e3, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"hifispeech_train_{B}x{T}", "model": "hifispeech", "batch_per_gpu": B, "frames": T,
+            "config": {"workload": f"{args.model}_train_{B}x{T}", "model": args.model, "batch_per_gpu": B, "frames": T,
                        "precision": "generator conv operands bf16 (fwd, dgrad, wgrad), fp32 accumulate and activations; "
                                     + ("discriminator convs fp32" if args.d_fp32 else "discriminator convs bf16 autocast (train.py:523)"),
                        "weights": "random-init (seed 0/1/2)", "dropout": 0.0,
