@@ -366,14 +366,16 @@ int mq_conv_wgrad(const mq_wgrad_params* p, mq_stream_t stream);
  * row_mask byte per row; parameters are DEVICE arrays [C] (bout: [1]) because they change every step.
  * mq_cb2d_backward returns ds (rows, C) = dL/ds and per-block partial sums part[blocks][3][C] of
  * (dL/dwpw, dL/dbpw, dL/dwout), blocks = mq_cb2d_grad_blocks(rows, C); dL/dbout = sum(dy) is the caller's.
- * The (B, C, C, T) expansion autograd would keep alive in the reference (train.py:380-501 -> backward of
+ * fast_tanh != 0: tanh.approx.f32 (one MUFU op, ~2^-11 relative) instead of the ~1e-7 ex2 + rcp form; the kernels
+ * are MUFU-bound (C tanh per pixel).  The (B, C, C, T) expansion autograd would keep alive in the reference (train.py:380-501 -> backward of
  * preencoder.py:288-295) never exists.
  */
 int mq_cb2d_point_forward(const float* s, const uint8_t* row_mask, int64_t rows, int C, const float* wpw,
-                          const float* bpw, const float* wout, const float* bout, float* y, mq_stream_t stream);
+                          const float* bpw, const float* wout, const float* bout, int fast_tanh, float* y,
+                          mq_stream_t stream);
 int mq_cb2d_grad_blocks(int64_t rows, int C);
 int mq_cb2d_backward(const float* s, const float* dy, const uint8_t* row_mask, int64_t rows, int C,
-                     const float* wpw, const float* bpw, const float* wout, float* ds, float* part,
+                     const float* wpw, const float* bpw, const float* wout, int fast_tanh, float* ds, float* part,
                      mq_stream_t stream);
 
 /* ---- f4 (training step): fused activation passes of the refiner's ConvBlock ----- */

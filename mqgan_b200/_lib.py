@@ -145,10 +145,10 @@ SIGNATURES = {
     "mq_conv_wgrad_split": (C.c_int, [C.POINTER(WgradParams)]),
     "mq_conv_wgrad": (C.c_int, [C.POINTER(WgradParams), C.c_void_p]),
     "mq_cb2d_point_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
-                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mq_cb2d_grad_blocks": (C.c_int, [C.c_int64, C.c_int]),
     "mq_cb2d_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mq_act_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float,
                                  C.c_void_p, C.c_void_p]),
     "mq_act_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float,

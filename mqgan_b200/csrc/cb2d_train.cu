@@ -24,15 +24,18 @@ constexpr int kCbPixPerThread = 4;
 constexpr int kCbThreads = 256;
 constexpr int kCbGradPix = 1024;        // pixels per block of the parameter-gradient kernel
 
+// kFast: tanh.approx.f32 (one MUFU op, ~2^-11 relative error - below the bf16 rounding of the convolutions around it)
+// instead of ex2 + rcp (two MUFU ops, ~1e-7 absolute): these kernels are MUFU-bound, so it is nearly 2x.
+template <bool kFast>
 __device__ __forceinline__ void cb_eval(float u, float& a, float& da) {
-  const float t = tanh_precise(u);
+  const float t = kFast ? tanh_fast(u) : tanh_precise(u);
   const float h = 0.5f * (1.0f + t);
   a = h * u;
   da = fmaf(0.5f * u, fmaf(-t, t, 1.0f), h);
 }
 
 // mode 0: y = g(s);  mode 1: ds = dy * g'(s)
-template <int kMode>
+template <int kMode, bool kFast>
 __global__ void __launch_bounds__(kCbThreads) cb2d_point_kernel(const float* __restrict__ s, const float* __restrict__ dy,
                                                                const uint8_t* __restrict__ row_mask, long long rows, int C,
                                                                const float* __restrict__ wpw, const float* __restrict__ bpw,
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(kCbThreads) cb2d_point_kernel(const float* __r
 #pragma unroll
     for (int i = 0; i < kCbPixPerThread; ++i) {
       float a, da;
-      cb_eval(fmaf(q.x, sv[i], q.y), a, da);
+      cb_eval<kFast>(fmaf(q.x, sv[i], q.y), a, da);
       acc[i] = kMode == 0 ? fmaf(q.z, a, acc[i]) : fmaf(q.w, da, acc[i]);
     }
   }
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(kCbThreads) cb2d_point_kernel(const float* __r
 }
 
 // parameter gradients: thread k, pixels [blockIdx.x * kCbGradPix, +kCbGradPix) broadcast from shared memory
+template <bool kFast>
 __global__ void __launch_bounds__(1024) cb2d_param_grad_kernel(const float* __restrict__ s, const float* __restrict__ dy,
                                                                 const uint8_t* __restrict__ row_mask, long long rows, int C,
                                                                 const float* __restrict__ wpw, const float* __restrict__ bpw,
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(1024) cb2d_param_grad_kernel(const float* __re
     for (int i = 0; i < kCbGradPix; ++i) {
       const float2 v = px[i];
       float a, da;
-      cb_eval(fmaf(w, v.x, b), a, da);
+      cb_eval<kFast>(fmaf(w, v.x, b), a, da);
       g_wout = fmaf(v.y, a, g_wout);
       const float g = v.y * da;
       g_bpw += g;
@@ -113,7 +117,8 @@ __global__ void __launch_bounds__(1024) cb2d_param_grad_kernel(const float* __re
 using namespace mq;
 
 extern "C" int mq_cb2d_point_forward(const float* s, const uint8_t* row_mask, int64_t rows, int C, const float* wpw,
-                                     const float* bpw, const float* wout, const float* bout, float* y, mq_stream_t stream_) {
+                                     const float* bpw, const float* wout, const float* bout, int fast_tanh, float* y,
+                                     mq_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MQ_REQUIRE(s && wpw && bpw && wout && bout && y, "mq_cb2d_point_forward: null pointer argument");
   MQ_REQUIRE(rows >= 0 && C >= 1 && C <= 2048, "mq_cb2d_point_forward: rows=%lld C=%d", (long long)rows, C);
@@ -122,8 +127,12 @@ extern "C" int mq_cb2d_point_forward(const float* s, const uint8_t* row_mask, in
   const long long per_block = static_cast<long long>(kCbThreads) * kCbPixPerThread;
   const long long grid = (total + per_block - 1) / per_block;
   MQ_REQUIRE(grid < (1LL << 31), "mq_cb2d_point_forward: too many pixels");
-  cb2d_point_kernel<0><<<static_cast<unsigned>(grid), kCbThreads, C * sizeof(float4), stream>>>(s, nullptr, row_mask, rows, C, wpw,
-                                                                                            bpw, wout, bout, y);
+  if (fast_tanh)
+    cb2d_point_kernel<0, true><<<static_cast<unsigned>(grid), kCbThreads, C * sizeof(float4), stream>>>(s, nullptr, row_mask, rows,
+                                                                                                    C, wpw, bpw, wout, bout, y);
+  else
+    cb2d_point_kernel<0, false><<<static_cast<unsigned>(grid), kCbThreads, C * sizeof(float4), stream>>>(s, nullptr, row_mask, rows,
+                                                                                                     C, wpw, bpw, wout, bout, y);
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -134,7 +143,7 @@ extern "C" int mq_cb2d_grad_blocks(int64_t rows, int C) {
 }
 
 extern "C" int mq_cb2d_backward(const float* s, const float* dy, const uint8_t* row_mask, int64_t rows, int C,
-                                const float* wpw, const float* bpw, const float* wout, float* ds, float* part,
+                                const float* wpw, const float* bpw, const float* wout, int fast_tanh, float* ds, float* part,
                                 mq_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MQ_REQUIRE(s && dy && wpw && bpw && wout && ds && part, "mq_cb2d_backward: null pointer argument");
@@ -145,12 +154,19 @@ extern "C" int mq_cb2d_backward(const float* s, const float* dy, const uint8_t* 
   const long long grid = (total + per_block - 1) / per_block;
   MQ_REQUIRE(grid < (1LL << 31), "mq_cb2d_backward: too many pixels");
   // bout is unused by the ds pass; wout stands in for the pointer
-  cb2d_point_kernel<1><<<static_cast<unsigned>(grid), kCbThreads, C * sizeof(float4), stream>>>(s, dy, row_mask, rows, C, wpw, bpw,
-                                                                                            wout, wout, ds);
+  if (fast_tanh)
+    cb2d_point_kernel<1, true><<<static_cast<unsigned>(grid), kCbThreads, C * sizeof(float4), stream>>>(s, dy, row_mask, rows, C, wpw,
+                                                                                                    bpw, wout, wout, ds);
+  else
+    cb2d_point_kernel<1, false><<<static_cast<unsigned>(grid), kCbThreads, C * sizeof(float4), stream>>>(s, dy, row_mask, rows, C, wpw,
+                                                                                                     bpw, wout, wout, ds);
   MQ_CUDA_OK(cudaGetLastError());
   const int gblocks = mq_cb2d_grad_blocks(rows, C);
   const int threads = C >= 1024 ? 1024 : ((C + 31) / 32 * 32);
-  cb2d_param_grad_kernel<<<gblocks, threads, 0, stream>>>(s, dy, row_mask, rows, C, wpw, bpw, wout, part);
+  if (fast_tanh)
+    cb2d_param_grad_kernel<true><<<gblocks, threads, 0, stream>>>(s, dy, row_mask, rows, C, wpw, bpw, wout, part);
+  else
+    cb2d_param_grad_kernel<false><<<gblocks, threads, 0, stream>>>(s, dy, row_mask, rows, C, wpw, bpw, wout, part);
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -607,7 +607,8 @@ def leaky_mask_backward(dout: torch.Tensor, y: torch.Tensor, pix_mask: torch.Ten
     return du
 
 
-def cb2d_point_forward(s: torch.Tensor, wpw, bpw, wout, bout, row_mask: Optional[torch.Tensor]) -> torch.Tensor:
+def cb2d_point_forward(s: torch.Tensor, wpw, bpw, wout, bout, row_mask: Optional[torch.Tensor],
+                       fast_tanh: bool = False) -> torch.Tensor:
     """s (B, T, C) fp32 (masked depth-wise output) -> y (B, T, C): mq_cb2d_point_forward."""
     _chk(s, torch.float32, "s")
     Cc = s.shape[-1]
@@ -617,11 +618,12 @@ def cb2d_point_forward(s: torch.Tensor, wpw, bpw, wout, bout, row_mask: Optional
         _chk(row_mask, torch.uint8, "row_mask")
     y = torch.empty_like(s)
     _lib.call("mq_cb2d_point_forward", s.data_ptr(), _ptr(row_mask), rows, Cc, prm[0].data_ptr(), prm[1].data_ptr(),
-              prm[2].data_ptr(), prm[3].data_ptr(), y.data_ptr(), _stream())
+              prm[2].data_ptr(), prm[3].data_ptr(), int(fast_tanh), y.data_ptr(), _stream())
     return y
 
 
-def cb2d_point_backward(s: torch.Tensor, dy: torch.Tensor, wpw, bpw, wout, row_mask: Optional[torch.Tensor]):
+def cb2d_point_backward(s: torch.Tensor, dy: torch.Tensor, wpw, bpw, wout, row_mask: Optional[torch.Tensor],
+                        fast_tanh: bool = False):
     """-> (ds, dwpw, dbpw, dwout, dbout) for y = cb2d_point_forward(s, ...): mq_cb2d_backward (two launches)."""
     _chk(s, torch.float32, "s")
     _chk(dy, torch.float32, "dy")
@@ -632,7 +634,7 @@ def cb2d_point_backward(s: torch.Tensor, dy: torch.Tensor, wpw, bpw, wout, row_m
     ds = torch.empty_like(s)
     part = torch.empty(nb, 3, Cc, dtype=torch.float32, device=s.device)
     _lib.call("mq_cb2d_backward", s.data_ptr(), dy.data_ptr(), _ptr(row_mask), rows, Cc, prm[0].data_ptr(),
-              prm[1].data_ptr(), prm[2].data_ptr(), ds.data_ptr(), part.data_ptr(), _stream())
+              prm[1].data_ptr(), prm[2].data_ptr(), int(fast_tanh), ds.data_ptr(), part.data_ptr(), _stream())
     g = part.sum(dim=0)
     return ds, g[0], g[1], g[2], dy.sum().reshape(1)
 

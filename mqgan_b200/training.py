@@ -125,20 +125,21 @@ class _Cb2dPointFn(torch.autograd.Function):
     """y[p] = sum_k wout_k * aptx(wpw_k * s[p] + bpw_k; 1, .5) + bout over valid rows, bout at padded rows."""
 
     @staticmethod
-    def forward(ctx, s, wpw, bpw, wout, bout, row_mask):
-        B, T, Cc = s.shape
-        y = ops.cb2d_point_forward(s, wpw, bpw, wout, bout, row_mask)
+    def forward(ctx, s, wpw, bpw, wout, bout, row_mask, fast_tanh):
+        y = ops.cb2d_point_forward(s, wpw, bpw, wout, bout, row_mask, fast_tanh)
         ctx.save_for_backward(s, wpw, bpw, wout, row_mask)
+        ctx.fast_tanh = fast_tanh
         return y
 
     @staticmethod
     def backward(ctx, dy):
         s, wpw, bpw, wout, row_mask = ctx.saved_tensors
-        ds, dwpw, dbpw, dwout, dbout = ops.cb2d_point_backward(s, dy.contiguous(), wpw, bpw, wout, row_mask)
-        return ds, dwpw, dbpw, dwout, dbout, None
+        ds, dwpw, dbpw, dwout, dbout = ops.cb2d_point_backward(s, dy.contiguous(), wpw, bpw, wout, row_mask, ctx.fast_tanh)
+        return ds, dwpw, dbpw, dwout, dbout, None, None
 
 
-def convblock2d(x: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], prefix: str, native: bool = True) -> Tensor:
+def convblock2d(x: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], prefix: str, native: bool = True,
+                fast_tanh: bool = True) -> Tensor:
     """x (B, T, C) -> (B, T, C).  The 5x5 depth-wise conv over the (channel, time) plane is a 25-tap torch
     conv2d; the C-fold point-wise expansion + APTx + contraction is one fused kernel each way."""
     B, T, Cc = x.shape
@@ -150,7 +151,7 @@ def convblock2d(x: Tensor, mask_bt: Tensor, w: Dict[str, Tensor], prefix: str, n
     wout = w[prefix + ".conv_out.weight"].reshape(Cc)
     bout = w[prefix + ".conv_out.bias"].reshape(1)
     if native:
-        return _Cb2dPointFn.apply(s.contiguous(), wpw, bpw, wout, bout, mask_bt.to(torch.uint8).contiguous())
+        return _Cb2dPointFn.apply(s.contiguous(), wpw, bpw, wout, bout, mask_bt.to(torch.uint8).contiguous(), fast_tanh)
     # plain-torch form of the same arithmetic (memory-hungry; kept as the on-device cross-check)
     u = (s.unsqueeze(-1) * wpw + bpw).masked_fill(mask_bt[:, :, None, None], 0.0)    # (B,T,C,K) :288-292
     return (aptx(u, 1.0, 0.5) * wout).sum(dim=-1) + bout                             # :293-295
@@ -326,13 +327,13 @@ def fsq_quantize_ste(z: Tensor, levels: Sequence[int]) -> Tensor:
 
 
 def generator_forward(params: Dict[str, Tensor], cfg: PreEncoderConfig, mel: Tensor, lengths: Tensor,
-                      native_cb2d: bool = True) -> Tuple[Tensor, Tensor]:
+                      native_cb2d: bool = True, cb2d_fast_tanh: bool = True) -> Tuple[Tensor, Tensor]:
     """PreEncoder.forward (preencoder.py:363-418), dropout 0 -> (x_recon, x_post), both (B, T, mel)."""
     w = effective_weights(params)
     B, T, n_mels = mel.shape
     mask_bt = torch.arange(T, device=mel.device)[None, :] >= lengths.to(mel.device)[:, None]
     x = conv(mel.reshape(B, T, 1, n_mels), w["proj.weight"], w["proj.bias"], "linear", "proj").reshape(B, T, -1)
-    x = convblock2d(x, mask_bt, w, "pre", native_cb2d)
+    x = convblock2d(x, mask_bt, w, "pre", native_cb2d, cb2d_fast_tanh)
     for i in range(len(cfg.encoder_layers)):
         x = _residual_block(x, mask_bt, w, f"encoder_blocks.{i}", causal=False)
     z = F.linear(x, w["q_in_proj.weight"], w["q_in_proj.bias"])
@@ -340,7 +341,7 @@ def generator_forward(params: Dict[str, Tensor], cfg: PreEncoderConfig, mel: Ten
     dec = F.linear(codes, w["q_out_proj.weight"], w["q_out_proj.bias"])
     for i in range(len(cfg.decoder_layers)):
         dec = _residual_block(dec, mask_bt, w, f"decoder_blocks.{i}", causal=True)
-    xr = convblock2d(dec, mask_bt, w, "post", native_cb2d)
+    xr = convblock2d(dec, mask_bt, w, "post", native_cb2d, cb2d_fast_tanh)
     x_recon = conv(xr.reshape(B, T, 1, -1), w["out_proj.weight"], w["out_proj.bias"], "linear", "out_proj").reshape(B, T, -1)
     hid = conv(dec.reshape(B, T, 1, -1), w["hidden_proj.weight"], w["hidden_proj.bias"], "linear", "hidden_proj").reshape(B, T, -1)
     r_in = torch.cat([x_recon, hid], dim=2).detach()                               # :411-413
@@ -609,7 +610,7 @@ class TrainStep:
 
     def __init__(self, cfg: PreEncoderConfig, pd_cfg: PatchDiscConfig, mb_cfg: MultiBinConfig, g_sd, pd_sd, mb_sd,
                  tcfg: dict, device, dropout_p: float = 0.0, d_autocast_bf16: bool = False, native_cb2d: bool = True,
-                 group=None):
+                 cb2d_fast_tanh: bool = True, group=None):
         if dropout_p != 0.0:
             raise NotImplementedError("mqgan_b200.training implements dropout = 0 only (see module docstring)")
         dev = torch.device(device)
@@ -618,7 +619,7 @@ class TrainStep:
         ops._lib.lib()                                    # fail now if the extension is missing
         self.cfg, self.pd_cfg, self.mb_cfg, self.tcfg = cfg, pd_cfg, mb_cfg, tcfg
         self.device, self.group = dev, group
-        self.d_autocast_bf16, self.native_cb2d = d_autocast_bf16, native_cb2d
+        self.d_autocast_bf16, self.native_cb2d, self.cb2d_fast_tanh = d_autocast_bf16, native_cb2d, cb2d_fast_tanh
         self.g = {k: v.detach().clone().float().to(dev).requires_grad_(True) for k, v in g_sd.items()}
         self.pd = {k: v.detach().clone().float().to(dev) for k, v in pd_sd.items()}
         self.mb = {k: v.detach().clone().float().to(dev) for k, v in mb_sd.items()}
@@ -710,7 +711,7 @@ class TrainStep:
         real = real.to(self.device, non_blocking=True)
         lengths = lengths.to(self.device, non_blocking=True)
         ac = self.d_autocast_bf16
-        recon_pre, recon_post = generator_forward(self.g, self.cfg, real, lengths, self.native_cb2d)
+        recon_pre, recon_post = generator_forward(self.g, self.cfg, real, lengths, self.native_cb2d, self.cb2d_fast_tanh)
         out: Dict[str, Tensor] = {"loss_d": real.new_zeros(())}
         if gan:                                                                     # _train_discriminator
             self.red_d.zero()

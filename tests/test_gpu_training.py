@@ -145,6 +145,12 @@ def test_cb2d_point_forward_backward_match_float64_autograd(B, T, C):
     assert close(dbpw, p[2].grad, 2e-5)
     assert close(dwout, p[3].grad, 2e-5)
     assert close(dbout, p[4].grad, 2e-5)
+    # tanh.approx mode (the training default: the kernels are MUFU-bound): ~2^-11 relative on each tanh
+    yf = ops.cb2d_point_forward(s.to(DEV), wpw.to(DEV), bpw.to(DEV), wout.to(DEV), bout.to(DEV), m8, fast_tanh=True)
+    gf = ops.cb2d_point_backward(s.to(DEV), dy.to(DEV), wpw.to(DEV), bpw.to(DEV), wout.to(DEV), m8, fast_tanh=True)
+    assert close(yf, y_ref.detach(), 2e-3)
+    for got, ref in zip(gf, (p[0].grad, p[1].grad, p[2].grad, p[3].grad, p[4].grad)):
+        assert close(got, ref, 4e-3)
 
 
 # ----------------------------------------------------------------------------
