@@ -228,9 +228,8 @@ def main():
     def step_e2e():
         x = mel_host.to(dev, non_blocking=True)
         idx = model.encode(x, None)
-        out = model.decode(idx, None)
-        out_host.copy_(out, non_blocking=True)
         idx_host.copy_(idx, non_blocking=True)
+        model.decode(idx, None, host_out=out_host)        # chunk-wise D2H overlapped with the remaining chunks' compute
 
     def barrier():
         torch.cuda.synchronize()

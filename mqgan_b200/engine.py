@@ -134,6 +134,7 @@ class PreEncoderEngine:
         self.enc_split = encoder_precision != "bf16"
         self.encoder_precision = encoder_precision
         self.max_chunk_frames = int(max_chunk_frames)
+        self._copy_stream = None
         # the encoder's live set is ~22 KB per frame (the refiner's is ~10x that), so it runs in 8x larger
         # utterance chunks: fewer, fuller waves of GEMM tiles and 8x fewer launches of the CBAM reductions
         self.max_chunk_frames_enc = int(max_chunk_frames_enc)
@@ -309,8 +310,12 @@ class PreEncoderEngine:
 
     # ------------------------------------------------------------------
     def decode(self, indices: torch.Tensor, mask: Optional[torch.Tensor] = None, return_hidden: bool = False,
-               taps: Optional[dict] = None, return_recon: bool = False):
-        """indices (B,T) int -> x_post (B,T,n_mels) fp32 [, decoder_out (B,C0,T)] [, x_recon (B,T,n_mels)]."""
+               taps: Optional[dict] = None, return_recon: bool = False, host_out: Optional[torch.Tensor] = None):
+        """indices (B,T) int -> x_post (B,T,n_mels) fp32 [, decoder_out (B,C0,T)] [, x_recon (B,T,n_mels)].
+
+        ``host_out``: optional pinned host tensor (B,T,n_mels) fp32.  Each refiner chunk's result is copied to it on a
+        side stream as soon as the chunk is done, so the device-to-host transfer of the re-encoded mels overlaps the
+        remaining chunks' compute; the caller's stream waits for the copies before ``decode`` returns."""
         if indices.dim() != 2:
             raise ValueError(f"indices must be (B, T), got {tuple(indices.shape)}")
         B, T = indices.shape
@@ -320,6 +325,14 @@ class PreEncoderEngine:
         hid = torch.empty(B, T, self.cfg.c0, dtype=torch.float32, device=self.device) if return_hidden else None
         recon = torch.empty_like(out) if return_recon else None
         bad = torch.zeros(1, dtype=torch.int32, device=self.device)      # out-of-range index flag, read once below
+        copy_stream = None
+        if host_out is not None:
+            if host_out.shape != out.shape or host_out.dtype != torch.float32 or not host_out.is_pinned():
+                raise ValueError("host_out must be a pinned float32 host tensor of shape (B, T, n_mels)")
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            copy_stream = self._copy_stream
+            main = torch.cuda.current_stream(self.device)
         # The 1-D decoder (live set ~10 KB per frame) runs in the large encoder-size chunks; only the
         # refiner (~0.2 MB per frame) is cut into the small ones.
         for c0, c1 in self._chunks(B, T, self.max_chunk_frames_enc):
@@ -333,6 +346,12 @@ class PreEncoderEngine:
             for b0, b1 in self._chunks(c1 - c0, T):
                 self._refiner(Rv[b0:b1].reshape((b1 - b0) * T, -1), None if mc is None else mc[b0:b1], b1 - b0, T,
                               out[c0 + b0:c0 + b1], taps)                                    # :496-499
+                if copy_stream is not None:
+                    copy_stream.wait_stream(main)
+                    with torch.cuda.stream(copy_stream):
+                        host_out[c0 + b0:c0 + b1].copy_(out[c0 + b0:c0 + b1], non_blocking=True)
+        if copy_stream is not None:
+            main.wait_stream(copy_stream)
         # one host sync per decode call (not per chunk: a sync drains the launch queue and idles the GPU)
         if int(bad.item()) != 0:
             raise IndexError("decode: index outside [0, codebook_size)")

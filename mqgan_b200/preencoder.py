@@ -127,9 +127,10 @@ class PreEncoder(nn.Module):
         return self.engine().encode(x.to(self._device()), x_mask)
 
     @torch.no_grad()
-    def decode(self, indices, x_mask=None, return_hidden=False):
-        """(B, T) int -> (B, T, mel) [, (B, C0, T)] (preencoder.py:453-504)."""
-        return self.engine().decode(indices.to(self._device()), x_mask, return_hidden=return_hidden)
+    def decode(self, indices, x_mask=None, return_hidden=False, *, host_out=None):
+        """(B, T) int -> (B, T, mel) [, (B, C0, T)] (preencoder.py:453-504).  ``host_out`` (additive, keyword-only):
+        a pinned host tensor that receives the result chunk by chunk while later chunks are still computing."""
+        return self.engine().decode(indices.to(self._device()), x_mask, return_hidden=return_hidden, host_out=host_out)
 
     def forward(self, x, x_lengths):
         """(x_recon, x_post) as preencoder.py:363-418, inference only."""

@@ -151,6 +151,29 @@ def test_batch_invariance_and_determinism():
     assert torch.equal(d1, d2)
 
 
+def test_decode_streams_result_to_pinned_host_buffer():
+    """decode(..., host_out=pinned) copies every refiner chunk to the host while later chunks compute; the host
+    buffer equals the returned device tensor once decode has returned and the stream is synchronised."""
+    cfg, sd, mel, lengths, fx = load_golden("tiny")
+    T = mel.shape[1]
+    mask = sequence_mask(T, lengths).unsqueeze(1)
+    model = _model(cfg, sd)
+    idx = model.encode(mel.cuda(), mask.cuda())
+    eng = model.engine()
+    old = eng.max_chunk_frames
+    eng.max_chunk_frames = T                                      # one utterance per refiner chunk -> several copies
+    try:
+        host = torch.full((mel.shape[0], T, cfg.mel_channels), float("nan")).pin_memory()
+        dev_out = model.decode(idx, mask.cuda(), host_out=host)
+        torch.cuda.synchronize()
+        assert torch.equal(host, dev_out.cpu())
+        assert torch.equal(dev_out, model.decode(idx, mask.cuda()))
+    finally:
+        eng.max_chunk_frames = old
+    with pytest.raises(ValueError):
+        model.decode(idx, mask.cuda(), host_out=torch.empty(mel.shape[0], T, cfg.mel_channels))     # not pinned
+
+
 def test_hifispeech_longer_ragged_batch_vs_oracle():
     """A larger seeded case than the fixtures (B=4, T=200, ragged), checked against the oracle run here."""
     cfg, sd, _, _, _ = load_golden("hifispeech")
