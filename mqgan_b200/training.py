@@ -536,6 +536,10 @@ class GradBucketReducer:
     def __init__(self, params: Sequence[Tensor], bucket_bytes: int = 25 << 20, group=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        # CUDA streams other than the hook's current one on which gradients of a bucket may have been produced (the
+        # multi-bin discriminator's bands run on side streams): the all-reduce must wait for all of them, not only for
+        # the stream the LAST gradient of the bucket arrived on
+        self.producer_streams: List["torch.cuda.Stream"] = []
         self.world = torch.distributed.get_world_size(group) if torch.distributed.is_initialized() else 1
         self.buckets: List[Tensor] = []
         self._bucket_of: Dict[int, int] = {}
@@ -576,6 +580,11 @@ class GradBucketReducer:
 
     def _launch(self, bi: int):
         self._launched[bi] = True
+        if self.producer_streams and self.buckets[bi].is_cuda:
+            cur = torch.cuda.current_stream(self.buckets[bi].device)
+            for st in self.producer_streams:
+                if st != cur:
+                    cur.wait_stream(st)
         self._handles.append(torch.distributed.all_reduce(self.buckets[bi], group=self.group, async_op=True))
 
     def _hook(self, p: Tensor):
@@ -643,6 +652,7 @@ class TrainStep:
         _fsq_constants(cfg.fsq_levels, dev)
         self.red_g = GradBucketReducer(list(self.g.values()), group=group)
         self.red_d = GradBucketReducer(self.d_params(), group=group)
+        self._band_streams = _side_streams(dev, mb_cfg.n_bins)
 
     def d_params(self) -> List[Tensor]:
         return [v for sd in (self.pd, self.mb) for v in sd.values() if v.requires_grad]
@@ -715,6 +725,9 @@ class TrainStep:
         out: Dict[str, Tensor] = {"loss_d": real.new_zeros(())}
         if gan:                                                                     # _train_discriminator
             self.red_d.zero()
+            # discriminator gradients are produced on the bands' side streams and on the stream this step runs on (the
+            # capture stream when a CUDA graph is being recorded)
+            self.red_d.producer_streams = self._band_streams + [torch.cuda.current_stream(self.device)]
             fake = recon_post.detach()
             if self.d_training:
                 # two passes, as the reference makes them: in training mode each forward advances the spectral-norm
