@@ -403,6 +403,19 @@ int mq_leaky_mask_forward(const void* u, int u_is_bf16, const float* bias, const
 int mq_leaky_mask_backward(const void* dy_bf16, const void* u, int u_is_bf16, const float* bias, const uint8_t* pix_mask,
                            int64_t pixels, int C, float slope, void* du_bf16, float* dbias_part, mq_stream_t stream);
 
+/* ---- f2: .npy file I/O of the re-encode CLI (host code; reencode_spectrograms.py:49-62, 69-81) ------------ */
+/*
+ * Foreign calls run without the Python GIL, so the CLI's I/O threads scale; np.load / np.save do not for small files.
+ * mq_npy_probe: shape of a C-order 2-D little-endian float32 / float64 / float16 .npy (dtype 0 / 1 / 2).
+ * mq_npy_read_f32: reads min(rows, dst_rows) rows into dst (dst_rows, cols) as float32 and zero-fills the rest (the
+ * reference's zero padding to the batch's longest utterance); *rows_out = rows in the file.
+ * mq_npy_write_f32: writes src (rows, cols) float32 exactly as np.save would (format 1.0, 64-byte aligned data).
+ * Return 0 ok, 1 bad argument / column mismatch, 4 unsupported file (the caller falls back to numpy), 5 I/O error.
+ */
+int mq_npy_probe(const char* path, int64_t* rows, int64_t* cols, int* dtype, int64_t* data_offset);
+int mq_npy_read_f32(const char* path, float* dst, int64_t dst_rows, int64_t cols, int64_t* rows_out);
+int mq_npy_write_f32(const char* path, const float* src, int64_t rows, int64_t cols);
+
 /* ---- sequence mask (preencoder.py:15-24) ----------------------------------- */
 int mq_sequence_mask(const int64_t* lengths, int B, int T, uint8_t* mask, mq_stream_t stream);
 

@@ -158,6 +158,9 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p]),
     "mq_leaky_mask_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                          C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mq_npy_probe": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "mq_npy_read_f32": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
+    "mq_npy_write_f32": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int64]),
     "mq_log_mel": (C.c_int, [C.POINTER(MelspecParams), C.c_void_p]),
     "mq_code_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

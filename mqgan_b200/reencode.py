@@ -65,14 +65,90 @@ def sort_batches_by_length(files: Sequence[str]) -> List[str]:
     (less padding).  NOT the reference's batch composition: batch composition influences the encoder
     through padding, so this can change indices; off by default."""
     def n_frames(p):
+        if NATIVE_IO:
+            sh = _native_probe(p)              # header only, GIL-free
+            if sh is not None:
+                return sh[0]
         return int(np.load(p, mmap_mode="r").shape[0])
     lens = list(_pool().map(n_frames, files))
     return [f for _, f in sorted(zip(lens, files), key=lambda t: (t[0], t[1]))]
 
 
-def load_and_pad(paths: Sequence[str]) -> Tuple[torch.Tensor, List[int]]:
-    """np.load each file, zero-pad to the longest, stack, float32 (reencode_spectrograms.py:49-62)."""
-    specs = list(_pool().map(np.load, paths)) if len(paths) > 1 and IO_THREADS > 1 else [np.load(p) for p in paths]
+NATIVE_IO = os.environ.get("MQ_NATIVE_IO", "1") != "0"     # .npy parsing / writing in the library (GIL-free), numpy otherwise
+
+
+class _PinnedPool:
+    """Reusable page-locked staging buffers: cudaHostAlloc per batch costs more than the copy it speeds up."""
+
+    def __init__(self):
+        self._free: List[torch.Tensor] = []
+        self._lock = threading.Lock()
+
+    def get(self, numel: int) -> torch.Tensor:
+        with self._lock:
+            for i, t in enumerate(self._free):
+                if t.numel() >= numel:
+                    return self._free.pop(i)
+        n = max(int(numel * 1.25), 1 << 20)
+        return torch.empty(n, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+
+    def put(self, t: Optional[torch.Tensor]) -> None:
+        if t is not None:
+            with self._lock:
+                if len(self._free) < 8:
+                    self._free.append(t)
+
+
+_pinned = _PinnedPool()
+
+
+def _native_probe(path: str):
+    """(rows, cols) of a float .npy the library can read, None if it needs numpy."""
+    from . import _lib
+    import ctypes as C
+    rows, cols = C.c_int64(), C.c_int64()
+    rc = _lib.lib().mq_npy_probe(os.fsencode(path), C.byref(rows), C.byref(cols), None, None)
+    if rc == 4:
+        return None
+    if rc != 0:
+        raise OSError(_lib.lib().mq_last_error().decode(errors="replace"))
+    return int(rows.value), int(cols.value)
+
+
+def load_and_pad(paths: Sequence[str], pooled: bool = False):
+    """Load each file, zero-pad to the longest, stack, float32 (reencode_spectrograms.py:49-62).  Returns
+    (batch (B, Tmax, M), lengths) - plus the pooled staging buffer to hand back to ``_pinned.put`` when ``pooled``."""
+    def done(batch, lengths, handle=None):
+        return (batch, lengths, handle) if pooled else (batch, lengths)
+
+    threaded = len(paths) > 1 and IO_THREADS > 1
+    if NATIVE_IO:
+        from . import _lib
+        import ctypes as C
+        shapes = list(_pool().map(_native_probe, paths)) if threaded else [_native_probe(p) for p in paths]
+        if all(sh is not None for sh in shapes):
+            lengths = [sh[0] for sh in shapes]
+            max_len, n_mels = max(lengths), shapes[0][1]
+            for p, sh in zip(paths, shapes):
+                if sh[1] != n_mels:
+                    raise ValueError(f"{p}: {sh[1]} mel channels, expected {n_mels}")
+            flat = _pinned.get(len(paths) * max_len * n_mels) if pooled else torch.empty(len(paths) * max_len * n_mels)
+            batch = flat[: len(paths) * max_len * n_mels].view(len(paths), max_len, n_mels)
+            base, pitch = batch.data_ptr(), max_len * n_mels * 4
+            lib = _lib.lib()
+
+            def read_one(i):
+                rc = lib.mq_npy_read_f32(os.fsencode(paths[i]), base + i * pitch, max_len, n_mels, None)
+                if rc != 0:
+                    raise OSError(lib.mq_last_error().decode(errors="replace"))
+
+            if threaded:
+                list(_pool().map(read_one, range(len(paths))))
+            else:
+                for i in range(len(paths)):
+                    read_one(i)
+            return done(batch, lengths, flat if pooled else None)
+    specs = list(_pool().map(np.load, paths)) if threaded else [np.load(p) for p in paths]
     lengths = [int(s.shape[0]) for s in specs]
     max_len = max(lengths)
     n_mels = specs[0].shape[1]
@@ -81,18 +157,29 @@ def load_and_pad(paths: Sequence[str]) -> Tuple[torch.Tensor, List[int]]:
         if s.shape[1] != n_mels:
             raise ValueError(f"{paths[i]}: {s.shape[1]} mel channels, expected {n_mels}")
         batch[i, : s.shape[0]] = s
-    return torch.from_numpy(batch), lengths
+    return done(torch.from_numpy(batch), lengths)
 
 
 def save_outputs(reencoded: torch.Tensor, lengths: Sequence[int], paths: Sequence[str], input_dir: str,
                  output_dir: str) -> None:
     """Trim to the original length and save under the mirrored path (:69-81)."""
-    arr = reencoded.numpy() if not reencoded.is_cuda else reencoded.cpu().numpy()
+    t = reencoded if not reencoded.is_cuda else reencoded.cpu()
+    native = NATIVE_IO and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 3
+    arr = None if native else t.numpy()
+    if native:
+        from . import _lib
+        lib = _lib.lib()
+        base, pitch, n_mels = t.data_ptr(), t.shape[1] * t.shape[2] * 4, t.shape[2]
 
     def save_one(i):
         out_path = os.path.join(output_dir, os.path.relpath(paths[i], input_dir))
         os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
-        np.save(out_path, np.ascontiguousarray(arr[i, : lengths[i], :], dtype=np.float32))
+        if native:
+            rc = lib.mq_npy_write_f32(os.fsencode(out_path), base + i * pitch, int(lengths[i]), n_mels)
+            if rc != 0:
+                raise OSError(lib.mq_last_error().decode(errors="replace"))
+        else:
+            np.save(out_path, np.ascontiguousarray(arr[i, : lengths[i], :], dtype=np.float32))
 
     if len(paths) > 1 and IO_THREADS > 1:
         list(_pool().map(save_one, range(len(paths))))
@@ -124,12 +211,12 @@ def reencode_tree(run_batch: Callable[[torch.Tensor, List[int]], torch.Tensor], 
         for bi in mine:
             paths = batches[bi]
             try:
-                batch, lengths = load_and_pad(paths)
-                if torch.cuda.is_available():
+                batch, lengths, handle = load_and_pad(paths, pooled=True)
+                if handle is None and torch.cuda.is_available():
                     batch = batch.pin_memory()
-                in_q.put((paths, batch, lengths, None))
+                in_q.put((paths, batch, lengths, None, handle))
             except Exception as e:  # noqa: BLE001 - mirror the reference's catch-all (:83-85)
-                in_q.put((paths, None, None, e))
+                in_q.put((paths, None, None, e, None))
         in_q.put(None)
 
     failed = [0]
@@ -139,12 +226,14 @@ def reencode_tree(run_batch: Callable[[torch.Tensor, List[int]], torch.Tensor], 
             item = out_q.get()
             if item is None:
                 return
-            paths, out, lengths = item
+            paths, out, lengths, handle = item
             try:
                 save_outputs(out, lengths, paths, input_dir, output_dir)
             except Exception as e:  # noqa: BLE001
                 failed[0] += 1
                 print(f"\nCould not save batch starting with {paths[0]}. Error: {e}")
+            finally:
+                _pinned.put(handle)
 
     rt = threading.Thread(target=reader, daemon=True)
     wt = threading.Thread(target=writer, daemon=True)
@@ -162,22 +251,29 @@ def reencode_tree(run_batch: Callable[[torch.Tensor, List[int]], torch.Tensor], 
         item = in_q.get()
         if item is None:
             break
-        paths, batch, lengths, err = item
+        paths, batch, lengths, err, in_handle = item
         try:
             if err is not None:
                 raise err
             out = run_batch(batch, lengths)
+            out_handle = None
             if out.is_cuda:
-                host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+                if out.dtype == torch.float32:
+                    out_handle = _pinned.get(out.numel())
+                    host = out_handle[: out.numel()].view(out.shape)
+                else:
+                    host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
                 host.copy_(out, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                torch.cuda.current_stream().synchronize()      # also: the input staging buffer has been consumed
                 out = host
-            out_q.put((paths, out, lengths))
+            out_q.put((paths, out, lengths, out_handle))
             done += len(paths)
         except Exception as e:  # noqa: BLE001
             failed[0] += 1
             print(f"\nCould not process batch starting with {paths[0]}. Error: {e}")
             continue
+        finally:
+            _pinned.put(in_handle)
     out_q.put(None)
     wt.join()
     return done, failed[0]

@@ -279,3 +279,75 @@ def test_sort_by_length_is_optional_and_io_pool_preserves_results(tmp_path):
         rel = os.path.relpath(p, src)
         a, b = np.load(os.path.join(dst1, rel)), np.load(os.path.join(dst2, rel))
         assert a.shape == (lens[os.path.basename(p)], 6) and np.array_equal(a, b) and np.array_equal(a, np.load(p) * 2.0)
+
+
+# ----------------------------------------------------------------------------
+# native .npy I/O of the CLI (mq_npy_probe / mq_npy_read_f32 / mq_npy_write_f32): host code, no GPU needed
+# ----------------------------------------------------------------------------
+def _npy_tree(root, dtypes=(np.float32, np.float64, np.float16), n=7, n_mels=12):
+    os.makedirs(os.path.join(root, "a", "b"), exist_ok=True)
+    g = np.random.default_rng(3)
+    paths = []
+    for i in range(n):
+        d = root if i % 3 == 0 else os.path.join(root, "a") if i % 3 == 1 else os.path.join(root, "a", "b")
+        arr = (g.standard_normal((5 + 7 * i, n_mels)) * 3 - 4).astype(dtypes[i % len(dtypes)])
+        p = os.path.join(d, f"u{i}.npy")
+        np.save(p, arr)
+        paths.append(p)
+    return paths
+
+
+def test_native_npy_reader_equals_numpy(tmp_path, monkeypatch):
+    from mqgan_b200 import reencode as R
+    paths = _npy_tree(str(tmp_path))
+    monkeypatch.setattr(R, "NATIVE_IO", True)
+    a, la = R.load_and_pad(paths)
+    monkeypatch.setattr(R, "NATIVE_IO", False)
+    b, lb = R.load_and_pad(paths)
+    assert la == lb and a.dtype == torch.float32 and torch.equal(a, b)
+    # pooled staging buffer variant: same content, buffer handed back for reuse
+    monkeypatch.setattr(R, "NATIVE_IO", True)
+    c, lc, handle = R.load_and_pad(paths, pooled=True)
+    assert torch.equal(c, b) and handle is not None and handle.numel() >= c.numel()
+    R._pinned.put(handle)
+    assert any(t is handle for t in R._pinned._free)
+    # a file numpy can read but the library does not handle (integers, Fortran order) -> whole batch through numpy
+    np.save(os.path.join(str(tmp_path), "ints.npy"), np.arange(24).reshape(2, 12))
+    np.save(os.path.join(str(tmp_path), "fort.npy"), np.asfortranarray(np.ones((3, 12), np.float32)))
+    mixed = paths[:2] + [os.path.join(str(tmp_path), "ints.npy"), os.path.join(str(tmp_path), "fort.npy")]
+    d, ld = R.load_and_pad(mixed)
+    assert ld[-2:] == [2, 3] and float(d[2, 1, 11]) == 23.0 and float(d[3, :3].min()) == 1.0
+    # mismatching mel width is an error either way
+    np.save(os.path.join(str(tmp_path), "wide.npy"), np.zeros((4, 13), np.float32))
+    with pytest.raises(ValueError):
+        R.load_and_pad(paths[:1] + [os.path.join(str(tmp_path), "wide.npy")])
+    with pytest.raises(OSError):
+        R.load_and_pad([os.path.join(str(tmp_path), "missing.npy")])
+
+
+def test_native_npy_writer_is_byte_identical_to_numpy(tmp_path, monkeypatch):
+    from mqgan_b200 import reencode as R
+    inp, out_a, out_b = str(tmp_path / "in"), str(tmp_path / "native"), str(tmp_path / "numpy")
+    paths = _npy_tree(inp, dtypes=(np.float32,))
+    batch, lengths = R.load_and_pad(paths)
+    monkeypatch.setattr(R, "NATIVE_IO", True)
+    R.save_outputs(batch, lengths, paths, inp, out_a)
+    monkeypatch.setattr(R, "NATIVE_IO", False)
+    R.save_outputs(batch, lengths, paths, inp, out_b)
+    for p in paths:
+        rel = os.path.relpath(p, inp)
+        a = open(os.path.join(out_a, rel), "rb").read()
+        assert a == open(os.path.join(out_b, rel), "rb").read()
+        assert a == open(p, "rb").read()                       # float32 in -> identical file out (identity "model")
+        assert np.load(os.path.join(out_a, rel)).dtype == np.float32
+
+
+def test_reencode_tree_identity_model_round_trips_files(tmp_path):
+    from mqgan_b200 import reencode as R
+    inp, out = str(tmp_path / "in"), str(tmp_path / "out")
+    paths = _npy_tree(inp, n=11)
+    done, failed = R.reencode_tree(lambda batch, lengths: batch.clone(), inp, out, batch_size=4, progress=False)
+    assert (done, failed) == (11, 0)
+    for p in paths:
+        got = np.load(os.path.join(out, os.path.relpath(p, inp)))
+        assert got.dtype == np.float32 and np.array_equal(got, np.load(p).astype(np.float32))
