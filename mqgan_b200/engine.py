@@ -20,7 +20,7 @@ Precision modes
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Sequence, Dict, List, Optional, Tuple
 
 import torch
 
@@ -135,6 +135,7 @@ class PreEncoderEngine:
         self.encoder_precision = encoder_precision
         self.max_chunk_frames = int(max_chunk_frames)
         self._copy_stream = None
+        self.group_cost_frames = 2048            # decode(lengths_host=...): fixed cost of one more refiner group, in frames
         # the encoder's live set is ~22 KB per frame (the refiner's is ~10x that), so it runs in 8x larger
         # utterance chunks: fewer, fuller waves of GEMM tiles and 8x fewer launches of the CBAM reductions
         self.max_chunk_frames_enc = int(max_chunk_frames_enc)
@@ -232,6 +233,42 @@ class PreEncoderEngine:
         for b0 in range(0, B, per):
             yield b0, min(B, b0 + per)
 
+    def _length_groups(self, lengths: Sequence[int], T: int):
+        """Partition a ragged batch into length-sorted groups [(member indices, T_group)], T_group = the group's longest
+        utterance rounded up to 8 frames plus one coarse row, when that saves at least 10 % of the padded frames; None otherwise.  Among
+        1, 2, 4, 8, ... equal-count groups the one minimising (frames computed + a fixed cost per group) wins, and no
+        group exceeds ``max_chunk_frames``."""
+        n = len(lengths)
+        if n < 2:
+            return None
+        lens = [max(1, min(int(l), T)) for l in lengths]
+        mult = 1 << self.cfg.refiner_depth
+        order = sorted(range(n), key=lambda i: (lens[i], i))
+        per_group_cost = self.group_cost_frames                        # launch tails of ~70 kernels per group
+        best = None
+        k = 1
+        while k <= n:
+            size = -(-n // k)
+            parts = [order[i:i + size] for i in range(0, n, size)]
+            groups, cost = [], 0
+            for part in parts:
+                # one whole coarse (1/8-resolution) row of padding must follow the longest utterance: ConvBlock does not
+                # mask between its two convolutions (preencoder.py:97-98), so the first padded row after an utterance
+                # carries aptx(bias + spill) into conv2 - it has to exist, as it does in the padded batch, not be
+                # replaced by the image border's zero padding
+                Tg = min(T, (-(-max(lens[i] for i in part) // mult) + 1) * mult)
+                cap = max(1, self.max_chunk_frames // Tg)              # split further if the group is too large
+                for j in range(0, len(part), cap):
+                    groups.append((sorted(part[j:j + cap]), Tg))
+                    cost += len(part[j:j + cap]) * Tg + per_group_cost
+            if best is None or cost < best[0]:
+                best = (cost, groups)
+            k *= 2
+        baseline = n * T + per_group_cost * -(-n * T // self.max_chunk_frames)
+        if best[0] > 0.9 * baseline:
+            return None
+        return best[1]
+
     @staticmethod
     def _mask_u8(mask: Optional[torch.Tensor], B: int, T: int, device) -> Optional[torch.Tensor]:
         """(B,1,T) / (B,T) bool or uint8, True = padded -> contiguous uint8 (B,T) on device."""
@@ -310,12 +347,18 @@ class PreEncoderEngine:
 
     # ------------------------------------------------------------------
     def decode(self, indices: torch.Tensor, mask: Optional[torch.Tensor] = None, return_hidden: bool = False,
-               taps: Optional[dict] = None, return_recon: bool = False, host_out: Optional[torch.Tensor] = None):
+               taps: Optional[dict] = None, return_recon: bool = False, host_out: Optional[torch.Tensor] = None,
+               lengths_host: Optional[Sequence[int]] = None):
         """indices (B,T) int -> x_post (B,T,n_mels) fp32 [, decoder_out (B,C0,T)] [, x_recon (B,T,n_mels)].
 
         ``host_out``: optional pinned host tensor (B,T,n_mels) fp32.  Each refiner chunk's result is copied to it on a
         side stream as soon as the chunk is done, so the device-to-host transfer of the re-encoded mels overlaps the
-        remaining chunks' compute; the caller's stream waits for the copies before ``decode`` returns."""
+        remaining chunks' compute; the caller's stream waits for the copies before ``decode`` returns.
+
+        ``lengths_host``: the utterance lengths as host integers (must describe the same padding as ``mask``).  The
+        decoder and refiner are padding-invariant (each utterance's output depends on its own frames
+        only), so a ragged batch is then run through the refiner - 95 % of the FLOPs - in length-sorted groups cut to
+        their own longest utterance instead of the batch's: same numbers, less padding to compute."""
         if indices.dim() != 2:
             raise ValueError(f"indices must be (B, T), got {tuple(indices.shape)}")
         B, T = indices.shape
@@ -343,6 +386,22 @@ class PreEncoderEngine:
             if return_recon:
                 recon[c0:c1] = R.view(c1 - c0, T, -1)[..., : self.cfg.mel_channels]
             Rv = R.view(c1 - c0, T, -1)
+            groups = self._length_groups(lengths_host[c0:c1], T) if (lengths_host is not None and taps is None
+                                                                    and mc is not None) else None
+            if groups is not None:
+                out[c0:c1] = Rv[..., : self.cfg.mel_channels]         # padded frames keep x_recon (App. B8)
+                for members, Tg in groups:
+                    sel = torch.tensor(members, dtype=torch.long, device=self.device)
+                    Rg = Rv.index_select(0, sel)[:, :Tg].contiguous()
+                    mg = mc.index_select(0, sel)[:, :Tg].contiguous()
+                    og = torch.empty(len(members), Tg, self.cfg.mel_channels, dtype=torch.float32, device=self.device)
+                    self._refiner(Rg.view(len(members) * Tg, -1), mg, len(members), Tg, og, None)
+                    out[c0:c1][sel, :Tg] = og
+                if copy_stream is not None:
+                    copy_stream.wait_stream(main)
+                    with torch.cuda.stream(copy_stream):
+                        host_out[c0:c1].copy_(out[c0:c1], non_blocking=True)
+                continue
             for b0, b1 in self._chunks(c1 - c0, T):
                 self._refiner(Rv[b0:b1].reshape((b1 - b0) * T, -1), None if mc is None else mc[b0:b1], b1 - b0, T,
                               out[c0 + b0:c0 + b1], taps)                                    # :496-499

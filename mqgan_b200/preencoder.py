@@ -127,10 +127,17 @@ class PreEncoder(nn.Module):
         return self.engine().encode(x.to(self._device()), x_mask)
 
     @torch.no_grad()
-    def decode(self, indices, x_mask=None, return_hidden=False, *, host_out=None):
-        """(B, T) int -> (B, T, mel) [, (B, C0, T)] (preencoder.py:453-504).  ``host_out`` (additive, keyword-only):
-        a pinned host tensor that receives the result chunk by chunk while later chunks are still computing."""
-        return self.engine().decode(indices.to(self._device()), x_mask, return_hidden=return_hidden, host_out=host_out)
+    def decode(self, indices, x_mask=None, return_hidden=False, *, host_out=None, lengths=None):
+        """(B, T) int -> (B, T, mel) [, (B, C0, T)] (preencoder.py:453-504).  Additive, keyword-only: ``host_out``, a
+        pinned host tensor that receives the result chunk by chunk while later chunks are still computing;
+        ``lengths``, the utterance lengths as HOST integers matching ``x_mask`` - a ragged batch then goes through the
+        refiner in length-sorted groups (identical output, less padding computed)."""
+        if lengths is not None and x_mask is None:
+            raise ValueError("decode(lengths=...) describes the padding of x_mask; pass both")
+        if lengths is not None:
+            lengths = [int(v) for v in (lengths.tolist() if isinstance(lengths, torch.Tensor) else lengths)]
+        return self.engine().decode(indices.to(self._device()), x_mask, return_hidden=return_hidden, host_out=host_out,
+                                    lengths_host=lengths)
 
     def forward(self, x, x_lengths):
         """(x_recon, x_post) as preencoder.py:363-418, inference only."""

@@ -94,6 +94,8 @@ class ScriptedPreEncoder:
         mask = self._mask(indices.shape[1], lengths)
         with torch.no_grad():
             try:
-                return self.model.decode(indices, mask)
+                # host-side lengths let the engine skip most of a ragged batch's padding (identical output)
+                host_lens = None if (lengths is None or (isinstance(lengths, torch.Tensor) and lengths.is_cuda)) else lengths
+                return self.model.decode(indices, mask, lengths=host_lens)
             except Exception as e:
                 raise RuntimeError(f"An error occurred during the decode operation: {e}")

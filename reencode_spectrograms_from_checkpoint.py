@@ -38,7 +38,7 @@ class _CheckpointModel:
 
     def decode(self, idx, lengths):
         with torch.no_grad():
-            return self.model.decode(idx, x_mask=self._mask(idx.shape[1], lengths))
+            return self.model.decode(idx, x_mask=self._mask(idx.shape[1], lengths), lengths=list(lengths))
 
 
 def _make_model(checkpoint_path, config, device):

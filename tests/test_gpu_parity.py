@@ -151,6 +151,55 @@ def test_batch_invariance_and_determinism():
     assert torch.equal(d1, d2)
 
 
+def test_decode_in_length_groups_is_bit_identical():
+    """decode(lengths=host ints): a ragged batch goes through the refiner in length-sorted groups cut to their own
+    longest utterance; decoder + refiner are padding-invariant, so every frame - valid and padded -
+    equals the plain padded-batch result bit for bit."""
+    cfg, sd, _, _, _ = load_golden("tiny")
+    B, T = 12, 160
+    lengths = torch.tensor([160, 31, 96, 17, 150, 64, 40, 8, 121, 77, 33, 5])
+    mask = sequence_mask(T, lengths).unsqueeze(1)
+    g = torch.Generator().manual_seed(3)
+    idx = torch.randint(0, cfg.codebook_size, (B, T), generator=g).cuda()
+    model = _model(cfg, sd)
+    eng = model.engine()
+    ref = model.decode(idx, mask.cuda())
+    eng.group_cost_frames = 0                                      # tiny batch: group whenever it saves frames
+    groups = eng._length_groups(lengths.tolist(), T)
+    assert groups is not None and len(groups) > 1
+    assert sorted(i for members, _ in groups for i in members) == list(range(B))
+    assert all(Tg % 8 == 0 and (Tg == T or Tg >= max(int(lengths[i]) for i in members) + 8) for members, Tg in groups)
+    got = model.decode(idx, mask.cuda(), lengths=lengths.tolist())
+    diff = (got - ref).abs()
+    print("length-group decode: max abs diff", float(diff.max()), "frames differing", int((diff.amax(dim=2) > 0).sum()),
+          "of", B * T, "max |ref|", float(ref.abs().max()))
+    assert torch.equal(got, ref)
+    host = torch.empty(B, T, cfg.mel_channels).pin_memory()
+    got2 = model.decode(idx, mask.cuda(), lengths=lengths, host_out=host)
+    torch.cuda.synchronize()
+    assert torch.equal(got2, ref) and torch.equal(host, ref.cpu())
+    assert eng._length_groups([T] * B, T) is None                  # nothing to save on a full-length batch
+    with pytest.raises(ValueError):
+        model.decode(idx, None, lengths=lengths.tolist())
+
+
+def test_decode_in_length_groups_hifispeech_sizes():
+    """The same at the real model's widths and CLI-like lengths."""
+    cfg, sd, _, _, _ = load_golden("hifispeech")
+    B, T = 16, 600
+    lengths = torch.tensor([600, 212, 433, 318, 590, 255, 377, 201, 512, 466, 289, 344, 230, 571, 405, 263])
+    mask = sequence_mask(T, lengths).unsqueeze(1)
+    g = torch.Generator().manual_seed(4)
+    idx = torch.randint(0, cfg.codebook_size, (B, T), generator=g).cuda()
+    model = _model(cfg, sd)
+    model.engine().group_cost_frames = 128          # 16 utterances are too few for the default cost model to split
+    groups = model.engine()._length_groups(lengths.tolist(), T)
+    assert groups is not None and len(groups) >= 2
+    ref = model.decode(idx, mask.cuda())
+    got = model.decode(idx, mask.cuda(), lengths=lengths.tolist())
+    assert torch.equal(got, ref)
+
+
 def test_decode_streams_result_to_pinned_host_buffer():
     """decode(..., host_out=pinned) copies every refiner chunk to the host while later chunks compute; the host
     buffer equals the returned device tensor once decode has returned and the stream is synchronised."""
