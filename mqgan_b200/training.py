@@ -26,15 +26,13 @@ fixtures pin); a non-zero ``dropout_p`` raises.
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
 
 from . import ops
-from .spec import (MultiBinConfig, PatchDiscConfig, PreEncoderConfig, is_disc_buffer, multibin_param_spec,
-                   patch_disc_param_spec)
+from .spec import MultiBinConfig, PatchDiscConfig, PreEncoderConfig, is_disc_buffer
 
 Tensor = torch.Tensor
 

@@ -21,8 +21,8 @@ autograd for the derivatives, no code from the reference) of one iteration of th
 
 Dropout is taken as 0 EVERYWHERE, including the 0.1 that DownBlock / UpBlock / ConvBlock2D hard-wire
 regardless of the ``dropout`` argument (preencoder.py:109, 121, 233): the reference draws it from torch's
-global RNG, which no other implementation can reproduce.  Everything else follows the reference, including its quirks: the discriminators see
-``recon_post`` only, ``_train_generator`` puts them in eval mode and never back (so from the second
+global RNG, which no other implementation can reproduce.  Everything else follows the reference, including
+its quirks: the discriminators see ``recon_post`` only, ``_train_generator`` puts them in eval mode and never back (so from the second
 iteration on the power iteration no longer runs - train.py:417-418, :504-506 resets it per epoch only),
 and the LeCam EMA is updated before it is used (losses.py:96-99).
 
@@ -33,7 +33,7 @@ container and commits losses, gradient norms and updated-parameter checksums to
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F

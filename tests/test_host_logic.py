@@ -351,3 +351,54 @@ def test_reencode_tree_identity_model_round_trips_files(tmp_path):
     for p in paths:
         got = np.load(os.path.join(out, os.path.relpath(p, inp)))
         assert got.dtype == np.float32 and np.array_equal(got, np.load(p).astype(np.float32))
+
+
+# ----------------------------------------------------------------------------
+# training-step configuration (spec.py) against the reference's YAML and parameter counts
+# ----------------------------------------------------------------------------
+def test_discriminator_configs_match_reference_yaml_and_sizes():
+    from mqgan_b200.synth import synth_disc_state_dict
+    patch_yaml = {"hidden_channels": [256, 256, 384, 512, 512], "kernel_sizes": [5, 5, 5, 3, 3, 3],
+                  "strides": [[1, 2], [2, 2], [2, 2], [2, 1], [2, 1], [2, 1]]}          # configs/model_config_hifispeech.yaml:23-26
+    mb_yaml = {"hidden_channels": [128, 128, 256, 256, 384], "kernel_sizes": [7, 5, 3, 3, 3, 3], "n_bins": 8, "n_no_strides": 2}
+    assert S.PatchDiscConfig.from_patch_yaml(128, patch_yaml) == S.HIFISPEECH_PATCH_D
+    assert S.MultiBinConfig.from_yaml(128, mb_yaml) == S.HIFISPEECH_MULTIBIN_D
+    # the logits conv always runs at stride 1 (discriminators.py:160-170); bands use (3, k) kernels and time-only strides
+    assert S.HIFISPEECH_PATCH_D.layer_stride(5) == (1, 1) and S.HIFISPEECH_PATCH_D.layer_stride(1) == (2, 2)
+    bc = S.HIFISPEECH_MULTIBIN_D.bin_config
+    assert bc.mel_channels == 16 and bc.kernels[0] == (3, 7) and bc.strides[:3] == ((1, 1), (1, 1), (1, 2))
+    assert S.HIFISPEECH_PATCH_D.feature_layers == (False, False, True, True, True, False)       # discriminators.py:108-112
+    n_pd = sum(v.numel() for k, v in synth_disc_state_dict(S.patch_disc_param_spec(S.HIFISPEECH_PATCH_D)).items()
+               if not S.is_disc_buffer(k))
+    n_mb = sum(v.numel() for k, v in synth_disc_state_dict(S.multibin_param_spec(S.HIFISPEECH_MULTIBIN_D)).items()
+               if not S.is_disc_buffer(k))
+    assert abs((n_pd + n_mb) / 1e6 - 24.8) < 0.1                  # 24.8 M discriminator parameters
+    with pytest.raises(ValueError):
+        S.MultiBinConfig(48, 3, (16, 24), (3, 3, 3), 2)           # hidden size must divide n_bins (discriminators.py:264)
+    with pytest.raises(ValueError):
+        S.PatchDiscConfig(32, (16,), ((3, 3),), ((1, 1),))        # kernel_sizes must be hidden_channels + 1
+
+
+def test_dgrad_weight_and_taps_are_consistent_on_cpu():
+    """ops.dgrad_weight / ops.conv_taps (host logic of the training step): the mirrored, transposed weight applied as a
+    plain correlation equals autograd's data gradient (float64, CPU)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 6, 9, 5, generator=g, dtype=torch.float64, requires_grad=True)          # (N, Cin, H, W)
+    w = torch.randn(4, 6, 3, 3, generator=g, dtype=torch.float64)
+    y = F.conv2d(x, w, padding=1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    wd, kind = ops.dgrad_weight(w, "conv2d3")
+    assert kind == "conv2d3" and wd.shape == (6, 4, 3, 3)
+    assert torch.allclose(F.conv2d(dy, wd, padding=1), x.grad, atol=1e-12)
+    x1 = torch.randn(2, 6, 11, generator=g, dtype=torch.float64, requires_grad=True)
+    w1 = torch.randn(4, 6, 5, generator=g, dtype=torch.float64)
+    y1 = F.conv1d(F.pad(x1, (4, 0)), w1)                                                        # causal (attentions.py:471-474)
+    dy1 = torch.randn_like(y1)
+    y1.backward(dy1)
+    wd1, kind1 = ops.dgrad_weight(w1, "causal1d")
+    assert kind1 == "anticausal1d"
+    assert torch.allclose(F.conv1d(F.pad(dy1, (0, 4)), wd1), x1.grad, atol=1e-12)               # taps at rows 0 .. k-1
+    assert ops.conv_taps("causal1d", w1.shape) == ([-4, -3, -2, -1, 0], [0] * 5)
+    assert ops.conv_taps("conv2d3", w.shape)[0] == [-1, -1, -1, 0, 0, 0, 1, 1, 1]
