@@ -661,9 +661,12 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
   __syncthreads();
   const int nrow = min(kStemRows, T8 - t0);
   __nv_bfloat16* ybase = y + (static_cast<int64_t>(b) * T8 + t0) * F * C;
-  for (int i = threadIdx.x; i < nrow * F * C8; i += blockDim.x) {
-    const int px = i / C8;                      // lt * F + f
-    const int lt = px / F, f = px - lt * F;
+  // thread = (pixel lane, channel group); pixels advance by blockDim.x / C8 per iteration with (lt, f) kept
+  // incrementally (no integer divisions in the loop: they cost as much as the nine FMAs per output)
+  const int ppb = blockDim.x / C8;
+  int px = threadIdx.x / C8;
+  int lt = px / F, f = px - lt * F;
+  for (; px < nrow * F; px += ppb) {
     float in[9];
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr)
@@ -679,6 +682,8 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
     }
     *reinterpret_cast<uint4*>(ybase + static_cast<int64_t>(px) * C + cg * 8) =
         make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    f += ppb;
+    while (f >= F) { f -= F; ++lt; }
   }
 }
 
