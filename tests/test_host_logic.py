@@ -402,3 +402,32 @@ def test_dgrad_weight_and_taps_are_consistent_on_cpu():
     assert torch.allclose(F.conv1d(F.pad(dy1, (0, 4)), wd1), x1.grad, atol=1e-12)               # taps at rows 0 .. k-1
     assert ops.conv_taps("causal1d", w1.shape) == ([-4, -3, -2, -1, 0], [0] * 5)
     assert ops.conv_taps("conv2d3", w.shape)[0] == [-1, -1, -1, 0, 0, 0, 1, 1, 1]
+
+
+def test_length_groups_partition_rules():
+    """PreEncoderEngine._length_groups (host logic of decode(lengths=...)): a partition of the batch into length-sorted
+    groups whose T is the longest member rounded up to 8 frames plus one coarse row, capped by the batch T and by
+    max_chunk_frames; None when nothing is saved."""
+    import types
+    from mqgan_b200.engine import PreEncoderEngine
+    stub = types.SimpleNamespace(max_chunk_frames=32768, group_cost_frames=2048, cfg=types.SimpleNamespace(refiner_depth=3))
+    groups = PreEncoderEngine._length_groups
+    rng = np.random.default_rng(0)
+    lens = rng.integers(300, 1100, size=32).tolist()
+    T = max(lens)
+    g = groups(stub, lens, T)
+    assert g is not None and len(g) >= 2
+    assert sorted(i for m, _ in g for i in m) == list(range(32))
+    for members, Tg in g:
+        longest = max(lens[i] for i in members)
+        assert Tg % 8 == 0 or Tg == T
+        assert Tg == T or Tg >= (-(-longest // 8) + 1) * 8          # a whole coarse row of padding follows the longest
+        assert Tg <= T and len(members) * Tg <= 32768
+    computed = sum(len(m) * Tg for m, Tg in g)
+    assert computed < 0.9 * 32 * T                                  # the point of it: fewer padded frames
+    assert groups(stub, [T] * 32, T) is None                        # rectangular batch
+    assert groups(stub, [500], 500) is None
+    assert groups(stub, [1000, 990, 1010, 1005], 1010) is None      # nearly rectangular: not worth another launch group
+    stub.max_chunk_frames = 4096                                    # groups are split to fit the refiner chunk size
+    g2 = groups(stub, lens, T)
+    assert all(len(m) * Tg <= 4096 or len(m) == 1 for m, Tg in g2)
