@@ -118,8 +118,8 @@ class PreEncoder(nn.Module):
     def _no_training(self, what):
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError(
-                f"{what}: the training step (backward kernels, SURVEY 8-f4) is not part of this build; "
-                "call .eval() / torch.no_grad() for inference")
+                f"{what}: this module is the inference boundary; the training step (SURVEY 8-f4) is "
+                "mqgan_b200.training.TrainStep (same state-dict).  Call .eval() / torch.no_grad() for inference")
 
     @torch.no_grad()
     def encode(self, x, x_mask=None):
