@@ -115,12 +115,6 @@ class PreEncoder(nn.Module):
             self._engine_key = key
         return self._engine
 
-    def _no_training(self, what):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError(
-                f"{what}: this module is the inference boundary; the training step (SURVEY 8-f4) is "
-                "mqgan_b200.training.TrainStep (same state-dict).  Call .eval() / torch.no_grad() for inference")
-
     @torch.no_grad()
     def encode(self, x, x_mask=None):
         """(B, T, mel) [+ (B,1,T) bool, True = padded] -> (B, T) int64 (preencoder.py:420-451)."""
@@ -140,8 +134,24 @@ class PreEncoder(nn.Module):
                                     lengths_host=lengths)
 
     def forward(self, x, x_lengths):
-        """(x_recon, x_post) as preencoder.py:363-418, inference only."""
-        self._no_training("PreEncoder.forward")
+        """(x_recon, x_post) as preencoder.py:363-418.
+
+        In eval mode / under ``torch.no_grad()`` this is encode + decode on the inference engine.  In training mode
+        with autograd on it is the differentiable training forward of ``mqgan_b200.training`` (tcgen05 forward /
+        data-gradient / weight-gradient convolutions, fused ConvBlock2D and activation passes, straight-through FSQ)
+        over this module's own parameters, so ``loss.backward()`` fills their ``.grad`` and any optimiser can step
+        them - what the reference's ``Trainer`` does with ``self.generator(real, lens)`` (train.py:524).  Dropout is not
+        applied (see training.py); a non-zero ``dropout`` argument is reported once and ignored."""
+        if self.training and torch.is_grad_enabled():
+            from . import training as _training
+            if self.dropout_p and not getattr(self, "_dropout_warned", False):
+                print(f"Warning: PreEncoder(dropout={self.dropout_p}) - the B200 training forward runs without dropout.")
+                self._dropout_warned = True
+            dev = self._device()
+            if dev.type != "cuda":
+                raise RuntimeError("mqgan_b200.PreEncoder runs on CUDA (B200) only - there is no CPU fallback")
+            params = dict(self.named_parameters())
+            return _training.generator_forward(params, self.cfg, x.to(dev), x_lengths.to(dev))
         with torch.no_grad():
             x = x.to(self._device())
             mask = sequence_mask(x.size(1), x_lengths.to(x.device)).unsqueeze(1)

@@ -363,3 +363,47 @@ def test_dgrad_wider_than_one_launch_is_sliced():
         TR._dgrad_launch(dy.to(DEV), w.float().to(DEV), "conv2d3", N, H, W, out, "t")
         tol = 2e-4 if dt == torch.float32 else 2.0 ** -7
         assert float((out.cpu().double() - gx).abs().max()) < tol * max(1.0, float(gx.abs().max()))
+
+
+def test_preencoder_module_trains_through_forward():
+    """The drop-in nn.Module: in train mode with autograd on, PreEncoder.forward is the differentiable training
+    forward over the module's own parameters (what the reference's Trainer calls, train.py:524), so a plain torch
+    optimiser loop works; in eval mode the same module keeps serving encode / decode from the inference engine and
+    sees the updated weights."""
+    from mqgan_b200 import spec as S
+    from mqgan_b200 import training as TR
+    from mqgan_b200.preencoder import PreEncoder
+    from mqgan_b200.synth import synth_state_dict
+    fx, cfg, ts = _tiny_train_step()
+    sd = synth_state_dict(cfg, seed=int(fx["seed"]))
+    sd["q_in_proj.weight"] = torch.from_numpy(fx["qin_w"]).clone()
+    sd["q_in_proj.bias"] = torch.from_numpy(fx["qin_b"]).clone()
+    model = PreEncoder(cfg.mel_channels, list(cfg.channels), list(cfg.kernel_sizes), fsq_levels=list(cfg.fsq_levels), dropout=0.0,
+                       refiner_base_channels=cfg.refiner_base_channels, refiner_depth=cfg.refiner_depth)
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV)
+    real, lens = _tiny_batch(1, int(fx["B"]), int(fx["T"]), cfg.mel_channels)
+    real, lens = real.to(DEV), lens.to(DEV)
+    model.eval()
+    idx0 = model.encode(real, None)
+    model.train()
+    x_recon, x_post = model(real, lens)
+    assert x_recon.requires_grad and x_post.requires_grad
+    # same numbers as the functional training forward on the same parameters, and as the reference (fixture s1)
+    r2, p2 = TR.generator_forward(dict(model.named_parameters()), cfg, real, lens)
+    assert torch.equal(x_recon, r2) and torch.equal(x_post, p2)
+    assert float((x_post.detach().cpu() - torch.from_numpy(fx["s1_recon_post"])).abs().max()) < 5e-3
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    loss = TR.masked_mel_loss(x_post, real, lens, 1) + TR.masked_mel_loss(x_recon, real, lens, 1)
+    loss.backward()
+    got = {k for k, p in model.named_parameters() if p.grad is not None}
+    assert "refiner.mid.conv1.parametrizations.weight.original1" in got and "proj.weight" in got
+    assert "hidden_proj.weight" not in got                         # detached refiner input (preencoder.py:411-413)
+    opt.step()
+    with torch.no_grad():                                          # inference forward of a training-mode module: engine path
+        a, b = model(real, lens)
+    assert not a.requires_grad and a.shape == real.shape
+    model.eval()
+    out = model.decode(model.encode(real, None), None)             # the engine re-packs the updated weights
+    assert out.shape == real.shape and torch.isfinite(out).all()
+    assert model.encode(real, None).shape == idx0.shape
