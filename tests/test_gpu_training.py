@@ -407,3 +407,88 @@ def test_preencoder_module_trains_through_forward():
     out = model.decode(model.encode(real, None), None)             # the engine re-packs the updated weights
     assert out.shape == real.shape and torch.isfinite(out).all()
     assert model.encode(real, None).shape == idx0.shape
+
+
+def test_reference_style_training_loop_on_dropin_modules():
+    """The reference's own loop structure (Trainer._train_discriminator / _train_generator, train.py:380-501) written
+    against the drop-in classes - mqgan_b200.PreEncoder as the generator, mqgan_b200.discriminators, mqgan_b200.losses,
+    torch.optim.Adam / LambdaLR / clip_grad_norm_ exactly as train.py uses them - reproduces the reference's logged
+    losses for two iterations (tests/golden/train_tiny.npz)."""
+    from mqgan_b200 import spec as S
+    from mqgan_b200.discriminators import MelSpectrogramPatchDiscriminator2D, MultiBinDiscriminator
+    from mqgan_b200.losses import LSGANLoss, MaskedMelLoss
+    from mqgan_b200.preencoder import PreEncoder
+    from mqgan_b200.synth import synth_disc_state_dict, synth_state_dict
+    from mqgan_b200.training import masked_mae
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    import os
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_tiny.npz"))
+    cfg, pdc, mbc, t = S.TINY, S.TINY_PATCH_D, S.TINY_MULTIBIN_D, S.TINY_TRAIN
+    seed = int(fx["seed"])
+    sd = synth_state_dict(cfg, seed=seed)
+    sd["q_in_proj.weight"], sd["q_in_proj.bias"] = torch.from_numpy(fx["qin_w"]).clone(), torch.from_numpy(fx["qin_b"]).clone()
+    generator = PreEncoder(cfg.mel_channels, list(cfg.channels), list(cfg.kernel_sizes), fsq_levels=list(cfg.fsq_levels),
+                           dropout=0.0, refiner_base_channels=cfg.refiner_base_channels, refiner_depth=cfg.refiner_depth)
+    generator.load_state_dict(sd, strict=True)
+    patch_d = MelSpectrogramPatchDiscriminator2D(pdc.mel_channels, list(pdc.hidden_channels), [k[0] for k in pdc.kernels],
+                                                 stride=[list(s) for s in pdc.strides], fast=False)
+    patch_d.load_state_dict(synth_disc_state_dict(S.patch_disc_param_spec(pdc), seed=seed), strict=True)
+    multibin_d = MultiBinDiscriminator(mbc.mel_channels, mbc.n_bins, list(mbc.hidden_channels), list(mbc.kernel_sizes),
+                                       mbc.n_no_strides, fast=False)
+    multibin_d.load_state_dict(synth_disc_state_dict(S.multibin_param_spec(mbc), seed=seed + 1), strict=True)
+    for m in (generator, patch_d, multibin_d):
+        m.to(DEV)
+    gan_loss = LSGANLoss().to(DEV)
+    recon_all, recon_group = MaskedMelLoss("mse"), MaskedMelLoss("mse", group_size=16)
+    opt_g = torch.optim.Adam(generator.parameters(), lr=t["lr"], betas=(t["beta1"], t["beta2"]))
+    d_params = list(patch_d.parameters()) + list(multibin_d.parameters())
+    opt_d = torch.optim.Adam(d_params, lr=t["lr"] * t["lr_d_factor"], betas=(t["d_beta1"], t["d_beta2"]))
+    sched_g = torch.optim.lr_scheduler.LambdaLR(opt_g, lambda s: min((s + 1) / t["warmup_steps"], 1.0))
+    lw = t["loss_weights"]
+    generator.train(); patch_d.train(); multibin_d.train()                       # train.py:504-506
+    for step in (1, 2):
+        real, lens = _tiny_batch(step, int(fx["B"]), int(fx["T"]), cfg.mel_channels)
+        real, lens = real.to(DEV), lens.to(DEV)
+        recon_pre, recon_post = generator(real, lens)                            # :524
+        # ---- _train_discriminator :380-412 ----
+        opt_d.zero_grad()
+        rl, rm, _ = patch_d(real, lens, return_features=True)
+        fl, fm = patch_d(recon_post.detach(), lens)
+        loss_d = gan_loss.discriminator_loss(rl, fl, rm, fm)
+        rl2, rm2, _ = multibin_d(real, lens, return_features=True)
+        fl2, fm2 = multibin_d(recon_post.detach(), lens)
+        loss_mbd = sum(gan_loss.discriminator_loss(r, f, rm2[0], fm2[0]) for r, f in zip(rl2, fl2)) / len(rl2)
+        loss_d = loss_d + loss_mbd
+        loss_d.backward()
+        torch.nn.utils.clip_grad_norm_(d_params, 1.0)
+        opt_d.step()
+        # ---- _train_generator :414-501 ----
+        opt_g.zero_grad()
+        patch_d.eval(); multibin_d.eval()
+        l_pre = recon_all(recon_pre, real, lens) + 0.25 * recon_group(recon_pre, real, lens)
+        l_post = recon_all(recon_post, real, lens) + 0.25 * recon_group(recon_post, real, lens)
+        gl, gm, gf = patch_d(recon_post, lens, return_features=True)
+        gl2, gm2, gf2 = multibin_d(recon_post, lens, return_features=True)
+        loss_gan = 0.5 * (gan_loss.generator_loss(gl, gm) + sum(gan_loss.generator_loss(g, gm2[0]) for g in gl2) / len(gl2))
+        loss_fm = real.new_zeros(())
+        if step == 2:                                                             # use_fm_loss :454-476
+            with torch.no_grad():
+                _, _, rf = patch_d(real, lens, return_features=True)
+                _, _, rf2 = multibin_d(real, lens, return_features=True)
+            fm_d1 = sum(masked_mae(ff, r, m) for (r, m), (ff, _) in zip(rf, gf)) / len(rf)
+            fm_mbd = real.new_zeros(())
+            for rfe, gfe in zip(rf2, gf2):
+                for (r, m), (ff, _) in zip(rfe, gfe):
+                    fm_mbd = fm_mbd + masked_mae(ff, r, m)
+                fm_mbd = fm_mbd / len(rfe)
+            loss_fm = 0.5 * (fm_d1 + fm_mbd / len(gf2))
+        total = l_pre * 1.0 + l_post * 2.0 + loss_gan * lw["Gloss_lambda"] + loss_fm * lw["fm_lambda"]
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(generator.parameters(), 1.0)
+        opt_g.step()
+        sched_g.step()
+        got = np.array([float(loss_d), float(total), float(l_pre), float(l_post), float(loss_gan), float(loss_fm)])
+        np.testing.assert_allclose(got, fx[f"s{step}_losses"], rtol=1e-3, atol=1e-6)
+    ps = np.array([float(p.detach().double().sum()) for p in (dict(generator.named_parameters())[str(k)] for k in fx["g_keys"])])
+    assert np.abs(ps - fx["s2_g_param_sums"]).max() < 2e-2
