@@ -131,7 +131,8 @@ def choose_bn(cout: int) -> Tuple[int, int]:
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, split=False,
-              in_seg_stride: Optional[int] = None, on_device: bool = False) -> PackedConv:
+              in_seg_stride: Optional[int] = None, on_device: bool = False,
+              taps: Optional[Tuple[Sequence[int], Sequence[int]]] = None) -> PackedConv:
     """Pack a folded conv/linear weight for mq_conv_gemm.
 
     kind: "linear" (Cout, Cin) | "same1d" / "causal1d" (Cout, Cin, k) | "conv2d3" (Cout, Cin, 3, 3).
@@ -142,7 +143,8 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, spl
     stride of the activation is ``in_seg_stride`` (default Cin).  K order is (segment, tap, channel
     chunk), matching the kernel.  ``on_device``: pack where the weight lives (the training step re-packs
     the folded weights every iteration); otherwise on the host, once at load.  "anticausal1d" (taps at
-    rows 0 .. k-1) is the data gradient of a causal convolution.
+    rows 0 .. k-1) is the data gradient of a causal convolution.  "taps2d": weight (Cout, Cin, ntaps) with explicit
+    per-tap (dh, dw) offsets in ``taps`` (at most MQ_MAX_TAPS; the lowered strided convolutions of the discriminators).
     """
     mode = split_mode(split)
     w = weight.detach().float()
@@ -171,6 +173,12 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], kind: str, spl
         wt = w.reshape(cout, cin, 9)
         dh = [i - 1 for i in range(3) for _ in range(3)]
         dw = [j - 1 for _ in range(3) for j in range(3)]
+    elif kind == "taps2d":
+        if taps is None or w.dim() != 3 or len(taps[0]) != w.shape[2] or len(taps[1]) != w.shape[2]:
+            raise ValueError("taps2d expects a (Cout, Cin, ntaps) weight and taps = (dh list, dw list) of that length")
+        cout, cin, _ = w.shape
+        wt = w
+        dh, dw = [int(v) for v in taps[0]], [int(v) for v in taps[1]]
     else:
         raise ValueError(kind)
     taps = wt.shape[2]
@@ -343,7 +351,8 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         for i in range(pc.taps):
             p.tap_dh_odd[i] = pc.tap_dh_odd[i]
         hm = 2
-    conv3 = pc.taps == 9 and pc.nseg == 1 and not pc.up_taps
+    conv3 = (pc.taps == 9 and pc.nseg == 1 and not pc.up_taps
+             and list(pc.tap_dh[:9]) == [-1, -1, -1, 0, 0, 0, 1, 1, 1] and list(pc.tap_dw[:9]) == [-1, 0, 1] * 3)
     conv1d = (W == 1 and not pc.up_taps and all(d == 0 for d in pc.tap_dw[:pc.taps])
               and all(pc.tap_dh[i] == pc.tap_dh[0] + i for i in range(pc.taps)))
     if pair is None and conv1d:
@@ -450,7 +459,7 @@ def _split_terms_of(out_split: torch.Tensor) -> int:
 DGRAD_KIND = {"linear": "linear", "same1d": "same1d", "causal1d": "anticausal1d", "conv2d3": "conv2d3"}
 
 
-def dgrad_weight(weight: torch.Tensor, kind: str) -> Tuple[torch.Tensor, str]:
+def dgrad_weight(weight: torch.Tensor, kind: str, taps=None):
     """The convolution whose forward pass is the data gradient of ``conv(x, weight)``: taps mirrored,
     in/out channels swapped.  dx = conv(dy, w'), w'[ci, co, j'] = w[co, ci, k-1-j']; a causal
     convolution (taps at rows -(k-1) .. 0, attentions.py:471-474) turns anti-causal (rows 0 .. k-1)."""
@@ -460,11 +469,15 @@ def dgrad_weight(weight: torch.Tensor, kind: str) -> Tuple[torch.Tensor, str]:
         return weight.flip(2).transpose(0, 1).contiguous(), DGRAD_KIND[kind]
     if kind == "conv2d3":
         return weight.flip(2, 3).transpose(0, 1).contiguous(), "conv2d3"
+    if kind == "taps2d":                       # same tap order, every offset negated: returns (weight, kind, taps)
+        return weight.transpose(0, 1).contiguous(), "taps2d", ([-int(v) for v in taps[0]], [-int(v) for v in taps[1]])
     raise ValueError(kind)
 
 
-def conv_taps(kind: str, wshape) -> Tuple[List[int], List[int]]:
+def conv_taps(kind: str, wshape, taps=None) -> Tuple[List[int], List[int]]:
     """(tap_dh, tap_dw) of a convolution kind in the weight's own tap order (as pack_conv)."""
+    if kind == "taps2d":
+        return [int(v) for v in taps[0]], [int(v) for v in taps[1]]
     if kind == "linear":
         return [0], [0]
     if kind == "same1d":

@@ -44,22 +44,26 @@ def _weight_from_taps(dw: Tensor, kind: str) -> Tensor:
     """(taps, cout, cin) -> the weight's own shape."""
     if kind == "linear":
         return dw[0]
-    if kind in ("same1d", "causal1d"):
+    if kind in ("same1d", "causal1d", "taps2d"):
         return dw.permute(1, 2, 0)
     return dw.permute(1, 2, 0).reshape(dw.shape[1], dw.shape[2], 3, 3)
 
 
-def _dgrad_launch(dyb: Tensor, weight: Tensor, kind: str, N: int, H: int, W: int, out: Tensor, tag: str, **epi) -> None:
+def _dgrad_launch(dyb: Tensor, weight: Tensor, kind: str, N: int, H: int, W: int, out: Tensor, tag: str, taps=None,
+                  **epi) -> None:
     """dx = conv(dy, mirrored weight) into ``out`` (N, H, W, Cin), fp32 or bf16.  mq_conv_gemm takes at most 1024 output
     channels per launch, and a data gradient's output channels are the layer's INPUT channels (1152 for hifimusic's
     first up-block): wider ones are produced in channel slices."""
-    wd, kd = ops.dgrad_weight(weight, kind)
+    if kind == "taps2d":
+        wd, kd, dtaps = ops.dgrad_weight(weight, kind, taps)
+    else:
+        (wd, kd), dtaps = ops.dgrad_weight(weight, kind), None
     cin = wd.shape[0]
     key = "out_bf16" if out.dtype == torch.bfloat16 else "out_f32"
     off = "bf16_coff" if out.dtype == torch.bfloat16 else "f32_coff"
     step = cin if cin <= 1024 else 768
     for c0 in range(0, cin, step):
-        pc = ops.pack_conv(wd[c0:c0 + step], None, kd, on_device=True)
+        pc = ops.pack_conv(wd[c0:c0 + step], None, kd, on_device=True, taps=dtaps)
         extra = {"res_coff": c0} if epi.get("res") is not None else {}
         ops.conv_gemm(dyb, pc, N, H, W, tag=tag, **{key: out, off: c0}, **epi, **extra)
 
@@ -68,15 +72,15 @@ class _ConvFn(torch.autograd.Function):
     """y = conv(x, w) + b on channel-last x (N, H, W, Cin); kind as ops.pack_conv."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, kind: str, tag: str):
+    def forward(ctx, x, weight, bias, kind: str, tag: str, taps=None, out_bf16: bool = False):
         N, H, W, cin = x.shape
         cout = weight.shape[0]
         xb = x.contiguous().to(torch.bfloat16)
-        pc = ops.pack_conv(weight, bias, kind, on_device=True)
-        out = torch.empty(N, H, W, cout, dtype=torch.float32, device=x.device)
-        ops.conv_gemm(xb, pc, N, H, W, out_f32=out, tag=tag)
+        pc = ops.pack_conv(weight, bias, kind, on_device=True, taps=taps)
+        out = torch.empty(N, H, W, cout, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+        ops.conv_gemm(xb, pc, N, H, W, tag=tag, **({"out_bf16": out} if out_bf16 else {"out_f32": out}))
         ctx.save_for_backward(xb, weight)
-        ctx.kind, ctx.tag, ctx.has_bias, ctx.x_dtype = kind, tag, bias is not None, x.dtype
+        ctx.kind, ctx.tag, ctx.has_bias, ctx.x_dtype, ctx.taps = kind, tag, bias is not None, x.dtype, taps
         return out
 
     @staticmethod
@@ -87,27 +91,30 @@ class _ConvFn(torch.autograd.Function):
         dyb = dy.contiguous().to(torch.bfloat16)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty(N, H, W, cin, dtype=torch.float32, device=dy.device)
-            _dgrad_launch(dyb, weight, ctx.kind, N, H, W, dx, ctx.tag + ".dgrad")
+            dx = torch.empty(N, H, W, cin, dtype=torch.bfloat16 if ctx.x_dtype == torch.bfloat16 else torch.float32,
+                             device=dy.device)
+            _dgrad_launch(dyb, weight, ctx.kind, N, H, W, dx, ctx.tag + ".dgrad", taps=ctx.taps)
             dx = dx.to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
-            dh, dwt = ops.conv_taps(ctx.kind, weight.shape)
+            dh, dwt = ops.conv_taps(ctx.kind, weight.shape, ctx.taps)
             dw = _weight_from_taps(ops.conv_wgrad(dyb, xb, N, H, W, cout, cin, dh, dwt, tag=ctx.tag + ".wgrad"), ctx.kind)
             dw = dw.reshape(weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(dim=(0, 1, 2))
-        return dx, dw, db, None, None
+            db = dy.sum(dim=(0, 1, 2), dtype=torch.float32)
+        return dx, dw, db, None, None, None, None
 
 
-def conv(x: Tensor, weight: Tensor, bias: Optional[Tensor], kind: str, tag: str = "") -> Tensor:
-    """Channel-last convolution / linear through the tcgen05 kernels.  x: (N, H, W, Cin) fp32."""
+def conv(x: Tensor, weight: Tensor, bias: Optional[Tensor], kind: str, tag: str = "", taps=None,
+         out_bf16: bool = False) -> Tensor:
+    """Channel-last convolution / linear through the tcgen05 kernels.  x: (N, H, W, Cin) fp32 or bf16 -> fp32 (bf16 with
+    ``out_bf16``).  kind "taps2d": weight (Cout, Cin, ntaps) with ``taps`` = (dh list, dw list)."""
     if not x.is_cuda:
         raise RuntimeError("mqgan_b200.training runs on CUDA (B200) only - there is no CPU fallback")
     if kind == "linear" and weight.dim() == 3:
         weight = weight[:, :, 0]                                  # a 1x1 Conv1d (ResidualBlock1D.residual)
     cout = weight.shape[0]
     x, weight, bias = _pad_channels(x, weight, bias)              # TMA needs 16-byte channel pitches
-    y = _ConvFn.apply(x, weight, bias, kind, tag)
+    y = _ConvFn.apply(x, weight, bias, kind, tag, taps, out_bf16)
     return y[..., :cout] if weight.shape[0] != cout else y
 
 
@@ -347,6 +354,88 @@ def generator_forward(params: Dict[str, Tensor], cfg: PreEncoderConfig, mel: Ten
 
 
 # ----------------------------------------------------------------------------
+# strided convolutions on the stride-1 tcgen05 kernels: space-to-depth lowering (host math, any device)
+# ----------------------------------------------------------------------------
+_LOWERING: Dict[tuple, tuple] = {}
+_LOWERING_INDEX: Dict[tuple, Tensor] = {}
+
+
+def strided_conv_lowering(kh: int, kw: int, sh: int, sw: int):
+    """A (kh, kw) convolution with stride (sh, sw) and padding ((kh-1)//2, (kw-1)//2) equals a STRIDE-1 convolution over
+    the space-to-depth image x'[h', w', (rh, rw, c)] = x[h' sh + rh, w' sw + rw, c]: input row h' sh + di (di = i - ph)
+    is row h' + floor(di / sh) of x', phase di mod sh.  Returns (dh, dw, index): the row-major tap offsets of the
+    lowered kernel and, for every original tap (i, j) in row-major order, its slot tap' * (sh sw) + rh sw + rw in the
+    lowered weight (slots that receive no tap stay zero: a 5x5 stride-2 kernel becomes 3x3 over 4C channels, 25 of
+    36 slots used)."""
+    key = (kh, kw, sh, sw)
+    if key not in _LOWERING:
+        ph, pw = (kh - 1) // 2, (kw - 1) // 2
+        rows = sorted({(i - ph) // sh for i in range(kh)})
+        cols = sorted({(j - pw) // sw for j in range(kw)})
+        dh = [a for a in rows for _ in cols]
+        dw = [b for _ in rows for b in cols]
+        index = []
+        for i in range(kh):
+            for j in range(kw):
+                a, rh = divmod(i - ph, sh)
+                b, rw = divmod(j - pw, sw)
+                index.append((rows.index(a) * len(cols) + cols.index(b)) * (sh * sw) + rh * sw + rw)
+        _LOWERING[key] = (dh, dw, index)
+    return _LOWERING[key]
+
+
+def space_to_depth(x: Tensor, sh: int, sw: int) -> Tensor:
+    """(B, H, W, C) -> (B, ceil(H/sh), ceil(W/sw), sh sw C), channel (rh sw + rw) C + c; zero rows / columns are appended
+    when H, W are not multiples of the stride."""
+    if sh == 1 and sw == 1:
+        return x
+    B, H, W, C = x.shape
+    eh, ew = (-H) % sh, (-W) % sw
+    if eh or ew:
+        x = F.pad(x, (0, 0, 0, ew, 0, eh))
+    return (x.reshape(B, (H + eh) // sh, sh, (W + ew) // sw, sw, C).permute(0, 1, 3, 2, 4, 5)
+            .reshape(B, (H + eh) // sh, (W + ew) // sw, sh * sw * C))
+
+
+def lower_strided_weight(w: Tensor, sh: int, sw: int):
+    """(Cout, Cin, kh, kw) -> ((Cout, sh sw Cin, ntaps') weight of the stride-1 convolution over space_to_depth(x),
+    (dh, dw)); differentiable (a scatter of the original taps into a zero tensor)."""
+    cout, cin, kh, kw = w.shape
+    dh, dw, index = strided_conv_lowering(kh, kw, sh, sw)
+    src = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    slots = len(dh) * sh * sw
+    ikey = (kh, kw, sh, sw, str(w.device))
+    if ikey not in _LOWERING_INDEX:                        # built once per device (no host-to-device copy inside a graph capture)
+        _LOWERING_INDEX[ikey] = torch.tensor(index, dtype=torch.long, device=w.device)
+    dst = w.new_zeros(cout, slots, cin).index_copy(1, _LOWERING_INDEX[ikey], src)
+    return dst.reshape(cout, len(dh), sh * sw * cin).permute(0, 2, 1), (dh, dw)
+
+
+def im2col_1ch(x: Tensor, kh: int, kw: int, sh: int, sw: int) -> Tensor:
+    """(B, H, W, 1) -> (B, Ho, Wo, kh kw) patches of a single-channel image (the discriminators' first layers:
+    with one input channel the convolution is a linear map of the kh kw patch)."""
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    xp = F.pad(x[..., 0], (pw, pw, ph, ph))
+    return xp.unfold(1, kh, sh).unfold(2, kw, sw).reshape(x.shape[0], -1, (x.shape[2] + 2 * pw - kw) // sw + 1, kh * kw)
+
+
+def strided_conv_nhwc(x: Tensor, w: Tensor, stride: Tuple[int, int], conv_fn) -> Tensor:
+    """conv2d(x, w, stride, padding=((kh-1)//2, (kw-1)//2)) on a channel-last image through a stride-1 convolution
+    ``conv_fn(x', weight, kind, taps)`` (the tcgen05 kernels on the GPU; tests pass a plain-torch one)."""
+    cout, cin, kh, kw = w.shape
+    sh, sw = stride
+    if cin == 1:
+        return conv_fn(im2col_1ch(x, kh, kw, sh, sw), w.reshape(cout, kh * kw), "linear", None)
+    if (sh, sw) == (1, 1) and (kh, kw) == (3, 3):
+        return conv_fn(x, w, "conv2d3", None)
+    wl, (dh, dw) = lower_strided_weight(w, sh, sw)
+    xs = space_to_depth(x, sh, sw)
+    if dh == [-1, -1, -1, 0, 0, 0, 1, 1, 1] and dw == [-1, 0, 1] * 3:
+        return conv_fn(xs, wl.reshape(cout, wl.shape[1], 3, 3), "conv2d3", None)
+    return conv_fn(xs, wl.contiguous(), "taps2d", (dh, dw))
+
+
+# ----------------------------------------------------------------------------
 # discriminators (discriminators.py), legacy spectral norm
 # ----------------------------------------------------------------------------
 def _spectral_weight(sd: Dict[str, Tensor], prefix: str, training: bool) -> Tensor:
@@ -385,13 +474,19 @@ class _LeakyMaskFn(torch.autograd.Function):
 
 
 def patch_discriminator(sd: Dict[str, Tensor], dc: PatchDiscConfig, x: Tensor, lengths: Tensor, training: bool,
-                        prefix: str = "", autocast_bf16: bool = False):
+                        prefix: str = "", autocast_bf16: bool = False, native_conv: bool = False):
     """MelSpectrogramPatchDiscriminator2D.forward (discriminators.py:208-257): x (B, T, F) ->
     (logits (B,1,H,W), valid-patch mask, [(feature, padded mask)]).
 
     ``autocast_bf16`` is the reference's CUDA training precision (train.py:523: convs under bf16 autocast, the
     activations after them bf16): feature maps stay bf16 and channels_last from layer to layer, and the
-    LeakyReLU + patch mask after each conv is one library pass.  Otherwise everything is fp32 (parity mode)."""
+    LeakyReLU + patch mask after each conv is one library pass.  Otherwise everything is fp32 (parity mode).
+
+    ``native_conv`` (with ``autocast_bf16``): the convolutions themselves run on the library's stride-1 tcgen05 kernels
+    instead of cuDNN - strided layers through the space-to-depth lowering (``strided_conv_nhwc``), one-channel first
+    layers as im2col + linear - with forward, data and weight gradients as for the generator's convolutions."""
+    if native_conv and autocast_bf16 and x.is_cuda:
+        return _patch_discriminator_native(sd, dc, x, lengths, training, prefix)
     B, T, Fm = x.shape
     n = len(dc.kernels)
     pad_mask = (torch.arange(T, device=x.device)[None, :] >= lengths.to(x.device)[:, None])[:, None, None, :].expand(-1, 1, Fm, -1)
@@ -431,6 +526,40 @@ def patch_discriminator(sd: Dict[str, Tensor], dc: PatchDiscConfig, x: Tensor, l
     return out.float(), ~pad_mask, feats
 
 
+def _patch_discriminator_native(sd: Dict[str, Tensor], dc: PatchDiscConfig, x: Tensor, lengths: Tensor, training: bool,
+                                prefix: str):
+    """patch_discriminator with channel-last bf16 feature maps (B, H, W, C) and every convolution on the tcgen05 kernels."""
+    B, T, Fm = x.shape
+    n = len(dc.kernels)
+    pad_mask = (torch.arange(T, device=x.device)[None, :] >= lengths.to(x.device)[:, None])[:, None, None, :].expand(-1, 1, Fm, -1)
+    out = x.transpose(1, 2).unsqueeze(-1).to(torch.bfloat16)                        # (B, F, T, 1)
+    feats = []
+    for i in range(n):
+        if i == n - 1:                                                              # masked squeeze-excite
+            valid = (~pad_mask).permute(0, 2, 3, 1)                                 # (B, H, W, 1)
+            denom = valid.sum(dim=(1, 2)).clamp(min=1)
+            sq = (out.float() * valid).sum(dim=(1, 2)) / denom
+            h = F.relu(F.linear(sq, sd[prefix + "se_block.fc1.weight"], sd[prefix + "se_block.fc1.bias"]))
+            ex = torch.sigmoid(F.linear(h, sd[prefix + "se_block.fc2.weight"], sd[prefix + "se_block.fc2.bias"]))
+            out = (out * ex[:, None, None, :]).to(torch.bfloat16)
+        sh, sw = dc.layer_stride(i)
+        wgt = _spectral_weight(sd, f"{prefix}convs.{i}", training)
+        bias = sd[f"{prefix}convs.{i}.bias"]
+        tag = f"{prefix}convs.{i}"
+        y = strided_conv_nhwc(out, wgt, (sh, sw),
+                              lambda xx, ww, kind, taps: conv(xx, ww, None, kind, tag, taps=taps, out_bf16=True))
+        if sh > 1 or sw > 1:
+            pad_mask = F.max_pool2d(pad_mask.float(), kernel_size=(sh, sw), stride=(sh, sw), ceil_mode=True).bool()
+        if wgt.shape[0] % 8 == 0:
+            out = _LeakyMaskFn.apply(y.permute(0, 3, 1, 2), bias,
+                                     pad_mask.reshape(B, y.shape[1], y.shape[2]).to(torch.uint8).contiguous()).permute(0, 2, 3, 1)
+        else:                                                                       # the 1-channel logits layer
+            out = F.leaky_relu(y.float() + bias, 0.2).masked_fill(pad_mask.permute(0, 2, 3, 1), 0.0)
+        if dc.feature_layers[i]:
+            feats.append((out.permute(0, 3, 1, 2), pad_mask))
+    return out.permute(0, 3, 1, 2).float(), ~pad_mask, feats
+
+
 _SIDE_STREAMS: Dict[str, List["torch.cuda.Stream"]] = {}
 
 
@@ -443,7 +572,7 @@ def _side_streams(device, n: int) -> List["torch.cuda.Stream"]:
 
 
 def multibin_discriminator(sd: Dict[str, Tensor], mc: MultiBinConfig, x: Tensor, lengths: Tensor, training: bool,
-                           autocast_bf16: bool = False, concurrent: bool = True):
+                           autocast_bf16: bool = False, concurrent: bool = True, native_conv: bool = False):
     """MultiBinDiscriminator.forward (discriminators.py:292-312).  The bands are independent networks on 1/n_bins of
     the mel axis, each too small to fill 148 SMs: with ``concurrent`` every band runs on its own CUDA stream (forked
     from / joined to the caller's stream; autograd replays each band's backward on the same stream, and a CUDA-graph
@@ -456,12 +585,14 @@ def multibin_discriminator(sd: Dict[str, Tensor], mc: MultiBinConfig, x: Tensor,
         for b, sub in enumerate(subs):
             streams[b].wait_stream(cur)
             with torch.cuda.stream(streams[b]):
-                res.append(patch_discriminator(sd, mc.bin_config, sub, lengths, training, f"discriminators.{b}.", autocast_bf16))
+                res.append(patch_discriminator(sd, mc.bin_config, sub, lengths, training, f"discriminators.{b}.", autocast_bf16,
+                                               native_conv))
         for st in streams:
             cur.wait_stream(st)
     else:
         for b, sub in enumerate(subs):
-            res.append(patch_discriminator(sd, mc.bin_config, sub, lengths, training, f"discriminators.{b}.", autocast_bf16))
+            res.append(patch_discriminator(sd, mc.bin_config, sub, lengths, training, f"discriminators.{b}.", autocast_bf16,
+                                           native_conv))
     return [r[0] for r in res], [r[1] for r in res], [r[2] for r in res]
 
 
@@ -617,7 +748,7 @@ class TrainStep:
 
     def __init__(self, cfg: PreEncoderConfig, pd_cfg: PatchDiscConfig, mb_cfg: MultiBinConfig, g_sd, pd_sd, mb_sd,
                  tcfg: dict, device, dropout_p: float = 0.0, d_autocast_bf16: bool = False, native_cb2d: bool = True,
-                 cb2d_fast_tanh: bool = True, group=None):
+                 cb2d_fast_tanh: bool = True, d_native: bool = False, group=None):
         if dropout_p != 0.0:
             raise NotImplementedError("mqgan_b200.training implements dropout = 0 only (see module docstring)")
         dev = torch.device(device)
@@ -627,6 +758,7 @@ class TrainStep:
         self.cfg, self.pd_cfg, self.mb_cfg, self.tcfg = cfg, pd_cfg, mb_cfg, tcfg
         self.device, self.group = dev, group
         self.d_autocast_bf16, self.native_cb2d, self.cb2d_fast_tanh = d_autocast_bf16, native_cb2d, cb2d_fast_tanh
+        self.d_native = bool(d_native) and d_autocast_bf16          # discriminator convolutions on the tcgen05 kernels too
         self.g = {k: v.detach().clone().float().to(dev).requires_grad_(True) for k, v in g_sd.items()}
         self.pd = {k: v.detach().clone().float().to(dev) for k, v in pd_sd.items()}
         self.mb = {k: v.detach().clone().float().to(dev) for k, v in mb_sd.items()}
@@ -654,6 +786,14 @@ class TrainStep:
 
     def d_params(self) -> List[Tensor]:
         return [v for sd in (self.pd, self.mb) for v in sd.values() if v.requires_grad]
+
+    def _patch(self, x, lengths, training):
+        return patch_discriminator(self.pd, self.pd_cfg, x, lengths, training, autocast_bf16=self.d_autocast_bf16,
+                                   native_conv=self.d_native)
+
+    def _multibin(self, x, lengths, training):
+        return multibin_discriminator(self.mb, self.mb_cfg, x, lengths, training, self.d_autocast_bf16,
+                                      native_conv=self.d_native)
 
     def start_epoch(self):
         """train.py:504-506: the discriminators go back to training mode (power iteration on) each epoch."""
@@ -730,17 +870,17 @@ class TrainStep:
             if self.d_training:
                 # two passes, as the reference makes them: in training mode each forward advances the spectral-norm
                 # power iteration (first iteration of an epoch only, train.py:417-418 vs :504-506)
-                rl, rm, _ = patch_discriminator(self.pd, self.pd_cfg, real, lengths, True, autocast_bf16=ac)
-                fl, fm, _ = patch_discriminator(self.pd, self.pd_cfg, fake, lengths, True, autocast_bf16=ac)
-                rl2, rm2, _ = multibin_discriminator(self.mb, self.mb_cfg, real, lengths, True, ac)
-                fl2, fm2, _ = multibin_discriminator(self.mb, self.mb_cfg, fake, lengths, True, ac)
+                rl, rm, _ = self._patch(real, lengths, True)
+                fl, fm, _ = self._patch(fake, lengths, True)
+                rl2, rm2, _ = self._multibin(real, lengths, True)
+                fl2, fm2, _ = self._multibin(fake, lengths, True)
             else:
                 # eval-mode discriminators are per-sample functions: real and fake go through as one batch of 2B
                 nb = real.shape[0]
                 both, len2 = torch.cat([real, fake], dim=0), torch.cat([lengths, lengths], dim=0)
-                lg, mk, _ = patch_discriminator(self.pd, self.pd_cfg, both, len2, False, autocast_bf16=ac)
+                lg, mk, _ = self._patch(both, len2, False)
                 rl, fl, rm, fm = lg[:nb], lg[nb:], mk[:nb], mk[nb:]
-                lg2, mk2, _ = multibin_discriminator(self.mb, self.mb_cfg, both, len2, False, ac)
+                lg2, mk2, _ = self._multibin(both, len2, False)
                 rl2, fl2 = [t_[:nb] for t_ in lg2], [t_[nb:] for t_ in lg2]
                 rm2, fm2 = [t_[:nb] for t_ in mk2], [t_[nb:] for t_ in mk2]
             loss_d = self.lecam.d_loss(rl, fl, rm, fm)
@@ -765,14 +905,14 @@ class TrainStep:
             loss_fm = real.new_zeros(())
             gl_lambda = fm_lambda = 0.0
             if gan:
-                gl, gm, gf = patch_discriminator(self.pd, self.pd_cfg, recon_post, lengths, False, autocast_bf16=ac)
-                gl2, gm2, gf2 = multibin_discriminator(self.mb, self.mb_cfg, recon_post, lengths, False, ac)
+                gl, gm, gf = self._patch(recon_post, lengths, False)
+                gl2, gm2, gf2 = self._multibin(recon_post, lengths, False)
                 loss_gan = 0.5 * (masked_mse(gl, 1.0, gm) + sum(masked_mse(g, 1.0, gm2[0]) for g in gl2) / len(gl2))
                 gl_lambda, fm_lambda = lw["Gloss_lambda"], lw["fm_lambda"]
                 if use_fm:                                                          # train.py:454-476
                     with torch.no_grad():
-                        _, _, rf = patch_discriminator(self.pd, self.pd_cfg, real, lengths, False, autocast_bf16=ac)
-                        _, _, rf2 = multibin_discriminator(self.mb, self.mb_cfg, real, lengths, False, ac)
+                        _, _, rf = self._patch(real, lengths, False)
+                        _, _, rf2 = self._multibin(real, lengths, False)
                     fm_d1 = sum(masked_mae(ff, r, m) for (r, m), (ff, _) in zip(rf, gf)) / max(len(rf), 1)
                     fm_mbd = real.new_zeros(())
                     for rfe, gfe in zip(rf2, gf2):                                  # the reference's running division :466-472

@@ -308,17 +308,29 @@ def test_discriminator_bf16_mode_tracks_fp32_mode():
         for _ in range(20):
             TR.patch_discriminator(sd, dc, synth_mels(2, 40, 32, seed=3).to(DEV), lens, training=True)
     outs, grads = [], []
-    for fast in (False, True):
+    for fast, native in ((False, False), (True, False), (True, True)):
         x = synth_mels(2, 40, 32, seed=3).to(DEV).requires_grad_(True)
-        logits, valid, feats = TR.patch_discriminator(sd, dc, x, lens, training=False, autocast_bf16=fast)
+        logits, valid, feats = TR.patch_discriminator(sd, dc, x, lens, training=False, autocast_bf16=fast, native_conv=native)
         (logits * valid).pow(2).sum().backward()
         outs.append(logits.detach())
         grads.append(x.grad.detach())
         assert len(feats) == 1
-    e_out = float((outs[0] - outs[1]).abs().max()) / float(outs[0].abs().max())
-    e_grad = float((grads[0] - grads[1]).norm() / grads[0].norm())
-    assert e_out < 3e-2, e_out                     # bf16 operands and bf16 feature maps through four layers
-    assert e_grad < 0.15, e_grad
+    for k in (1, 2):                               # cuDNN bf16 path, then every convolution on the tcgen05 kernels
+        e_out = float((outs[0] - outs[k]).abs().max()) / float(outs[0].abs().max())
+        e_grad = float((grads[0] - grads[k]).norm() / grads[0].norm())
+        assert e_out < 3e-2, (k, e_out)            # bf16 operands and bf16 feature maps through four layers
+        assert e_grad < 0.15, (k, e_grad)
+    # weight gradients of the native path against the fp32 path
+    gw = []
+    for fast, native in ((False, False), (True, True)):
+        sdg = {k: (v.clone().requires_grad_(True) if not S.is_disc_buffer(k) else v.clone()) for k, v in sd.items()}
+        x = synth_mels(2, 40, 32, seed=3).to(DEV)
+        logits, valid, _ = TR.patch_discriminator(sdg, dc, x, lens, training=False, autocast_bf16=fast, native_conv=native)
+        (logits * valid).pow(2).sum().backward()
+        gw.append({k: v.grad for k, v in sdg.items() if v.requires_grad})
+    for k in gw[0]:
+        ref = gw[0][k]
+        assert float((gw[1][k] - ref).norm()) <= 0.15 * float(ref.norm()) + 1e-6 * float(ref.abs().max() + 1), k
 
 
 def test_graph_replayed_iterations_equal_eager_iterations():

@@ -108,3 +108,48 @@ def test_loss_modules_match_oracle():
     assert torch.allclose(ch, ref.mean(), rtol=1e-5)
     with pytest.raises(AssertionError):
         MaskedMelLoss("l1")
+
+
+# ----------------------------------------------------------------------------
+# space-to-depth lowering of strided convolutions (host math of mqgan_b200.training, checked against F.conv2d)
+# ----------------------------------------------------------------------------
+def _taps_conv_reference(x, weight, kind, taps):
+    """Plain-torch stride-1 convolution over a channel-last image in the library's conventions."""
+    import torch.nn.functional as F
+    if kind == "linear":
+        return x @ weight.t()
+    if kind == "conv2d3":
+        return F.conv2d(x.permute(0, 3, 1, 2), weight, padding=1).permute(0, 2, 3, 1)
+    dh, dw = taps
+    B, H, W, C = x.shape
+    pad = max(max(abs(v) for v in dh), max(abs(v) for v in dw))
+    xp = F.pad(x, (0, 0, pad, pad, pad, pad))
+    y = 0
+    for t, (a, b) in enumerate(zip(dh, dw)):
+        y = y + xp[:, pad + a:pad + a + H, pad + b:pad + b + W, :] @ weight[:, :, t].t()
+    return y
+
+
+@pytest.mark.parametrize("kh,kw,sh,sw,H,W,cin", [
+    (5, 5, 2, 2, 16, 12, 6), (5, 5, 1, 2, 9, 14, 1), (5, 5, 2, 2, 15, 11, 3),      # odd sizes: zero rows appended
+    (3, 3, 2, 1, 8, 10, 4), (3, 3, 1, 2, 16, 9, 5), (3, 3, 1, 1, 7, 7, 2),
+    (3, 7, 1, 1, 16, 20, 1), (3, 5, 1, 1, 16, 20, 8), (7, 7, 2, 2, 20, 16, 2), (7, 7, 1, 2, 10, 16, 1),
+])
+def test_strided_conv_lowering_equals_conv2d(kh, kw, sh, sw, H, W, cin):
+    import torch.nn.functional as F
+    from mqgan_b200 import training as TR
+    g = torch.Generator().manual_seed(kh * 100 + sh * 10 + cin)
+    cout = 5
+    x = torch.randn(2, H, W, cin, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64, requires_grad=True)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, stride=(sh, sw), padding=((kh - 1) // 2, (kw - 1) // 2)).permute(0, 2, 3, 1)
+    got = TR.strided_conv_nhwc(x, w, (sh, sw), _taps_conv_reference)
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, atol=1e-10)
+    dy = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    gx, gw = torch.autograd.grad(ref, (x, w), dy, retain_graph=True)
+    hx, hw = torch.autograd.grad(got, (x, w), dy)
+    assert torch.allclose(gx, hx, atol=1e-10) and torch.allclose(gw, hw, atol=1e-10)      # the lowering is differentiable
+    if cin > 1 and (sh, sw) != (1, 1):
+        dh, dw, index = TR.strided_conv_lowering(kh, kw, sh, sw)
+        assert len(dh) <= 16 and len(set(index)) == kh * kw                               # fits MQ_MAX_TAPS; a bijection

@@ -108,6 +108,8 @@ def main():
     ap.add_argument("--ref_batch", type=int, default=1)
     ap.add_argument("--ref_frames", type=int, default=64)
     ap.add_argument("--d_fp32", action="store_true", help="discriminator convs in fp32 instead of bf16 autocast")
+    ap.add_argument("--d_native", action="store_true", help="discriminator convolutions on the library's tcgen05 kernels "
+                                                            "(space-to-depth lowering) instead of cuDNN")
     ap.add_argument("--torch_cb2d", action="store_true", help="ConvBlock2D through plain torch ops (cross-check)")
     ap.add_argument("--layers", default=None, help="write the per-kernel table of one instrumented step here")
     ap.add_argument("--no_graph", action="store_true", help="eager launches instead of replaying the captured CUDA graph")
@@ -132,7 +134,7 @@ def main():
     B, T = args.batch, args.frames
     ts = TR.TrainStep(cfg, pdc, mbc, synth_state_dict(cfg, 0), synth_disc_state_dict(S.patch_disc_param_spec(pdc), 1),
                       synth_disc_state_dict(S.multibin_param_spec(mbc), 2), dict(S.TRAIN_DEFAULTS), dev,
-                      d_autocast_bf16=not args.d_fp32, native_cb2d=not args.torch_cb2d)
+                      d_autocast_bf16=not args.d_fp32, native_cb2d=not args.torch_cb2d, d_native=args.d_native)
     nbuf = 4
     host = [synth_mels(B, T, cfg.mel_channels, seed=100 * rank + i).pin_memory() for i in range(nbuf)]
     lens_h = torch.full((B,), T, dtype=torch.long).pin_memory()
@@ -243,7 +245,8 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.model}_train_{B}x{T}", "model": args.model, "batch_per_gpu": B, "frames": T,
                        "precision": "generator conv operands bf16 (fwd, dgrad, wgrad), fp32 accumulate and activations; "
-                                    + ("discriminator convs fp32" if args.d_fp32 else "discriminator convs bf16 autocast (train.py:523)"),
+                                    + ("discriminator convs fp32" if args.d_fp32 else "discriminator convs bf16 autocast (train.py:523)")
+                                    + (", on the tcgen05 kernels via space-to-depth" if args.d_native else ", cuDNN"),
                        "weights": "random-init (seed 0/1/2)", "dropout": 0.0,
                        "launch": "whole iteration replayed from one CUDA graph" if use_graph else "eager launches",
                        "l2": "activations saved for backward exceed L2 (GBs per step)",
