@@ -178,6 +178,26 @@ def run_case(T_, name, cfg_name, pd_name, mb_name, B, T, seed):
         print(f"[step {step}] G param-sum diff max {np.abs(ps_o - out[pre + 'g_param_sums']).max():.3e}; "
               f"u diff {float((st.pd['convs.1.weight_u'] - dsd_now['pd:convs.1.weight_u']).abs().max()):.3e}")
 
+    # ---- a third iteration before the GAN phase (epoch < discriminator_train_start_epoch): no discriminator step, no
+    # adversarial / feature-matching terms (train.py:526-527, 447-450) ----
+    me.epoch = tcfg["discriminator_train_start_epoch"] - 1
+    me.config["training"]["use_fm_loss"] = False
+    real = synth_mels(B, T, cfg.mel_channels, seed=43)
+    lens = synth_lengths(B, T, seed=43, ragged=True)
+    real = real.masked_fill((torch.arange(T)[None, :] >= lens[:, None]).unsqueeze(-1), 0.0)
+    recon_pre, recon_post = gen(real, lens)
+    g_losses = T_.Trainer._train_generator(me, real, recon_pre, recon_post, lens)
+    g_named = dict(gen.named_parameters())
+    out["s3_losses"] = np.array([0.0, g_losses["loss_g_total"], g_losses["loss_recon_pre"], g_losses["loss_recon_post"],
+                                 g_losses["loss_gan"], g_losses["loss_fm"]], np.float64)
+    out["s3_g_grad_norms"] = np.array([float(g_named[k].grad.norm()) if g_named[k].grad is not None else -1.0 for k in g_sd],
+                                      np.float64)
+    gsd_now = gen.state_dict()
+    out["s3_g_param_sums"] = np.array([float(gsd_now[k].double().sum()) for k in g_sd], np.float64)
+    o = TO.train_iteration(st, real, lens, gan=False)
+    print(f"[step 3, recon only] reference {out['s3_losses']}  oracle "
+          f"{[o['loss_d'], o['loss_g_total'], o['loss_recon_pre'], o['loss_recon_post'], o['loss_gan'], o['loss_fm']]}")
+
     out["B"], out["T"], out["seed"] = np.array(B), np.array(T), np.array(seed)
     out["configs"] = np.array([cfg_name, pd_name, mb_name])
     out["qin_w"], out["qin_b"] = g_sd["q_in_proj.weight"].numpy(), g_sd["q_in_proj.bias"].numpy()

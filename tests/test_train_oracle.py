@@ -71,6 +71,31 @@ def test_train_oracle_matches_reference_two_iterations(name):
         np.testing.assert_allclose(dps, fx[pre + "d_param_sums"], rtol=1e-6, atol=1e-5)
 
 
+@pytest.mark.parametrize("name", FIXTURES)
+def test_train_oracle_recon_only_iteration_after_two_gan_iterations(name):
+    """The third pinned iteration runs before the GAN phase (epoch < discriminator_train_start_epoch): no discriminator
+    step, no adversarial terms (train.py:526-527, 447-450)."""
+    fx = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg, pdc, mbc, g_sd, pd_sd, mb_sd = tiny_train_state(name)
+    st = TO.TrainState(cfg, g_sd, pd_sd, mb_sd, TO.patch_cfg([k[0] for k in pdc.kernels], pdc.strides),
+                       TO.multibin_cfg(mbc.kernel_sizes, mbc.n_bins, mbc.n_no_strides), dict(S.TINY_TRAIN))
+    B, T = int(fx["B"]), int(fx["T"])
+    for step in (1, 2):
+        real, lens = tiny_batch(step, B, T, cfg.mel_channels)
+        TO.train_iteration(st, real, lens, gan=True, use_fm=step == 2)
+    d_before = {k: v.detach().clone() for k, v in st.pd.items()}
+    real, lens = tiny_batch(3, B, T, cfg.mel_channels)
+    o = TO.train_iteration(st, real, lens, gan=False)
+    got = np.array([o["loss_d"], o["loss_g_total"], o["loss_recon_pre"], o["loss_recon_post"], o["loss_gan"], o["loss_fm"]])
+    np.testing.assert_allclose(got, fx["s3_losses"], rtol=2e-6, atol=1e-7)
+    g_keys = [str(k) for k in fx["g_keys"]]
+    gn = np.array([float(st.g[k].grad.norm()) if st.g[k].grad is not None else -1.0 for k in g_keys])
+    np.testing.assert_allclose(gn, fx["s3_g_grad_norms"], rtol=1e-4, atol=1e-9)
+    ps = np.array([float(st.g[k].detach().double().sum()) for k in g_keys])
+    np.testing.assert_allclose(ps, fx["s3_g_param_sums"], rtol=1e-6, atol=1e-5)
+    assert all(torch.equal(st.pd[k].detach(), d_before[k]) for k in d_before)          # the discriminators did not move
+
+
 def test_hidden_proj_gets_no_gradient_and_refiner_input_is_detached():
     """preencoder.py:411-413: only the refiner sees x_post's gradient through the residual."""
     cfg, _, _, g_sd, _, _ = tiny_train_state()
