@@ -431,3 +431,43 @@ def test_length_groups_partition_rules():
     stub.max_chunk_frames = 4096                                    # groups are split to fit the refiner chunk size
     g2 = groups(stub, lens, T)
     assert all(len(m) * Tg <= 4096 or len(m) == 1 for m, Tg in g2)
+
+
+def test_native_npy_io_property_random_shapes_and_dtypes(tmp_path):
+    """Property test (hypothesis) of mq_npy_read_f32 / mq_npy_write_f32 against numpy over random shapes, dtypes, header
+    versions and padding targets."""
+    import ctypes as C
+    from hypothesis import given, settings, strategies as st
+    import numpy.lib.format as nf
+    lib = _lib.lib()
+    path = str(tmp_path / "p.npy").encode()
+
+    @settings(max_examples=60, deadline=None)
+    @given(rows=st.integers(0, 40), cols=st.integers(1, 33), dt=st.sampled_from(["<f4", "<f8", "<f2"]),
+           version=st.sampled_from([(1, 0), (2, 0), (3, 0)]), extra=st.integers(0, 5), seed=st.integers(0, 2 ** 16))
+    def check(rows, cols, dt, version, extra, seed):
+        arr = (np.random.default_rng(seed).standard_normal((rows, cols)) * 100).astype(np.dtype(dt))
+        with open(path, "wb") as f:
+            nf.write_array(f, arr, version=version)
+        r, c, d = C.c_int64(), C.c_int64(), C.c_int()
+        assert lib.mq_npy_probe(path, C.byref(r), C.byref(c), C.byref(d), None) == 0
+        assert (r.value, c.value, d.value) == (rows, cols, {"<f4": 0, "<f8": 1, "<f2": 2}[dt])
+        dst = np.full((rows + extra, cols), np.nan, np.float32)
+        got_rows = C.c_int64()
+        assert lib.mq_npy_read_f32(path, dst.ctypes.data, rows + extra, cols, C.byref(got_rows)) == 0
+        assert got_rows.value == rows
+        assert np.array_equal(dst[:rows], arr.astype(np.float32)) and (dst[rows:] == 0).all()
+        if rows > 1:                                   # destination shorter than the file: the head is read
+            short = np.full((rows - 1, cols), np.nan, np.float32)
+            assert lib.mq_npy_read_f32(path, short.ctypes.data, rows - 1, cols, None) == 0
+            assert np.array_equal(short, arr[: rows - 1].astype(np.float32))
+        out = str(tmp_path / "w.npy")
+        a32 = np.ascontiguousarray(arr.astype(np.float32))
+        assert lib.mq_npy_write_f32(out.encode(), a32.ctypes.data, rows, cols) == 0
+        ref = str(tmp_path / "r.npy")
+        np.save(ref, a32)
+        assert open(out, "rb").read() == open(ref, "rb").read()
+
+    check()
+    bad = np.full((2, 3), np.nan, np.float32)
+    assert lib.mq_npy_read_f32(path, bad.ctypes.data, 2, 999, None) in (1, 4, 5)      # column mismatch is reported, not read
