@@ -99,6 +99,24 @@ def split_dataset(n: int, validation_split: float, seed: int) -> Tuple[List[int]
     return perm[:train_size], perm[train_size:]
 
 
+def epoch_schedule(train_idx: Sequence[int], batch_size: int, seed: int, epoch: int, rank: int, world: int, crop_len):
+    """[(dataset indices, crop length)] of one replica for one epoch.  The shuffle and the crop-length draws come from ONE
+    random stream seeded by (seed, epoch), identical on every replica: all replicas see the same crop length in the same
+    iteration (the reference draws it per batch, train.py:153-158), so they capture / replay the same CUDA graphs and
+    issue their gradient all-reduces in lock-step; rank r takes batches r, r + world, ...; a trailing group of fewer than
+    ``world`` batches is dropped so every replica runs the same number of iterations."""
+    order = list(train_idx)
+    shared = random.Random(seed * 1000003 + epoch)
+    shared.shuffle(order)
+    chunks = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
+    usable = len(chunks) - (len(chunks) % world if world > 1 else 0)
+    out = []
+    for i0 in range(0, usable, world):
+        tgt = shared.choice(list(crop_len)) if isinstance(crop_len, (list, tuple)) else crop_len
+        out.append((chunks[i0 + rank], tgt))
+    return out
+
+
 def latest_checkpoint(output_dir: str) -> Optional[str]:
     return max(glob.glob(os.path.join(output_dir, "checkpoint_epoch_*.pth")), key=os.path.getctime, default=None)
 
@@ -186,17 +204,9 @@ class Trainer:
 
     def batches(self, epoch: int):
         """Shuffled training batches of this epoch; rank r takes batches r, r + world, ..."""
-        order = list(self.train_idx)
-        shared = random.Random(int(self.config["training"]["seed"]) * 1000003 + epoch)             # same stream on every rank
-        shared.shuffle(order)
-        bs = int(self.config["data"]["batch_size"])
-        chunks = [order[i:i + bs] for i in range(0, len(order), bs)]
-        crop = self.config["data"].get("crop_len")
-        usable = len(chunks) - (len(chunks) % self.world if self.world > 1 else 0)
-        for i0 in range(0, usable, self.world):
-            # one crop length per iteration, the same on every replica (the reference draws it per batch, train.py:153-158)
-            tgt = shared.choice(list(crop)) if isinstance(crop, (list, tuple)) else crop
-            yield pad_collate_fn([self.dataset[j] for j in chunks[i0 + self.rank]], crop_lens=tgt)
+        for idx, tgt in epoch_schedule(self.train_idx, int(self.config["data"]["batch_size"]), int(self.config["training"]["seed"]),
+                                       epoch, self.rank, self.world, self.config["data"].get("crop_len")):
+            yield pad_collate_fn([self.dataset[j] for j in idx], crop_lens=tgt)
 
     def train_epoch(self, epoch: int) -> Optional[dict]:
         self.step.start_epoch()                                        # train.py:504-506

@@ -124,3 +124,20 @@ def test_train_cli_runs_checkpoints_and_resumes(tmp_path):
     assert os.path.exists(os.path.join(out, "checkpoint_epoch_004.pth"))
     log2 = [json.loads(l) for l in open(os.path.join(out, "train_log.jsonl"))]
     assert len(log2) == 20 and log2[-1]["epoch"] == 4
+
+
+def test_epoch_schedule_is_lockstep_across_replicas():
+    idx = list(range(103))
+    world = 4
+    per_rank = [TC.epoch_schedule(idx, 8, seed=42, epoch=3, rank=r, world=world, crop_len=[128, 192, 256]) for r in range(world)]
+    n_it = {len(s) for s in per_rank}
+    assert n_it == {3}                                              # 13 batches -> 12 usable -> 3 iterations each
+    for it in range(3):
+        assert len({per_rank[r][it][1] for r in range(world)}) == 1            # same crop length on every replica
+    seen = [j for s in per_rank for b, _ in s for j in b]
+    assert len(seen) == len(set(seen)) == 96                        # disjoint batches
+    assert per_rank[1] == TC.epoch_schedule(idx, 8, 42, 3, 1, world, [128, 192, 256])          # deterministic
+    assert per_rank[1] != TC.epoch_schedule(idx, 8, 42, 4, 1, world, [128, 192, 256])          # reshuffled every epoch
+    single = TC.epoch_schedule(idx, 8, 42, 3, 0, 1, 256)
+    assert len(single) == 13 and sorted(j for b, _ in single for j in b) == idx and {t for _, t in single} == {256}
+    assert TC.epoch_schedule(idx, 8, 42, 3, 0, 1, None)[0][1] is None
