@@ -35,6 +35,14 @@ constexpr int kATileBytes = kTileM * kBlockK * 2;   // 16 KiB
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBiasSmemFloats = 1024;       // the whole (padded) bias vector is staged in shared memory once per CTA
 
+// Bench-only bottleneck probes (MQ_CONV_DEBUG bit mask: 1 no epilogue math/stores, 2 no MMA, 4 no TMA, 8 no stores)
+// exist only in a -DMQ_CONV_PROBES build; release kernels carry no probe branches in their MMA / TMA / epilogue loops.
+#ifdef MQ_CONV_PROBES
+#define MQ_PROBE(a, bit) ((a).debug & (bit))
+#else
+#define MQ_PROBE(a, bit) 0
+#endif
+
 struct ConvArgs {
   int N, H, W;
   int tiles_h, tiles_w, tiles_n, num_tiles;
@@ -253,7 +261,7 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
   uint32_t u[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) u[j] = zero_post ? 0u : pack_bf16x2(x[2 * j], x[2 * j + 1]);
-  if ((a.debug & 8) && x[0] != 1234.5678f) valid = false;   // probe: math without the global stores
+  if (MQ_PROBE(a, 8) && x[0] != 1234.5678f) valid = false;   // probe: math without the global stores
   if (valid) {
     __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
 #pragma unroll
@@ -354,7 +362,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
         tmem_ld_32x32(t_row + c, v);
         tmem_ld_wait();
         const int co0 = n0 + c;
-        if (a.debug & 1) continue;
+        if (MQ_PROBE(a, 1)) continue;
         if (kLean) {
           epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked, valid, pix_pool);
         } else {
@@ -449,7 +457,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
             }
             for (int kc = 0; kc < nch; ++kc, ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              if (a.debug & 4) {
+              if (MQ_PROBE(a, 4)) {
                 mbar_arrive(&full_bar[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
                 continue;
@@ -480,7 +488,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
     {
       const uint32_t idesc = a.op_f16 ? umma_idesc_f16(kTileM, a.bn) : umma_idesc_bf16(kTileM, a.bn);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
-      const int msub = (a.debug & 2) ? 0 : a.msub;
+      const int msub = MQ_PROBE(a, 2) ? 0 : a.msub;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -606,7 +614,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         decode_tile(a, tile, n_idx, h0, w0, n0, par);
         for (int kc = 0; kc < a.kchunks; ++kc) {
           mbar_wait(&emptyA[sa], pa ^ 1);
-          if (a.debug & 4) {
+          if (MQ_PROBE(a, 4)) {
             mbar_arrive(&fullA[sa]);
           } else {
             mbar_expect_tx(&fullA[sa], a.halo_tx_bytes);
@@ -615,7 +623,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
           if (++sa == nA) { sa = 0; pa ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&emptyB[sb], pb ^ 1);
-            if (a.debug & 4) {
+            if (MQ_PROBE(a, 4)) {
               mbar_arrive(&fullB[sb]);
             } else {
               mbar_expect_tx(&fullB[sb], a.b_tile_bytes);
@@ -632,7 +640,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       const uint32_t idesc = a.op_f16 ? umma_idesc_f16(kTileM, a.bn) : umma_idesc_bf16(kTileM, a.bn);
       constexpr uint32_t hi_a = umma_desc_hi_sw128(kHaloW * 128), hi_b = umma_desc_hi_sw128(1024);
       constexpr uint32_t kSubStep = (kHaloSubRows * kHaloW * 128) >> 4;      // one sub-tile down the halo, 16-byte units
-      const int msub = (a.debug & 2) ? 0 : a.msub;
+      const int msub = MQ_PROBE(a, 2) ? 0 : a.msub;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -774,12 +782,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             mbar_wait(&emptyA[sa], pa ^ 1);
             const uint32_t fa = smem_u32(&fullA[sa]) & kPeerBitMask;
             uint8_t* dst = smem_a + sa * a.halo_slot_bytes;
-            if (a.debug & 4) {
+            if (MQ_PROBE(a, 4)) {
               if (rank == 0) mbar_arrive(&fullA[sa]);
             } else if (rank == 0) {
               mbar_expect_tx(&fullA[sa], 2u * static_cast<uint32_t>(grp ? a.pair_tx1 : a.pair_tx0));
             }
-            if (a.debug & 4) {
+            if (MQ_PROBE(a, 4)) {
             } else if (!grp) {
               tma_load_4d_2cta(&map_a, fa, dst, kc * kBlockK, w0 - 1, hc - 1, n_idx);
             } else {
@@ -789,7 +797,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             if (++sa == nA) { sa = 0; pa ^= 1; }
             for (int tap = t0; tap < t1; tap += a.pair_bgrp) {
               mbar_wait(&emptyB[sb], pb ^ 1);
-              if (a.debug & 4) {
+              if (MQ_PROBE(a, 4)) {
                 if (rank == 0) mbar_arrive(&fullB[sb]);
               } else {
                 if (rank == 0) mbar_expect_tx(&fullB[sb], 2u * a.b_tile_bytes * a.pair_bgrp);
@@ -809,7 +817,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
       const uint32_t idesc = a.op_f16 ? umma_idesc_f16(2 * kTileM, a.bn) : umma_idesc_bf16(2 * kTileM, a.bn);
       constexpr uint32_t hi_a = umma_desc_hi_sw128(kHaloW * 128), hi_b = umma_desc_hi_sw128(1024);
       constexpr uint32_t kSubStep = (kHaloSubRows * kHaloW * 128) >> 4;
-      const int msub = (a.debug & 2) ? 0 : a.msub;
+      const int msub = MQ_PROBE(a, 2) ? 0 : a.msub;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -1063,6 +1071,22 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Experiment knobs from the environment, read ONCE per process (not per launch).
+struct ConvEnv {
+  int nbuf = 0, debug = 0, stages = 0, bgrp = 0;
+  ConvEnv() {
+    auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
+    nbuf = geti("MQ_CONV_NBUF");
+    debug = geti("MQ_CONV_DEBUG");
+    stages = geti("MQ_CONV_STAGES");
+    bgrp = geti("MQ_PAIR_BGRP");
+  }
+};
+static const ConvEnv& conv_env() {
+  static const ConvEnv env;
+  return env;
+}
+
 static int conv_smem_bytes(int stages, int a_stage_bytes, int b_tile_bytes) {
   return 1024 /*alignment slack*/ + stages * (a_stage_bytes + b_tile_bytes) +
          (2 * kMaxStages + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4;
@@ -1111,10 +1135,8 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.acc_stride = (a.msub * p->bn + 31) / 32 * 32;
   a.nbuf = kTmemCols / a.acc_stride;               // 1 (msub*bn > 256), 2, or up to 4 stages for small tiles
   if (a.nbuf > kMaxAccBufs) a.nbuf = kMaxAccBufs;
-  {
-    const char* nb = getenv("MQ_CONV_NBUF");
-    if (nb && atoi(nb) >= 1 && atoi(nb) < a.nbuf) a.nbuf = atoi(nb);
-  }
+  const ConvEnv& env = conv_env();
+  if (env.nbuf >= 1 && env.nbuf < a.nbuf) a.nbuf = env.nbuf;
   const bool pair = p->pair != 0;
   a.tile_rows = p->bh * a.msub * (pair ? 2 : 1);
   a.tiles_h = (p->H + a.tile_rows - 1) / a.tile_rows;
@@ -1168,12 +1190,8 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   if (stages > kMaxStages) stages = kMaxStages;
   MQ_REQUIRE(stages >= 2, "mq_conv_gemm: not enough shared memory for 2 stages");
   a.stages = stages;
-  {
-    const char* dbg = getenv("MQ_CONV_DEBUG");
-    a.debug = dbg ? atoi(dbg) : 0;
-    const char* st = getenv("MQ_CONV_STAGES");
-    if (st && atoi(st) >= 2 && atoi(st) <= stages) a.stages = stages = atoi(st);
-  }
+  a.debug = env.debug;
+  if (env.stages >= 2 && env.stages <= stages) a.stages = stages = env.stages;
   a.bias = p->bias; a.row_mask = p->row_mask;
   a.mask_pre = p->mask_pre; a.mask_post = p->mask_post; a.act = p->act; a.res_mode = p->res_mode;
   a.beta = p->beta; a.gamma = p->gamma;
@@ -1291,10 +1309,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     // weight ring: slots of pair_bgrp taps (3 = one filter row; every tap count on this path is a
     // multiple of 3) -> one full/empty barrier round trip and one multicast commit per slot
     int bgrp = 3;
-    {
-      const char* g = getenv("MQ_PAIR_BGRP");
-      if (g && (atoi(g) == 1 || atoi(g) == 3)) bgrp = atoi(g);
-    }
+    if (env.bgrp == 1 || env.bgrp == 3) bgrp = env.bgrp;
     if (p->taps % 3 != 0 || (up && p->up_taps % 3 != 0)) bgrp = 1;
     int nA = 0, nB = 0;
     for (;;) {

@@ -280,6 +280,7 @@ class PreEncoderEngine:
         return m.to(device).contiguous()
 
     # ------------------------------------------------------------------
+    @ops.on_device
     def encode(self, mel: torch.Tensor, mask: Optional[torch.Tensor] = None, return_latents: bool = False,
                taps: Optional[dict] = None):
         """mel (B,T,n_mels) fp32 on device; mask (B,1,T)|(B,T), True = padded -> (B,T) int64."""
@@ -346,6 +347,7 @@ class PreEncoderEngine:
         return out.view(B, T), None
 
     # ------------------------------------------------------------------
+    @ops.on_device
     def decode(self, indices: torch.Tensor, mask: Optional[torch.Tensor] = None, return_hidden: bool = False,
                taps: Optional[dict] = None, return_recon: bool = False, host_out: Optional[torch.Tensor] = None,
                lengths_host: Optional[Sequence[int]] = None):

@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import MelspecParams
+from .ops import on_device
 
 REQUIRED_KEYS = ("sampling_rate", "filter_length", "hop_length", "win_length", "n_mel_channels", "mel_fmin", "mel_fmax")
 
@@ -77,6 +78,7 @@ class LogMelExtractor:
     def num_frames(self, n_samples: int) -> int:
         return 1 + n_samples // self.hop if n_samples > self.n_fft // 2 else 0
 
+    @on_device
     def __call__(self, wav: torch.Tensor, lengths: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, List[int]]:
         """wav (B, Tmax) fp32 (zero-padded past each length) -> (log-mel (B, Fmax, n_mels) on the device,
         frames per utterance).  Rows past an utterance's frame count are zero."""

@@ -23,10 +23,28 @@ PAIR_DEFAULT = os.environ.get("MQ_PAIR", "1") != "0"   # CTA-pair (cta_group::2)
 PAIR_MIN_BN = int(os.environ.get("MQ_PAIR_MIN_BN", "0"))
 PAIR_1D = os.environ.get("MQ_PAIR_1D", "1") != "0"     # row-halo CTA-pair loop for 1-D convolutions
 PAIR_1D_MIN_BN = int(os.environ.get("MQ_PAIR_1D_MIN_BN", "128"))
+MSUB_OVERRIDE = int(os.environ.get("MQ_MSUB", "0"))            # experiment knobs, read once at import
+MSUB_PAIR_OVERRIDE = int(os.environ.get("MQ_MSUB_PAIR", "0"))
 
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(fn):
+    """Method decorator: run with ``self.device`` as the current CUDA device.  Every launch in this module goes to the
+    CURRENT device's current stream, so an engine living on cuda:1 must not be driven while cuda:0 is current (the
+    reference accepts ``get_pre_encoder(path, 'cuda:1')`` without a ``set_device``)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        dev = torch.device(self.device)
+        if dev.type != "cuda" or (dev.index is not None and dev.index == torch.cuda.current_device()):
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapped
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -276,9 +294,8 @@ def choose_msub(bn: int, N: int, H: int, W: int, bh: int, bw: int, up: bool = Fa
     """Sub-tiles per CTA tile.  Narrow layers (bn <= 128) are bound by L2->SM operand traffic:
     stacking 2-4 pixel sub-tiles on one weight tile amortises the weight loads.
     Only when there are still >= 2 waves of tiles for 148 SMs."""
-    override = os.environ.get("MQ_MSUB")
-    if override:
-        m = int(override)
+    if MSUB_OVERRIDE:
+        m = MSUB_OVERRIDE
         return m if m * bn <= 512 else (2 if 2 * bn <= 512 else 1)
     # measured on B200 (tools/conv_bench.py): bn <= 64 -> 4; bn <= 128 -> 2 (4 for the fused up-conv);
     # bn = 256 -> 2 with a single TMEM accumulator buffer (halves the weight traffic per pixel,
@@ -297,8 +314,7 @@ def choose_msub(bn: int, N: int, H: int, W: int, bh: int, bw: int, up: bool = Fa
 def choose_msub_pair(bn: int, N: int, H: int, W: int, up: bool) -> int:
     """Sub-tiles per CTA of a CTA pair (a pair tile is 2*msub sub-tiles of 16 rows x 8 columns).
     msub*bn <= 256 keeps two TMEM accumulator buffers so the epilogue overlaps the next main loop."""
-    override = os.environ.get("MQ_MSUB_PAIR")
-    m = int(override) if override else (4 if bn <= 64 else (2 if bn <= 128 else 1))
+    m = MSUB_PAIR_OVERRIDE if MSUB_PAIR_OVERRIDE else (4 if bn <= 64 else (2 if bn <= 128 else 1))
     if up:
         m = min(m, 2)             # the two skip-parity boxes of msub = 4 do not fit shared memory twice
     while m > 1 and m * bn > 512:

@@ -151,8 +151,9 @@ class PreEncoder(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("mqgan_b200.PreEncoder runs on CUDA (B200) only - there is no CPU fallback")
             params = dict(self.named_parameters())
-            return _training.generator_forward(params, self.cfg, x.to(dev), x_lengths.to(dev))
-        with torch.no_grad():
+            with torch.cuda.device(dev):               # launches go to the current device's stream
+                return _training.generator_forward(params, self.cfg, x.to(dev), x_lengths.to(dev))
+        with torch.no_grad(), torch.cuda.device(self._device()):
             x = x.to(self._device())
             mask = sequence_mask(x.size(1), x_lengths.to(x.device)).unsqueeze(1)
             eng = self.engine()

@@ -114,11 +114,12 @@ def recalibrate_q_in_proj(sd: Dict[str, torch.Tensor], latents: torch.Tensor,
     return w, b
 
 
-def synth_disc_state_dict(spec, seed: int = 0) -> Dict[str, torch.Tensor]:
+def synth_disc_state_dict(spec, seed: int = 0, zero_bias: bool = False) -> Dict[str, torch.Tensor]:
     """Seeded state-dict for a discriminator from ``spec.patch_disc_param_spec`` / ``multibin_param_spec``:
     conv weights ~ N(0, 0.02) as discriminators.py:193-198 initialises them, small non-zero biases (the
     reference's zeros would leave the bias path untested), unit-norm spectral-norm vectors u and v, and
-    PyTorch-default uniform squeeze-excite linears."""
+    PyTorch-default uniform squeeze-excite linears.  ``zero_bias=True`` gives the reference's own init (conv biases
+    zero, discriminators.py:177-181): what the training CLI uses; the tests keep the non-zero variant."""
     sd: Dict[str, torch.Tensor] = {}
     shapes = dict(spec)
     for key, shape in spec:
@@ -130,6 +131,8 @@ def synth_disc_state_dict(spec, seed: int = 0) -> Dict[str, torch.Tensor]:
             t = t / t.norm().clamp_min(1e-12)
         elif key.endswith(".bias") and (key[: -len(".bias")] + ".weight_orig") in shapes:
             t = torch.randn(shape, generator=g) * 0.01
+            if zero_bias:
+                t = torch.zeros(shape)
         else:
             wshape = shapes[key[: -len(".bias")] + ".weight"] if key.endswith(".bias") else shape
             bound = 1.0 / math.sqrt(max(wshape[1], 1))

@@ -188,8 +188,9 @@ class Trainer:
         else:
             print("No pretrained checkpoint specified or found. Training from scratch.")
         # discriminators: N(0, 0.02) conv weights as discriminators.py:193-198 (never checkpointed, App. B13)
-        pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(self.pd_cfg), seed=seed)
-        mb_sd = synth_disc_state_dict(S.multibin_param_spec(self.mb_cfg), seed=seed + 1)
+        # with zero conv biases as discriminators.py:177-181 / :199-200 initialise them
+        pd_sd = synth_disc_state_dict(S.patch_disc_param_spec(self.pd_cfg), seed=seed, zero_bias=True)
+        mb_sd = synth_disc_state_dict(S.multibin_param_spec(self.mb_cfg), seed=seed + 1, zero_bias=True)
         tcfg = dict(S.TRAIN_DEFAULTS)
         tcfg.update(config["training"])
         self.step = TrainStep(self.cfg, self.pd_cfg, self.mb_cfg, g_sd, pd_sd, mb_sd, tcfg, self.device, d_autocast_bf16=True)
@@ -199,6 +200,9 @@ class Trainer:
                     opt.load_state_dict(resume[name])
                 except Exception as e:                                 # a reference-written optimiser state (different layout)
                     print(f"Warning: could not restore {name}: {e}")
+            # load_state_dict replaces param_groups[*]['lr'] with a deep-copied CPU tensor: re-bind the live device
+            # tensors the step writes the warm-up schedule into, or the LR would stay frozen at the checkpoint's value
+            self.step.rebind_lr()
             self.step.g_steps = int(resume.get("g_steps", 0))
         self.iterations = 0
 
@@ -213,7 +217,15 @@ class Trainer:
         gan = epoch >= int(self.config["training"]["discriminator_train_start_epoch"])
         last = None
         for real, lens, _ in self.batches(epoch):
-            if real is None or real.size(0) == 0:
+            have = real is not None and real.size(0) > 0
+            if self.world > 1:
+                import torch.distributed as dist
+                # the step issues collectives (LeCam means, gradient buckets): skipping must be unanimous or the other
+                # ranks block in their all-reduces
+                flag = torch.tensor([1 if have else 0], device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                have = bool(int(flag.item()))
+            if not have:
                 continue
             key = (tuple(real.shape), bool(gan), None)
             # graphs are captured per batch shape once the discriminators have left their first (training-mode) iteration

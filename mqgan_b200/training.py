@@ -802,11 +802,21 @@ class TrainStep:
     def generator_state_dict(self) -> Dict[str, Tensor]:
         return {k: v.detach() for k, v in self.g.items()}
 
+    def rebind_lr(self) -> None:
+        """Point both optimisers' ``lr`` back at the live device tensors.  ``Optimizer.load_state_dict`` replaces
+        ``param_groups[*]['lr']`` with a copy, after which ``lr_g.fill_()`` would no longer reach Adam (and a later
+        graph capture would bake the stale value in)."""
+        for grp in self.opt_g.param_groups:
+            grp["lr"] = self.lr_g
+        for grp in self.opt_d.param_groups:
+            grp["lr"] = self.lr_d
+
     def current_lr_g(self) -> float:
         """LambdaLR(min((step + 1) / warmup_steps, 1)) of train.py:326-329 for the step about to run."""
         t = self.tcfg
         return float(t["lr"]) * min((self.g_steps + 1) / t["warmup_steps"], 1.0)
 
+    @ops.on_device
     def step(self, real: Tensor, lengths: Tensor, gan: bool = True, use_fm: Optional[bool] = None) -> Dict[str, Tensor]:
         """train.py:521-529 for one batch.  ``gan``: epoch >= discriminator_train_start_epoch.  Losses are
         returned as 0-d device tensors (one host read at the caller's discretion)."""
@@ -815,6 +825,7 @@ class TrainStep:
         self.g_steps += 1
         return out
 
+    @ops.on_device
     def capture(self, real: Tensor, lengths: Tensor, gan: bool = True, use_fm: Optional[bool] = None, warmup: int = 3):
         """Record the whole iteration for this batch shape into a CUDA graph (≈ 7 000 launches become one replay).
         Runs ``warmup`` real iterations on a side stream first (they train: LeCam / spectral-norm state must be past
@@ -836,6 +847,7 @@ class TrainStep:
         self._graphs[key] = (graph, s_real, s_len, outs, self.last_recon)
         return key
 
+    @ops.on_device
     def step_graphed(self, real: Tensor, lengths: Tensor, gan: bool = True, use_fm: Optional[bool] = None) -> Dict[str, Tensor]:
         """Replay the captured iteration on a new batch of the captured shape.  The returned loss tensors are the
         graph's static outputs (overwritten by the next replay)."""

@@ -124,6 +124,14 @@ def test_train_cli_runs_checkpoints_and_resumes(tmp_path):
     assert os.path.exists(os.path.join(out, "checkpoint_epoch_004.pth"))
     log2 = [json.loads(l) for l in open(os.path.join(out, "train_log.jsonl"))]
     assert len(log2) == 20 and log2[-1]["epoch"] == 4
+    # a resumed trainer's optimisers read the LIVE learning-rate tensors (load_state_dict replaces them with copies):
+    # the warm-up schedule must keep reaching Adam after a resume
+    t = TC.Trainer(cfg, max_steps=1)
+    assert t.start_epoch == 5
+    assert all(g["lr"] is t.step.lr_g for g in t.step.opt_g.param_groups)
+    assert all(g["lr"] is t.step.lr_d for g in t.step.opt_d.param_groups)
+    t.step.lr_g.fill_(0.125)
+    assert float(t.step.opt_g.param_groups[0]["lr"]) == 0.125
 
 
 def test_epoch_schedule_is_lockstep_across_replicas():
