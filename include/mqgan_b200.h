@@ -252,6 +252,13 @@ typedef struct mq_vq_params {
 } mq_vq_params;
 int mq_vq_nearest(const mq_vq_params* p, mq_stream_t stream);
 
+/* Measurement aid for mq_vq_nearest's roofline (bench.py secondary.vq_lookup): one CTA per SM, eight warps that do
+ * nothing but read their 128 lanes x 512 columns of tensor memory with tcgen05.ld (the epilogue's access pattern,
+ * no MMA, no score math) `iters` times.  Bytes read = sm_count * iters * 128 * 512 * 4; the caller times the launch
+ * and gets the chip's TMEM read bandwidth - the ceiling of any kernel that must read every one of the n x k fp32
+ * scores from TMEM once.  `sink` (1 float, device) only keeps the loads alive.  No reference counterpart. */
+int mq_tmem_read_probe(int iters, float* sink, mq_stream_t stream);
+
 /* ---- K8: indices_to_codes + q_out_proj as a table gather (quantizer.py:183-205,
  *          preencoder.py:464-466) -------------------------------------------- */
 /* table (n_codes, C) fp32 = q_out_proj(implicit_codebook); idx (rows) int64;

@@ -130,6 +130,7 @@ SIGNATURES = {
     "mq_last_error": (C.c_char_p, []),
     "mq_device_check": (C.c_int, []),
     "mq_sm_count": (C.c_int, []),
+    "mq_tmem_read_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "mq_conv_gemm": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
     "mq_split_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "mq_convblock2d": (C.c_int, [C.POINTER(Cb2dParams), C.c_void_p]),

@@ -422,6 +422,75 @@ __device__ __forceinline__ int64_t fsq_index(const float* z, const FsqDev& f, fl
   return static_cast<int64_t>(idx);
 }
 
+// q_in_proj + FSQ, HBM-bound form: the weights live in shared memory as DOUBLES (converted once per CTA - the first
+// version converted every weight for every frame and was bound by the F2F.F64 pipe at 0.22 of HBM speed), a warp
+// handles four consecutive frames per pass so each shared-memory weight read feeds four DFMAs, and the activations
+// are converted once per element.  Same arithmetic as before: exact fp64 products of fp32 values, fp64 accumulation,
+// one rounding to fp32 at the end - the index gate is untouched.
+constexpr int kQinRows = 4;
+
+__global__ void __launch_bounds__(256)
+qin_fsq_kernel4(const float* __restrict__ y, int64_t rows, int C, const float* __restrict__ w,
+                const float* __restrict__ bias, const FsqDev f, int64_t* __restrict__ idx,
+                float* __restrict__ z_out) {
+  extern __shared__ double wd[];                       // [D][C]
+  for (int i = threadIdx.x; i < f.D * C; i += blockDim.x) wd[i] = static_cast<double>(w[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t groups = (rows + kQinRows - 1) / kQinRows;
+  for (int64_t g = warp0; g < groups; g += nwarps) {
+    const int64_t r0 = g * kQinRows;
+    double acc[kQinRows][8];
+#pragma unroll
+    for (int j = 0; j < kQinRows; ++j)
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[j][d] = 0.0;
+    for (int c = lane * 4; c < C; c += 128) {
+      double v[kQinRows][4];
+#pragma unroll
+      for (int j = 0; j < kQinRows; ++j) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + j < rows) t = __ldcs(reinterpret_cast<const float4*>(y + (r0 + j) * C + c));   // streamed once
+        v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
+      }
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        if (d < f.D) {
+          const double2 w01 = *reinterpret_cast<const double2*>(wd + d * C + c);
+          const double2 w23 = *reinterpret_cast<const double2*>(wd + d * C + c + 2);
+#pragma unroll
+          for (int j = 0; j < kQinRows; ++j) {
+            // same summation order as the one-row kernel: ((x0 w0 + x1 w1) + x2 w2) + x3 w3, then += acc
+            acc[j][d] += v[j][0] * w01.x + v[j][1] * w01.y + v[j][2] * w23.x + v[j][3] * w23.y;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kQinRows; ++j)
+#pragma unroll
+      for (int d = 0; d < 8; ++d)
+        if (d < f.D) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) acc[j][d] += __shfl_xor_sync(0xffffffffu, acc[j][d], off);
+        }
+    if (lane < kQinRows && r0 + lane < rows) {
+      float z[8];
+#pragma unroll
+      for (int j = 0; j < kQinRows; ++j)
+        if (j == lane)
+#pragma unroll
+          for (int d = 0; d < 8; ++d) z[d] = d < f.D ? static_cast<float>(acc[j][d] + static_cast<double>(bias[d])) : 0.0f;
+      const int64_t r = r0 + lane;
+      if (z_out)
+        for (int d = 0; d < f.D; ++d) z_out[r * f.D + d] = z[d];
+      idx[r] = fsq_index(z, f, nullptr);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 qin_fsq_kernel(const float* __restrict__ y, int64_t rows, int C, const float* __restrict__ w,
                const float* __restrict__ bias, const FsqDev f, int64_t* __restrict__ idx,
@@ -849,7 +918,20 @@ extern "C" int mq_qin_fsq(const float* y, int64_t rows, int C, const float* w, c
   MQ_REQUIRE(y && w && b && idx && rows > 0 && C > 0 && C % 4 == 0, "mq_qin_fsq: bad args");
   FsqDev f;
   MQ_REQUIRE(fill_fsq(fsq, &f) == 0, "mq_qin_fsq: bad fsq params");
-  qin_fsq_kernel<<<grid_for(rows, 8), 256, 0, STREAM(stream)>>>(y, rows, C, w, b, f, idx, z_out);
+  const size_t wbytes = static_cast<size_t>(f.D) * C * sizeof(double);
+  if (wbytes <= 96 * 1024) {
+    int dev = 0, sms = 0;
+    MQ_CUDA_OK(cudaGetDevice(&dev));
+    MQ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MQ_CUDA_OK(cudaFuncSetAttribute(qin_fsq_kernel4, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wbytes)));
+    const int64_t groups = (rows + kQinRows - 1) / kQinRows;
+    int64_t blocks = (groups + 7) / 8;                       // 8 warps per CTA, one 4-frame group per warp per pass
+    const int64_t cap = static_cast<int64_t>(sms) * 2 * 4;   // a few waves of resident CTAs: the weight conversion amortises
+    if (blocks > cap) blocks = cap;
+    qin_fsq_kernel4<<<static_cast<unsigned>(blocks), 256, wbytes, STREAM(stream)>>>(y, rows, C, w, b, f, idx, z_out);
+  } else {
+    qin_fsq_kernel<<<grid_for(rows, 8), 256, 0, STREAM(stream)>>>(y, rows, C, w, b, f, idx, z_out);
+  }
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

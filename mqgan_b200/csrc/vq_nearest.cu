@@ -347,9 +347,52 @@ __global__ void __launch_bounds__(kVqThreads, 1) vq_nearest_kernel(const VqArgs 
   }
 }
 
+// TMEM read-bandwidth probe: the epilogue's tcgen05.ld pattern alone (see mq_tmem_read_probe in the header).
+__global__ void __launch_bounds__(256, 1) tmem_read_probe_kernel(int iters, float* sink) {
+  __shared__ uint32_t tmem_ptr_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(&tmem_ptr_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr_s;
+  const int q = warp & 3, half = warp >> 2;
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  uint32_t acc = 0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+    for (int c = half * 64; c < 512; c += 128) {
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(t_row + c, v0);
+      tmem_ld_32x32(t_row + c + 32, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= v0[j] + v1[j];
+    }
+  }
+  if (acc == 0x9e3779b9u && sink != nullptr) *sink = 1.0f;       // never true in practice: keeps the loads live
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace mq
 
 using namespace mq;
+
+extern "C" int mq_tmem_read_probe(int iters, float* sink, mq_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MQ_REQUIRE(iters >= 1 && iters <= (1 << 20), "mq_tmem_read_probe: iters=%d", iters);
+  int dev = 0, sms = 0;
+  MQ_CUDA_OK(cudaGetDevice(&dev));
+  MQ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  tmem_read_probe_kernel<<<sms, 256, 0, stream>>>(iters, sink);
+  MQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int mq_vq_nearest(const mq_vq_params* p, mq_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

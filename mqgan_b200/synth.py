@@ -139,3 +139,27 @@ def synth_disc_state_dict(spec, seed: int = 0, zero_bias: bool = False) -> Dict[
             t = (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
         sd[key] = t
     return sd
+
+
+def amplify_state_dict(sd: Dict[str, torch.Tensor], g_gain: float = 2.2, refiner_gain: float = 2.35,
+                       proj_gain: float = 8.0, head_gain: float = 3.0, mel_offset: float = -4.0) -> Dict[str, torch.Tensor]:
+    """A copy of ``sd`` with larger weights, for parity fixtures at realistic magnitudes.
+
+    Random-init keeps every activation below ~0.5, where APTx is nearly linear and errors are tiny.  Here every
+    weight-norm gain ``g`` (both flavours) is multiplied by ``g_gain`` (``refiner_gain`` inside the refiner), ``proj``
+    by ``proj_gain`` (ConvBlock2D's stencil value then leaves the +-64 range of its table), ``q_out_proj`` /
+    ``out_proj`` / ``hidden_proj`` by ``head_gain`` and ``out_proj.bias`` is shifted by ``mel_offset``: activations reach
+    |x| ~ 5-60 (tanh saturated) and the re-encoded mels the log-mel range of convert_spectrograms.py:34."""
+    out = {}
+    for k, v in sd.items():
+        t = v.clone()
+        if k.endswith("original0") or k.endswith("weight_g"):
+            t = t * (refiner_gain if k.startswith("refiner.") else g_gain)
+        elif k in ("proj.weight", "proj.bias"):
+            t = t * proj_gain
+        elif k in ("q_out_proj.weight", "out_proj.weight", "hidden_proj.weight"):
+            t = t * head_gain
+        elif k == "out_proj.bias":
+            t = t + mel_offset
+        out[k] = t
+    return out

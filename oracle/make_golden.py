@@ -70,12 +70,53 @@ CASES = {
     "tiny": ("TINY", 4, 53, (4, 96)),
     "hifispeech": ("HIFISPEECH", 3, 50, (4, 96)),
     "hifimusic": ("HIFIMUSIC", 2, 43, (4, 96)),
+    # amplified weights (mqgan_b200.synth.amplify_state_dict): APTx saturated, ConvBlock2D's stencil value outside its
+    # +-64 table, re-encoded mels in the log-mel range [-11.5, 5] - the magnitudes random-init never reaches
+    "tiny_amp": ("TINY", 4, 53, (4, 96)),
+    "hifispeech_amp": ("HIFISPEECH", 3, 50, (4, 96)),
 }
+
+
+def fsq_adversarial(levels):
+    """Latents whose bounded image sits ON a rounding boundary k + 0.5 (ties: half to even, quantizer.py:137 via
+    torch.round), their +-1..3 ulp neighbours, saturating |z| and zeros - the cases a random fixture never hits."""
+    lv = torch.tensor(levels, dtype=torch.float64)
+    half_l = (lv - 1) * (1 + 1e-3) / 2
+    offset = torch.where(lv % 2 == 0, 0.5, 0.0).double()
+    shift = torch.atanh(offset / half_l)
+    rows = []
+    D = len(levels)
+    for d in range(D):
+        L = levels[d]
+        lo = -(L // 2)
+        for k in range(lo, lo + L - 1):                      # boundaries between adjacent levels
+            b = k + 0.5
+            arg = (b + float(offset[d])) / float(half_l[d])
+            if abs(arg) >= 1:
+                continue
+            z0 = torch.tensor(float(torch.atanh(torch.tensor(arg, dtype=torch.float64)) - shift[d]), dtype=torch.float32)
+            cands = [z0]
+            up, dn = z0.clone(), z0.clone()
+            for _ in range(3):
+                up = torch.nextafter(up, torch.tensor(float("inf")))
+                dn = torch.nextafter(dn, torch.tensor(float("-inf")))
+                cands += [up.clone(), dn.clone()]
+            for c in cands:
+                for base in (0.0, 0.3, -0.7):                # the other dims sit safely inside a level
+                    row = torch.full((D,), base, dtype=torch.float32)
+                    row[d] = c
+                    rows.append(row)
+    for big in (8.0, 20.0, 88.0, 1e4, 3e38):
+        rows.append(torch.full((D,), big))
+        rows.append(torch.full((D,), -big))
+    rows.append(torch.zeros(D))
+    rows.append(torch.full((D,), -0.0))
+    return torch.stack(rows)
 
 
 def main():
     from mqgan_b200 import spec as S
-    from mqgan_b200.synth import synth_state_dict, synth_mels, synth_lengths, recalibrate_q_in_proj
+    from mqgan_b200.synth import synth_state_dict, synth_mels, synth_lengths, recalibrate_q_in_proj, amplify_state_dict
     from oracle import preencoder_oracle as O
 
     ref_pre = import_reference()
@@ -86,6 +127,9 @@ def main():
     for name, (cfg_name, B, T, (cb, ct)) in CASES.items():
         cfg = getattr(S, cfg_name)
         sd = synth_state_dict(cfg, seed=0)
+        amplified = name.endswith("_amp")
+        if amplified:
+            sd = amplify_state_dict(sd)
         model = build_reference_model(ref_pre, cfg, sd)
         # --- SURVEY D4 calibration, with the reference's own encoder ---------
         cal = synth_mels(cb, ct, cfg.mel_channels, seed=100)
@@ -106,6 +150,7 @@ def main():
             rand_recon = model.decode(rand_idx, mask)
             nm_idx = model.encode(mel[:1], None)
             nm_recon = model.decode(nm_idx, None)
+        print(f"[{name}] magnitudes: |recon| max {float(recon.abs().max()):.2f} range [{float(recon.min()):.2f}, {float(recon.max()):.2f}]")
         print(f"[{name}] calibrated: unique indices {idx.unique().numel()} of {idx.numel()} frames")
         # --- cross-check the restatement before committing ---------------------
         w = O.effective_weights(sd)
@@ -116,7 +161,7 @@ def main():
               f"idx mismatches {int((idx_o != idx).sum())}  |drecon|max {float((recon_o - recon).abs().max()):.3e}")
         np.savez_compressed(
             os.path.join(out_dir, f"{name}.npz"),
-            config=np.array(cfg_name), seed=np.array(0), mel_seed=np.array(1),
+            config=np.array(cfg_name), seed=np.array(0), mel_seed=np.array(1), amplified=np.array(int(amplified)),
             qin_w=sd["q_in_proj.weight"].numpy(), qin_b=sd["q_in_proj.bias"].numpy(),
             lengths=lengths.numpy(), T=np.array(T),
             z=z.numpy(), indices=idx.numpy().astype(np.int16), recon=recon.numpy(),
@@ -131,14 +176,24 @@ def main():
         fsq = ref_q.FSQ(levels=levels).eval()
         g = torch.Generator().manual_seed(11)
         zz = torch.randn(1, 4096, len(levels), generator=g) * 1.5
-        # adversarial: values whose bounded image sits on / next to k + 0.5
+        # adversarial: values whose bounded image sits on / next to k + 0.5, saturating magnitudes, zeros
+        z_adv = fsq_adversarial(levels).unsqueeze(0)
+        # 2^20 random latents, regenerated from the seed by the tests (only the reference's answers are stored)
+        g2 = torch.Generator().manual_seed(12)
+        z_big = torch.randn(1, 1 << 20, len(levels), generator=g2) * 1.5
         with torch.no_grad():
             codes, idx = fsq(zz)
+            codes_adv, idx_adv = fsq(z_adv)
+            _, idx_big = fsq(z_big)
             all_idx = torch.arange(int(np.prod(levels)))
             all_codes = fsq.indices_to_codes(all_idx)
         np.savez_compressed(os.path.join(out_dir, "fsq_" + "_".join(map(str, levels)) + ".npz"),
                             levels=np.array(levels), z=zz.numpy(), codes=codes.numpy(),
-                            indices=idx.numpy().astype(np.int32), all_codes=all_codes.numpy())
+                            indices=idx.numpy().astype(np.int32), all_codes=all_codes.numpy(),
+                            z_adv=z_adv[0].numpy(), codes_adv=codes_adv[0].numpy(), indices_adv=idx_adv[0].numpy().astype(np.int32),
+                            big_seed=np.array(12), big_n=np.array(1 << 20), big_scale=np.array(1.5),
+                            indices_big=idx_big[0].numpy().astype(np.uint16))
+        print(f"[fsq {levels}] adversarial rows {z_adv.shape[1]}, big rows {z_big.shape[1]}")
         print(f"[fsq {levels}] wrote fixture")
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from mqgan_b200 import spec as S
-from mqgan_b200.synth import synth_state_dict, synth_mels
+from mqgan_b200.synth import synth_state_dict, synth_mels, amplify_state_dict
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -15,6 +15,8 @@ def load_golden(name):
     fx = np.load(os.path.join(GOLDEN, name + ".npz"))
     cfg = getattr(S, str(fx["config"]))
     sd = synth_state_dict(cfg, seed=int(fx["seed"]))
+    if "amplified" in fx.files and int(fx["amplified"]):
+        sd = amplify_state_dict(sd)
     sd["q_in_proj.weight"] = torch.from_numpy(fx["qin_w"]).clone()
     sd["q_in_proj.bias"] = torch.from_numpy(fx["qin_b"]).clone()
     lengths = torch.from_numpy(fx["lengths"]).long()

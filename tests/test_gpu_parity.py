@@ -6,8 +6,11 @@ Gates (BASELINE north_star):
     terms): indices equal to the reference on every frame whose float64 distance to an FSQ
     rounding boundary exceeds TAU; raw agreement reported and required >= 99.5 %.
   * bf16 encoder mode: agreement rate reported, required >= 80 %.
-  * reconstructed mels (bf16 operands, fp32 accumulate, bf16 activations):
-    max-abs error <= MEL_ATOL + MEL_RTOL * max|ref|.
+  * reconstructed mels, default decoder (bf16 operands, fp32 accumulate, bf16 activations):
+    max-abs error <= MEL_ATOL + MEL_RTOL * max|ref| and relative L2 <= MEL_REL_L2 - about 3x the measured error
+    (1.0-1.2e-3 max-abs at |ref| <= 0.5, rel-L2 2e-3), also on the amplified fixtures (|ref| up to 20);
+  * reconstructed mels, fp32-grade decoder (decoder_precision="f16x2"): max-abs <= MEL32_RTOL * max(1, max|ref|),
+    relative L2 <= MEL32_REL_L2 (1e-4, the reference's own fp32 noise level).
 """
 import json
 import os
@@ -25,8 +28,11 @@ from tests.helpers import load_golden, index_report  # noqa: E402
 
 TAU = 2e-4          # bounded-latent units (rounding boundaries are 1 apart)
 Z_ATOL = 5e-5       # pre-quantiser latents (unit std) vs float64; measured 4e-6 .. 1.4e-5 (reference fp32: 4e-6 .. 9e-6)
-MEL_ATOL = 2e-2
-MEL_RTOL = 2e-2
+MEL_ATOL = 3e-3
+MEL_RTOL = 3e-3
+MEL_REL_L2 = 5e-3
+MEL32_RTOL = 1e-4
+MEL32_REL_L2 = 1e-4
 
 REPORT = {}
 
@@ -38,16 +44,17 @@ def _dump():
         json.dump(REPORT, f, indent=1)
 
 
-def _model(cfg, sd, precision="f16x2"):
+def _model(cfg, sd, precision="f16x2", decoder_precision="bf16"):
     m = PreEncoder(cfg.mel_channels, list(cfg.channels), list(cfg.kernel_sizes), fsq_levels=list(cfg.fsq_levels),
                    dropout=0.0, refiner_base_channels=cfg.refiner_base_channels, refiner_depth=cfg.refiner_depth,
-                   refiner_hidden_proj_divisor=cfg.refiner_hidden_proj_divisor, encoder_precision=precision)
+                   refiner_hidden_proj_divisor=cfg.refiner_hidden_proj_divisor, encoder_precision=precision,
+                   decoder_precision=decoder_precision)
     m.load_state_dict(sd, strict=True)
     return m.to("cuda").eval()
 
 
 @pytest.mark.parametrize("precision", ["f16x2", "bf16x3"])
-@pytest.mark.parametrize("name", ["tiny", "hifispeech", "hifimusic"])
+@pytest.mark.parametrize("name", ["tiny", "hifispeech", "hifimusic", "tiny_amp", "hifispeech_amp"])
 def test_encode_indices_vs_reference(name, precision):
     cfg, sd, mel, lengths, fx = load_golden(name)
     T = mel.shape[1]
@@ -67,20 +74,22 @@ def test_encode_indices_vs_reference(name, precision):
     print(name, precision, rep)
     assert rep["safe_mismatch"] == 0, rep
     assert rep["agree"] >= 0.995, rep
-    # latents (unit std) within Z_ATOL of float64; the reference's own fp32 error is reported beside it
-    assert rep["z_maxabs_vs_fp64"] <= Z_ATOL, rep
+    # latents (unit std) within Z_ATOL of float64 (or 3x the reference's own fp32 error on the amplified fixtures,
+    # whose activations are 10-100x larger); the reference's own fp32 error is reported beside it
+    assert rep["z_maxabs_vs_fp64"] <= max(Z_ATOL, 3.0 * rep["ref32_maxabs_vs_fp64"]), rep
     # API contract: (B, T) int64 on the module's device
     out = model.encode(mel, mask)
     assert out.dtype == torch.int64 and tuple(out.shape) == tuple(mel.shape[:2]) and out.is_cuda
     assert torch.equal(out, idx)
 
 
-@pytest.mark.parametrize("name", ["tiny", "hifispeech", "hifimusic"])
-def test_decode_mels_vs_reference(name):
+@pytest.mark.parametrize("decoder_precision", ["bf16", "f16x2"])
+@pytest.mark.parametrize("name", ["tiny", "hifispeech", "hifimusic", "tiny_amp", "hifispeech_amp"])
+def test_decode_mels_vs_reference(name, decoder_precision):
     cfg, sd, mel, lengths, fx = load_golden(name)
     T = mel.shape[1]
     mask = sequence_mask(T, lengths).unsqueeze(1)
-    model = _model(cfg, sd)
+    model = _model(cfg, sd, decoder_precision=decoder_precision)
     for ik, rk in (("indices", "recon"), ("rand_indices", "rand_recon")):
         idx = torch.from_numpy(fx[ik].astype(np.int64))
         ref = torch.from_numpy(fx[rk])
@@ -89,10 +98,15 @@ def test_decode_mels_vs_reference(name):
         err = float((out - ref).abs().max())
         scale = float(ref.abs().max())
         rel = float((out - ref).norm() / ref.norm())
-        REPORT[f"decode/{name}/{ik}"] = {"max_abs_err": err, "ref_max": scale, "rel_l2": rel}
+        REPORT[f"decode/{name}/{ik}/{decoder_precision}"] = {"max_abs_err": err, "ref_max": scale, "rel_l2": rel}
         _dump()
-        print(name, ik, REPORT[f"decode/{name}/{ik}"])
-        assert err <= MEL_ATOL + MEL_RTOL * scale, (err, scale)
+        print(name, ik, decoder_precision, REPORT[f"decode/{name}/{ik}/{decoder_precision}"])
+        if decoder_precision == "bf16":
+            assert err <= MEL_ATOL + MEL_RTOL * scale, (err, scale)
+            assert rel <= MEL_REL_L2, rel
+        else:
+            assert err <= MEL32_RTOL * max(1.0, scale), (err, scale)
+            assert rel <= MEL32_REL_L2, rel
     # return_hidden: (x_post, last_hid (B, C0, T))
     x_post, hid = model.decode(idx.cuda(), mask.cuda(), return_hidden=True)
     assert tuple(hid.shape) == (mel.shape[0], cfg.c0, T)

@@ -96,7 +96,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -114,7 +114,11 @@ def main():
     ap.add_argument("--layers", default=None, help="write the per-kernel table of one instrumented step here")
     ap.add_argument("--no_graph", action="store_true", help="eager launches instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu_baseline", action="store_true", help="also time the CPU oracle port on a bounded sample")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def main():
+    args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
@@ -122,13 +126,31 @@ def main():
             run_reference(args)
         return
     import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure(args)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        # captured graphs hold NCCL work: tearing the communicator down under them hangs, so leave without it
+        sys.stdout.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
+def measure(args):
+    """One measurement on the already-initialised process group (bench.py's ``secondary.train`` calls this too).
+    Every rank runs it; rank 0 gets the JSON-able dict, the others None."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch.distributed as dist
     from mqgan_b200 import _lib
     from mqgan_b200 import training as TR
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     cfg, pdc, mbc = ((S.HIFISPEECH, S.HIFISPEECH_PATCH_D, S.HIFISPEECH_MULTIBIN_D) if args.model == "hifispeech" else
                      (S.HIFIMUSIC, S.HIFIMUSIC_PATCH_D, S.HIFIMUSIC_MULTIBIN_D))
     B, T = args.batch, args.frames
@@ -287,13 +309,8 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": rb * rt / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"one iteration on {rb} x {rt} frames, oracle/train_oracle.py ({dt:.1f} s)"}
-        print(json.dumps(line))
-    if world > 1:
-        # captured graphs hold NCCL work: tearing the communicator down under them hangs, so leave without it
-        sys.stdout.flush()
-        dist.barrier()
-        torch.cuda.synchronize()
-        os._exit(0)
+        return line
+    return None
 
 
 if __name__ == "__main__":
