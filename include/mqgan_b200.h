@@ -291,6 +291,14 @@ int mq_avgpool_mask(const void* x, void* y, const uint8_t* mask_out, int B, int 
  * x (B, H/2, F, Cx), skip (B, H, F, Cs) -> y (B, H, F, Cx+Cs) bf16. */
 int mq_upcat_mask(const void* x, const void* skip, void* y, const uint8_t* mask_out, int B, int H,
                   int F, int Cx, int Cs, mq_stream_t stream);
+/* The same two passes for the fp32-grade decoder mode (decoder_precision "f16x2"), whose activations are two fp16
+ * terms [h0 | h1] along channels (2C per pixel, x = h0 + h1 to 22 bits).  The pool averages h0 + h1 of both rows in
+ * fp32 - the reference pools in fp32, preencoder.py:112 - and re-splits; the concat is a pure copy into
+ * [x_h0 | skip_h0 | x_h1 | skip_h1], the term layout mq_conv_gemm's a_coff expects with term stride Cx + Cs. */
+int mq_avgpool_mask_split(const void* x, void* y, const uint8_t* mask_out, int B, int H, int F, int C,
+                          mq_stream_t stream);
+int mq_upcat_mask_split(const void* x, const void* skip, void* y, const uint8_t* mask_out, int B, int H,
+                        int F, int Cx, int Cs, mq_stream_t stream);
 
 /* ---- K12: thin refiner convolutions --------------------------------------- */
 /* refiner.pre.conv1 (1 -> C, 3x3, pad 1) + APTx on the masked, T-padded refiner
@@ -298,6 +306,9 @@ int mq_upcat_mask(const void* x, const void* skip, void* y, const uint8_t* mask_
  * w (C, 9) folded, b (C).  y (B, T8, F, C) bf16. */
 int mq_refiner_stem(const float* r, const uint8_t* mask, int B, int T, int T8, int F, int C,
                     const float* w, const float* b, int fast_tanh, void* y, mq_stream_t stream);
+/* The same with precise tanh and a two-term fp16 output y (B, T8, F, 2C) = [h0 | h1] (fp32-grade decoder mode). */
+int mq_refiner_stem_split(const float* r, const uint8_t* mask, int B, int T, int T8, int F, int C,
+                          const float* w, const float* b, void* y, mq_stream_t stream);
 /* refiner.post (C -> 1, 3x3) + crop + mask + reproj (F -> M, no bias) + x_recon add
  * (preencoder.py:191-200, 499).  The C -> 1 3x3 convolution is split into a 1x1 tcgen05 GEMM
  * C -> 9 (mq_conv_gemm with the (9, C) folded weight, tap k = 3*(dt+1) + (df+1)) producing

@@ -763,6 +763,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
   const int R = kHaloSubRows * a.msub;          // rows of this CTA's share of a tile
   const int hoff = static_cast<int>(rank) * R;
   const int ntap0 = a.up_mode ? a.up_taps : 9;
+  const int nsegs = a.up_mode ? 1 : a.nseg;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -774,10 +775,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
         decode_tile(a, tile, n_idx, h0, w0, n0, par);
         const int hc = h0 + hoff;
         const int brow = n0 + par * a.cout_pad + brow_half;
+        // fp32-grade split operands (nseg > 1, plain 3x3 only): segment-major K order as packed (smallest products
+        // first); a segment pairs the activation term at channel offset a_coff[seg] with its own weight block
+        for (int seg = 0; seg < nsegs; ++seg)
         for (int grp = 0; grp < (a.up_mode ? 2 : 1); ++grp) {
           const int nch = grp ? a.kchunks2 : a.kchunks;
           const int t0 = grp ? a.up_taps : 0, t1 = grp ? a.taps : ntap0;
-          const int kbase = grp ? a.up_taps * a.kchunks : 0;
+          const int kbase = grp ? a.up_taps * a.kchunks : seg * a.taps * a.kchunks;
+          const int cseg = a.a_coff[seg];
           for (int kc = 0; kc < nch; ++kc) {
             mbar_wait(&emptyA[sa], pa ^ 1);
             const uint32_t fa = smem_u32(&fullA[sa]) & kPeerBitMask;
@@ -789,7 +794,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             }
             if (MQ_PROBE(a, 4)) {
             } else if (!grp) {
-              tma_load_4d_2cta(&map_a, fa, dst, kc * kBlockK, w0 - 1, hc - 1, n_idx);
+              tma_load_4d_2cta(&map_a, fa, dst, cseg + kc * kBlockK, w0 - 1, hc - 1, n_idx);
             } else {
               tma_load_5d_2cta(&map_a2, fa, dst, kc * kBlockK, w0 - 1, par, hc, n_idx);
               tma_load_5d_2cta(&map_a2, fa, dst + a.pair_boxb_off, kc * kBlockK, w0 - 1, par ^ 1, hc - 1 + par, n_idx);
@@ -828,6 +833,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * a.acc_stride;
         uint32_t acc = 0;
+        for (int seg = 0; seg < nsegs; ++seg)
         for (int grp = 0; grp < (a.up_mode ? 2 : 1); ++grp) {
           const int nch = grp ? a.kchunks2 : a.kchunks;
           const int t0 = grp ? a.up_taps : 0, t1 = grp ? a.taps : ntap0;
@@ -1168,8 +1174,8 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     for (int t = 0; t < p->taps; ++t)
       MQ_REQUIRE(p->tap_dw[t] == 0 && p->tap_dh[t] == p->tap_dh[0] + t, "mq_conv_gemm: 1-D pair mode needs consecutive row taps");
   } else if (pair) {
-    MQ_REQUIRE(!halo && p->nseg == 1 && p->bw == 8 && p->bh == kHaloSubRows && p->bn % 32 == 0,
-               "mq_conv_gemm: pair mode needs nseg == 1, a 16x8 sub-tile and bn a multiple of 32");
+    MQ_REQUIRE(!halo && (p->nseg == 1 || !up) && p->bw == 8 && p->bh == kHaloSubRows && p->bn % 32 == 0,
+               "mq_conv_gemm: pair mode needs a 16x8 sub-tile, bn a multiple of 32 and nseg == 1 for the fused up-conv");
     if (!up) {
       MQ_REQUIRE(p->taps == 9, "mq_conv_gemm: pair mode needs a 3x3 convolution");
       for (int t = 0; t < 9; ++t)
@@ -1314,7 +1320,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     int nA = 0, nB = 0;
     for (;;) {
       const int bslot = bgrp * static_cast<int>(a.b_tile_bytes);
-      nA = (a.kchunks + a.kchunks2 >= 3) ? 3 : 2;
+      nA = (a.nseg * a.kchunks + a.kchunks2 >= 3) ? 3 : 2;
       while (nA > 2 && budget - nA * a.halo_slot_bytes < 2 * bslot) --nA;
       nB = (budget - nA * a.halo_slot_bytes) / bslot;
       if (nB >= 2 || bgrp == 1) break;

@@ -694,12 +694,78 @@ upcat_mask_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, u
   }
 }
 
+// fp32-grade decoder mode: activations are two fp16 terms [h0 | h1] along channels (2C per pixel).
+// AvgPool2d((2,1)) in fp32 on h0 + h1 of both rows (the reference pools in fp32, preencoder.py:112), re-split.
+__global__ void __launch_bounds__(256)
+avgpool_mask_split_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
+                          const uint8_t* __restrict__ mask_out, int B, int Ho, int F, int C) {
+  const int C4 = C / 4;
+  const int64_t rowlen = static_cast<int64_t>(F) * C4;          // 4-channel groups per (b, h) row
+  const int64_t total = static_cast<int64_t>(B) * Ho * rowlen;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / rowlen;
+    const int64_t in = i - row * rowlen;
+    const int64_t f = in / C4;
+    const int c = static_cast<int>(in - f * C4) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mask_out == nullptr || mask_out[row] == 0) {
+      const uint16_t* a = x + ((2 * row) * F + f) * (2 * C) + c;
+      const uint16_t* b = x + ((2 * row + 1) * F + f) * (2 * C) + c;
+      const uint2 a0 = *reinterpret_cast<const uint2*>(a), a1 = *reinterpret_cast<const uint2*>(a + C);
+      const uint2 b0 = *reinterpret_cast<const uint2*>(b), b1 = *reinterpret_cast<const uint2*>(b + C);
+      const __half2* pa0 = reinterpret_cast<const __half2*>(&a0);
+      const __half2* pa1 = reinterpret_cast<const __half2*>(&a1);
+      const __half2* pb0 = reinterpret_cast<const __half2*>(&b0);
+      const __half2* pb1 = reinterpret_cast<const __half2*>(&b1);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float2 fa0 = __half22float2(pa0[e]), fa1 = __half22float2(pa1[e]);
+        const float2 fb0 = __half22float2(pb0[e]), fb1 = __half22float2(pb1[e]);
+        v[2 * e] = 0.5f * ((fa0.x + fa1.x) + (fb0.x + fb1.x));
+        v[2 * e + 1] = 0.5f * ((fa0.y + fa1.y) + (fb0.y + fb1.y));
+      }
+    }
+    store_terms4(y + (row * F + f) * (2 * C) + c, C, 1, v);
+  }
+}
+
+// nearest Upsample((2,1)) of x + concat with skip + mask on split tensors:
+// [x_h0 | x_h1] (2Cx), [s_h0 | s_h1] (2Cs) -> [x_h0 | s_h0 | x_h1 | s_h1] (2(Cx+Cs)); pure 16-byte copies.
+__global__ void __launch_bounds__(256)
+upcat_mask_split_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, uint4* __restrict__ y,
+                        const uint8_t* __restrict__ mask_out, int B, int H, int F, int Cx8, int Cs8) {
+  const int Cy8 = Cx8 + Cs8;
+  const int64_t total = static_cast<int64_t>(B) * H * F * 2 * Cy8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c2 = static_cast<int>(i % (2 * Cy8));
+    const int term = c2 / Cy8, c = c2 - term * Cy8;
+    const int64_t pix = i / (2 * Cy8);
+    const int f = static_cast<int>(pix % F);
+    const int64_t row = pix / F;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (mask_out == nullptr || mask_out[row] == 0) {
+      if (c < Cx8) {
+        const int64_t b = row / H;
+        const int h = static_cast<int>(row - b * H);
+        const int64_t src_row = b * (H / 2) + (h >> 1);
+        r = x[(src_row * F + f) * (2 * Cx8) + term * Cx8 + c];
+      } else {
+        r = skip[pix * (2 * Cs8) + term * Cs8 + (c - Cx8)];
+      }
+    }
+    y[i] = r;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K12a: refiner.pre.conv1 (1 -> C) + APTx.  Thread = (pixel, 8 channels).
 // ---------------------------------------------------------------------------
 constexpr int kStemRows = 8;
 
-template <bool kFast>
+// kSplit: write the two fp16 terms [h0 | h1] (2C channels per pixel) of the fp32-grade decoder mode instead of bf16.
+template <bool kFast, bool kSplit>
 __global__ void __launch_bounds__(256)
 refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mask, int B, int T, int T8,
                     int F, int C, const float* __restrict__ w, const float* __restrict__ bias,
@@ -729,7 +795,8 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
   }
   __syncthreads();
   const int nrow = min(kStemRows, T8 - t0);
-  __nv_bfloat16* ybase = y + (static_cast<int64_t>(b) * T8 + t0) * F * C;
+  const int ldy = kSplit ? 2 * C : C;
+  __nv_bfloat16* ybase = y + (static_cast<int64_t>(b) * T8 + t0) * F * ldy;
   // thread = (pixel lane, channel group); pixels advance by blockDim.x / C8 per iteration with (lt, f) kept
   // incrementally (no integer divisions in the loop: they cost as much as the nine FMAs per output)
   const int ppb = blockDim.x / C8;
@@ -749,8 +816,15 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
       for (int k = 0; k < 9; ++k) acc = fmaf(wr[e][k], in[k], acc);
       v[e] = aptx<kFast>(acc, 1.0f, 0.5f);
     }
-    *reinterpret_cast<uint4*>(ybase + static_cast<int64_t>(px) * C + cg * 8) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    if (kSplit) {
+      uint16_t* o = reinterpret_cast<uint16_t*>(ybase) + static_cast<int64_t>(px) * ldy + cg * 8;
+      const float lo4[4] = {v[0], v[1], v[2], v[3]}, hi4[4] = {v[4], v[5], v[6], v[7]};
+      store_terms4(o, C, 1, lo4);
+      store_terms4(o + 4, C, 1, hi4);
+    } else {
+      *reinterpret_cast<uint4*>(ybase + static_cast<int64_t>(px) * C + cg * 8) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
     f += ppb;
     while (f >= F) { f -= F; ++lt; }
   }
@@ -1005,6 +1079,28 @@ extern "C" int mq_upcat_mask(const void* x, const void* skip, void* y, const uin
   return 0;
 }
 
+extern "C" int mq_avgpool_mask_split(const void* x, void* y, const uint8_t* mask_out, int B, int H, int F, int C,
+                                     mq_stream_t stream) {
+  MQ_REQUIRE(x && y && B > 0 && H > 0 && H % 2 == 0 && F > 0 && C % 4 == 0, "mq_avgpool_mask_split: bad args");
+  const int64_t total = static_cast<int64_t>(B) * (H / 2) * F * (C / 4);
+  avgpool_mask_split_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint16_t*>(y), mask_out, B, H / 2, F, C);
+  MQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mq_upcat_mask_split(const void* x, const void* skip, void* y, const uint8_t* mask_out, int B, int H,
+                                   int F, int Cx, int Cs, mq_stream_t stream) {
+  MQ_REQUIRE(x && skip && y && B > 0 && H > 0 && H % 2 == 0 && F > 0 && Cx % 8 == 0 && Cs % 8 == 0,
+             "mq_upcat_mask_split: bad args");
+  const int64_t total = static_cast<int64_t>(B) * H * F * 2 * ((Cx + Cs) / 8);
+  upcat_mask_split_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(skip), reinterpret_cast<uint4*>(y), mask_out,
+      B, H, F, Cx / 8, Cs / 8);
+  MQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mq_refiner_stem(const float* r, const uint8_t* mask, int B, int T, int T8, int F, int C,
                                const float* w, const float* b, int fast_tanh, void* y, mq_stream_t stream) {
   MQ_REQUIRE(r && w && b && y && B > 0 && T > 0 && T8 >= T && F > 0 && C % 8 == 0 && C / 8 <= 256,
@@ -1014,9 +1110,23 @@ extern "C" int mq_refiner_stem(const float* r, const uint8_t* mask, int B, int T
   const size_t smem = (kStemRows + 2) * static_cast<size_t>(F + 2) * sizeof(float);
   dim3 grid((T8 + kStemRows - 1) / kStemRows, B);
   if (fast_tanh)
-    refiner_stem_kernel<true><<<grid, threads, smem, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
+    refiner_stem_kernel<true, false><<<grid, threads, smem, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
   else
-    refiner_stem_kernel<false><<<grid, threads, smem, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
+    refiner_stem_kernel<false, false><<<grid, threads, smem, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b, reinterpret_cast<__nv_bfloat16*>(y));
+  MQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mq_refiner_stem_split(const float* r, const uint8_t* mask, int B, int T, int T8, int F, int C,
+                                     const float* w, const float* b, void* y, mq_stream_t stream) {
+  MQ_REQUIRE(r && w && b && y && B > 0 && T > 0 && T8 >= T && F > 0 && C % 8 == 0 && C / 8 <= 256,
+             "mq_refiner_stem_split: bad args");
+  MQ_REQUIRE(B <= 65535, "mq_refiner_stem_split: B too large for one launch");
+  const int threads = 256 / (C / 8) * (C / 8);
+  const size_t smem = (kStemRows + 2) * static_cast<size_t>(F + 2) * sizeof(float);
+  dim3 grid((T8 + kStemRows - 1) / kStemRows, B);
+  refiner_stem_kernel<false, true><<<grid, threads, smem, STREAM(stream)>>>(r, mask, B, T, T8, F, C, w, b,
+                                                                           reinterpret_cast<__nv_bfloat16*>(y));
   MQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

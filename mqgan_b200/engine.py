@@ -16,7 +16,11 @@ Precision modes
       reference except within rounding distance of an FSQ boundary.
   encoder "bf16x3": the same with six bf16 products of 3-term splits (24 bits, twice the MMAs).
   encoder "bf16": single bf16 pass (index agreement rate is reported, not exact).
-  decoder: bf16 operands, fp32 accumulate, bf16 activations between layers.
+  decoder "bf16" (default): bf16 operands, fp32 accumulate, bf16 activations between layers (mel error ~1e-3).
+  decoder "f16x2": the fp32-grade mode of the decoder and refiner (the reference's decode is fp32, preencoder.py:453-504):
+      every GEMM as three fp16 products of 2-term splits like the encoder, activations carried as two fp16 terms
+      [h0 | h1] (22 bits) plus fp32 where an element-wise pass or a residual reads them, precise tanh.  Three times
+      the MMA work of the bf16 decoder; mel error ~1e-6 relative.
 """
 from __future__ import annotations
 
@@ -124,9 +128,15 @@ class _CB2D:
 class PreEncoderEngine:
     def __init__(self, cfg: PreEncoderConfig, state_dict: Dict[str, torch.Tensor], device="cuda",
                  encoder_precision: str = "f16x2", max_chunk_frames: int = 32768, cb2d_table: bool = True,
-                 fuse_upcat: bool = True, max_chunk_frames_enc: int = 262144, fuse_pool: bool = True):
+                 fuse_upcat: bool = True, max_chunk_frames_enc: int = 262144, fuse_pool: bool = True,
+                 decoder_precision: str = "bf16"):
         if encoder_precision not in ("f16x2", "bf16x3", "bf16"):
             raise ValueError("encoder_precision must be 'f16x2', 'bf16x3' or 'bf16'")
+        if decoder_precision not in ("bf16", "f16x2"):
+            raise ValueError("decoder_precision must be 'bf16' or 'f16x2'")
+        self.decoder_precision = decoder_precision
+        self.dec_split = decoder_precision == "f16x2"
+        dp = "f16x2" if self.dec_split else False      # operand format of every decoder / refiner GEMM
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -187,18 +197,18 @@ class PreEncoderEngine:
             p = f"decoder_blocks.{i}"
             blk = {
                 "cin": cin, "cout": cout,
-                "conv1": pack_conv(w[p + ".conv1.weight"], w[p + ".conv1.bias"], "causal1d", False).to(dev),
-                "conv2": pack_conv(w[p + ".conv2.weight"], w[p + ".conv2.bias"], "causal1d", False).to(dev),
+                "conv1": pack_conv(w[p + ".conv1.weight"], w[p + ".conv1.bias"], "causal1d", dp).to(dev),
+                "conv2": pack_conv(w[p + ".conv2.weight"], w[p + ".conv2.bias"], "causal1d", dp).to(dev),
                 "res": None,
                 "beta": float(w[p + ".relu.beta"]), "gamma": float(w[p + ".relu.gamma"]),
             }
             if (p + ".residual.weight") in w:
                 blk["res"] = pack_conv(w[p + ".residual.weight"].squeeze(-1), w[p + ".residual.bias"],
-                                       "linear", False).to(dev)
+                                       "linear", dp).to(dev)
             self.dec.append(blk)
         self.post = _CB2D(w, "post", dev, cb2d_table)
-        self.out_proj = pack_conv(w["out_proj.weight"], w["out_proj.bias"], "linear", False).to(dev)
-        self.hidden_proj = pack_conv(w["hidden_proj.weight"], w["hidden_proj.bias"], "linear", False).to(dev)
+        self.out_proj = pack_conv(w["out_proj.weight"], w["out_proj.bias"], "linear", dp).to(dev)
+        self.hidden_proj = pack_conv(w["hidden_proj.weight"], w["hidden_proj.bias"], "linear", dp).to(dev)
 
         # ---------------- refiner ----------------
         chs = cfg.refiner_channels
@@ -209,21 +219,22 @@ class PreEncoderEngine:
         def cb(prefix, first=True):
             out = {}
             if first:
-                out["conv1"] = pack_conv(w[prefix + ".conv1.weight"], w[prefix + ".conv1.bias"], "conv2d3", False).to(dev)
-            out["conv2"] = pack_conv(w[prefix + ".conv2.weight"], w[prefix + ".conv2.bias"], "conv2d3", False).to(dev)
+                out["conv1"] = pack_conv(w[prefix + ".conv1.weight"], w[prefix + ".conv1.bias"], "conv2d3", dp).to(dev)
+            out["conv2"] = pack_conv(w[prefix + ".conv2.weight"], w[prefix + ".conv2.bias"], "conv2d3", dp).to(dev)
             return out
 
         self.ref_pre = cb("refiner.pre", first=False)
         self.ref_downs = [cb(f"refiner.downs.{i}.conv") for i in range(d)]
         self.ref_mid = cb("refiner.mid")
         self.ref_ups = [cb(f"refiner.ups.{i}.conv") for i in range(d)]
-        self.fuse_upcat = bool(fuse_upcat)
-        self.fuse_pool = bool(fuse_pool)       # DownBlock's AvgPool2d written by the producing conv's epilogue
-        for i in range(d):          # fused nearest-upsample + concat variant of ups[i].conv1
+        # the fused upsample-concat conv and the fused pool epilogue exist for bf16 operands only
+        self.fuse_upcat = bool(fuse_upcat) and not self.dec_split
+        self.fuse_pool = bool(fuse_pool) and not self.dec_split    # DownBlock's AvgPool2d written by the producing conv's epilogue
+        for i in range(d if self.fuse_upcat else 0):          # fused nearest-upsample + concat variant of ups[i].conv1
             pfx = f"refiner.ups.{i}.conv.conv1"
             self.ref_ups[i]["conv1_up"] = pack_upconv(w[pfx + ".weight"], w[pfx + ".bias"], chs[d - i], chs[d - i - 1]).to(dev)
         # refiner.post: (1, C, 3, 3) -> (9, C) with tap = 3*(dt+1) + (df+1), run as a 1x1 GEMM C -> 9
-        self.tail = pack_conv(w["refiner.post.weight"].reshape(chs[0], 9).t().contiguous(), None, "linear", False).to(dev)
+        self.tail = pack_conv(w["refiner.post.weight"].reshape(chs[0], 9).t().contiguous(), None, "linear", dp).to(dev)
         self.tail_b = float(w["refiner.post.bias"].reshape(()))
         self.reproj_t = w["refiner.reproj.weight"].t().float().contiguous().to(dev)       # (F, M)
 
@@ -382,7 +393,7 @@ class PreEncoderEngine:
         # refiner (~0.2 MB per frame) is cut into the small ones.
         for c0, c1 in self._chunks(B, T, self.max_chunk_frames_enc):
             mc = None if m8 is None else m8[c0:c1]
-            h, R = self._decode_1d(idx[c0:c1], mc, return_hidden, taps, bad)
+            h, R = (self._decode_1d_split if self.dec_split else self._decode_1d)(idx[c0:c1], mc, return_hidden, taps, bad)
             if return_hidden:
                 hid[c0:c1] = h
             if return_recon:
@@ -458,7 +469,98 @@ class PreEncoderEngine:
             taps["refiner_in"] = R
         return (dec_out.view(B, T, cfg.c0).float() if want_hidden else None), R
 
+    def _decode_1d_split(self, idx, m8, want_hidden, taps, bad):
+        """_decode_1d in the fp32-grade mode: activations as two fp16 terms + fp32, precise tanh."""
+        cfg, dev = self.cfg, self.device
+        B, T = idx.shape
+        rows = B * T
+        _, x32 = ops.code_gather(idx.reshape(rows), self.code_table, bf16=False, f32=True, bad=bad)
+        xs = ops.split_bf16(x32, 2)
+        for i, blk in enumerate(self.dec):
+            cout = blk["cout"]
+            o1 = torch.empty(rows, 2 * cout, dtype=torch.float16, device=dev)
+            ops.conv_gemm(xs, blk["conv1"], B, T, 1, row_mask=m8, mask_pre=m8 is not None, act=True, beta=blk["beta"],
+                          gamma=blk["gamma"], fast_tanh=False, out_split=o1, tag=f"dec{i}.conv1")
+            if blk["res"] is not None:
+                r32 = torch.empty(rows, cout, dtype=torch.float32, device=dev)
+                ops.conv_gemm(xs, blk["res"], B, T, 1, out_f32=r32, tag=f"dec{i}.res")
+            else:
+                r32 = x32
+            y32 = torch.empty(rows, cout, dtype=torch.float32, device=dev)
+            ys = torch.empty(rows, 2 * cout, dtype=torch.float16, device=dev)
+            ops.conv_gemm(o1, blk["conv2"], B, T, 1, row_mask=m8, mask_pre=m8 is not None, act=True, beta=blk["beta"],
+                          gamma=blk["gamma"], fast_tanh=False, res=r32, res_mode=1, out_f32=y32, out_split=ys,
+                          tag=f"dec{i}.conv2")
+            x32, xs = y32, ys
+            if taps is not None:
+                taps[f"dec{i}"] = y32
+        pz = torch.empty(rows, 2 * cfg.c0, dtype=torch.float16, device=dev)
+        ops.convblock2d(x32, B, T, cfg.c0, self.post.dw, self.post.pw, self.post.bout, m8, False,
+                        out_split=pz, **self.post.kwargs())
+        F, M = cfg.refiner_width, cfg.mel_channels
+        R = torch.empty(rows, F, dtype=torch.float32, device=dev)
+        ops.conv_gemm(pz, self.out_proj, B, T, 1, out_f32=R, f32_coff=0, tag="dec.out_proj")
+        ops.conv_gemm(xs, self.hidden_proj, B, T, 1, out_f32=R, f32_coff=M, tag="dec.hidden_proj")
+        if taps is not None:
+            taps["refiner_in"] = R
+        return (x32.view(B, T, cfg.c0) if want_hidden else None), R
+
+    def _refiner_split(self, R, m8, B, T, out, taps):
+        """_refiner in the fp32-grade mode (preencoder.py:169-202): two-term fp16 activations, three fp16 products per
+        GEMM on the CTA-pair kernel, AvgPool / upsample-concat as separate split-aware passes."""
+        cfg, dev = self.cfg, self.device
+        d = cfg.refiner_depth
+        chs = cfg.refiner_channels
+        F = cfg.refiner_width
+        T8, down, up = ops.refiner_masks(m8, B, T, d, dev)
+        H = [T8 >> l for l in range(d + 1)]
+
+        def buf(l, c):
+            return torch.empty(B, H[l], F, 2 * c, dtype=torch.float16, device=dev)
+
+        def convblock(x, blk, l, mask, cout, first=True, tag="", x32=None, want_f32=False):
+            """ConvBlock (preencoder.py:86-102); x32 = fp32 copy of the input when the block has the +x skip."""
+            if first:
+                t = buf(l, cout)
+                ops.conv_gemm(x, blk["conv1"], B, H[l], F, act=True, fast_tanh=False, out_split=t, tag=tag + ".conv1")
+            else:
+                t = x
+            y = buf(l, cout)
+            y32 = torch.empty(B, H[l], F, cout, dtype=torch.float32, device=dev) if want_f32 else None
+            ops.conv_gemm(t, blk["conv2"], B, H[l], F, act=True, fast_tanh=False, row_mask=mask, mask_post=True,
+                          res=x32, res_mode=2 if x32 is not None else 0, out_split=y, out_f32=y32, tag=tag + ".conv2")
+            return (y, y32) if want_f32 else y
+
+        s1 = ops.refiner_stem_split(R, m8, B, T, T8, F, chs[0], self.stem_w, self.stem_b)
+        x = convblock(s1, self.ref_pre, 0, down[0], chs[0], first=False, tag="ref.pre")
+        skips = []
+        x32 = None
+        for i in range(d):
+            skips.append(x)
+            p = ops.avgpool_mask_split(x, down[i + 1], B, H[i], F, chs[i])
+            if i + 1 < d:
+                x = convblock(p, self.ref_downs[i], i + 1, down[i + 1], chs[i + 1], tag=f"ref.down{i}")
+            else:       # the deepest block's output is mid's residual: also kept in fp32
+                x, x32 = convblock(p, self.ref_downs[i], i + 1, down[i + 1], chs[i + 1], tag=f"ref.down{i}", want_f32=True)
+            if taps is not None:
+                taps[f"refiner.downs.{i}"] = x
+        x = convblock(x, self.ref_mid, d, down[d], chs[d], tag="ref.mid", x32=x32)
+        if taps is not None:
+            taps["refiner.mid"] = x
+        for i in range(d):
+            l = d - 1 - i
+            skip = skips.pop()
+            u = ops.upcat_mask_split(x, skip, up[l], B, H[l], F, chs[l + 1], chs[l])
+            x = convblock(u, self.ref_ups[i], l, up[l], chs[l], tag=f"ref.up{i}")
+            if taps is not None:
+                taps[f"refiner.ups.{i}"] = x
+        tp = torch.empty(B, T8, F, 12, dtype=torch.float32, device=dev)
+        ops.conv_gemm(x, self.tail, B, T8, F, out_f32=tp, tag="ref.post")
+        ops.refiner_tail(tp, m8, B, T, T8, F, self.tail_b, self.reproj_t, cfg.mel_channels, R, out=out)
+
     def _refiner(self, R, m8, B, T, out, taps):
+        if self.dec_split:
+            return self._refiner_split(R, m8, B, T, out, taps)
         cfg, dev = self.cfg, self.device
         d = cfg.refiner_depth
         chs = cfg.refiner_channels

@@ -367,7 +367,7 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         for i in range(pc.taps):
             p.tap_dh_odd[i] = pc.tap_dh_odd[i]
         hm = 2
-    conv3 = (pc.taps == 9 and pc.nseg == 1 and not pc.up_taps
+    conv3 = (pc.taps == 9 and not pc.up_taps
              and list(pc.tap_dh[:9]) == [-1, -1, -1, 0, 0, 0, 1, 1, 1] and list(pc.tap_dw[:9]) == [-1, 0, 1] * 3)
     conv1d = (W == 1 and not pc.up_taps and all(d == 0 for d in pc.tap_dw[:pc.taps])
               and all(pc.tap_dh[i] == pc.tap_dh[0] + i for i in range(pc.taps)))
@@ -389,7 +389,7 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         pair = (PAIR_DEFAULT and (conv3 or bool(pc.up_taps)) and pc.bn > PAIR_MIN_BN and W >= 8 and H >= 32
                 and tile is None and halo is not True and pc.bn % 32 == 0)
     if halo is None:
-        halo = HALO_DEFAULT and conv3 and W >= 8 and tile is None and not pair
+        halo = HALO_DEFAULT and conv3 and pc.nseg == 1 and W >= 8 and tile is None and not pair
     if pair and halo:
         raise ValueError("pair and halo main loops are exclusive")
     p.pair = int(bool(pair))
@@ -934,6 +934,31 @@ def refiner_stem(r: torch.Tensor, mask: Optional[torch.Tensor], B, T, T8, F, Cc,
     y = torch.empty(B, T8, F, Cc, dtype=torch.bfloat16, device=r.device)
     _lib.call("mq_refiner_stem", r.data_ptr(), _ptr(mask), B, T, T8, F, Cc, w.data_ptr(), b.data_ptr(),
               int(fast_tanh), y.data_ptr(), _stream())
+    return y
+
+
+def avgpool_mask_split(x: torch.Tensor, mask_out: Optional[torch.Tensor], B, H, F, Cc) -> torch.Tensor:
+    """fp32-grade decoder mode: x fp16 (B, H, F, 2C) two-term -> (B, H/2, F, 2C)."""
+    _chk(x, torch.float16, "x")
+    y = torch.empty(B, H // 2, F, 2 * Cc, dtype=torch.float16, device=x.device)
+    _lib.call("mq_avgpool_mask_split", x.data_ptr(), y.data_ptr(), _ptr(mask_out), B, H, F, Cc, _stream())
+    return y
+
+
+def upcat_mask_split(x: torch.Tensor, skip: torch.Tensor, mask_out: Optional[torch.Tensor], B, H, F, Cx, Cs) -> torch.Tensor:
+    """fp32-grade decoder mode: x (B, H/2, F, 2Cx), skip (B, H, F, 2Cs) fp16 -> (B, H, F, 2(Cx+Cs)) = [x0|s0|x1|s1]."""
+    _chk(x, torch.float16, "x")
+    _chk(skip, torch.float16, "skip")
+    y = torch.empty(B, H, F, 2 * (Cx + Cs), dtype=torch.float16, device=x.device)
+    _lib.call("mq_upcat_mask_split", x.data_ptr(), skip.data_ptr(), y.data_ptr(), _ptr(mask_out), B, H, F, Cx, Cs, _stream())
+    return y
+
+
+def refiner_stem_split(r: torch.Tensor, mask: Optional[torch.Tensor], B, T, T8, F, Cc, w, b) -> torch.Tensor:
+    _chk(r, torch.float32, "r")
+    y = torch.empty(B, T8, F, 2 * Cc, dtype=torch.float16, device=r.device)
+    _lib.call("mq_refiner_stem_split", r.data_ptr(), _ptr(mask), B, T, T8, F, Cc, w.data_ptr(), b.data_ptr(),
+              y.data_ptr(), _stream())
     return y
 
 

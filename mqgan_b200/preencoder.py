@@ -49,13 +49,15 @@ def _attach(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
 class PreEncoder(nn.Module):
     def __init__(self, mel_channels, channels, kernel_sizes, fsq_levels=[8, 8, 5, 5, 5], dropout=0.1,
                  refiner_base_channels=128, refiner_depth=3, refiner_hidden_proj_divisor=8,
-                 encoder_precision: str = "f16x2"):
+                 encoder_precision: str = "f16x2", decoder_precision: str = "bf16"):
         super().__init__()
         self.cfg = PreEncoderConfig(int(mel_channels), tuple(channels), tuple(kernel_sizes), tuple(fsq_levels),
                                     int(refiner_base_channels), int(refiner_depth),
                                     int(refiner_hidden_proj_divisor))
         self.dropout_p = dropout            # eval-only path: dropout is the identity
         self.encoder_precision = encoder_precision
+        # additive: "bf16" (default, fastest) or "f16x2" = fp32-grade decoder / refiner (the reference's decode is fp32)
+        self.decoder_precision = decoder_precision
         # attributes the reference exposes (preencoder.py:323, 337-341, 355)
         self.quantizer_dim = self.cfg.quantizer_dim
         self.codebook_size = self.cfg.codebook_size
@@ -109,9 +111,10 @@ class PreEncoder(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("mqgan_b200.PreEncoder runs on CUDA (B200) only - there is no CPU fallback; "
                                "move the module with .to('cuda')")
-        key = (dev, self.encoder_precision) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (dev, self.encoder_precision, self.decoder_precision) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._engine is None or key != self._engine_key:
-            self._engine = PreEncoderEngine(self.cfg, self.state_dict(), dev, self.encoder_precision)
+            self._engine = PreEncoderEngine(self.cfg, self.state_dict(), dev, self.encoder_precision,
+                                            decoder_precision=self.decoder_precision)
             self._engine_key = key
         return self._engine
 

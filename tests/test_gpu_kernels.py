@@ -708,3 +708,73 @@ def test_conv_pair_1d_matches_tap_mode(kind, N, H, Cin, Cout, tail, mode):
             ops.conv_gemm(xin, pc, N, H, 1, row_mask=mask.to(DEV), mask_pre=True, act=True, beta=0.9, gamma=0.6,
                           res=rb.to(DEV), res_mode=1, out_bf16=ob, pair=True)
             assert (ob.cpu().double() - ref2).abs().max().item() < 2e-2 * max(1.0, ref2.abs().max().item())
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,pair", [
+    (2, 64, 24, 64, 64, True),           # narrow layer, msub 4 on the CTA-pair kernel, three product segments
+    (1, 64, 144, 192, 64, True),         # ups.2.conv1 shape: three 64-channel chunks per segment
+    (1, 32, 16, 128, 256, True),
+    (2, 24, 20, 64, 96, False),          # H < 32: generic tap loop with segments
+])
+def test_conv3x3_f16x2_on_pair_kernel_is_fp32_grade(N, H, W, Cin, Cout, pair):
+    """fp32-grade decoder mode: a 3x3 convolution as three fp16 products of 2-term operand splits on conv_pair_kernel
+    (segment-major K loop over the halo), against float64; error within 4x the reference's own fp32 error."""
+    x = _rand(N, H, W, Cin, seed=60) * 2.0
+    w = _rand(Cout, Cin, 3, 3, seed=61) / (9 * Cin) ** 0.5
+    b = _rand(Cout, seed=62)
+    ref = _ref_conv(x.double(), w.double(), b.double(), "conv2d3")
+    ref32 = _ref_conv(x, w, b, "conv2d3")
+    err32 = (ref32.double() - ref).abs().max().item()
+    pc = ops.pack_conv(w, b, "conv2d3", split="f16x2").to(DEV)
+    xs = ops.split_bf16(x.reshape(-1, Cin).to(DEV), 2)
+    out = torch.empty(N, H, W, Cout, dtype=torch.float32, device=DEV)
+    osp = torch.empty(N, H, W, 2 * Cout, dtype=torch.float16, device=DEV)
+    mask = (torch.arange(N * H) % 7 == 3).to(torch.uint8).to(DEV)
+    ops.conv_gemm(xs, pc, N, H, W, out_f32=out, out_split=osp, pair=pair if pair else None, row_mask=mask, mask_post=True)
+    ref = ref.masked_fill(mask.cpu().bool().reshape(N, H, 1, 1), 0.0)
+    err = (out.cpu().double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err < max(4 * err32, 2e-5 * scale), (err, err32, scale)
+    s2 = osp.cpu().float().reshape(N, H, W, 2, Cout).sum(dim=3)
+    assert (s2 - out.cpu()).abs().max().item() < 1e-6 * max(1.0, scale) + 2e-7
+    if pair:       # the generic tap loop gives the same numbers up to accumulation order
+        out2 = torch.empty_like(out)
+        ops.conv_gemm(xs, pc, N, H, W, out_f32=out2, pair=False, halo=False, row_mask=mask, mask_post=True)
+        assert (out2 - out).abs().max().item() < 1e-5 * max(1.0, scale)
+
+
+def test_split_pool_upcat_stem_for_fp32_grade_decoder():
+    """mq_avgpool_mask_split / mq_upcat_mask_split / mq_refiner_stem_split against the reference ops in float64."""
+    B, T, depth, Fw, Cc = 2, 21, 3, 20, 16
+    lengths = torch.tensor([21, 13])
+    mask = O.sequence_mask(T, lengths)
+    T8, down, up = ops.refiner_masks(mask.to(torch.uint8).to(DEV), B, T, depth, DEV)
+    x = _rand(B, T8, Fw, Cc, seed=70) * 3.0
+    xs = ops.split_bf16(x.reshape(-1, Cc).to(DEV), 2).reshape(B, T8, Fw, 2 * Cc)
+
+    def join(t, c):
+        return t.cpu().float().reshape(*t.shape[:-1], 2, c).sum(dim=-2)
+
+    assert (join(xs, Cc) - x).abs().max().item() < 2e-6
+    m1 = down[1].cpu().bool().reshape(B, T8 // 2, 1, 1)
+    y = ops.avgpool_mask_split(xs, down[1], B, T8, Fw, Cc)
+    ref = (0.5 * (x[:, 0::2] + x[:, 1::2])).masked_fill(m1, 0.0)
+    assert (join(y, Cc) - ref).abs().max().item() < 4e-6
+    lo = _rand(B, T8 // 2, Fw, 2 * Cc, seed=71)
+    los = ops.split_bf16(lo.reshape(-1, 2 * Cc).to(DEV), 2).reshape(B, T8 // 2, Fw, 4 * Cc)
+    u = ops.upcat_mask_split(los, xs, up[0], B, T8, Fw, 2 * Cc, Cc)
+    m0 = up[0].cpu().bool().reshape(B, T8, 1, 1)
+    ref = torch.cat([lo.repeat_interleave(2, dim=1), x], dim=-1).masked_fill(m0, 0.0)
+    assert tuple(u.shape) == (B, T8, Fw, 2 * 3 * Cc)
+    assert (join(u, 3 * Cc) - ref).abs().max().item() < 4e-6
+    # exact copy semantics: term 0 of the concat is [lo_h0 | x_h0]
+    assert torch.equal(u[..., :2 * Cc][~m0.squeeze(-1).squeeze(-1).to(DEV)],
+                       los[..., :2 * Cc].repeat_interleave(2, dim=1)[~m0.squeeze(-1).squeeze(-1).to(DEV)])
+    r = _rand(B, T, Fw, seed=72)
+    w1, b1 = _rand(Cc, 1, 3, 3, seed=73) * 0.3, _rand(Cc, seed=74) * 0.1
+    md = down[0].cpu().bool().reshape(B, 1, T8, 1)
+    img = torch.cat([r, torch.zeros(B, T8 - T, Fw)], 1).unsqueeze(1).masked_fill(md, 0.0)
+    ref = O.aptx(F.conv2d(img.double(), w1.double(), b1.double(), padding=1), 1, 0.5).permute(0, 2, 3, 1)
+    s = ops.refiner_stem_split(r.to(DEV), mask.to(torch.uint8).to(DEV), B, T, T8, Fw, Cc,
+                               w1.reshape(Cc, 9).contiguous().to(DEV), b1.to(DEV))
+    assert (join(s, Cc).double() - ref).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item())
