@@ -552,7 +552,10 @@ def main():
         "e2e": {"value": world * frames / (head["ms_e2e"] * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": head["h2d"],
                 "d2h_bytes_per_step": head["d2h"], "ms_per_step": head["ms_e2e"]},
         "gpu_launches": head["launches"], "clocks": head["clocks"], "roofline": roofline,
-        "launch_gap_ms_per_step": ms_step - roofline["kernel_ms_sum"],
+        # timed step minus the sum of per-launch CUDA-event durations of one instrumented step: <= 0 means the launch queue
+        # never runs dry (the host enqueues ~200 launches per step far ahead of the GPU); event pairs around single
+        # launches over-count by the inter-kernel gap, hence slightly negative values
+        "step_ms_minus_kernel_ms_sum": ms_step - roofline["kernel_ms_sum"],
         "pass_frac_of_tensor_roofline": value / world * fpf / (peaks["bf16_tflops_sustained"] * 1e12),
         "cpu_baseline": None, "parity": None, "secondary": None,
     }

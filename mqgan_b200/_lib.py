@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmqgan_b200.so")
+LIB_PATH = os.environ.get("MQ_LIB") or os.path.join(_HERE, "libmqgan_b200.so")   # MQ_LIB: a bench-only probe build
 CSRC = os.path.join(_HERE, "csrc")
 
 MQ_MAX_TAPS = 16

@@ -34,6 +34,8 @@ constexpr int kMaxAccBufs = 4;              // TMEM accumulator stages: 512 / (m
 constexpr int kATileBytes = kTileM * kBlockK * 2;   // 16 KiB
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBiasSmemFloats = 1024;       // the whole (padded) bias vector is staged in shared memory once per CTA
+constexpr int kStageBytesPerWarp = 32 * 64; // lean epilogue store staging: 32 pixels x 32 bf16 channels per warp
+constexpr int kStageBytes = (kEpiThreads / 32) * kStageBytesPerWarp;
 
 // Bench-only bottleneck probes (MQ_CONV_DEBUG bit mask: 1 no epilogue math/stores, 2 no MMA, 4 no TMA, 8 no stores)
 // exist only in a -DMQ_CONV_PROBES build; release kernels carry no probe branches in their MMA / TMA / epilogue loops.
@@ -77,6 +79,8 @@ struct ConvArgs {
   int pool_ld;
   uint16_t* out_split;
   int split_ld, split_seg, split_kind;
+  int stage_out;                  // lean epilogue: transpose each warp's 32 px x 32 ch chunk through shared memory so a
+                                  // store instruction writes 8 pixels x 64 contiguous bytes instead of 32 pixels x 16
   int op_f16;                     // operands are fp16 (f16x2 mode) instead of bf16
   float acc_scale;                // accumulator scale applied before the bias (undoes the f16x2 weight scale)
 };
@@ -213,9 +217,26 @@ __device__ __forceinline__ void epilogue_generic(const ConvArgs& a, const uint32
 // Lean variant for the bf16 decoder / refiner layers: cout % 32 == 0, bf16 output only, optional
 // bf16 residual.  Dead branches of the generic body are compiled out (narrow layers are
 // epilogue-issue bound, ncu profiles/ncu_conv_small_r01).
+// Warp-private 32 px x 64 B staging tile of the lean epilogue (narrow layers).  A thread owns one accumulator row
+// (pixel), so a direct 16-byte store per lane touches 32 different 128-byte lines per instruction: on the 64-channel
+// refiner layers the L1 tag stage (one line per clock) took longer than the MMA main loop (ncu
+// profiles/ncu_conv_pair_narrow_r02_summary.md: pre.conv2 tensor pipe 37 % active, l1tex 63 %).  Staged, lane l of pass
+// `it` stores vector l % 4 of pixel it * 8 + l / 4: eight pixels x 64 contiguous bytes per instruction, 4x fewer tags.
+// Slot swizzle v ^ ((px >> 1) & 3) keeps both the 16-byte writes (row per lane) and reads (4 lanes per row) conflict-free.
+__device__ __forceinline__ void stage_write(uint8_t* st, int lane, const uint32_t (&u)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(st + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+        make_uint4(u[4 * g], u[4 * g + 1], u[4 * g + 2], u[4 * g + 3]);
+}
+__device__ __forceinline__ uint4 stage_read(const uint8_t* st, int px, int vec) {
+  return *reinterpret_cast<const uint4*>(st + px * 64 + ((vec ^ ((px >> 1) & 3)) << 4));
+}
+
 template <bool kFast>
 __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t (&v)[32], const float* bs,
-                                              int64_t pix, int co0, bool masked, bool valid, int64_t pix_pool) {
+                                              int64_t pix, int co0, bool masked, bool valid, int64_t pix_pool,
+                                              uint8_t* stage) {
   float x[32];
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
@@ -262,7 +283,21 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
 #pragma unroll
   for (int j = 0; j < 16; ++j) u[j] = zero_post ? 0u : pack_bf16x2(x[2 * j], x[2 * j + 1]);
   if (MQ_PROBE(a, 8) && x[0] != 1234.5678f) valid = false;   // probe: math without the global stores
-  if (valid) {
+  const int lane_ = threadIdx.x & 31;
+  if (stage != nullptr) {
+    stage_write(stage, lane_, u);
+    __syncwarp();
+    const int vec = lane_ & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int px = it * 8 + (lane_ >> 2);
+      const int64_t pix_o = __shfl_sync(0xffffffffu, pix, px);
+      const bool valid_o = __shfl_sync(0xffffffffu, static_cast<int>(valid), px) != 0;
+      const uint4 w4 = stage_read(stage, px, vec);
+      if (valid_o) *reinterpret_cast<uint4*>(a.out_bf16 + pix_o * a.bf16_ld + a.bf16_coff + co0 + 8 * vec) = w4;
+    }
+    __syncwarp();                 // the tile is rewritten by the pooled words / the next chunk
+  } else if (valid) {
     __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
@@ -287,7 +322,23 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
                                                 *reinterpret_cast<const __nv_bfloat162*>(&o)), half2);
       r[j] = pz ? 0u : *reinterpret_cast<const uint32_t*>(&s2);
     }
-    if (valid && (lane & 8u) == 0u) {
+    if (stage != nullptr) {
+      // the 16 pooled pixels of this warp (lanes 0-7 and 16-23) go through rows 0..15 of the same tile
+      const int prow = static_cast<int>((lane & 7u) | ((lane >> 4) << 3));
+      if ((lane & 8u) == 0u) stage_write(stage, prow, r);
+      __syncwarp();
+      const int vec = lane_ & 3;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int px = it * 8 + (lane_ >> 2);                     // pooled pixel 0..15
+        const int src = (px & 7) | ((px >> 3) << 4);              // the lane that owns it
+        const int64_t pp_o = __shfl_sync(0xffffffffu, pix_pool, src);
+        const bool valid_o = __shfl_sync(0xffffffffu, static_cast<int>(valid), src) != 0;
+        const uint4 w4 = stage_read(stage, px, vec);
+        if (valid_o) *reinterpret_cast<uint4*>(a.out_pool + pp_o * a.pool_ld + co0 + 8 * vec) = w4;
+      }
+      __syncwarp();
+    } else if (valid && (lane & 8u) == 0u) {
       __nv_bfloat16* pp = a.out_pool + pix_pool * a.pool_ld + co0;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
@@ -303,6 +354,10 @@ template <bool kFast, bool kLean>
 __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_base, uint64_t* tfull_bar,
                                              uint32_t tempty_addr, float* bias_s, int warp, int lane,
                                              int tile0, int tstep, int hoff) {
+  // optional warp-private store staging tile (2 KB per epilogue warp) right behind the bias vector
+  uint8_t* stage = (kLean && a.stage_out)
+                       ? reinterpret_cast<uint8_t*>(bias_s + kBiasSmemFloats) + (warp - 4) * kStageBytesPerWarp
+                       : nullptr;
   // Warp w may only read TMEM lanes [32*(w%4), +32); warps w and w+4 share a lane quarter and
   // split the 32-column chunks of the accumulator between them.
   const int q = warp & 3;
@@ -364,7 +419,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
         const int co0 = n0 + c;
         if (MQ_PROBE(a, 1)) continue;
         if (kLean) {
-          epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked, valid, pix_pool);
+          epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked, valid, pix_pool, stage);
         } else {
           if (valid && co0 < a.cout) epilogue_generic<kFast>(a, v, bs + c, pix, co0, masked);
         }
@@ -1079,13 +1134,14 @@ static EncodeTiledFn get_encode_fn() {
 
 // Experiment knobs from the environment, read ONCE per process (not per launch).
 struct ConvEnv {
-  int nbuf = 0, debug = 0, stages = 0, bgrp = 0;
+  int nbuf = 0, debug = 0, stages = 0, bgrp = 0, stage_out = -1;
   ConvEnv() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     nbuf = geti("MQ_CONV_NBUF");
     debug = geti("MQ_CONV_DEBUG");
     stages = geti("MQ_CONV_STAGES");
     bgrp = geti("MQ_PAIR_BGRP");
+    if (getenv("MQ_STAGE_OUT")) stage_out = geti("MQ_STAGE_OUT");     // 0 = never, 1 = bn <= 128 (default), 2 = always
   }
 };
 static const ConvEnv& conv_env() {
@@ -1209,6 +1265,14 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   a.split_kind = p->split_kind; a.op_f16 = p->op_f16;
   a.acc_scale = p->acc_scale != 0.0f ? p->acc_scale : 1.0f;
   const CUtensorMapDataType op_dt = p->op_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const bool lean = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->out_split == nullptr &&
+                    p->cout % 32 == 0 && (p->res_mode == 0 || p->res_is_bf16) && a.acc_scale == 1.0f;
+  {
+    const int mode = env.stage_out < 0 ? 1 : env.stage_out;
+    // halo / CTA-pair kernels only (the tap-loop kernel sizes its ring before this point and serves 1x1 layers)
+    a.stage_out = (lean && (pair || halo) && (mode == 2 || (mode == 1 && p->bn <= 128))) ? 1 : 0;
+  }
+  const int stage_bytes = a.stage_out ? kStageBytes : 0;
 
   // --- tensor maps ---
   CUtensorMap map_a, map_b, map_a2;
@@ -1276,7 +1340,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     const int halo_px = (kHaloSubRows * a.msub + 2) * kHaloW;
     a.halo_tx_bytes = halo_px * 128;
     a.halo_slot_bytes = (a.halo_tx_bytes + 1023) / 1024 * 1024;
-    const int tail_bytes = (2 * kHaloMaxA + 2 * kHaloMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4;
+    const int tail_bytes = (2 * kHaloMaxA + 2 * kHaloMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4 + stage_bytes;
     const int budget = kSmemBudget - 1024 - tail_bytes - 256;
     int nA = a.kchunks >= 3 ? 3 : 2;
     while (nA > 2 && budget - nA * a.halo_slot_bytes < 4 * static_cast<int>(a.b_tile_bytes)) --nA;
@@ -1290,7 +1354,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   if (pair1d) {
     a.pair_tx0 = (kTileM * a.msub + p->taps - 1) * 128;
     a.halo_slot_bytes = (a.pair_tx0 + 1023) / 1024 * 1024;
-    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4;
+    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4 + stage_bytes;
     const int budget = kSmemBudget - 1024 - tail_bytes - 256;
     const int bslot = kPair1dGroup * static_cast<int>(a.b_tile_bytes);
     int nA = (a.nseg * a.kchunks >= 3) ? 3 : 2;
@@ -1310,7 +1374,7 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     int slot = a.pair_tx0;
     if (up && a.pair_boxb_off + box1 > slot) slot = a.pair_boxb_off + box1;
     a.halo_slot_bytes = (slot + 1023) / 1024 * 1024;
-    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4;
+    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4 + stage_bytes;
     const int budget = kSmemBudget - 1024 - tail_bytes - 256;
     // weight ring: slots of pair_bgrp taps (3 = one filter row; every tap count on this path is a
     // multiple of 3) -> one full/empty barrier round trip and one multicast commit per slot
@@ -1333,8 +1397,6 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     const int pairs = sms / 2;
     grid = 2 * (a.num_tiles < pairs ? a.num_tiles : pairs);
   }
-  const bool lean = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->out_split == nullptr &&
-                    p->cout % 32 == 0 && (p->res_mode == 0 || p->res_is_bf16) && a.acc_scale == 1.0f;
   if (p->out_pool != nullptr)
     MQ_REQUIRE(lean && !up && p->bw == 8 && p->bh % 2 == 0 && p->H % 2 == 0 && p->pool_ld % 8 == 0 &&
                    (reinterpret_cast<uintptr_t>(p->out_pool) & 15) == 0,

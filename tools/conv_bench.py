@@ -40,7 +40,7 @@ def bench(fn, n=10):
 
 
 for name, H, W, Cin, Cout in SHAPES:
-    if FILT and FILT not in name:
+    if FILT and not any(f in name for f in FILT.split(",")):
         continue
     up = isinstance(Cin, tuple)
     mask = torch.zeros(B, H, dtype=torch.uint8, device=dev)
@@ -63,9 +63,12 @@ for name, H, W, Cin, Cout in SHAPES:
         fl = 2.0 * B * H * W * Cout * Cin * 9
         variants = [("halo", None)] + [("pair", m) for m in (1, 2, 4) if m * pc.bn <= 512]
 
+        yp = (torch.empty(B, H // 2, W, Cout, dtype=torch.bfloat16, device=dev)
+              if os.environ.get("CONV_BENCH_POOL") == "1" and Cout % 32 == 0 else None)      # fused AvgPool epilogue, as in the step
+
         def run(mode, m):
             ops.conv_gemm(x, pc, B, H, W, act=True, row_mask=mask, mask_post=True, out_bf16=y, msub=m,
-                          pair=(mode == "pair"), halo=(mode == "halo"))
+                          pair=(mode == "pair"), halo=(mode == "halo"), out_pool=yp)
     for mode, m in variants:
         try:
             ms = bench(lambda: run(mode, m))
