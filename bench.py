@@ -505,6 +505,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="headline only (skip the other BASELINE configs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size float64 parity check")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="--impl reference: wall-clock target for all steps")
+    ap.add_argument("--secondary-timeout-s", type=float, default=900.0, help="watchdog for the secondary block")
     ap.add_argument("--layer-table", default=None, help="write the per-layer kernel table (markdown) here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -595,8 +596,25 @@ def main():
     torch.cuda.empty_cache()
 
     # ---------------- the other BASELINE configs, each timed like the headline ----------------
+    def emit(tag=None):
+        if tag is not None:
+            line["secondary_incomplete"] = tag
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+
     if not args.no_secondary:
         sec = {}
+        line["secondary"] = sec
+        # safety net: the secondary block must never cost the headline line.  If it has not finished in time (a hung
+        # collective on some rank, a stuck capture), every rank's timer fires, rank 0 prints what has been measured and
+        # the processes leave without touching NCCL again.
+        def _bail():
+            emit(f"secondary block exceeded {args.secondary_timeout_s:.0f} s; printed what was measured")
+            sys.stdout.flush()
+            os._exit(0)
+        watchdog = threading.Timer(args.secondary_timeout_s, _bail)
+        watchdog.daemon = True
+        watchdog.start()
         ssteps = max(3, min(args.steps, 5))
 
         def reencode_line(name, want_parity):
@@ -654,10 +672,9 @@ def main():
             sec["train_step"] = {"error": repr(e)}
             if world > 1:
                 raise
-        line["secondary"] = sec
+        watchdog.cancel()
 
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    emit()
     if dist is not None:
         # the training step's captured graphs hold NCCL work: tearing the communicator down under them hangs
         sys.stdout.flush()

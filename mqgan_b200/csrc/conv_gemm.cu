@@ -79,6 +79,7 @@ struct ConvArgs {
   int pool_ld;
   uint16_t* out_split;
   int split_ld, split_seg, split_kind;
+  int slim;                       // lean + APTx(tanh.approx) + no residual: epilogue_slim
   int stage_out;                  // lean epilogue: transpose each warp's 32 px x 32 ch chunk through shared memory so a
                                   // store instruction writes 8 pixels x 64 contiguous bytes instead of 32 pixels x 16
   int op_f16;                     // operands are fp16 (f16x2 mode) instead of bf16
@@ -268,7 +269,10 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
   }
   const bool zero_pre = a.mask_pre && masked;
   const bool zero_post = a.mask_post && masked;
-  if (a.act) {
+  if (MQ_PROBE(a, 16)) {            // probe: activation without the MUFU op
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = fmaf(a.gamma * x[j], a.beta * x[j], a.gamma * x[j]);
+  } else if (a.act) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = aptx<kFast>(zero_pre ? 0.0f : x[j], a.beta, a.gamma);
   } else if (zero_pre) {
@@ -347,6 +351,99 @@ __device__ __forceinline__ void epilogue_lean(const ConvArgs& a, const uint32_t 
   }
 }
 
+// Slim variant of the lean body for the refiner's ConvBlock layers (bias + APTx with tanh.approx, optional row mask,
+// optional fused pool, no residual): what the 64- and 128-channel layers spend their time in.  On those layers the
+// epilogue, not the MMA loop, sets the pace (probe build, tools/conv_probe2.sh: pre.conv2 0.36 ms of epilogue against
+// 0.28 ms of MMA + loads), and the generic lean body issued 469 instructions per 32 x 32 chunk.  Here the row mask is
+// folded into the APTx gain (g = 0 on padded rows: aptx(x) * 0, no per-element selects), beta == 1 costs nothing, the
+// pooled mask is folded into the 0.5 of the average, and every flag is a template parameter: ~260 instructions.
+template <bool kPool, bool kStage>
+__device__ __forceinline__ void epilogue_slim(const ConvArgs& a, const uint32_t (&v)[32], const float* bs, int64_t pix,
+                                              int co0, bool masked, bool valid, int64_t pix_pool, uint8_t* stage,
+                                              int lane) {
+  const float g = masked ? 0.0f : a.gamma;          // the launcher only selects this body when a mask flag is set or no mask is given
+  float x[32];
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * q4);
+    x[4 * q4] = __uint_as_float(v[4 * q4]) + b4.x;
+    x[4 * q4 + 1] = __uint_as_float(v[4 * q4 + 1]) + b4.y;
+    x[4 * q4 + 2] = __uint_as_float(v[4 * q4 + 2]) + b4.z;
+    x[4 * q4 + 3] = __uint_as_float(v[4 * q4 + 3]) + b4.w;
+  }
+  uint32_t u[16];
+  if (a.beta == 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float t0 = tanh_fast(x[2 * j]), t1 = tanh_fast(x[2 * j + 1]);
+      const float g0 = g * x[2 * j], g1 = g * x[2 * j + 1];
+      u[j] = pack_bf16x2(fmaf(g0, t0, g0), fmaf(g1, t1, g1));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float t0 = tanh_fast(a.beta * x[2 * j]), t1 = tanh_fast(a.beta * x[2 * j + 1]);
+      const float g0 = g * x[2 * j], g1 = g * x[2 * j + 1];
+      u[j] = pack_bf16x2(fmaf(g0, t0, g0), fmaf(g1, t1, g1));
+    }
+  }
+  if (kStage) {
+    stage_write(stage, lane, u);
+    __syncwarp();
+    const int vec = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int px = it * 8 + (lane >> 2);
+      const int64_t pix_o = __shfl_sync(0xffffffffu, pix, px);
+      const bool valid_o = __shfl_sync(0xffffffffu, static_cast<int>(valid), px) != 0;
+      const uint4 w4 = stage_read(stage, px, vec);
+      if (valid_o) *reinterpret_cast<uint4*>(a.out_bf16 + pix_o * a.bf16_ld + a.bf16_coff + co0 + 8 * vec) = w4;
+    }
+    __syncwarp();
+  } else if (valid) {
+    __nv_bfloat16* op = a.out_bf16 + pix * a.bf16_ld + a.bf16_coff + co0;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+      *reinterpret_cast<uint4*>(op + 8 * q4) = make_uint4(u[4 * q4], u[4 * q4 + 1], u[4 * q4 + 2], u[4 * q4 + 3]);
+  }
+  if (kPool) {
+    // see epilogue_lean: rows of a pooling pair sit 8 lanes apart; bf16 add (one rounding) then an exact scaling by 0.5,
+    // or by 0 when either source row is padded (max-pooled mask)
+    const bool pm = (__shfl_xor_sync(0xffffffffu, static_cast<int>(masked), 8) != 0) || masked;
+    const float hf = pm ? 0.0f : 0.5f;
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(hf, hf);
+    uint32_t r[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, u[j], 8);
+      const __nv_bfloat162 s2 = __hmul2(__hadd2(*reinterpret_cast<const __nv_bfloat162*>(&u[j]),
+                                                *reinterpret_cast<const __nv_bfloat162*>(&o)), h2);
+      r[j] = *reinterpret_cast<const uint32_t*>(&s2);
+    }
+    if (kStage) {
+      const int prow = (lane & 7) | ((lane >> 4) << 3);
+      if ((lane & 8) == 0) stage_write(stage, prow, r);
+      __syncwarp();
+      const int vec = lane & 3;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int px = it * 8 + (lane >> 2);
+        const int src = (px & 7) | ((px >> 3) << 4);
+        const int64_t pp_o = __shfl_sync(0xffffffffu, pix_pool, src);
+        const bool valid_o = __shfl_sync(0xffffffffu, static_cast<int>(valid), src) != 0;
+        const uint4 w4 = stage_read(stage, px, vec);
+        if (valid_o) *reinterpret_cast<uint4*>(a.out_pool + pp_o * a.pool_ld + co0 + 8 * vec) = w4;
+      }
+      __syncwarp();
+    } else if (valid && (lane & 8) == 0) {
+      __nv_bfloat16* pp = a.out_pool + pix_pool * a.pool_ld + co0;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4)
+        *reinterpret_cast<uint4*>(pp + 8 * q4) = make_uint4(r[4 * q4], r[4 * q4 + 1], r[4 * q4 + 2], r[4 * q4 + 3]);
+    }
+  }
+}
+
 // The epilogue role (warps 4..11), shared by both main-loop variants.
 // (tile0, tstep): this CTA's tile sequence; hoff: row offset of this CTA inside the tile (CTA pairs);
 // tempty_addr: shared::cluster address of the accumulator-drained barriers (the leader's for a pair).
@@ -414,11 +511,24 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
       for (int c = half * 32; c < a.bn; c += 64) {
         uint32_t v[32];
         __syncwarp();                         // tcgen05.ld is .sync.aligned: reconverge first
-        tmem_ld_32x32(t_row + c, v);
-        tmem_ld_wait();
+        if (MQ_PROBE(a, 64)) {                // probe: no TMEM read
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(0.25f * static_cast<float>(j + lane));
+        } else {
+          tmem_ld_32x32(t_row + c, v);
+          tmem_ld_wait();
+        }
         const int co0 = n0 + c;
         if (MQ_PROBE(a, 1)) continue;
-        if (kLean) {
+        if (kLean && kFast && a.slim) {
+          if (a.out_pool != nullptr) {
+            if (stage != nullptr) epilogue_slim<true, true>(a, v, bs + c, pix, co0, masked, valid, pix_pool, stage, lane);
+            else epilogue_slim<true, false>(a, v, bs + c, pix, co0, masked, valid, pix_pool, stage, lane);
+          } else {
+            if (stage != nullptr) epilogue_slim<false, true>(a, v, bs + c, pix, co0, masked, valid, pix_pool, stage, lane);
+            else epilogue_slim<false, false>(a, v, bs + c, pix, co0, masked, valid, pix_pool, stage, lane);
+          }
+        } else if (kLean) {
           epilogue_lean<kFast>(a, v, bs + c, pix, co0, masked, valid, pix_pool, stage);
         } else {
           if (valid && co0 < a.cout) epilogue_generic<kFast>(a, v, bs + c, pix, co0, masked);
@@ -1134,13 +1244,14 @@ static EncodeTiledFn get_encode_fn() {
 
 // Experiment knobs from the environment, read ONCE per process (not per launch).
 struct ConvEnv {
-  int nbuf = 0, debug = 0, stages = 0, bgrp = 0, stage_out = -1;
+  int nbuf = 0, debug = 0, stages = 0, bgrp = 0, stage_out = -1, slim = 1;
   ConvEnv() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     nbuf = geti("MQ_CONV_NBUF");
     debug = geti("MQ_CONV_DEBUG");
     stages = geti("MQ_CONV_STAGES");
     bgrp = geti("MQ_PAIR_BGRP");
+    if (getenv("MQ_SLIM")) slim = geti("MQ_SLIM");                    // 0 = always the generic lean body
     if (getenv("MQ_STAGE_OUT")) stage_out = geti("MQ_STAGE_OUT");     // 0 = never, 1 = bn <= 128 (default), 2 = always
   }
 };
@@ -1273,6 +1384,10 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     a.stage_out = (lean && (pair || halo) && (mode == 2 || (mode == 1 && p->bn <= 128))) ? 1 : 0;
   }
   const int stage_bytes = a.stage_out ? kStageBytes : 0;
+  // `masked` rows are zeroed through the gain, which is right whenever a row mask is given at all (mask_pre before
+  // APTx and mask_post after it both give 0 = aptx(0)); a mask pointer without either flag must not zero anything
+  a.slim = (env.slim && lean && p->act && p->fast_tanh && p->res_mode == 0 &&
+            (p->row_mask == nullptr || p->mask_pre || p->mask_post)) ? 1 : 0;
 
   // --- tensor maps ---
   CUtensorMap map_a, map_b, map_a2;

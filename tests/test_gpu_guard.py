@@ -35,9 +35,9 @@ class GuardedAlloc:
             shape = tuple(shape[0])
         dev = torch.device(device) if device is not None else None
         if dev is None or dev.type != "cuda" or kw.get("pin_memory"):
-            return self.orig(*shape, dtype=dtype, device=device, **kw)
+            return self.orig(tuple(shape), dtype=dtype, device=device, **kw)
         dtype = dtype or torch.get_default_dtype()
-        n = int(math.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        n = int(math.prod(shape)) * torch.zeros(1, dtype=dtype).element_size()
         pad = (-n) % 16
         raw = self.orig(n + pad + 2 * GUARD, dtype=torch.uint8, device=dev)
         raw.fill_(CANARY)

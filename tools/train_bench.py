@@ -282,12 +282,9 @@ def measure(args):
             "roofline": {"bound": "tensor", "kernel": "conv_gemm / conv_pair / conv_wgrad kernels (tcgen05), all launches of one step",
                          "achieved": conv_fl / conv_ms / 1e9 if conv_ms else None, "peak": peak, "unit": "TFLOP/s",
                          "frac": (conv_fl / conv_ms / 1e9 / peak) if conv_ms else None, "peak_source": "measured bf16 sustained",
-                         # DRAM bytes of ONE launch of the slowest-per-FLOP tensor kernel of the step, mq_conv_wgrad on refiner
-                         # mid.conv1 (512 -> 512, 16 x 32 x 144 pixels), from the committed ncu --set full capture
-                         # (profiles/ncu_conv_wgrad_mid_r01.csv: dram__bytes_read.sum + dram__bytes_write.sum); algorithmic:
-                         # 75.5 MB dY + 75.5 MB X + 47 MB fp32 partial sums
-                         "traffic": 496940288 if args.model == "hifispeech" else None,
-                         "traffic_algorithmic_bytes": 198180864 if args.model == "hifispeech" else None,
+                         # not measured in this run: the committed ncu capture (profiles/ncu_conv_wgrad_mid_r01_summary.md) is of
+                         # one layer's first launch geometry, not of the aggregate this object describes
+                         "traffic": None,
                          "share_of_step": conv_ms / ms,
                          "by_kind": {k: {"launches": a[0], "ms": a[1], "tflops": a[2] / a[1] / 1e9 if a[2] else None} for k, a in by_kind.items()}},
             "native_share_of_step": lib_ms / ms,
