@@ -249,6 +249,12 @@ typedef struct mq_vq_params {
   int64_t* idx;            /* (n) */
   float* codes_out;        /* (n, d) or NULL */
   float* dist_out;         /* (n) or NULL */
+  /* fold != 0: the packed codebook carries -2 c (times the pre-scale) and, in three extra K columns d .. d+2 of every
+   * code, the terms of ||c||^2 * pre-scale / zconst; the kernel writes zconst into the same columns of the latent
+   * operand, so the accumulator is the score itself and the epilogue is a bare running minimum (ops.py:pack_codebook
+   * chooses this whenever d + 3 fits the code's K-steps, i.e. d <= 13, 29 or 61).  c2 is then unused. */
+  int fold;
+  float zconst;
 } mq_vq_params;
 int mq_vq_nearest(const mq_vq_params* p, mq_stream_t stream);
 

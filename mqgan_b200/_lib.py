@@ -88,6 +88,7 @@ class VqParams(C.Structure):
         ("cb_img", C.c_void_p), ("c2", C.c_void_p), ("codebook", C.c_void_p),
         ("k", C.c_int), ("k_pad", C.c_int), ("mode", C.c_int), ("acc_scale", C.c_float),
         ("idx", C.c_void_p), ("codes_out", C.c_void_p), ("dist_out", C.c_void_p),
+        ("fold", C.c_int), ("zconst", C.c_float),
     ]
 
 

@@ -31,8 +31,9 @@
 
 namespace mq {
 
-constexpr int kVqThreads = 384;            // warp 0 codebook producer, warp 1 MMA, warps 2-3 latent converters, 4-11 epilogue
-constexpr int kVqEpiThreads = 256;
+constexpr int kVqThreads = 640;            // warp 0 codebook producer, warp 1 MMA, warps 2-3 latent converters, 4-19 epilogue
+constexpr int kVqEpiThreads = 512;         // 16 epilogue warps: 4 per TMEM lane quarter, each owning 64 of a unit's 256 columns
+constexpr int kVqEpiParts = 4;
 constexpr int kVqCvtThreads = 64;
 constexpr int kVqTileM = 128;
 constexpr int kVqTileN = 256;
@@ -53,6 +54,9 @@ struct VqArgs {
   int units, tiles;               // 256-code accumulator blocks; codebook images per term
   long long row_tiles;
   float score_scale;              // -2 / codebook pre-scale
+  int fold;                       // ||c||^2 and the -2 are inside the GEMM (augmented K columns): score == accumulator
+  float zconst;                   // value the converters write into the three augmented latent columns (2^p)
+  float dist_scale;               // accumulator units -> distance units (fold mode)
   int op_f16;
   long long* idx;
   float* codes_out;
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(kVqThreads, 1) vq_nearest_kernel(const VqArgs 
   uint8_t* smem_b = smem;                                          // [kVqStages][32 KB]
   uint8_t* smem_a = smem_b + kVqStages * kVqImgBytes;              // [2 buffers][nterm][16 KB]
   float* c2_s = reinterpret_cast<float*>(smem_a + 2 * 2 * kVqATileBytes);   // [min(k_pad, kVqMaxC2)]
-  float* comb_best = c2_s + kVqMaxC2;                              // [128] second half's running best
+  float* comb_best = c2_s + kVqMaxC2;                              // [128] one column part's running best at a time
   int* comb_idx = reinterpret_cast<int*>(comb_best + kVqTileM);    // [128]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(comb_idx + kVqTileM);
   uint64_t* empty_bar = full_bar + kVqStages;
@@ -203,29 +207,25 @@ __global__ void __launch_bounds__(kVqThreads, 1) vq_nearest_kernel(const VqArgs 
       for (int rr = ct; rr < kVqTileM; rr += kVqCvtThreads) {
         const long long row = rt * kVqTileM + rr;
         const float* zr = a.z + row * a.d;
-        // the whole row is fetched before any conversion starts (one global-latency exposure per row,
-        // 128-bit loads when the row pitch allows), zero beyond d and beyond n
-        float xr[64];
         const bool live = row < a.n;
-        if ((a.d & 3) == 0) {
-#pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live && i < a.d) f = __ldg(reinterpret_cast<const float4*>(zr + i));
-            xr[i] = f.x; xr[i + 1] = f.y; xr[i + 2] = f.z; xr[i + 3] = f.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) xr[i] = (live && i < a.d) ? __ldg(zr + i) : 0.0f;
-        }
-        // one slice worth of terms (slice_cols <= 64 columns), then replicated into every slice
-#pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {                       // 16-byte chunks (8 columns) of one slice
+        // one slice worth of terms (slice_cols <= 64 columns) in 16-byte chunks of 8 columns, replicated into every
+        // slice; columns d .. d+2 carry the constant that multiplies the ||c||^2 terms of the folded codebook
+#pragma unroll 2
+        for (int c8 = 0; c8 < 8; ++c8) {
           if (c8 * 8 < slice_cols) {
+            float x8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = c8 * 8 + e;
+              float x = 0.0f;
+              if (col < a.d) x = live ? __ldg(zr + col) : 0.0f;
+              else if (a.fold && col < a.d + 3) x = a.zconst;
+              x8[e] = x;
+            }
             uint32_t w0[4], w1[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float x0 = xr[c8 * 8 + 2 * e], x1 = xr[c8 * 8 + 2 * e + 1];
+              const float x0 = x8[2 * e], x1 = x8[2 * e + 1];
               if (a.op_f16) {
                 uint16_t t0[3], t1[3];
                 split_terms(x0, 1, t0);
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(kVqThreads, 1) vq_nearest_kernel(const VqArgs 
                 w1[e] = 0;
               }
             }
-            for (int s = 0; s < a.slices; ++s) {
-              const int chunk = s * (slice_cols / 8) + c8;                  // 16-byte chunk index in the 128-byte row
+            for (int sl = 0; sl < a.slices; ++sl) {
+              const int chunk = sl * (slice_cols / 8) + c8;                  // 16-byte chunk index in the 128-byte row
               const uint32_t off = static_cast<uint32_t>(rr * 128 + ((chunk ^ (rr & 7)) << 4));
               *reinterpret_cast<uint4*>(abuf + off) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
               if (a.nterm == 2)
@@ -253,12 +253,16 @@ __global__ void __launch_bounds__(kVqThreads, 1) vq_nearest_kernel(const VqArgs 
     }
   } else {
     // ===================== epilogue: scores, running argmin, gather =====================
+    // 16 warps: warp (q, part) owns TMEM lanes [32 q, +32) and columns [64 part, +64) of every 256-code unit.  In fold
+    // mode the accumulator IS the score (||c||^2 - 2 z.c, scaled): the body per unit is two tcgen05.ld, a 64-input
+    // minimum as a tree of three-input FMNMX3 and one compare; the column scan only runs when the unit improves the
+    // running best (about ln K times per row).  Strict '<' in ascending k keeps the lowest index on ties.
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int part = (warp - 4) >> 2;
     const int r = q * 32 + lane;
     const int et = threadIdx.x - 128;
     const bool c2_in_smem = a.k_pad <= kVqMaxC2;
-    if (c2_in_smem)
+    if (!a.fold && c2_in_smem)
       for (int j = et; j < a.k_pad; j += kVqEpiThreads) c2_s[j] = a.c2[j];
     named_bar_sync(1, kVqEpiThreads);
     int uit = 0;
@@ -269,65 +273,85 @@ __global__ void __launch_bounds__(kVqThreads, 1) vq_nearest_kernel(const VqArgs 
         const uint32_t buf = uit & 1;
         mbar_wait(&tfull_bar[buf], (uit >> 1) & 1);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kVqTileN;
-        // two 32-column chunks per tcgen05.wait::ld (the TMEM read latency is paid once per pair), and
-        // four partial minima per chunk instead of one 32-long dependent chain
-#pragma unroll 1
-        for (int cp = 0; cp < 2; ++cp) {
-          uint32_t v[2][32];
-          __syncwarp();
-          tmem_ld_32x32(t_row + half * 32 + 128 * cp, v[0]);
-          tmem_ld_32x32(t_row + half * 32 + 128 * cp + 64, v[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = half * 32 + 128 * cp + 64 * h;
-            const int k0 = u * kVqTileN + c;
-            float sc[32];
-            if (c2_in_smem) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 cc = *reinterpret_cast<const float4*>(c2_s + k0 + 4 * g);
-                sc[4 * g] = fmaf(__uint_as_float(v[h][4 * g]), a.score_scale, cc.x);
-                sc[4 * g + 1] = fmaf(__uint_as_float(v[h][4 * g + 1]), a.score_scale, cc.y);
-                sc[4 * g + 2] = fmaf(__uint_as_float(v[h][4 * g + 2]), a.score_scale, cc.z);
-                sc[4 * g + 3] = fmaf(__uint_as_float(v[h][4 * g + 3]), a.score_scale, cc.w);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sc[j] = fmaf(__uint_as_float(v[h][j]), a.score_scale, __ldg(a.c2 + k0 + j));
-            }
-            float m4[4] = {sc[0], sc[1], sc[2], sc[3]};
-#pragma unroll
-            for (int j = 4; j < 32; ++j) m4[j & 3] = fminf(m4[j & 3], sc[j]);
-            const float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
-            if (m < best) {                            // rare after the first blocks: ~ln K improvements per row
-              best = m;
-              int jj = 31;
-#pragma unroll
-              for (int j = 30; j >= 0; --j) jj = (sc[j] == m) ? j : jj;     // first (lowest) column attaining the min
-              bidx = k0 + jj;
-            }
-          }
-        }
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kVqTileN + part * 64;
+        uint32_t v[2][32];
+        __syncwarp();
+        tmem_ld_32x32(t_row, v[0]);
+        tmem_ld_32x32(t_row + 32, v[1]);
+        tmem_ld_wait();
+        // the TMEM buffer is free as soon as the values sit in registers
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        const int k0 = u * kVqTileN + part * 64;
+        float sc[64];
+        if (a.fold) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) sc[j] = __uint_as_float(v[j >> 5][j & 31]);
+        } else if (c2_in_smem) {
+#pragma unroll
+          for (int g = 0; g < 16; ++g) {
+            const float4 cc = *reinterpret_cast<const float4*>(c2_s + k0 + 4 * g);
+            sc[4 * g] = fmaf(__uint_as_float(v[g >> 3][(4 * g) & 31]), a.score_scale, cc.x);
+            sc[4 * g + 1] = fmaf(__uint_as_float(v[g >> 3][(4 * g + 1) & 31]), a.score_scale, cc.y);
+            sc[4 * g + 2] = fmaf(__uint_as_float(v[g >> 3][(4 * g + 2) & 31]), a.score_scale, cc.z);
+            sc[4 * g + 3] = fmaf(__uint_as_float(v[g >> 3][(4 * g + 3) & 31]), a.score_scale, cc.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            sc[j] = fmaf(__uint_as_float(v[j >> 5][j & 31]), a.score_scale, __ldg(a.c2 + k0 + j));
+        }
+        if (a.fold && k0 + 64 > a.k) {              // padding codes of the last unit carry no ||c||^2: exclude them
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (k0 + j >= a.k) sc[j] = INFINITY;
+        }
+        // 64 -> 1 with three-input minima (FMNMX3): 21 triples + sc[63], then 7 triples of those + one pair, then 8 -> 1.
+        // min / compare / select all issue on the half-rate ALU pipe, which is what bounds this kernel (ncu
+        // profiles/ncu_vq_nearest_r02_summary.md), so the index search below touches as few of them as it can.
+        float m1[22];
+#pragma unroll
+        for (int j = 0; j < 21; ++j) m1[j] = fminf(fminf(sc[3 * j], sc[3 * j + 1]), sc[3 * j + 2]);
+        m1[21] = sc[63];
+        float m2[8];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) m2[j] = fminf(fminf(m1[3 * j], m1[3 * j + 1]), m1[3 * j + 2]);
+        m2[7] = m1[21];
+        const float m = fminf(fminf(fminf(fminf(m2[0], m2[1]), m2[2]), fminf(fminf(m2[3], m2[4]), m2[5])), fminf(m2[6], m2[7]));
+        if (m < best) {
+          // Taken by a warp whenever any of its 32 rows improves - at K = 8192 that is most units (a row improves
+          // ~ln K times, 32 rows share the branch), so the scan is plain select code without divergence.  A per-lane
+          // switch over the nine-column group that holds the minimum was measured and is no faster (the early units
+          // execute every case).
+          best = m;
+          int jj = 63;
+#pragma unroll
+          for (int j = 62; j >= 0; --j) jj = (sc[j] == m) ? j : jj;       // first (lowest) column attaining the min
+          bidx = k0 + jj;
+        }
       }
-      // combine the two column halves of each row (lexicographic on (score, index)), write, gather
-      if (half == 1) {
-        comb_best[r] = best;
-        comb_idx[r] = bidx;
+      // combine the four column parts of each row (lexicographic on (score, index)) through one 1 KB exchange area,
+      // one part per round (six named barriers per row tile, against K / 256 accumulator units of work), write, gather
+#pragma unroll 1
+      for (int pp = 1; pp < kVqEpiParts; ++pp) {
+        if (part == pp) {
+          comb_best[r] = best;
+          comb_idx[r] = bidx;
+        }
+        named_bar_sync(1, kVqEpiThreads);
+        if (part == 0) {
+          const float ob = comb_best[r];
+          const int oi = comb_idx[r];
+          if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        if (pp + 1 < kVqEpiParts) named_bar_sync(1, kVqEpiThreads);
       }
-      named_bar_sync(1, kVqEpiThreads);
-      if (half == 0) {
-        const float ob = comb_best[r];
-        const int oi = comb_idx[r];
-        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      if (part == 0) {
         const long long row = rt * kVqTileM + r;
         if (row < a.n) {
           a.idx[row] = bidx;
-          if (a.dist_out != nullptr) a.dist_out[row] = best;
+          if (a.dist_out != nullptr) a.dist_out[row] = a.fold ? best * a.dist_scale : best;
           if (a.codes_out != nullptr && bidx < a.k) {
             const float* src = a.codebook + static_cast<long long>(bidx) * a.d;
             float* dst = a.codes_out + row * a.d;
@@ -418,6 +442,12 @@ extern "C" int mq_vq_nearest(const mq_vq_params* p, mq_stream_t stream_) {
   a.tiles = a.units / a.slices;
   a.row_tiles = (p->n + kVqTileM - 1) / kVqTileM;
   a.score_scale = -2.0f * (p->acc_scale != 0.0f ? p->acc_scale : 1.0f);
+  a.fold = p->fold != 0;
+  if (a.fold) {
+    MQ_REQUIRE(p->d + 3 <= 16 * a.ks && p->zconst > 0.0f, "mq_vq_nearest: folded codebook needs d + 3 <= %d and zconst > 0", 16 * a.ks);
+    a.zconst = p->zconst;
+    a.dist_scale = p->acc_scale != 0.0f ? p->acc_scale : 1.0f;
+  }
   a.idx = reinterpret_cast<long long*>(p->idx); a.codes_out = p->codes_out; a.dist_out = p->dist_out;
 
   int dev = 0, sms = 0;

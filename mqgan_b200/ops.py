@@ -787,16 +787,23 @@ class PackedCodebook:
     d: int
     mode: int                  # 0 = bf16, 1 = f16x2
     acc_scale: float
+    fold: bool = False         # ||c||^2 and the factor -2 live inside the GEMM (three augmented K columns per code)
+    zconst: float = 1.0        # what the kernel writes into those columns of the latent operand
 
     def to(self, device):
         self.cb_img, self.c2, self.codebook = self.cb_img.to(device), self.c2.to(device), self.codebook.to(device)
         return self
 
 
-def pack_codebook(codebook: torch.Tensor, precision: str = "f16x2") -> PackedCodebook:
+def pack_codebook(codebook: torch.Tensor, precision: str = "f16x2", fold: Optional[bool] = None) -> PackedCodebook:
     """Pack a (K, D <= 64) fp32 codebook for mq_vq_nearest: 16-bit operand terms laid out as the
     128-byte-swizzled [256 codes][64 K] shared-memory tiles the tensor core reads (slices = 4/ks codes side
-    by side per 128-byte row when D <= 32), plus ||c||^2 in fp32 (computed in float64)."""
+    by side per 128-byte row when D <= 32), plus ||c||^2 in fp32 (computed in float64).
+
+    ``fold`` (default: whenever D + 3 fits the code's K-steps): the score ||c||^2 - 2 z.c comes out of the GEMM itself.
+    The codebook is stored as -2 c and three augmented K columns D .. D+2 hold multi-term splits of ||c||^2 / zconst
+    (f16x2: two 2-term fp16 splits = 44 bits; bf16: three bf16 terms = 24 bits), multiplied in the kernel by the
+    constant zconst = 2^p written into the latent operand; p keeps the fp16 terms in range."""
     if precision not in ("f16x2", "bf16"):
         raise ValueError("precision must be 'f16x2' or 'bf16'")
     cb = codebook.detach().float().cpu().contiguous()
@@ -804,21 +811,44 @@ def pack_codebook(codebook: torch.Tensor, precision: str = "f16x2") -> PackedCod
     if not 1 <= D <= 64:
         raise ValueError("codebook width must be in [1, 64]")
     ks = 1 if D <= 16 else (2 if D <= 32 else 4)
+    if fold is None:
+        fold = D + 3 <= 16 * ks
+    if fold and D + 3 > 16 * ks:
+        raise ValueError("fold needs D + 3 <= 16 * ks columns")
     slices = 4 // ks
     per_tile = 256 * slices
     k_pad = (K + per_tile - 1) // per_tile * per_tile
     tiles = k_pad // per_tile
-    acc_scale = 1.0
+    acc_scale, zconst = 1.0, 1.0
+    c2_64 = (cb.double() ** 2).sum(1)
+    src = cb * (-2.0) if fold else cb                             # exact: a power of two
+    aug: List[torch.Tensor] = []                                  # per term: (K, 3) augmented columns
     if precision == "f16x2":
-        cmax = float(cb.abs().max())
+        cmax = float(src.abs().max())
         e = 0 if cmax == 0.0 else 13 - math.floor(math.log2(cmax))
         e = max(-24, min(24, e))
-        terms = list(split2_f16(cb * (2.0 ** e)))                 # g0, g1
+        terms = list(split2_f16(src * (2.0 ** e)))                # g0, g1
         acc_scale = 2.0 ** (-e)
         dt = torch.float16
+        if fold:
+            c2s = c2_64 * (2.0 ** e)                              # in accumulator units
+            top = float(c2s.max())
+            p = 0 if top <= 0 else max(0, math.ceil(math.log2(top)) - 14)
+            if p > 15:
+                raise ValueError("codebook norms too large for the folded fp16 form; pass fold=False")
+            zconst = 2.0 ** p
+            v = c2s / zconst
+            a0, b0 = split2_f16(v.float())
+            r = v - a0.double() - b0.double()
+            a1, b1 = split2_f16(r.float())
+            zero = torch.zeros_like(a0)
+            aug = [torch.stack([a0, a1, zero], 1), torch.stack([b0, b1, zero], 1)]
     else:
-        terms = [cb.to(torch.bfloat16)]
+        terms = [src.to(torch.bfloat16)]
         dt = torch.bfloat16
+        if fold:
+            t0, t1, t2 = split3_bf16(c2_64.float())
+            aug = [torch.stack([t0, t1, t2], 1)]
     dense = torch.zeros(tiles, len(terms), 256, 64, dtype=dt)          # [tile][term][row n][K column]
     code = torch.arange(k_pad)
     t, rem = code // per_tile, code % per_tile
@@ -827,15 +857,18 @@ def pack_codebook(codebook: torch.Tensor, precision: str = "f16x2") -> PackedCod
     for j, tj in enumerate(terms):
         for i in range(D):
             dense[t[valid], j, n[valid], (s[valid] * 16 * ks + i)] = tj[code[valid], i]
+        if fold:
+            for i in range(3):
+                dense[t[valid], j, n[valid], (s[valid] * 16 * ks + D + i)] = aug[j][code[valid], i].to(dt)
     # 128-byte swizzle of a 1024-byte-aligned tile: 16-byte chunk c of row n lives at chunk c ^ (n & 7)
     chunks = dense.view(tiles, len(terms), 256, 8, 8)
     rows = torch.arange(256)
-    src = (torch.arange(8)[None, :] ^ (rows[:, None] & 7))              # image chunk p holds data chunk p ^ (n&7)
-    img = torch.gather(chunks, 3, src[None, None, :, :, None].expand(tiles, len(terms), 256, 8, 8))
+    srcc = (torch.arange(8)[None, :] ^ (rows[:, None] & 7))             # image chunk p holds data chunk p ^ (n&7)
+    img = torch.gather(chunks, 3, srcc[None, None, :, :, None].expand(tiles, len(terms), 256, 8, 8))
     c2 = torch.full((k_pad,), float("inf"), dtype=torch.float32)
-    c2[:K] = (cb.double() ** 2).sum(1).float()
+    c2[:K] = c2_64.float()
     return PackedCodebook(img.contiguous().view(torch.uint8).reshape(-1), c2, cb, K, k_pad, D,
-                          1 if precision == "f16x2" else 0, acc_scale)
+                          1 if precision == "f16x2" else 0, acc_scale, bool(fold), float(zconst))
 
 
 def vq_nearest(z: torch.Tensor, pc: PackedCodebook, want_codes: bool = True, want_dist: bool = False):
@@ -854,6 +887,7 @@ def vq_nearest(z: torch.Tensor, pc: PackedCodebook, want_codes: bool = True, wan
     p.codebook = _chk(pc.codebook, torch.float32, "codebook").data_ptr()
     p.k, p.k_pad, p.mode, p.acc_scale = pc.k, pc.k_pad, pc.mode, float(pc.acc_scale)
     p.idx, p.codes_out, p.dist_out = idx.data_ptr(), _ptr(codes), _ptr(dist)
+    p.fold, p.zconst = int(pc.fold), float(pc.zconst)
     meta = None
     if _lib.profiler is not None:
         meta = {"tag": f"vq k={pc.k} d={pc.d}", "flops": 2.0 * n * pc.k * pc.d}

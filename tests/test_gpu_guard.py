@@ -63,10 +63,11 @@ def _rnd(*shape, seed=0):
 @pytest.mark.parametrize("cfg_name,B,T,lengths", [
     ("TINY", 3, 277, [277, 130, 9]),        # T % 8 = 5, pair kernels on the 1-D (T >= 256) and 3x3 layers, ragged
     ("TINY", 2, 37, [37, 20]),              # small: tap-loop / halo kernels
-    ("TINY_M", 2, 301, [301, 77]),          # refiner widths 24 / 48 / 96 / 192, image width 54 (partial 8-wide tiles)
+    ("ODD", 2, 301, [301, 77]),             # 48-channel 1-D blocks, refiner widths 24 / 48 / 96 / 192, image width 72
 ])
 def test_encode_decode_write_only_inside_their_buffers(cfg_name, B, T, lengths, decoder_precision):
-    cfg = getattr(S, cfg_name)
+    # "ODD": channel counts that are not multiples of 32 / 64 anywhere (the engine needs mel + mel/8 to be a multiple of 4)
+    cfg = S.PreEncoderConfig(64, (48, 48, 64, 64), (3, 3, 5, 7), (8, 5, 5, 5), 24, 3, 8) if cfg_name == "ODD" else getattr(S, cfg_name)
     sd = synth_state_dict(cfg, 0)
     model = PreEncoder(cfg.mel_channels, list(cfg.channels), list(cfg.kernel_sizes), fsq_levels=list(cfg.fsq_levels),
                        dropout=0.0, refiner_base_channels=cfg.refiner_base_channels, refiner_depth=cfg.refiner_depth,
@@ -130,4 +131,4 @@ def test_conv_vq_wgrad_mel_write_only_inside_their_buffers():
                                "n_mel_channels": 128, "mel_fmin": 0.0, "mel_fmax": 22050.0}, dev)
         ext(_rnd(3, 9001, seed=11).to(dev), [9001, 5000, 1025])
         n = g.check()
-    assert n > 30
+    assert n > 20

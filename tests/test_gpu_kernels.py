@@ -778,3 +778,30 @@ def test_split_pool_upcat_stem_for_fp32_grade_decoder():
     s = ops.refiner_stem_split(r.to(DEV), mask.to(torch.uint8).to(DEV), B, T, T8, Fw, Cc,
                                w1.reshape(Cc, 9).contiguous().to(DEV), b1.to(DEV))
     assert (join(s, Cc).double() - ref).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("n,K,D", [(3000, 1000, 20), (4097, 512, 4), (2048, 8192, 5)])
+def test_vq_nearest_folded_and_unfolded_forms_agree(n, K, D):
+    """||c||^2 inside the GEMM (augmented K columns, the default for d <= 61) and ||c||^2 added in the epilogue give the
+    same argmin as the float64 reference and the same distances to fp32 accuracy."""
+    z = _rand(n, D, seed=51) * 2.0
+    cb = _rand(K, D, seed=52) * 3.0
+    ref_idx, gap, d64 = _vq_ref(z, cb)
+    scale = float(d64.min(dim=1).values.mean()) + 1.0
+    out = {}
+    for fold in (True, False):
+        pc = ops.pack_codebook(cb, "f16x2", fold=fold).to(DEV)
+        assert pc.fold == fold
+        idx, dist = ops.vq_nearest(z.to(DEV), pc, want_codes=False, want_dist=True)
+        neq = idx.cpu() != ref_idx
+        assert int((neq & (gap > 1e-5 * scale)).sum()) == 0, (fold, int(neq.sum()))
+        out[fold] = (idx.cpu(), dist.cpu())
+    assert float((out[True][0] == out[False][0]).float().mean()) > 0.9995
+    assert (out[True][1] - out[False][1]).abs().max().item() < 2e-5 * scale
+    # bf16 form: folded ||c||^2 keeps 24 bits (three bf16 terms), so its agreement matches the unfolded bf16 form
+    ag = []
+    for fold in (True, False):
+        ib = ops.vq_nearest(z.to(DEV), ops.pack_codebook(cb, "bf16", fold=fold).to(DEV), want_codes=False).cpu()
+        ag.append(float((ib == ref_idx).float().mean()))
+    print("bf16 agreement folded / unfolded", ag)
+    assert abs(ag[0] - ag[1]) < 0.02
