@@ -188,11 +188,25 @@ def save_outputs(reencoded: torch.Tensor, lengths: Sequence[int], paths: Sequenc
             save_one(i)
 
 
+def _cap_host_threads(world: int) -> None:
+    """The host side of this path is file I/O and launches; torch's intra-op pool (as wide as the machine by default)
+    only adds spinning threads.  Measured with 4 workers on a 32-core box (tools/cli_probe4.sh): 0.73 M frames/s with
+    the default pools, 2.60 M with them capped at 4 threads, 3.05 M with one I/O thread per worker as well.
+    MQ_WORKER_THREADS=0 / MQ_IO_THREADS=<n> override."""
+    global IO_THREADS, _io_pool
+    nthr = int(os.environ.get("MQ_WORKER_THREADS", str(max(1, min(4, (os.cpu_count() or 1) // max(1, world))))))
+    if nthr > 0:
+        torch.set_num_threads(nthr)
+    if "MQ_IO_THREADS" not in os.environ and world >= 4 and _io_pool is None:
+        IO_THREADS = 1
+
+
 def reencode_tree(run_batch: Callable[[torch.Tensor, List[int]], torch.Tensor], input_dir: str, output_dir: str,
                   batch_size: int, rank: int = 0, world: int = 1, progress: bool = True,
                   prefetch: int = 2, sort_by_length: bool = False) -> Tuple[int, int]:
     """Process this worker's share of the tree.  ``run_batch(batch (B,T,M) float32 CPU, lengths)``
     returns the re-encoded (B,T,M) tensor (any device).  Returns (files done, batches failed)."""
+    _cap_host_threads(world)
     files = list_npy_files(input_dir)
     if not files:
         print("Warning: No .npy files were found.")
@@ -305,15 +319,21 @@ def finish_distributed(done: int, failed: int, backend: Optional[str] = None) ->
 
 def _worker(rank: int, world: int, make_model: Callable[[str], object], input_dir: str, output_dir: str,
             batch_size: int, ret, sort_by_length: bool = False) -> None:
+    import time
     torch.cuda.set_device(rank)
+    t_load = time.time()
     model = make_model(f"cuda:{rank}")
 
     def run(batch, lengths):
         idx = model.encode(batch, lengths=lengths)
         return model.decode(idx, lengths=lengths)
 
-    ret[rank] = reencode_tree(run, input_dir, output_dir, batch_size, rank, world, progress=(rank == 0),
-                              sort_by_length=sort_by_length)
+    t0 = time.time()
+    done, failed = reencode_tree(run, input_dir, output_dir, batch_size, rank, world, progress=(rank == 0),
+                                 sort_by_length=sort_by_length)
+    torch.cuda.synchronize()
+    # (done, failed, model load seconds, processing start / end as epoch seconds): tools/cli_bench_multi.py reads the span
+    ret[rank] = (done, failed, t0 - t_load, t0, time.time())
 
 
 def run_multi_gpu(make_model: Callable[[str], object], input_dir: str, output_dir: str, batch_size: int,
@@ -332,4 +352,11 @@ def run_multi_gpu(make_model: Callable[[str], object], input_dir: str, output_di
             p.join()
         done = sum(v[0] for v in ret.values())
         failed = sum(v[1] for v in ret.values()) + sum(1 for p in procs if p.exitcode != 0)
+        if os.environ.get("MQ_CLI_TIMING") == "1" and len(ret) > 0:
+            import json
+            vals = list(ret.values())
+            print("MQ_CLI_TIMING " + json.dumps({
+                "workers": gpus, "load_s_max": max(v[2] for v in vals),
+                "process_span_s": max(v[4] for v in vals) - min(v[3] for v in vals),
+                "process_s_per_worker": [v[4] - v[3] for v in vals]}), flush=True)
     return done, failed

@@ -66,8 +66,16 @@ def reencode_spectrograms(checkpoint_path, config, input_dir, output_dir, device
         def run(batch, lengths):
             return model.decode(model.encode(batch, lengths), lengths)
 
+        import time
+        t0 = time.time()
         done, failed = R.reencode_tree(run, input_dir, output_dir, batch_size, rank, world,
                                         sort_by_length=sort_by_length)
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize()
+        if os.environ.get("MQ_CLI_TIMING") == "1":
+            import json
+            print("MQ_CLI_TIMING " + json.dumps({"workers": world, "process_span_s": time.time() - t0,
+                                                 "process_s_per_worker": [time.time() - t0]}), flush=True)
         done, failed = R.finish_distributed(done, failed)
     if rank == 0:
         print("\nProcessing complete.")
@@ -101,7 +109,7 @@ def main():
         print(f"Error loading config file: {e}")
         return
     reencode_spectrograms(args.checkpoint, config, args.input_dir, args.output_dir, args.device, args.batch_size,
-                          args.gpus)
+                          args.gpus, args.sort_by_length)
 
 
 if __name__ == '__main__':
