@@ -80,6 +80,7 @@ struct ConvArgs {
   uint16_t* out_split;
   int split_ld, split_seg, split_kind;
   int slim;                       // lean + APTx(tanh.approx) + no residual: epilogue_slim
+  int slim16;                     // ... on the 16-epilogue-warp variant of conv_pair_kernel (bn = 64 / 128)
   int stage_out;                  // lean epilogue: transpose each warp's 32 px x 32 ch chunk through shared memory so a
                                   // store instruction writes 8 pixels x 64 contiguous bytes instead of 32 pixels x 16
   int op_f16;                     // operands are fp16 (f16x2 mode) instead of bf16
@@ -861,6 +862,165 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
 }
 
 // ---------------------------------------------------------------------------
+// Sixteen epilogue warps for the narrow ConvBlock layers (bn = 64 / 128, slim epilogue conditions).
+//
+// ncu on pre.conv2 (profiles/ncu_conv_pair_narrow_r02_summary.md): the eight epilogue warps - two per scheduler - issue
+// 16 % of the time and wait on their own dependency chains for the rest (TMEM load, MUFU, shuffle and store
+// latencies), while the MMA loop of these short-K layers would be done in two thirds of the epilogue's time.  More
+// warps hide that latency: four warps share a TMEM lane quarter and take 16-column chunks round robin
+// (tcgen05.ld.32x32b.x16, half the registers, so 640 threads fit the register file), everything else as epilogue_slim.
+// ---------------------------------------------------------------------------
+constexpr int kEpi16Warps = 16;
+constexpr int kEpi16Threads = kEpi16Warps * 32;
+constexpr int kThreads16 = 128 + kEpi16Threads;
+constexpr int kStage16BytesPerWarp = 32 * 32;          // 32 pixels x 16 bf16 channels
+
+__device__ __forceinline__ void stage16_write(uint8_t* st, int row, const uint32_t (&u)[8]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g)
+    *reinterpret_cast<uint4*>(st + row * 32 + ((g ^ ((row >> 2) & 1)) << 4)) =
+        make_uint4(u[4 * g], u[4 * g + 1], u[4 * g + 2], u[4 * g + 3]);
+}
+__device__ __forceinline__ uint4 stage16_read(const uint8_t* st, int px, int vec) {
+  return *reinterpret_cast<const uint4*>(st + px * 32 + ((vec ^ ((px >> 2) & 1)) << 4));
+}
+
+template <bool kPool>
+__device__ __forceinline__ void epilogue_slim16(const ConvArgs& a, const uint32_t (&v)[16], const float* bs, int64_t pix,
+                                                int co0, bool masked, bool valid, int64_t pix_pool, uint8_t* stage,
+                                                int lane) {
+  const float g = masked ? 0.0f : a.gamma;
+  float x[16];
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * q4);
+    x[4 * q4] = __uint_as_float(v[4 * q4]) + b4.x;
+    x[4 * q4 + 1] = __uint_as_float(v[4 * q4 + 1]) + b4.y;
+    x[4 * q4 + 2] = __uint_as_float(v[4 * q4 + 2]) + b4.z;
+    x[4 * q4 + 3] = __uint_as_float(v[4 * q4 + 3]) + b4.w;
+  }
+  uint32_t u[8];
+  if (a.beta == 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t0 = tanh_fast(x[2 * j]), t1 = tanh_fast(x[2 * j + 1]);
+      const float g0 = g * x[2 * j], g1 = g * x[2 * j + 1];
+      u[j] = pack_bf16x2(fmaf(g0, t0, g0), fmaf(g1, t1, g1));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t0 = tanh_fast(a.beta * x[2 * j]), t1 = tanh_fast(a.beta * x[2 * j + 1]);
+      const float g0 = g * x[2 * j], g1 = g * x[2 * j + 1];
+      u[j] = pack_bf16x2(fmaf(g0, t0, g0), fmaf(g1, t1, g1));
+    }
+  }
+  // staged store: lane l of pass `it` writes vector l % 2 of pixel it * 16 + l / 2 (16 pixels x 32 contiguous bytes)
+  stage16_write(stage, lane, u);
+  __syncwarp();
+  {
+    const int vec = lane & 1;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int px = it * 16 + (lane >> 1);
+      const int64_t pix_o = __shfl_sync(0xffffffffu, pix, px);
+      const bool valid_o = __shfl_sync(0xffffffffu, static_cast<int>(valid), px) != 0;
+      const uint4 w4 = stage16_read(stage, px, vec);
+      if (valid_o) *reinterpret_cast<uint4*>(a.out_bf16 + pix_o * a.bf16_ld + a.bf16_coff + co0 + 8 * vec) = w4;
+    }
+  }
+  __syncwarp();
+  if (kPool) {
+    const bool pm = (__shfl_xor_sync(0xffffffffu, static_cast<int>(masked), 8) != 0) || masked;
+    const float hf = pm ? 0.0f : 0.5f;
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(hf, hf);
+    uint32_t r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, u[j], 8);
+      const __nv_bfloat162 s2 = __hmul2(__hadd2(*reinterpret_cast<const __nv_bfloat162*>(&u[j]),
+                                                *reinterpret_cast<const __nv_bfloat162*>(&o)), h2);
+      r[j] = *reinterpret_cast<const uint32_t*>(&s2);
+    }
+    const int prow = (lane & 7) | ((lane >> 4) << 3);          // pooled pixel 0..15 owned by lanes 0-7, 16-23
+    if ((lane & 8) == 0) stage16_write(stage, prow, r);
+    __syncwarp();
+    const int px = lane >> 1, vec = lane & 1;
+    const int src = (px & 7) | ((px >> 3) << 4);
+    const int64_t pp_o = __shfl_sync(0xffffffffu, pix_pool, src);
+    const bool valid_o = __shfl_sync(0xffffffffu, static_cast<int>(valid), src) != 0;
+    const uint4 w4 = stage16_read(stage, px, vec);
+    if (valid_o) *reinterpret_cast<uint4*>(a.out_pool + pp_o * a.pool_ld + co0 + 8 * vec) = w4;
+    __syncwarp();
+  }
+}
+
+// The epilogue role with sixteen warps (warps 4..19): warp (q, part) owns TMEM lanes [32 q, +32) and the 16-column
+// chunks part, part + 4, ... of every sub-tile.  Tile walk, mask prefetch and barrier protocol as run_epilogue.
+__device__ __forceinline__ void run_epilogue_slim16(const ConvArgs& a, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                    uint32_t tempty_addr, float* bias_s, int warp, int lane,
+                                                    int tile0, int tstep, int hoff) {
+  uint8_t* stage = reinterpret_cast<uint8_t*>(bias_s + kBiasSmemFloats) + (warp - 4) * kStage16BytesPerWarp;
+  const int q = warp & 3;
+  const int part = (warp - 4) >> 2;
+  const int r = q * 32 + lane;
+  const int lh = r / a.bw;
+  const int lw = r - lh * a.bw;
+  const int et = threadIdx.x - 128;
+  for (int j = et; j < a.cout_pad; j += kEpi16Threads)
+    bias_s[j] = (a.bias != nullptr && j < a.cout) ? a.bias[j] : 0.0f;
+  named_bar_sync(1, kEpi16Threads);
+  auto fetch_masks = [&](int tile, uint8_t (&m)[4]) {
+    int n_idx, h0, w0, n0, par;
+    decode_tile(a, tile, n_idx, h0, w0, n0, par);
+    h0 += hoff;
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      const int h = h0 + sub * a.bh + lh;
+      m[sub] = 0;
+      if (sub < a.msub && h < a.H) m[sub] = a.row_mask[static_cast<int64_t>(n_idx) * a.H + h];
+    }
+  };
+  uint8_t mnext[4] = {0, 0, 0, 0};
+  if (a.row_mask != nullptr && tile0 < a.num_tiles) fetch_masks(tile0, mnext);
+  int it = 0;
+  for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
+    int n_idx, h0, w0, n0, par;
+    decode_tile(a, tile, n_idx, h0, w0, n0, par);
+    h0 += hoff;
+    const uint32_t buf = it % a.nbuf;
+    const float* bs = bias_s + n0;
+    uint32_t mbits = 0;
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) mbits |= (mnext[sub] != 0 ? 1u : 0u) << sub;
+    if (a.row_mask != nullptr && tile + tstep < a.num_tiles) fetch_masks(tile + tstep, mnext);
+    mbar_wait(&tfull_bar[buf], (it / a.nbuf) & 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int sub = 0; sub < a.msub; ++sub) {
+      const int h = h0 + sub * a.bh + lh, w = w0 + lw;
+      const bool valid = (h < a.H) && (w < a.W);
+      const int64_t pix = (static_cast<int64_t>(n_idx) * a.H + h) * a.W + w;
+      const int64_t pix_pool = (static_cast<int64_t>(n_idx) * (a.H >> 1) + (h >> 1)) * a.W + w;
+      const bool masked = (mbits >> sub) & 1u;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * a.acc_stride + sub * a.bn;
+#pragma unroll 1
+      for (int c = part * 16; c < a.bn; c += 64) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld_32x16(t_row + c, v);
+        tmem_ld_wait();
+        if (a.out_pool != nullptr) epilogue_slim16<true>(a, v, bs + c, pix, n0 + c, masked, valid, pix_pool, stage, lane);
+        else epilogue_slim16<false>(a, v, bs + c, pix, n0 + c, masked, valid, pix_pool, stage, lane);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(tempty_addr + buf * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // CTA-pair halo kernel (cta_group::2) for the refiner's 3x3 convolutions, plain and fused
 // nearest-upsample + concat.
 //
@@ -882,8 +1042,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
 // ---------------------------------------------------------------------------
 constexpr int kPairMaxA = 4, kPairMaxB = 16;
 
-template <bool kFast, bool kLean>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <bool kFast, bool kLean, int kEpiWarps>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * kEpiWarps, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_a2, const ConvArgs a) {
@@ -912,7 +1072,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
     if (a.up_mode) tma_prefetch_desc(&map_a2);
     for (int i = 0; i < nA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * (kEpiThreads / 32)); }
+    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -1051,7 +1211,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
   } else if (warp >= 4) {
-    run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, smem_u32(tempty_bar) & kPeerBitMask, bias_s, warp, lane,
+    if constexpr (kEpiWarps == kEpi16Warps)
+      run_epilogue_slim16(a, tmem_base, tfull_bar, smem_u32(tempty_bar) & kPeerBitMask, bias_s, warp, lane, tile0, tstep, hoff);
+    else
+      run_epilogue<kFast, kLean>(a, tmem_base, tfull_bar, smem_u32(tempty_bar) & kPeerBitMask, bias_s, warp, lane,
                                tile0, tstep, hoff);
   }
 
@@ -1244,13 +1407,14 @@ static EncodeTiledFn get_encode_fn() {
 
 // Experiment knobs from the environment, read ONCE per process (not per launch).
 struct ConvEnv {
-  int nbuf = 0, debug = 0, stages = 0, bgrp = 0, stage_out = -1, slim = 1;
+  int nbuf = 0, debug = 0, stages = 0, bgrp = 0, stage_out = -1, slim = 1, slim16 = 1;
   ConvEnv() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     nbuf = geti("MQ_CONV_NBUF");
     debug = geti("MQ_CONV_DEBUG");
     stages = geti("MQ_CONV_STAGES");
     bgrp = geti("MQ_PAIR_BGRP");
+    if (getenv("MQ_SLIM16")) slim16 = geti("MQ_SLIM16");              // 0 = eight epilogue warps everywhere
     if (getenv("MQ_SLIM")) slim = geti("MQ_SLIM");                    // 0 = always the generic lean body
     if (getenv("MQ_STAGE_OUT")) stage_out = geti("MQ_STAGE_OUT");     // 0 = never, 1 = bn <= 128 (default), 2 = always
   }
@@ -1383,11 +1547,15 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     // halo / CTA-pair kernels only (the tap-loop kernel sizes its ring before this point and serves 1x1 layers)
     a.stage_out = (lean && (pair || halo) && (mode == 2 || (mode == 1 && p->bn <= 128))) ? 1 : 0;
   }
-  const int stage_bytes = a.stage_out ? kStageBytes : 0;
   // `masked` rows are zeroed through the gain, which is right whenever a row mask is given at all (mask_pre before
   // APTx and mask_post after it both give 0 = aptx(0)); a mask pointer without either flag must not zero anything
   a.slim = (env.slim && lean && p->act && p->fast_tanh && p->res_mode == 0 &&
             (p->row_mask == nullptr || p->mask_pre || p->mask_post)) ? 1 : 0;
+  // sixteen epilogue warps: the 3x3 pair kernel's narrow layers (plain or fused up-conv output rows are handled by the
+  // eight-warp body: the 16-warp tile walk assumes one output row per input row)
+  a.slim16 = (env.slim16 && a.slim && pair && !pair1d && !up && p->bn % 64 == 0 && p->bn <= 128) ? 1 : 0;
+  if (a.slim16) a.stage_out = 1;
+  const int stage_bytes = a.stage_out ? kStageBytes : 0;   // 8 warps x 2 KB == 16 warps x 1 KB
 
   // --- tensor maps ---
   CUtensorMap map_a, map_b, map_a2;
@@ -1528,8 +1696,8 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   } while (0)
 #define MQ_LAUNCH_PAIR(FAST, LEAN)                                                                          \
   do {                                                                                                      \
-    MQ_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<FAST, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    conv_pair_kernel<FAST, LEAN><<<grid, kThreads, smem, stream>>>(map_a, map_b, map_a2, a);                \
+    MQ_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<FAST, LEAN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    conv_pair_kernel<FAST, LEAN, 8><<<grid, kThreads, smem, stream>>>(map_a, map_b, map_a2, a);             \
   } while (0)
 #define MQ_LAUNCH_PAIR1D(FAST, LEAN)                                                                        \
   do {                                                                                                      \
@@ -1542,6 +1710,9 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     } else {
       if (lean) MQ_LAUNCH_PAIR1D(false, true); else MQ_LAUNCH_PAIR1D(false, false);
     }
+  } else if (pair && a.slim16) {
+    MQ_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<true, true, kEpi16Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv_pair_kernel<true, true, kEpi16Warps><<<grid, kThreads16, smem, stream>>>(map_a, map_b, map_a2, a);
   } else if (pair) {
     if (p->fast_tanh) {
       if (lean) MQ_LAUNCH_PAIR(true, true); else MQ_LAUNCH_PAIR(true, false);

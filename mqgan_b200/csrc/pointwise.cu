@@ -834,22 +834,25 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
 // K12b/K14: refiner.post (C -> 1) + crop + mask + reproj + x_recon add.
 // Block = 4 frames of one batch element.
 // ---------------------------------------------------------------------------
-constexpr int kTailT = 4;
+constexpr int kTailT = 8;
 
 // taps: (B, T8, F, ldp) fp32, channel k = 3*(dt+1)+(df+1) holds sum_c x[.., c] * w[k][c] (a 1x1
 // tcgen05 GEMM, C -> 9).  post(x)[t,f] = bias + sum_k taps[t+dt, f+df, k].
+// Phase 2 (reproj, F -> M per frame) was one global load per FMA; now a thread owns one output channel m of four
+// frames and walks f four at a time: 4 coalesced weight loads + 4 shared-memory float4 reads feed 16 FMAs.
 __global__ void __launch_bounds__(256)
 refiner_tail_kernel(const float* __restrict__ taps, int ldp, const uint8_t* __restrict__ mask, int T, int T8,
                     int F, float bias, const float* __restrict__ reproj_t, int M,
                     const float* __restrict__ r, float* __restrict__ out) {
-  extern __shared__ float osm[];                // o[kTailT][F]
+  extern __shared__ __align__(16) float osm[];  // o[kTailT][Fp], Fp = F rounded up to 4 (zero tail)
+  const int Fp = (F + 3) & ~3;
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kTailT;
-  for (int i = threadIdx.x; i < kTailT * F; i += blockDim.x) {
-    const int lt = i / F, f = i - lt * F;
+  for (int i = threadIdx.x; i < kTailT * Fp; i += blockDim.x) {
+    const int lt = i / Fp, f = i - lt * Fp;
     const int t = t0 + lt;
     float acc = 0.0f;
-    if (t < T && !(mask != nullptr && mask[static_cast<int64_t>(b) * T + t] != 0)) {
+    if (f < F && t < T && !(mask != nullptr && mask[static_cast<int64_t>(b) * T + t] != 0)) {
       acc = bias;
 #pragma unroll
       for (int dt = -1; dt <= 1; ++dt) {
@@ -866,15 +869,32 @@ refiner_tail_kernel(const float* __restrict__ taps, int ldp, const uint8_t* __re
     osm[i] = acc;                                  // masked rows -> 0 (preencoder.py:198)
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kTailT * M; i += blockDim.x) {
-    const int lt = i / M, m = i - lt * M;
-    const int t = t0 + lt;
-    if (t >= T) continue;
-    float acc = 0.0f;
-    const float* orow = osm + lt * F;
-    for (int f = 0; f < F; ++f) acc = fmaf(__ldg(reproj_t + static_cast<int64_t>(f) * M + m), orow[f], acc);
-    const int64_t row = static_cast<int64_t>(b) * T + t;
-    out[row * M + m] = r[row * F + m] + acc;       // x_post = x_recon + residual (preencoder.py:499)
+  for (int idx = threadIdx.x; idx < M * (kTailT / 4); idx += blockDim.x) {
+    const int tg = idx / M, m = idx - tg * M;
+    const float* o0 = osm + (tg * 4) * Fp;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int f = 0; f < Fp; f += 4) {
+      float w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[e] = (f + e < F) ? __ldg(reproj_t + static_cast<int64_t>(f + e) * M + m) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 ov = *reinterpret_cast<const float4*>(o0 + j * Fp + f);
+        // same summation order per output as before: f ascending
+        acc[j] = fmaf(w[0], ov.x, acc[j]);
+        acc[j] = fmaf(w[1], ov.y, acc[j]);
+        acc[j] = fmaf(w[2], ov.z, acc[j]);
+        acc[j] = fmaf(w[3], ov.w, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + tg * 4 + j;
+      if (t < T) {
+        const int64_t row = static_cast<int64_t>(b) * T + t;
+        out[row * M + m] = r[row * F + m] + acc[j];  // x_post = x_recon + residual (preencoder.py:499)
+      }
+    }
   }
 }
 
@@ -1136,7 +1156,7 @@ extern "C" int mq_refiner_tail(const float* taps, int ldp, const uint8_t* mask, 
                                mq_stream_t stream) {
   MQ_REQUIRE(taps && reproj_t && r && out && B > 0 && T > 0 && T8 >= T && F >= M && ldp >= 9,
              "mq_refiner_tail: bad args");
-  const size_t smem = kTailT * static_cast<size_t>(F) * sizeof(float);
+  const size_t smem = kTailT * static_cast<size_t>((F + 3) & ~3) * sizeof(float);
   dim3 grid((T + kTailT - 1) / kTailT, B);
   refiner_tail_kernel<<<grid, 256, smem, STREAM(stream)>>>(taps, ldp, mask, T, T8, F, bias, reproj_t, M, r, out);
   MQ_CUDA_OK(cudaGetLastError());
