@@ -17,11 +17,16 @@ import os
 from collections import OrderedDict
 from typing import List, Optional, Sequence
 
+import threading
+
 import torch
 import torch.nn as nn
 
 from .engine import PreEncoderEngine
 from .spec import PreEncoderConfig, param_spec
+
+
+_ENGINE_LOCK = threading.Lock()
 
 
 def sequence_mask(max_length, x_lengths):
@@ -113,9 +118,11 @@ class PreEncoder(nn.Module):
                                "move the module with .to('cuda')")
         key = (dev, self.encoder_precision, self.decoder_precision) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._engine is None or key != self._engine_key:
-            self._engine = PreEncoderEngine(self.cfg, self.state_dict(), dev, self.encoder_precision,
-                                            decoder_precision=self.decoder_precision)
-            self._engine_key = key
+            with _ENGINE_LOCK:                  # the CLI drives one model from two compute threads
+                if self._engine is None or key != self._engine_key:
+                    self._engine = PreEncoderEngine(self.cfg, self.state_dict(), dev, self.encoder_precision,
+                                                    decoder_precision=self.decoder_precision)
+                    self._engine_key = key
         return self._engine
 
     @torch.no_grad()

@@ -313,3 +313,21 @@ def test_decode_rejects_out_of_range_indices():
     with pytest.raises((IndexError, RuntimeError)):
         model.decode(idx.cuda(), None)
     model.decode(torch.zeros(1, 16, dtype=torch.int64).cuda(), None)      # the engine is still usable afterwards
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_module_on_second_gpu_while_first_is_current():
+    """The reference accepts get_pre_encoder(path, 'cuda:1') without a torch.cuda.set_device: every launch path here
+    switches to the module's own device (ops.on_device), so results on cuda:1 equal those on cuda:0 bit for bit."""
+    cfg, sd, mel, lengths, fx = load_golden("tiny")
+    mask = sequence_mask(mel.shape[1], lengths).unsqueeze(1)
+    torch.cuda.set_device(0)
+    m0 = _model(cfg, sd)
+    ref_idx = m0.encode(mel.cuda(0), mask.cuda(0))
+    ref_out = m0.decode(ref_idx, mask.cuda(0))
+    m1 = _model(cfg, sd).to("cuda:1")
+    assert torch.cuda.current_device() == 0
+    idx = m1.encode(mel.to("cuda:1"), mask.to("cuda:1"))
+    out = m1.decode(idx, mask.to("cuda:1"))
+    assert idx.device.index == 1 and out.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(idx.cpu(), ref_idx.cpu()) and torch.equal(out.cpu(), ref_out.cpu())
