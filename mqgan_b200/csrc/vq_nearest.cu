@@ -321,14 +321,33 @@ __global__ void __launch_bounds__(kVqThreads, 1) vq_nearest_kernel(const VqArgs 
         const float m = fminf(fminf(fminf(fminf(m2[0], m2[1]), m2[2]), fminf(fminf(m2[3], m2[4]), m2[5])), fminf(m2[6], m2[7]));
         if (m < best) {
           // Taken by a warp whenever any of its 32 rows improves - at K = 8192 that is most units (a row improves
-          // ~ln K times, 32 rows share the branch), so the scan is plain select code without divergence.  A per-lane
-          // switch over the nine-column group that holds the minimum was measured and is no faster (the early units
-          // execute every case).
+          // ~ln K times, 32 rows share the branch), so the search for the first column attaining m is on the hot path.
+          // A compare + select chain is 126 instructions on the half-rate ALU pipe, which is what bounds this kernel;
+          // instead w_j = (sc_j - m) * 2^100 + j runs on the FMA pipe (the difference of two nearby floats is exact: 0
+          // exactly where sc_j == m, otherwise at least one ulp of m, which the factor lifts far above 64), and the
+          // minimum of the w_j - the same FMNMX3 tree - IS the lowest such column.
+          // (For |m| below 2^-60 one ulp of m times 2^100 no longer clears 64: that corner takes the plain scan.)
           best = m;
-          int jj = 63;
+          if (fabsf(m) < 0x1p-60f) {
+            int jj = 63;
 #pragma unroll
-          for (int j = 62; j >= 0; --j) jj = (sc[j] == m) ? j : jj;       // first (lowest) column attaining the min
-          bidx = k0 + jj;
+            for (int j = 62; j >= 0; --j) jj = (sc[j] == m) ? j : jj;
+            bidx = k0 + jj;
+            continue;
+          }
+          float w[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) w[j] = fmaf(sc[j] - m, 0x1p100f, static_cast<float>(j));
+          float w1[22];
+#pragma unroll
+          for (int j = 0; j < 21; ++j) w1[j] = fminf(fminf(w[3 * j], w[3 * j + 1]), w[3 * j + 2]);
+          w1[21] = w[63];
+          float w2[8];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) w2[j] = fminf(fminf(w1[3 * j], w1[3 * j + 1]), w1[3 * j + 2]);
+          w2[7] = w1[21];
+          const float wm = fminf(fminf(fminf(fminf(w2[0], w2[1]), w2[2]), fminf(fminf(w2[3], w2[4]), w2[5])), fminf(w2[6], w2[7]));
+          bidx = k0 + static_cast<int>(wm);
         }
       }
       // combine the four column parts of each row (lexicographic on (score, index)) through one 1 KB exchange area,

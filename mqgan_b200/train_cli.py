@@ -163,7 +163,11 @@ class Trainer:
         mc = config["model"]
         gen = mc["generator"]
         if float(gen.get("dropout", 0.0)) != 0.0:
-            print(f"Warning: generator.dropout = {gen['dropout']} ignored; this training step implements dropout 0.")
+            print(f"Warning: generator.dropout = {gen['dropout']} ignored; this training step implements dropout 0 "
+                  "(recorded as effective_dropout: 0.0 in every checkpoint's config).")
+        # the regularisation actually applied, so a checkpoint says what produced it (the reference also hard-wires
+        # p = 0.1 layers, preencoder.py:109,121,233, which this step does not apply either)
+        config.setdefault("training", {})["effective_dropout"] = 0.0
         self.cfg = S.PreEncoderConfig.from_yaml_dict(config)
         self.pd_cfg = S.PatchDiscConfig.from_patch_yaml(self.cfg.mel_channels, mc["discriminator_patch"])
         self.mb_cfg = S.MultiBinConfig.from_yaml(self.cfg.mel_channels, mc["discriminator_multibin"])
