@@ -375,7 +375,24 @@ def write_layer_table(path, table, workload, frames):
         f.write(f"\ntotal {total_ms:.3f} ms for {frames} frames\n")
 
 
-def full_parity(model, sd, cfg, mel_host, dev, mel_frames=16384, chunk=16):
+def reference_on_gpu(cfg, sd, dev):
+    """The UNMODIFIED reference PreEncoder as an fp32 CUDA module (TF32 off) - a second checker for the index gate:
+    north_star asks for indices "bit-exact against the fp32 reference", and this is that reference, run on the same
+    box over the same frames.  None when no copy of the reference is reachable."""
+    try:
+        from oracle import reference_runner as RR
+        ref = RR.import_preencoder()
+        if ref is None:
+            return None
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        return RR.build_model(ref, cfg, sd).to(dev)
+    except Exception as e:                                       # pragma: no cover
+        print(f"bench: reference-on-GPU checker unavailable ({e!r})", file=sys.stderr)
+        return None
+
+
+def full_parity(model, sd, cfg, mel_host, dev, mel_frames=16384, chunk=16, ref_model=None):
     """Checker, outside every timed region: float64 restatement on the GPU (oracle/gpu_checker.py) over ALL frames of
     the workload for the indices, and over ``mel_utts`` utterances for the re-encoded mels."""
     from oracle import gpu_checker as G
@@ -387,6 +404,7 @@ def full_parity(model, sd, cfg, mel_host, dev, mel_frames=16384, chunk=16):
     tau = 2e-4
     mel_err = mel_ref_max = 0.0
     num = den = 0.0
+    ref32 = {"frames": 0, "mismatch": 0, "mismatch_outside_tau": 0, "ref32_vs_fp64_mismatch": 0}
     with torch.no_grad():
         idx_gpu = model.encode(mel_host.to(dev), None)
         per = max(1, min(chunk, (16 * 1024) // T if T > 1024 else chunk))
@@ -398,6 +416,16 @@ def full_parity(model, sd, cfg, mel_host, dev, mel_frames=16384, chunk=16):
             mism += int(neq.sum())
             safe += int(ok.sum())
             safe_mism += int((neq & ok).sum())
+            if ref_model is not None:                    # the reference's own fp32 indices (micro-batches of <= 4096 frames:
+                sub_r = max(1, 4096 // T)                # its ConvBlock2D expands to 1 MiB per frame per tensor)
+                for c0 in range(0, min(per, B - b0), sub_r):
+                    xr = mel_host[b0 + c0:b0 + c0 + sub_r].to(dev)
+                    ir = ref_model.encode(xr, None)
+                    ng = ir != idx_gpu[b0 + c0:b0 + c0 + sub_r]
+                    ref32["mismatch"] += int(ng.sum())
+                    ref32["mismatch_outside_tau"] += int((ng & ok[c0:c0 + sub_r]).sum())
+                    ref32["ref32_vs_fp64_mismatch"] += int((ir != ref_idx[c0:c0 + sub_r]).sum())
+                    ref32["frames"] += int(ir.numel())
             if b0 < mel_utts:
                 n = min(per, mel_utts - b0)
                 sub = max(1, 4096 // T)              # the float64 refiner holds ~1 MB per frame
@@ -412,7 +440,13 @@ def full_parity(model, sd, cfg, mel_host, dev, mel_frames=16384, chunk=16):
                     den += float((ref * ref).sum())
     torch.cuda.synchronize()
     frames = B * T
-    return {"checker": "float64 restatement on the GPU (oracle/gpu_checker.py, pinned to the oracle / reference goldens in "
+    extra = {}
+    if ref_model is not None and ref32["frames"] > 0:
+        ref32["index_match"] = 1.0 - ref32["mismatch"] / ref32["frames"]
+        ref32["what"] = ("the unmodified reference PreEncoder.encode as an fp32 CUDA module (allow_tf32 off) on the same frames; "
+                         "ref32_vs_fp64_mismatch = how often the reference's own fp32 answer differs from the float64 checker")
+        extra["vs_reference_fp32_gpu"] = ref32
+    return {**extra, "checker": "float64 restatement on the GPU (oracle/gpu_checker.py, pinned to the oracle / reference goldens in "
                        "tests/test_oracle_golden.py); outside the timed region",
             "frames": frames, "index_mismatches": mism, "index_match": 1.0 - mism / frames,
             "safe_frames": safe, "safe_mismatch": safe_mism, "margin_tau": tau,
@@ -565,7 +599,11 @@ def main():
     mel_host = head.pop("mel_host")
     if world == 1 and not args.no_parity:
         try:
-            line["parity"] = full_parity(model, sd, cfg, mel_host, dev)
+            tf32_flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            ref_gpu = reference_on_gpu(cfg, sd, dev)
+            line["parity"] = full_parity(model, sd, cfg, mel_host, dev, ref_model=ref_gpu)
+            del ref_gpu
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_flags
         except Exception as e:                                   # the headline must survive a checker failure
             line["parity"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
