@@ -264,12 +264,22 @@ class LaunchProfiler:
 profiler = None
 
 
+NVTX = os.environ.get("MQ_NVTX", "0") == "1"     # NVTX range per library launch, named "<entry point> <layer tag>" (nsys / ncu --nvtx)
+
+
 def call(name: str, *args, meta=None) -> None:
     """Invoke a launching entry point and raise on a non-zero status."""
     global launch_count
     if profiler is not None:
         profiler.begin(name, meta)
-    rc = getattr(lib(), name)(*args)
+    if NVTX:
+        import torch
+        torch.cuda.nvtx.range_push(name + (" " + meta["tag"] if meta and meta.get("tag") else ""))
+    try:
+        rc = getattr(lib(), name)(*args)
+    finally:
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
     if rc != 0:
         check(rc, name)
     launch_count += 1

@@ -445,7 +445,7 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, N: int, H: int, W: int, *,
         p.out_split, p.split_ld, p.split_seg = out_split.data_ptr(), out_split.shape[-1], out_split.shape[-1] // nt
         p.split_kind = int(nt == 2)
     meta = None
-    if _lib.profiler is not None:
+    if _lib.profiler is not None or _lib.NVTX:
         pix = float(N) * H * W * hm
         if pc.up_taps:
             meta = {"tag": tag, "flops": 2.0 * pix * pc.cout * (pc.cin + pc.cin2) * 9,  # the reference's conv

@@ -204,17 +204,20 @@ def _cap_host_threads(world: int) -> None:
 
 def reencode_tree(run_batch: Callable[[torch.Tensor, List[int]], torch.Tensor], input_dir: str, output_dir: str,
                   batch_size: int, rank: int = 0, world: int = 1, progress: bool = True,
-                  prefetch: int = 2, sort_by_length: bool = False) -> Tuple[int, int]:
+                  prefetch: int = 2, sort_by_length: bool = False,
+                  files: Optional[Sequence[str]] = None) -> Tuple[int, int]:
     """Process this worker's share of the tree.  ``run_batch(batch (B,T,M) float32 CPU, lengths)``
     returns the re-encoded (B,T,M) tensor (any device).  Returns (files done, batches failed)."""
     _cap_host_threads(world)
-    files = list_npy_files(input_dir)
+    listed = files is not None              # run_multi_gpu lists (and sorts) once in the parent and hands the order down
+    if not listed:
+        files = list_npy_files(input_dir)
     if not files:
         print("Warning: No .npy files were found.")
         return 0, 0
     if rank == 0:
         print(f"Found {len(files)} spectrogram files to process.")
-    if sort_by_length:
+    if sort_by_length and not listed:
         files = sort_batches_by_length(files)
     batches = make_batches(files, batch_size)
     mine = shard_indices(len(batches), rank, world)
@@ -351,7 +354,7 @@ def finish_distributed(done: int, failed: int, backend: Optional[str] = None) ->
 
 
 def _worker(rank: int, world: int, make_model: Callable[[str], object], input_dir: str, output_dir: str,
-            batch_size: int, ret, sort_by_length: bool = False) -> None:
+            batch_size: int, ret, sort_by_length: bool = False, files: Optional[Sequence[str]] = None) -> None:
     import time
     torch.cuda.set_device(rank)
     t_load = time.time()
@@ -363,7 +366,7 @@ def _worker(rank: int, world: int, make_model: Callable[[str], object], input_di
 
     t0 = time.time()
     done, failed = reencode_tree(run, input_dir, output_dir, batch_size, rank, world, progress=(rank == 0),
-                                 sort_by_length=sort_by_length)
+                                 sort_by_length=sort_by_length, files=files)
     torch.cuda.synchronize()
     # (done, failed, model load seconds, processing start / end as epoch seconds): tools/cli_bench_multi.py reads the span
     ret[rank] = (done, failed, t0 - t_load, t0, time.time())
@@ -374,10 +377,15 @@ def run_multi_gpu(make_model: Callable[[str], object], input_dir: str, output_di
     """One worker process per GPU (``--gpus N``); each builds its own model copy."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
+    # the tree is listed - and, for --sort_by_length, its headers probed - once here, not once per worker (with eight
+    # workers the per-worker probe of all files took longer than the re-encoding itself)
+    files = list_npy_files(input_dir)
+    if sort_by_length and files:
+        files = sort_batches_by_length(files)
     with ctx.Manager() as mgr:
         ret = mgr.dict()
         procs = [ctx.Process(target=_worker, args=(r, gpus, make_model, input_dir, output_dir, batch_size, ret,
-                                                   sort_by_length))
+                                                   sort_by_length, files))
                  for r in range(gpus)]
         for p in procs:
             p.start()
