@@ -863,6 +863,14 @@ class TrainStep:
         self.last_recon = recon
         return outs
 
+    def _mark(self, name: str) -> None:
+        """Phase boundary for tools/train_phases.py (CUDA event on the step's stream); a no-op unless a list is attached."""
+        ev = getattr(self, "phase_events", None)
+        if ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e))
+
     def _step_body(self, real: Tensor, lengths: Tensor, gan: bool, use_fm: Optional[bool]) -> Dict[str, Tensor]:
         t = self.tcfg
         clip = t.get("clip_grad_norm", 1.0)
@@ -871,7 +879,9 @@ class TrainStep:
         real = real.to(self.device, non_blocking=True)
         lengths = lengths.to(self.device, non_blocking=True)
         ac = self.d_autocast_bf16
+        self._mark("start")
         recon_pre, recon_post = generator_forward(self.g, self.cfg, real, lengths, self.native_cb2d, self.cb2d_fast_tanh)
+        self._mark("generator forward")
         out: Dict[str, Tensor] = {"loss_d": real.new_zeros(())}
         if gan:                                                                     # _train_discriminator
             self.red_d.zero()
@@ -897,11 +907,14 @@ class TrainStep:
                 rm2, fm2 = [t_[:nb] for t_ in mk2], [t_[nb:] for t_ in mk2]
             loss_d = self.lecam.d_loss(rl, fl, rm, fm)
             loss_d = loss_d + sum(self.lecam.d_loss(r, f, rm2[0], fm2[0]) for r, f in zip(rl2, fl2)) / len(rl2)
+            self._mark("D step: discriminators forward (real + fake) + losses")
             loss_d.backward()
             self.red_d.finish()
+            self._mark("D step: backward")
             if clip:
                 torch.nn.utils.clip_grad_norm_(self.d_params(), clip)
             self.opt_d.step()
+            self._mark("D step: clip + Adam")
             out["loss_d"] = loss_d.detach()
         # _train_generator
         self.red_g.zero()
@@ -935,7 +948,9 @@ class TrainStep:
                     loss_fm = 0.5 * (fm_d1 + fm_mbd / max(len(gf2), 1))
             total = (loss_recon_pre * lw.get("recon_lambda_pre", 1.0) + loss_recon_post * lw.get("recon_lambda_post", 2.0)
                      + loss_gan * gl_lambda + loss_fm * fm_lambda)
+            self._mark("G step: mel losses + discriminators forward (fake) + GAN / FM losses")
             total.backward()
+            self._mark("G step: backward (discriminators dgrad + generator)")
         finally:
             for p in d_all:
                 p.requires_grad_(True)
@@ -943,6 +958,7 @@ class TrainStep:
         if clip:
             torch.nn.utils.clip_grad_norm_(list(self.g.values()), clip)
         self.opt_g.step()
+        self._mark("G step: reduce + clip + Adam")
         out.update(loss_g_total=total.detach(), loss_recon_pre=loss_recon_pre.detach(),
                    loss_recon_post=loss_recon_post.detach(), loss_gan=loss_gan.detach(), loss_fm=loss_fm.detach())
         self.last_recon = (recon_pre.detach(), recon_post.detach())
