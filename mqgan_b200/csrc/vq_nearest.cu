@@ -214,13 +214,27 @@ __global__ void __launch_bounds__(kVqThreads, 1) vq_nearest_kernel(const VqArgs 
         for (int c8 = 0; c8 < 8; ++c8) {
           if (c8 * 8 < slice_cols) {
             float x8[8];
+            if ((a.d & 3) == 0) {                     // 128-bit loads when the row pitch allows (d = 4, 8, ..., 64)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int col = c8 * 8 + e;
-              float x = 0.0f;
-              if (col < a.d) x = live ? __ldg(zr + col) : 0.0f;
-              else if (a.fold && col < a.d + 3) x = a.zconst;
-              x8[e] = x;
+              for (int h = 0; h < 2; ++h) {
+                const int col0 = c8 * 8 + 4 * h;
+                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col0 < a.d) {
+                  if (live) f = __ldg(reinterpret_cast<const float4*>(zr + col0));
+                } else if (a.fold) {                   // d % 4 == 0: the three constant columns start a 4-column group
+                  if (col0 == a.d) f = make_float4(a.zconst, a.zconst, a.zconst, 0.f);
+                }
+                x8[4 * h] = f.x; x8[4 * h + 1] = f.y; x8[4 * h + 2] = f.z; x8[4 * h + 3] = f.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int col = c8 * 8 + e;
+                float x = 0.0f;
+                if (col < a.d) x = live ? __ldg(zr + col) : 0.0f;
+                else if (a.fold && col < a.d + 3) x = a.zconst;
+                x8[e] = x;
+              }
             }
             uint32_t w0[4], w1[4];
 #pragma unroll
