@@ -176,6 +176,14 @@ __device__ __forceinline__ void epilogue_generic(const ConvArgs& a, const uint32
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<float4*>(op + 4 * g) =
               make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+      } else if ((nvalid & 3) == 0) {
+        // a partial chunk whose width is a multiple of four channels still goes out as 16-byte stores (the refiner's
+        // 64 -> 9 tap-plane GEMM is declared 12 wide for this: nine 4-byte stores per lane at a 48-byte pitch were
+        // three times the L1 tag traffic and paced that kernel)
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (4 * g < nvalid)
+            *reinterpret_cast<float4*>(op + 4 * g) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)

@@ -234,7 +234,11 @@ class PreEncoderEngine:
             pfx = f"refiner.ups.{i}.conv.conv1"
             self.ref_ups[i]["conv1_up"] = pack_upconv(w[pfx + ".weight"], w[pfx + ".bias"], chs[d - i], chs[d - i - 1]).to(dev)
         # refiner.post: (1, C, 3, 3) -> (9, C) with tap = 3*(dt+1) + (df+1), run as a 1x1 GEMM C -> 9
-        self.tail = pack_conv(w["refiner.post.weight"].reshape(chs[0], 9).t().contiguous(), None, "linear", dp).to(dev)
+        # ... declared 12 wide (three zero rows): the planes buffer has 12 floats per pixel anyway, and a width that is a
+        # multiple of four lets the epilogue write it with 16-byte stores
+        w9 = torch.zeros(12, chs[0])
+        w9[:9] = w["refiner.post.weight"].reshape(chs[0], 9).t()
+        self.tail = pack_conv(w9, None, "linear", dp).to(dev)
         self.tail_b = float(w["refiner.post.bias"].reshape(()))
         self.reproj_t = w["refiner.reproj.weight"].t().float().contiguous().to(dev)       # (F, M)
 
