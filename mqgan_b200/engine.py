@@ -613,7 +613,8 @@ class PreEncoderEngine:
             skip = skips.pop()
             if self.fuse_upcat:
                 # upsample + cat + mask folded into conv1's operand loads (no (Cx+Cs)-channel copy)
-                ops.zero_rows(skip, up[l], down[l])
+                if m8 is not None or T8 != T:       # without a mask and without T padding both masks are all-valid
+                    ops.zero_rows(skip, up[l], down[l])
                 t = torch.empty(B, H[l], F, chs[l], dtype=torch.bfloat16, device=dev)
                 ops.conv_gemm(x, self.ref_ups[i]["conv1_up"], B, H[l + 1], F, x2=skip, act=True, out_bf16=t,
                               tag=f"ref.up{i}.conv1")
