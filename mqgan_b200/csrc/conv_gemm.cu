@@ -62,6 +62,8 @@ struct ConvArgs {
   int tile_rows;                  // rows of H one tile covers: bh * msub (x2 for a CTA pair)
   int pair_boxb_off, pair_tx0, pair_tx1;   // conv_pair_kernel: byte offset of the second skip box, A bytes per chunk of group 0 / 1
   int pair_bgrp;                  // taps per weight-ring slot (one barrier round trip and one commit per slot)
+  int b_resident;                 // conv_pair_kernel: the whole weight set of the (single) N tile stays in shared memory for the
+                                  // kernel's lifetime - loaded once, no weight ring, no weight barriers in the tile loop
   int debug;                      // bench-only bottleneck probes (MQ_CONV_DEBUG): 1 no epilogue math/stores, 2 no MMA, 4 no TMA, 8 no stores
   uint32_t a_tx_bytes, b_tile_bytes;
   // epilogue
@@ -1061,7 +1063,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
   const int nA = a.halo_nA, nB = a.halo_nB;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + nA * a.halo_slot_bytes;
-  uint8_t* tail = smem_b + nB * a.pair_bgrp * a.b_tile_bytes;
+  uint8_t* tail = smem_b + (a.b_resident ? a.taps * a.kchunks : nB * a.pair_bgrp) * a.b_tile_bytes;
   uint64_t* fullA = reinterpret_cast<uint64_t*>(tail);        // used in the leader only
   uint64_t* emptyA = fullA + kPairMaxA;                       // per CTA (multicast commit)
   uint64_t* fullB = emptyA + kPairMaxA;                       // leader only
@@ -1103,6 +1105,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const int brow_half = static_cast<int>(rank) * (a.bn >> 1);
+      if (a.b_resident && tile0 < a.num_tiles) {
+        // Weights-stationary layers (one N tile, K loop of one or two chunks): all taps x chunks of this CTA's half of the
+        // weight tile are fetched once.  With a ring, the 64-channel layers had room for exactly one tile's worth of
+        // weight slots next to their two 85 KB halo slots, so every tile started by waiting for its own weights.
+        const uint32_t fb = smem_u32(&fullB[0]) & kPeerBitMask;
+        const int nkb = a.taps * a.kchunks;
+        if (rank == 0) mbar_expect_tx(&fullB[0], 2u * a.b_tile_bytes * nkb);
+        for (int kb = 0; kb < nkb; ++kb)
+          tma_load_2d_2cta(&map_b, fb, smem_b + kb * a.b_tile_bytes, kb * kBlockK, brow_half);
+      }
       for (int tile = tile0; tile < a.num_tiles; tile += tstep) {
         int n_idx, h0, w0, n0, par;
         decode_tile(a, tile, n_idx, h0, w0, n0, par);
@@ -1133,6 +1145,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
               tma_load_5d_2cta(&map_a2, fa, dst + a.pair_boxb_off, kc * kBlockK, w0 - 1, par ^ 1, hc - 1 + par, n_idx);
             }
             if (++sa == nA) { sa = 0; pa ^= 1; }
+            if (a.b_resident) continue;
             for (int tap = t0; tap < t1; tap += a.pair_bgrp) {
               mbar_wait(&emptyB[sb], pb ^ 1);
               if (MQ_PROBE(a, 4)) {
@@ -1159,6 +1172,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
+      const bool resident = a.b_resident != 0;
+      if (resident && tile0 < a.num_tiles) {
+        mbar_wait(&fullB[0], 0);                  // the one-off weight load
+        tc_fence_after();
+      }
+      const uint32_t b_res_lo = umma_desc_lo(smem_u32(smem_b));
       for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
         const int par = (tile / a.tiles_n) % a.par_tiles;
         const uint32_t buf = it % a.nbuf;
@@ -1172,11 +1191,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
           const int t0 = grp ? a.up_taps : 0, t1 = grp ? a.taps : ntap0;
           for (int kc = 0; kc < nch; ++kc) {
             mbar_wait(&fullA[sa], pa);
+            if (resident) tc_fence_after();
             const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + sa * a.halo_slot_bytes));
             for (int tg = t0; tg < t1; tg += a.pair_bgrp) {
-              mbar_wait(&fullB[sb], pb);
-              tc_fence_after();
-              const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + sb * a.pair_bgrp * a.b_tile_bytes));
+              if (!resident) {
+                mbar_wait(&fullB[sb], pb);
+                tc_fence_after();
+              }
+              // ring slot of this tap group, or the group's place in the resident weight image (tap-major, then chunk)
+              const uint32_t b_lo = resident ? b_res_lo + ((tg * nch + kc) * (a.b_tile_bytes >> 4))
+                                             : umma_desc_lo(smem_u32(smem_b + sb * a.pair_bgrp * a.b_tile_bytes));
+              const uint32_t b_step = resident ? nch * (a.b_tile_bytes >> 4) : (a.b_tile_bytes >> 4);
               for (int j = 0; j < a.pair_bgrp; ++j) {
                 const int tap = tg + j;
                 // offset (16-byte units) of this tap's shifted view inside the halo slot
@@ -1190,7 +1215,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                   toff = static_cast<uint32_t>(((dh != 0 ? a.pair_boxb_off : 0) >> 4) + ((dh == 1 ? kHaloW : 0) + tx) * 8);
                 }
                 const uint32_t a_tap = a_lo + toff;
-                const uint32_t b_tap = b_lo + j * (a.b_tile_bytes >> 4);
+                const uint32_t b_tap = b_lo + j * b_step;
                 if (elect_one_sync()) {
 #pragma unroll
                   for (int sub = 0; sub < 4; ++sub) {
@@ -1205,9 +1230,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
                 __syncwarp();
                 acc = 1;
               }
-              if (elect_one_sync()) umma_commit_2cta(&emptyB[sb]);
-              __syncwarp();
-              if (++sb == nB) { sb = 0; pb ^= 1; }
+              if (!resident) {
+                if (elect_one_sync()) umma_commit_2cta(&emptyB[sb]);
+                __syncwarp();
+                if (++sb == nB) { sb = 0; pb ^= 1; }
+              }
             }
             if (elect_one_sync()) umma_commit_2cta(&emptyA[sa]);
             __syncwarp();
@@ -1415,13 +1442,14 @@ static EncodeTiledFn get_encode_fn() {
 
 // Experiment knobs from the environment, read ONCE per process (not per launch).
 struct ConvEnv {
-  int nbuf = 0, debug = 0, stages = 0, bgrp = 0, stage_out = -1, slim = 1, slim16 = 1;
+  int nbuf = 0, debug = 0, stages = 0, bgrp = 0, stage_out = -1, slim = 1, slim16 = 1, b_resident = 1;
   ConvEnv() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     nbuf = geti("MQ_CONV_NBUF");
     debug = geti("MQ_CONV_DEBUG");
     stages = geti("MQ_CONV_STAGES");
     bgrp = geti("MQ_PAIR_BGRP");
+    if (getenv("MQ_B_RESIDENT")) b_resident = geti("MQ_B_RESIDENT");   // 0 = always the weight ring
     if (getenv("MQ_SLIM16")) slim16 = geti("MQ_SLIM16");              // 0 = eight epilogue warps everywhere
     if (getenv("MQ_SLIM")) slim = geti("MQ_SLIM");                    // 0 = always the generic lean body
     if (getenv("MQ_STAGE_OUT")) stage_out = geti("MQ_STAGE_OUT");     // 0 = never, 1 = bn <= 128 (default), 2 = always
@@ -1685,6 +1713,18 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     MQ_REQUIRE(nB >= 2, "mq_conv_gemm: pair mode does not fit shared memory (msub=%d bn=%d)", a.msub, p->bn);
     a.halo_nA = nA; a.halo_nB = nB; a.pair_bgrp = bgrp;
     smem = 1024 + nA * a.halo_slot_bytes + nB * bgrp * static_cast<int>(a.b_tile_bytes) + tail_bytes;
+    // weights-stationary: a single N tile whose taps x chunks fit beside two halo slots (the 64 -> 64 and 64 -> 128
+    // layers) keeps its weights in shared memory for the whole kernel instead of cycling them through the ring
+    if (env.b_resident && !up && a.nseg == 1 && a.tiles_n == 1 && p->taps % bgrp == 0) {
+      const int resident = p->taps * a.kchunks * static_cast<int>(a.b_tile_bytes);
+      const int nA2 = 2;
+      if (nA2 * a.halo_slot_bytes + resident <= budget) {
+        a.b_resident = 1;
+        a.halo_nA = nA2;
+        a.halo_nB = 1;
+        smem = 1024 + nA2 * a.halo_slot_bytes + resident + tail_bytes;
+      }
+    }
     const int pairs = sms / 2;
     grid = 2 * (a.num_tiles < pairs ? a.num_tiles : pairs);
   }
