@@ -461,7 +461,15 @@ def vq_microbench(dev, peaks, n=1 << 20):
     that must read each of the N x K fp32 scores from tensor memory once (64 B/clk/SM)."""
     import numpy as np
     from mqgan_b200 import ops, _lib
-    from oracle import preencoder_oracle as O
+
+    def implicit_codebook(levels):
+        """FSQ's implicit codebook (quantizer.py:101-104, 183-187): every index's code in [-1, 1]^D - input data of the
+        microbench, built here (the oracle is only ever the checker)."""
+        lv = torch.tensor(levels)
+        basis = torch.cumprod(torch.tensor([1] + list(levels[:-1])), dim=0)
+        digits = (torch.arange(int(np.prod(levels)))[:, None] // basis) % lv
+        hw = lv // 2
+        return ((digits - hw) / hw).float()
     # measured ceiling: the chip's TMEM read bandwidth with the epilogue's own tcgen05.ld pattern and nothing else
     sink = torch.zeros(1, device=dev)
     iters = 2000
@@ -482,7 +490,7 @@ def vq_microbench(dev, peaks, n=1 << 20):
         g = torch.Generator().manual_seed(0)
         if levels is not None:
             K, D = int(np.prod(levels)), len(levels)
-            cb = O.fsq_indices_to_codes(torch.arange(K), levels)
+            cb = implicit_codebook(levels)
             z = (torch.randn(n, D, generator=g) * 0.6).clamp(-1.05, 1.05)
         else:
             K, D = shape
