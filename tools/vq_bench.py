@@ -10,7 +10,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from mqgan_b200 import ops
-from oracle import preencoder_oracle as O
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 dev = "cuda"
@@ -21,7 +20,9 @@ for name, levels, shape in CASES:
     g = torch.Generator().manual_seed(0)
     if levels is not None:
         K, D = int(np.prod(levels)), len(levels)
-        cb = O.fsq_indices_to_codes(torch.arange(K), levels)
+        lv = torch.tensor(levels)                                   # FSQ implicit codebook (quantizer.py:101-104, 183-187)
+        basis = torch.cumprod(torch.tensor([1] + list(levels[:-1])), dim=0)
+        cb = ((((torch.arange(K)[:, None] // basis) % lv) - lv // 2) / (lv // 2)).float()
         z = (torch.randn(N, D, generator=g) * 0.6).clamp(-1.05, 1.05)
     else:
         K, D = shape
