@@ -45,6 +45,18 @@ constexpr int kStageBytes = (kEpiThreads / 32) * kStageBytesPerWarp;
 #define MQ_PROBE(a, bit) 0
 #endif
 
+#ifdef MQ_CONV_PROBES
+// cycle counters of the epilogue role, summed over all epilogue warps' lane 0 (probe build only; tools/conv_cycles.py):
+// [0] waiting for the accumulator, [1] tcgen05.ld + wait, [2] epilogue body (math + stores), [3] whole tile loop,
+// [4] tiles x warps, [5] MMA warp: waiting for a free accumulator, [6] MMA warp: waiting for operands, [7] MMA warp total
+__device__ unsigned long long mq_probe_cycles[8];
+#define MQ_CLK() clock64()
+#define MQ_ACC(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&mq_probe_cycles[i], static_cast<unsigned long long>(v)); } while (0)
+#else
+#define MQ_CLK() 0LL
+#define MQ_ACC(i, v) do { } while (0)
+#endif
+
 struct ConvArgs {
   int N, H, W;
   int tiles_h, tiles_w, tiles_n, num_tiles;
@@ -497,6 +509,8 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
   uint8_t mnext[4] = {0, 0, 0, 0};
   if (a.row_mask != nullptr && tile0 < a.num_tiles) fetch_masks(tile0, mnext);
   int it = 0;
+  long long pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0, pk4 = 0;      // probe build: cycle sums, flushed once at the end
+  (void)pk0; (void)pk1; (void)pk2; (void)pk3; (void)pk4;
   for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
     int n_idx, h0, w0, n0, par;
     decode_tile(a, tile, n_idx, h0, w0, n0, par);
@@ -508,8 +522,12 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
     for (int sub = 0; sub < 4; ++sub) mbits |= (mnext[sub] != 0 ? 1u : 0u) << sub;
     if (a.row_mask != nullptr && tile + tstep < a.num_tiles) fetch_masks(tile + tstep, mnext);
 
+    const long long pc0 = MQ_CLK();
     mbar_wait(&tfull_bar[buf], (it / a.nbuf) & 1);
     tc_fence_after();
+    const long long pc1 = MQ_CLK();
+    pk0 += pc1 - pc0;
+    pk4 += 1;
 #pragma unroll 1
     for (int sub = 0; sub < a.msub; ++sub) {
       const int h = h0 + sub * a.bh + lh, w = w0 + lw;
@@ -526,11 +544,14 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(0.25f * static_cast<float>(j + lane));
         } else {
+          const long long pl0 = MQ_CLK();
           tmem_ld_32x32(t_row + c, v);
           tmem_ld_wait();
+          pk1 += MQ_CLK() - pl0;
         }
         const int co0 = n0 + c;
         if (MQ_PROBE(a, 1)) continue;
+        const long long pb0 = MQ_CLK();
         if (kLean && kFast && a.slim) {
           if (a.out_pool != nullptr) {
             if (stage != nullptr) epilogue_slim<true, true>(a, v, bs + c, pix, co0, masked, valid, pix_pool, stage, lane);
@@ -544,13 +565,16 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
         } else {
           if (valid && co0 < a.cout) epilogue_generic<kFast>(a, v, bs + c, pix, co0, masked);
         }
+        pk2 += MQ_CLK() - pb0;
       }
     }
     // all TMEM reads of this buffer are complete (tcgen05.wait::ld above)
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(tempty_addr + buf * 8);
+    pk3 += MQ_CLK() - pc0;
   }
+  MQ_ACC(0, pk0); MQ_ACC(1, pk1); MQ_ACC(2, pk2); MQ_ACC(3, pk3); MQ_ACC(4, pk4);
 }
 
 template <bool kFast, bool kLean>
@@ -1173,6 +1197,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
       uint32_t pa = 0, pb = 0;
       int it = 0;
       const bool resident = a.b_resident != 0;
+      long long pm5 = 0, pm6 = 0, pm7 = 0;
+      (void)pm5; (void)pm6; (void)pm7;
       if (resident && tile0 < a.num_tiles) {
         mbar_wait(&fullB[0], 0);                  // the one-off weight load
         tc_fence_after();
@@ -1181,8 +1207,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
       for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
         const int par = (tile / a.tiles_n) % a.par_tiles;
         const uint32_t buf = it % a.nbuf;
+        const long long pm0 = MQ_CLK();
         mbar_wait(&tempty_bar[buf], ((it / a.nbuf) & 1) ^ 1);
         tc_fence_after();
+        pm5 += MQ_CLK() - pm0;
         const uint32_t d_tmem = tmem_base + buf * a.acc_stride;
         uint32_t acc = 0;
         for (int seg = 0; seg < nsegs; ++seg)
@@ -1190,7 +1218,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
           const int nch = grp ? a.kchunks2 : a.kchunks;
           const int t0 = grp ? a.up_taps : 0, t1 = grp ? a.taps : ntap0;
           for (int kc = 0; kc < nch; ++kc) {
+            const long long pa0 = MQ_CLK();
             mbar_wait(&fullA[sa], pa);
+            pm6 += MQ_CLK() - pa0;
             if (resident) tc_fence_after();
             const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + sa * a.halo_slot_bytes));
             for (int tg = t0; tg < t1; tg += a.pair_bgrp) {
@@ -1243,7 +1273,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         if (elect_one_sync()) umma_commit_2cta(&tfull_bar[buf]);
         __syncwarp();
+        pm7 += MQ_CLK() - pm0;
       }
+      MQ_ACC(5, pm5); MQ_ACC(6, pm6); MQ_ACC(7, pm7);
     }
   } else if (warp >= 4) {
     if constexpr (kEpiWarps == kEpi16Warps)
@@ -1468,6 +1500,18 @@ static int conv_smem_bytes(int stages, int a_stage_bytes, int b_tile_bytes) {
 }  // namespace mq
 
 using namespace mq;
+
+#ifdef MQ_CONV_PROBES
+extern "C" int mq_conv_probe_cycles(unsigned long long* out8, int reset) {
+  MQ_CUDA_OK(cudaDeviceSynchronize());
+  MQ_CUDA_OK(cudaMemcpyFromSymbol(out8, mq_probe_cycles, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    MQ_CUDA_OK(cudaMemcpyToSymbol(mq_probe_cycles, z, sizeof(z)));
+  }
+  return 0;
+}
+#endif
 
 extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
