@@ -60,26 +60,33 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// try_wait suspends the thread until the phase completes or a time limit passes.  With the default limit a waiting warp
+// comes back every ~150 clocks: in the wide refiner layers, whose epilogue warps wait for an accumulator 70 % of the time,
+// these polls were half of all executed instructions (ncu source page of mid.conv1) - issue slots and power on a
+// power-capped step.  The hint asks for a longer sleep; completion still wakes the thread at once.
+#ifndef MQ_MBAR_SUSPEND_NS
+#define MQ_MBAR_SUSPEND_NS 2000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(MQ_MBAR_SUSPEND_NS))
       : "memory");
   return ok != 0;
 }
 
 // Bounded spin: a mis-programmed pipeline traps (reported as a launch failure) instead of
-// hanging the GPU.  2^26 polls of a ~100-cycle try_wait is several seconds.
+// hanging the GPU.  2^24 polls of a try_wait that sleeps 0.1 - 2 us each is 1 - 30 seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 

@@ -49,7 +49,7 @@ constexpr int kStageBytes = (kEpiThreads / 32) * kStageBytesPerWarp;
 // cycle counters of the epilogue role, summed over all epilogue warps' lane 0 (probe build only; tools/conv_cycles.py):
 // [0] waiting for the accumulator, [1] tcgen05.ld + wait, [2] epilogue body (math + stores), [3] whole tile loop,
 // [4] tiles x warps, [5] MMA warp: waiting for a free accumulator, [6] MMA warp: waiting for operands, [7] MMA warp total
-__device__ unsigned long long mq_probe_cycles[8];
+__device__ unsigned long long mq_probe_cycles[12];
 #define MQ_CLK() clock64()
 #define MQ_ACC(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&mq_probe_cycles[i], static_cast<unsigned long long>(v)); } while (0)
 #else
@@ -74,6 +74,7 @@ struct ConvArgs {
   int tile_rows;                  // rows of H one tile covers: bh * msub (x2 for a CTA pair)
   int pair_boxb_off, pair_tx0, pair_tx1;   // conv_pair_kernel: byte offset of the second skip box, A bytes per chunk of group 0 / 1
   int pair_bgrp;                  // taps per weight-ring slot (one barrier round trip and one commit per slot)
+  int mma_issuers;                // conv_pair_kernel: 1, or 2 = warps 1 and 2 of the leader each issue the MMAs of half the sub-tiles
   int b_resident;                 // conv_pair_kernel: the whole weight set of the (single) N tile stays in shared memory for the
                                   // kernel's lifetime - loaded once, no weight ring, no weight barriers in the tile loop
   int debug;                      // bench-only bottleneck probes (MQ_CONV_DEBUG): 1 no epilogue math/stores, 2 no MMA, 4 no TMA, 8 no stores
@@ -919,19 +920,27 @@ __device__ __forceinline__ uint4 stage16_read(const uint8_t* st, int px, int vec
   return *reinterpret_cast<const uint4*>(st + px * 32 + ((vec ^ ((px >> 2) & 1)) << 4));
 }
 
+// Store addressing without shuffles: a sub-tile of the pair kernel is 16 rows x 8 pixels, so the lane that STORES pixel
+// px of the warp's 32 (pass it, px = 16 it + lane / 2) knows that pixel's row and column from its own lane id.  The
+// pointers and bounds of both passes (and of the pooled row pair) are computed once per sub-tile, before the TMEM load
+// lands; the chunk body is then load-free index arithmetic: math -> stage -> 16-byte predicated stores.
+struct Slim16Out {
+  __nv_bfloat16* p0;        // pass 0: pixel (row 4 q + lane / 16, column (lane / 2) % 8), channel 8 (lane % 2) of the N tile
+  __nv_bfloat16* pp;        // pooled pixel lane / 2 of the warp's 16
+  int64_t pass_step;        // elements between pass 0 and pass 1 (two image rows)
+  bool ok0, ok1, okp;
+};
+
 template <bool kPool>
-__device__ __forceinline__ void epilogue_slim16(const ConvArgs& a, const uint32_t (&v)[16], const float* bs, int64_t pix,
-                                                int co0, bool masked, bool valid, int64_t pix_pool, uint8_t* stage,
-                                                int lane) {
-  const float g = masked ? 0.0f : a.gamma;
+__device__ __forceinline__ void epilogue_slim16(const ConvArgs& a, const uint32_t (&v)[16], const float4 (&b4)[4], float g,
+                                                float pool_half, const Slim16Out& o, int c, uint8_t* stage, int lane) {
   float x[16];
 #pragma unroll
   for (int q4 = 0; q4 < 4; ++q4) {
-    const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * q4);
-    x[4 * q4] = __uint_as_float(v[4 * q4]) + b4.x;
-    x[4 * q4 + 1] = __uint_as_float(v[4 * q4 + 1]) + b4.y;
-    x[4 * q4 + 2] = __uint_as_float(v[4 * q4 + 2]) + b4.z;
-    x[4 * q4 + 3] = __uint_as_float(v[4 * q4 + 3]) + b4.w;
+    x[4 * q4] = __uint_as_float(v[4 * q4]) + b4[q4].x;
+    x[4 * q4 + 1] = __uint_as_float(v[4 * q4 + 1]) + b4[q4].y;
+    x[4 * q4 + 2] = __uint_as_float(v[4 * q4 + 2]) + b4[q4].z;
+    x[4 * q4 + 3] = __uint_as_float(v[4 * q4 + 3]) + b4[q4].w;
   }
   uint32_t u[8];
   if (a.beta == 1.0f) {
@@ -953,40 +962,30 @@ __device__ __forceinline__ void epilogue_slim16(const ConvArgs& a, const uint32_
   stage16_write(stage, lane, u);
   __syncwarp();
   {
-    const int vec = lane & 1;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int px = it * 16 + (lane >> 1);
-      const int64_t pix_o = __shfl_sync(0xffffffffu, pix, px);
-      const bool valid_o = __shfl_sync(0xffffffffu, static_cast<int>(valid), px) != 0;
-      const uint4 w4 = stage16_read(stage, px, vec);
-      if (valid_o) *reinterpret_cast<uint4*>(a.out_bf16 + pix_o * a.bf16_ld + a.bf16_coff + co0 + 8 * vec) = w4;
-    }
+    const int vec = lane & 1, px = lane >> 1;
+    const uint4 w0 = stage16_read(stage, px, vec);
+    const uint4 w1 = stage16_read(stage, 16 + px, vec);
+    if (o.ok0) *reinterpret_cast<uint4*>(o.p0 + c) = w0;
+    if (o.ok1) *reinterpret_cast<uint4*>(o.p0 + o.pass_step + c) = w1;
   }
-  __syncwarp();
   if (kPool) {
-    const bool pm = (__shfl_xor_sync(0xffffffffu, static_cast<int>(masked), 8) != 0) || masked;
-    const float hf = pm ? 0.0f : 0.5f;
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(hf, hf);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(pool_half, pool_half);
     uint32_t r[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint32_t o = __shfl_xor_sync(0xffffffffu, u[j], 8);
+      const uint32_t ot = __shfl_xor_sync(0xffffffffu, u[j], 8);
       const __nv_bfloat162 s2 = __hmul2(__hadd2(*reinterpret_cast<const __nv_bfloat162*>(&u[j]),
-                                                *reinterpret_cast<const __nv_bfloat162*>(&o)), h2);
+                                                *reinterpret_cast<const __nv_bfloat162*>(&ot)), h2);
       r[j] = *reinterpret_cast<const uint32_t*>(&s2);
     }
+    __syncwarp();                                              // pass reads of the stage tile are done
     const int prow = (lane & 7) | ((lane >> 4) << 3);          // pooled pixel 0..15 owned by lanes 0-7, 16-23
     if ((lane & 8) == 0) stage16_write(stage, prow, r);
     __syncwarp();
-    const int px = lane >> 1, vec = lane & 1;
-    const int src = (px & 7) | ((px >> 3) << 4);
-    const int64_t pp_o = __shfl_sync(0xffffffffu, pix_pool, src);
-    const bool valid_o = __shfl_sync(0xffffffffu, static_cast<int>(valid), src) != 0;
-    const uint4 w4 = stage16_read(stage, px, vec);
-    if (valid_o) *reinterpret_cast<uint4*>(a.out_pool + pp_o * a.pool_ld + co0 + 8 * vec) = w4;
-    __syncwarp();
+    const uint4 w4 = stage16_read(stage, lane >> 1, lane & 1);
+    if (o.okp) *reinterpret_cast<uint4*>(o.pp + c) = w4;
   }
+  __syncwarp();
 }
 
 // The epilogue role with sixteen warps (warps 4..19): warp (q, part) owns TMEM lanes [32 q, +32) and the 16-column
@@ -997,9 +996,9 @@ __device__ __forceinline__ void run_epilogue_slim16(const ConvArgs& a, uint32_t 
   uint8_t* stage = reinterpret_cast<uint8_t*>(bias_s + kBiasSmemFloats) + (warp - 4) * kStage16BytesPerWarp;
   const int q = warp & 3;
   const int part = (warp - 4) >> 2;
-  const int r = q * 32 + lane;
-  const int lh = r / a.bw;
-  const int lw = r - lh * a.bw;
+  const int lh = q * 4 + (lane >> 3);                 // own accumulator row: pixel (lh, lane % 8) of the 16 x 8 sub-tile
+  const int slh = q * 4 + (lane >> 4), slw = (lane >> 1) & 7;      // pixel this lane stores in pass 0 (pass 1: two rows down)
+  const int plh = q * 4 + ((lane >> 4) << 1);                       // first row of the pooled pair this lane stores
   const int et = threadIdx.x - 128;
   for (int j = et; j < a.cout_pad; j += kEpi16Threads)
     bias_s[j] = (a.bias != nullptr && j < a.cout) ? a.bias[j] : 0.0f;
@@ -1017,6 +1016,7 @@ __device__ __forceinline__ void run_epilogue_slim16(const ConvArgs& a, uint32_t 
   };
   uint8_t mnext[4] = {0, 0, 0, 0};
   if (a.row_mask != nullptr && tile0 < a.num_tiles) fetch_masks(tile0, mnext);
+  const int64_t pass_step = static_cast<int64_t>(2) * a.W * a.bf16_ld;
   int it = 0;
   for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
     int n_idx, h0, w0, n0, par;
@@ -1028,24 +1028,46 @@ __device__ __forceinline__ void run_epilogue_slim16(const ConvArgs& a, uint32_t 
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub) mbits |= (mnext[sub] != 0 ? 1u : 0u) << sub;
     if (a.row_mask != nullptr && tile + tstep < a.num_tiles) fetch_masks(tile + tstep, mnext);
+    // rows of the neighbour in the pooled pair (lane ^ 8 holds row lh ^ 1)
+    const uint32_t mbits_pair = mbits | __shfl_xor_sync(0xffffffffu, mbits, 8);
+    const bool okw = (w0 + slw) < a.W;
+    // store-lane pointers of sub-tile 0; a sub-tile further down is 16 image rows (8 pooled rows) away
+    const int64_t spix = (static_cast<int64_t>(n_idx) * a.H + h0 + slh) * a.W + w0 + slw;
+    __nv_bfloat16* const out0 = a.out_bf16 + spix * a.bf16_ld + a.bf16_coff + n0 + 8 * (lane & 1);
+    const int64_t sub_step = static_cast<int64_t>(a.bh) * a.W * a.bf16_ld;
+    __nv_bfloat16* pool0 = nullptr;
+    int64_t pool_step = 0;
+    if (a.out_pool != nullptr) {
+      const int64_t ppix = (static_cast<int64_t>(n_idx) * (a.H >> 1) + ((h0 + plh) >> 1)) * a.W + w0 + slw;
+      pool0 = a.out_pool + ppix * a.pool_ld + n0 + 8 * (lane & 1);
+      pool_step = static_cast<int64_t>(a.bh >> 1) * a.W * a.pool_ld;
+    }
     mbar_wait(&tfull_bar[buf], (it / a.nbuf) & 1);
     tc_fence_after();
 #pragma unroll 1
     for (int sub = 0; sub < a.msub; ++sub) {
-      const int h = h0 + sub * a.bh + lh, w = w0 + lw;
-      const bool valid = (h < a.H) && (w < a.W);
-      const int64_t pix = (static_cast<int64_t>(n_idx) * a.H + h) * a.W + w;
-      const int64_t pix_pool = (static_cast<int64_t>(n_idx) * (a.H >> 1) + (h >> 1)) * a.W + w;
-      const bool masked = (mbits >> sub) & 1u;
+      const int hs = h0 + sub * a.bh;
+      Slim16Out o;
+      o.p0 = out0 + sub * sub_step;
+      o.pp = pool0 + sub * pool_step;
+      o.pass_step = pass_step;
+      o.ok0 = okw && (hs + slh) < a.H;
+      o.ok1 = okw && (hs + slh + 2) < a.H;
+      o.okp = okw && (hs + plh) < a.H;
+      const float g = ((mbits >> sub) & 1u) ? 0.0f : a.gamma;
+      const float pool_half = ((mbits_pair >> sub) & 1u) ? 0.0f : 0.5f;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * a.acc_stride + sub * a.bn;
 #pragma unroll 1
       for (int c = part * 16; c < a.bn; c += 64) {
         uint32_t v[16];
+        float4 b4[4];
         __syncwarp();
         tmem_ld_32x16(t_row + c, v);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) b4[q4] = *reinterpret_cast<const float4*>(bs + c + 4 * q4);   // under the TMEM load
         tmem_ld_wait();
-        if (a.out_pool != nullptr) epilogue_slim16<true>(a, v, bs + c, pix, n0 + c, masked, valid, pix_pool, stage, lane);
-        else epilogue_slim16<false>(a, v, bs + c, pix, n0 + c, masked, valid, pix_pool, stage, lane);
+        if (a.out_pool != nullptr) epilogue_slim16<true>(a, v, b4, g, pool_half, o, c, stage, lane);
+        else epilogue_slim16<false>(a, v, b4, g, pool_half, o, c, stage, lane);
       }
     }
     tc_fence_before();
@@ -1104,9 +1126,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (a.up_mode) tma_prefetch_desc(&map_a2);
-    for (int i = 0; i < nA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < nB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * kEpiWarps); }
+    // every issuing warp commits once per slot / per accumulator
+    for (int i = 0; i < nA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], a.mma_issuers); }
+    for (int i = 0; i < nB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], a.mma_issuers); }
+    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(&tfull_bar[b], a.mma_issuers); mbar_init(&tempty_bar[b], 2 * kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -1187,23 +1210,42 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
         }
       }
     }
-  } else if (warp == 1) {
-    if (rank == 0) {       // the leader's warp walks the loop, one elected lane issues for both CTAs
+  } else if (warp == 1 || (warp == 2 && a.mma_issuers == 2)) {
+    // The leader's warp walks the loop, one elected lane issues for both CTAs.  A tcgen05.mma with N = 64 runs for 32
+    // clocks but costs the issuing thread ~48 (two 64-bit descriptors through uniform registers per instruction, plus the
+    // per-tap offsets and barrier traffic: profiles/conv_cycles_r02.log), so layers with several sub-tiles per tile split
+    // them between two issuing warps: accumulators are disjoint, both warps wait on the same "operands landed"
+    // barriers and each commits its own MMAs to the "slot free" / "accumulator ready" barriers (count = issuers).
+    if (rank == 0) {
       const uint32_t idesc = a.op_f16 ? umma_idesc_f16(2 * kTileM, a.bn) : umma_idesc_bf16(2 * kTileM, a.bn);
       constexpr uint32_t hi_a = umma_desc_hi_sw128(kHaloW * 128), hi_b = umma_desc_hi_sw128(1024);
       constexpr uint32_t kSubStep = (kHaloSubRows * kHaloW * 128) >> 4;
       const int msub = MQ_PROBE(a, 2) ? 0 : a.msub;
+      const int sub_lo = (warp - 1) * msub / a.mma_issuers, sub_hi = (warp * msub) / a.mma_issuers;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
       const bool resident = a.b_resident != 0;
-      long long pm5 = 0, pm6 = 0, pm7 = 0;
-      (void)pm5; (void)pm6; (void)pm7;
+      long long pm5 = 0, pm6 = 0, pm7 = 0, pm8 = 0, pm9 = 0, pm10 = 0;
+      (void)pm5; (void)pm6; (void)pm7; (void)pm8; (void)pm9; (void)pm10;
       if (resident && tile0 < a.num_tiles) {
         mbar_wait(&fullB[0], 0);                  // the one-off weight load
         tc_fence_after();
       }
       const uint32_t b_res_lo = umma_desc_lo(smem_u32(smem_b));
+      // lane t holds the offset (16-byte units) of tap t's shifted view inside a halo slot, for even / odd output rows
+      uint32_t toff_even = 0, toff_odd = 0;
+      if (lane < a.taps) {
+        const int tx = a.tap_dw[lane] + 1;
+        if (!a.up_mode || lane < a.up_taps) {
+          toff_even = static_cast<uint32_t>(((a.tap_dh[lane] + 1) * kHaloW + tx) * 8);
+          toff_odd = a.up_mode ? static_cast<uint32_t>(((a.tap_dh_odd[lane] + 1) * kHaloW + tx) * 8) : toff_even;
+        } else {
+          const int dh = a.tap_dh[lane];
+          toff_even = toff_odd =
+              static_cast<uint32_t>(((dh != 0 ? a.pair_boxb_off : 0) >> 4) + ((dh == 1 ? kHaloW : 0) + tx) * 8);
+        }
+      }
       for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++it) {
         const int par = (tile / a.tiles_n) % a.par_tiles;
         const uint32_t buf = it % a.nbuf;
@@ -1225,49 +1267,51 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + sa * a.halo_slot_bytes));
             for (int tg = t0; tg < t1; tg += a.pair_bgrp) {
               if (!resident) {
+                const long long pb0 = MQ_CLK();
                 mbar_wait(&fullB[sb], pb);
                 tc_fence_after();
+                pm8 += MQ_CLK() - pb0;
               }
               // ring slot of this tap group, or the group's place in the resident weight image (tap-major, then chunk)
               const uint32_t b_lo = resident ? b_res_lo + ((tg * nch + kc) * (a.b_tile_bytes >> 4))
                                              : umma_desc_lo(smem_u32(smem_b + sb * a.pair_bgrp * a.b_tile_bytes));
               const uint32_t b_step = resident ? nch * (a.b_tile_bytes >> 4) : (a.b_tile_bytes >> 4);
-              for (int j = 0; j < a.pair_bgrp; ++j) {
-                const int tap = tg + j;
-                // offset (16-byte units) of this tap's shifted view inside the halo slot
-                const int tx = a.tap_dw[tap] + 1;
-                uint32_t toff;
-                if (!grp) {
-                  const int ty = ((a.up_mode && par) ? a.tap_dh_odd[tap] : a.tap_dh[tap]) + 1;
-                  toff = static_cast<uint32_t>((ty * kHaloW + tx) * 8);
-                } else {
-                  const int dh = a.tap_dh[tap];
-                  toff = static_cast<uint32_t>(((dh != 0 ? a.pair_boxb_off : 0) >> 4) + ((dh == 1 ? kHaloW : 0) + tx) * 8);
-                }
-                const uint32_t a_tap = a_lo + toff;
-                const uint32_t b_tap = b_lo + j * b_step;
-                if (elect_one_sync()) {
+              // this slot's tap offsets from the lanes that hold them (no indexed constant loads in the loop)
+              uint32_t toffs[3];
 #pragma unroll
-                  for (int sub = 0; sub < 4; ++sub) {
-                    if (sub < msub) {
+              for (int j = 0; j < 3; ++j) toffs[j] = __shfl_sync(0xffffffffu, par ? toff_odd : toff_even, (tg + j) & 31);
+              const long long pi0 = MQ_CLK();
+              // one elected lane issues the whole slot - taps x its sub-tiles x four K steps - and commits it
+              if (elect_one_sync()) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                  if (j < a.pair_bgrp) {
+                    const uint32_t a_tap = a_lo + toffs[j];
+                    const uint32_t b_tap = b_lo + j * b_step;
+#pragma unroll 1
+                    for (int sub = sub_lo; sub < sub_hi; ++sub) {
+                      const uint32_t d_sub = d_tmem + sub * a.bn, a_sub = a_tap + sub * kSubStep;
 #pragma unroll
                       for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                        umma_bf16_2cta(d_tmem + sub * a.bn, umma_desc_make(a_tap + sub * kSubStep + 2 * k, hi_a),
-                                       umma_desc_make(b_tap + 2 * k, hi_b), idesc, k != 0 ? 1u : acc);
+                        umma_bf16_2cta(d_sub, umma_desc_make(a_sub + 2 * k, hi_a), umma_desc_make(b_tap + 2 * k, hi_b), idesc,
+                                       k != 0 ? 1u : acc);
                     }
+                    acc = 1;
                   }
                 }
-                __syncwarp();
-                acc = 1;
+                if (!resident) umma_commit_2cta(&emptyB[sb]);
               }
+              __syncwarp();
+              acc = 1;
+              pm9 += MQ_CLK() - pi0;
               if (!resident) {
-                if (elect_one_sync()) umma_commit_2cta(&emptyB[sb]);
-                __syncwarp();
                 if (++sb == nB) { sb = 0; pb ^= 1; }
               }
             }
+            const long long pc1 = MQ_CLK();
             if (elect_one_sync()) umma_commit_2cta(&emptyA[sa]);
             __syncwarp();
+            pm10 += MQ_CLK() - pc1;
             if (++sa == nA) { sa = 0; pa ^= 1; }
           }
         }
@@ -1275,7 +1319,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
         __syncwarp();
         pm7 += MQ_CLK() - pm0;
       }
-      MQ_ACC(5, pm5); MQ_ACC(6, pm6); MQ_ACC(7, pm7);
+      if (warp == 1) { MQ_ACC(5, pm5); MQ_ACC(6, pm6); MQ_ACC(7, pm7); MQ_ACC(8, pm8); MQ_ACC(9, pm9); MQ_ACC(10, pm10); }
     }
   } else if (warp >= 4) {
     if constexpr (kEpiWarps == kEpi16Warps)
@@ -1474,7 +1518,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // Experiment knobs from the environment, read ONCE per process (not per launch).
 struct ConvEnv {
-  int nbuf = 0, debug = 0, stages = 0, bgrp = 0, stage_out = -1, slim = 1, slim16 = 1, b_resident = 1;
+  int nbuf = 0, debug = 0, stages = 0, bgrp = 0, stage_out = -1, slim = 1, slim16 = 1, b_resident = 1, issuers = 2;
   ConvEnv() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     nbuf = geti("MQ_CONV_NBUF");
@@ -1482,6 +1526,7 @@ struct ConvEnv {
     stages = geti("MQ_CONV_STAGES");
     bgrp = geti("MQ_PAIR_BGRP");
     if (getenv("MQ_B_RESIDENT")) b_resident = geti("MQ_B_RESIDENT");   // 0 = always the weight ring
+    if (getenv("MQ_MMA_ISSUERS")) issuers = geti("MQ_MMA_ISSUERS");   // 1 = a single MMA-issuing warp everywhere
     if (getenv("MQ_SLIM16")) slim16 = geti("MQ_SLIM16");              // 0 = eight epilogue warps everywhere
     if (getenv("MQ_SLIM")) slim = geti("MQ_SLIM");                    // 0 = always the generic lean body
     if (getenv("MQ_STAGE_OUT")) stage_out = geti("MQ_STAGE_OUT");     // 0 = never, 1 = bn <= 128 (default), 2 = always
@@ -1502,11 +1547,11 @@ static int conv_smem_bytes(int stages, int a_stage_bytes, int b_tile_bytes) {
 using namespace mq;
 
 #ifdef MQ_CONV_PROBES
-extern "C" int mq_conv_probe_cycles(unsigned long long* out8, int reset) {
+extern "C" int mq_conv_probe_cycles(unsigned long long* out12, int reset) {
   MQ_CUDA_OK(cudaDeviceSynchronize());
-  MQ_CUDA_OK(cudaMemcpyFromSymbol(out8, mq_probe_cycles, sizeof(unsigned long long) * 8));
+  MQ_CUDA_OK(cudaMemcpyFromSymbol(out12, mq_probe_cycles, sizeof(unsigned long long) * 12));
   if (reset) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     MQ_CUDA_OK(cudaMemcpyToSymbol(mq_probe_cycles, z, sizeof(z)));
   }
   return 0;
@@ -1635,7 +1680,9 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   // eight-warp body: the 16-warp tile walk assumes one output row per input row)
   a.slim16 = (env.slim16 && a.slim && pair && !pair1d && !up && p->bn % 64 == 0 && p->bn <= 128) ? 1 : 0;
   if (a.slim16) a.stage_out = 1;
-  const int stage_bytes = a.stage_out ? kStageBytes : 0;   // 8 warps x 2 KB == 16 warps x 1 KB
+  // two MMA-issuing warps where a tile has several sub-tiles of a narrow N (the issue rate, not the tensor pipe, paces those)
+  a.mma_issuers = (pair && !pair1d && env.issuers == 2 && a.msub >= 2 && p->bn <= 128) ? 2 : 1;
+  int stage_bytes = a.stage_out ? kStageBytes : 0;   // 8 warps x 2 KB == 16 warps x 1 KB
 
   // --- tensor maps ---
   CUtensorMap map_a, map_b, map_a2;
@@ -1737,22 +1784,41 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     int slot = a.pair_tx0;
     if (up && a.pair_boxb_off + box1 > slot) slot = a.pair_boxb_off + box1;
     a.halo_slot_bytes = (slot + 1023) / 1024 * 1024;
-    const int tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4 + stage_bytes;
-    const int budget = kSmemBudget - 1024 - tail_bytes - 256;
     // weight ring: slots of pair_bgrp taps (3 = one filter row; every tap count on this path is a
     // multiple of 3) -> one full/empty barrier round trip and one multicast commit per slot
-    int bgrp = 3;
-    if (env.bgrp == 1 || env.bgrp == 3) bgrp = env.bgrp;
-    if (p->taps % 3 != 0 || (up && p->up_taps % 3 != 0)) bgrp = 1;
-    int nA = 0, nB = 0;
-    for (;;) {
-      const int bslot = bgrp * static_cast<int>(a.b_tile_bytes);
-      nA = (a.nseg * a.kchunks + a.kchunks2 >= 3) ? 3 : 2;
-      while (nA > 2 && budget - nA * a.halo_slot_bytes < 2 * bslot) --nA;
-      nB = (budget - nA * a.halo_slot_bytes) / bslot;
-      if (nB >= 2 || bgrp == 1) break;
-      bgrp = 1;
+    int bgrp = 3, nA = 0, nB = 0, tail_bytes = 0, budget = 0;
+    auto plan_ring = [&](int stage_b) {
+      tail_bytes = (2 * kPairMaxA + 2 * kPairMaxB + 2 * kMaxAccBufs) * 8 + 16 + kBiasSmemFloats * 4 + stage_b;
+      budget = kSmemBudget - 1024 - tail_bytes - 256;
+      bgrp = 3;
+      if (env.bgrp == 1 || env.bgrp == 3) bgrp = env.bgrp;
+      if (p->taps % 3 != 0 || (up && p->up_taps % 3 != 0)) bgrp = 1;
+      for (;;) {
+        const int bslot = bgrp * static_cast<int>(a.b_tile_bytes);
+        nA = (a.nseg * a.kchunks + a.kchunks2 >= 3) ? 3 : 2;
+        while (nA > 2 && budget - nA * a.halo_slot_bytes < 2 * bslot) --nA;
+        nB = (budget - nA * a.halo_slot_bytes) / bslot;
+        if (nB >= 2 || bgrp == 1) break;
+        bgrp = 1;
+      }
+      return nB * bgrp;                                   // weight taps in flight
+    };
+    int taps_in_flight = plan_ring(stage_bytes);
+    // The staging tile costs 16 KB of ring.  Where the activation slots leave little room (fused up-concat, bn = 128:
+    // two 85 KB slots) that drops the weight ring from two 3-tap slots to four 1-tap slots and the layer from 1.08 to
+    // 1.52 ms (profiles/conv_probe3_r02.log); coalesced stores are worth nothing next to that, so they go first.
+    if (a.stage_out && !a.slim16 && env.stage_out < 0 && taps_in_flight < 9) {
+      const int staged = taps_in_flight, staged_grp = bgrp;
+      const int plain = plan_ring(0);
+      if (plain > staged || bgrp > staged_grp) {
+        a.stage_out = 0;
+        stage_bytes = 0;
+        taps_in_flight = plain;
+      } else {
+        taps_in_flight = plan_ring(stage_bytes);
+      }
     }
+    (void)taps_in_flight;
     if (nB > kPairMaxB) nB = kPairMaxB;
     MQ_REQUIRE(nB >= 2, "mq_conv_gemm: pair mode does not fit shared memory (msub=%d bn=%d)", a.msub, p->bn);
     a.halo_nA = nA; a.halo_nB = nB; a.pair_bgrp = bgrp;
