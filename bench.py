@@ -718,6 +718,17 @@ def main():
             sec["train_step"] = {"error": repr(e)}
             if world > 1:
                 raise
+        if world == 1 and "error" not in sec.get("train_step", {}):
+            # the same step with the discriminator convolutions on the library's tcgen05 kernels too (TrainStep(d_native=True)):
+            # slower than cuDNN's strided kernels, so not the default - reported for its native share
+            try:
+                targs = TB.parse_args(["--steps", "5", "--warmup", "3", "--d_native"])
+                tl = TB.measure(targs)
+                if tl is not None:
+                    sec["train_step_d_native"] = {k: tl[k] for k in ("value", "unit", "ms_per_step", "native_share_of_step",
+                                                                     "gpu_launches", "config")}
+            except Exception as e:
+                sec["train_step_d_native"] = {"error": repr(e)}
         watchdog.cancel()
 
     emit()

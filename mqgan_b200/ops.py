@@ -25,6 +25,7 @@ PAIR_1D = os.environ.get("MQ_PAIR_1D", "1") != "0"     # row-halo CTA-pair loop 
 PAIR_1D_MIN_BN = int(os.environ.get("MQ_PAIR_1D_MIN_BN", "128"))
 MSUB_OVERRIDE = int(os.environ.get("MQ_MSUB", "0"))            # experiment knobs, read once at import
 MSUB_PAIR_OVERRIDE = int(os.environ.get("MQ_MSUB_PAIR", "0"))
+MSUB_PAIR_WIDE = int(os.environ.get("MQ_MSUB_PAIR_WIDE", "1"))   # sub-tiles per CTA for bn = 256 pair layers (2 = one TMEM buffer)
 
 
 def _stream() -> int:
@@ -314,7 +315,7 @@ def choose_msub(bn: int, N: int, H: int, W: int, bh: int, bw: int, up: bool = Fa
 def choose_msub_pair(bn: int, N: int, H: int, W: int, up: bool) -> int:
     """Sub-tiles per CTA of a CTA pair (a pair tile is 2*msub sub-tiles of 16 rows x 8 columns).
     msub*bn <= 256 keeps two TMEM accumulator buffers so the epilogue overlaps the next main loop."""
-    m = MSUB_PAIR_OVERRIDE if MSUB_PAIR_OVERRIDE else (4 if bn <= 64 else (2 if bn <= 128 else 1))
+    m = MSUB_PAIR_OVERRIDE if MSUB_PAIR_OVERRIDE else (4 if bn <= 64 else (2 if bn <= 128 else MSUB_PAIR_WIDE))
     if up:
         m = min(m, 2)             # the two skip-parity boxes of msub = 4 do not fit shared memory twice
     while m > 1 and m * bn > 512:
