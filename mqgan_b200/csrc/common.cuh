@@ -90,6 +90,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Waits that are long by design - an epilogue warp waiting for the next accumulator of a wide layer (70 % of its time),
+// the producer waiting for a free ring slot: after a few polls, sleep between polls.  The hardware caps try_wait's own
+// suspend time at ~150 clocks whatever the hint, so without this the polls stay 40 % of a wide layer's instructions.
+#ifndef MQ_RELAXED_WAIT_NS
+#define MQ_RELAXED_WAIT_NS 256
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+    if (MQ_RELAXED_WAIT_NS > 0 && spins > 4) __nanosleep(MQ_RELAXED_WAIT_NS);
+  }
+}
+
 // barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

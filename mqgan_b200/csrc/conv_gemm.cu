@@ -524,7 +524,7 @@ __device__ __forceinline__ void run_epilogue(const ConvArgs& a, uint32_t tmem_ba
     if (a.row_mask != nullptr && tile + tstep < a.num_tiles) fetch_masks(tile + tstep, mnext);
 
     const long long pc0 = MQ_CLK();
-    mbar_wait(&tfull_bar[buf], (it / a.nbuf) & 1);
+    mbar_wait_relaxed(&tfull_bar[buf], (it / a.nbuf) & 1);
     tc_fence_after();
     const long long pc1 = MQ_CLK();
     pk0 += pc1 - pc0;
@@ -657,7 +657,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
               hh = h0 + (orow >> 1);
             }
             for (int kc = 0; kc < nch; ++kc, ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
               if (MQ_PROBE(a, 4)) {
                 mbar_arrive(&full_bar[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -814,7 +814,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         int n_idx, h0, w0, n0, par;
         decode_tile(a, tile, n_idx, h0, w0, n0, par);
         for (int kc = 0; kc < a.kchunks; ++kc) {
-          mbar_wait(&emptyA[sa], pa ^ 1);
+          mbar_wait_relaxed(&emptyA[sa], pa ^ 1);
           if (MQ_PROBE(a, 4)) {
             mbar_arrive(&fullA[sa]);
           } else {
@@ -823,7 +823,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
           }
           if (++sa == nA) { sa = 0; pa ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&emptyB[sb], pb ^ 1);
+            mbar_wait_relaxed(&emptyB[sb], pb ^ 1);
             if (MQ_PROBE(a, 4)) {
               mbar_arrive(&fullB[sb]);
             } else {
@@ -1042,7 +1042,7 @@ __device__ __forceinline__ void run_epilogue_slim16(const ConvArgs& a, uint32_t 
       pool0 = a.out_pool + ppix * a.pool_ld + n0 + 8 * (lane & 1);
       pool_step = static_cast<int64_t>(a.bh >> 1) * a.W * a.pool_ld;
     }
-    mbar_wait(&tfull_bar[buf], (it / a.nbuf) & 1);
+    mbar_wait_relaxed(&tfull_bar[buf], (it / a.nbuf) & 1);
     tc_fence_after();
 #pragma unroll 1
     for (int sub = 0; sub < a.msub; ++sub) {
@@ -1176,7 +1176,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
           const int kbase = grp ? a.up_taps * a.kchunks : seg * a.taps * a.kchunks;
           const int cseg = a.a_coff[seg];
           for (int kc = 0; kc < nch; ++kc) {
-            mbar_wait(&emptyA[sa], pa ^ 1);
+            mbar_wait_relaxed(&emptyA[sa], pa ^ 1);
             const uint32_t fa = smem_u32(&fullA[sa]) & kPeerBitMask;
             uint8_t* dst = smem_a + sa * a.halo_slot_bytes;
             if (MQ_PROBE(a, 4)) {
@@ -1194,7 +1194,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
             if (++sa == nA) { sa = 0; pa ^= 1; }
             if (a.b_resident) continue;
             for (int tap = t0; tap < t1; tap += a.pair_bgrp) {
-              mbar_wait(&emptyB[sb], pb ^ 1);
+              mbar_wait_relaxed(&emptyB[sb], pb ^ 1);
               if (MQ_PROBE(a, 4)) {
                 if (rank == 0) mbar_arrive(&fullB[sb]);
               } else {
@@ -1409,14 +1409,14 @@ conv_pair1d_kernel(const __grid_constant__ CUtensorMap map_a,
         const int hc = h0 + hoff;
         for (int seg = 0; seg < a.nseg; ++seg) {
           for (int kc = 0; kc < a.kchunks; ++kc) {
-            mbar_wait(&emptyA[sa], pa ^ 1);
+            mbar_wait_relaxed(&emptyA[sa], pa ^ 1);
             if (rank == 0) mbar_expect_tx(&fullA[sa], 2u * static_cast<uint32_t>(a.pair_tx0));
             tma_load_4d_2cta(&map_a, smem_u32(&fullA[sa]) & kPeerBitMask, smem_a + sa * a.halo_slot_bytes,
                              a.a_coff[seg] + kc * kBlockK, 0, hc + dh0, n_idx);
             if (++sa == nA) { sa = 0; pa ^= 1; }
             for (int tap = 0; tap < a.taps; tap += kPair1dGroup) {
               const int g = min(kPair1dGroup, a.taps - tap);
-              mbar_wait(&emptyB[sb], pb ^ 1);
+              mbar_wait_relaxed(&emptyB[sb], pb ^ 1);
               if (rank == 0) mbar_expect_tx(&fullB[sb], 2u * a.b_tile_bytes * g);
               const uint32_t fb = smem_u32(&fullB[sb]) & kPeerBitMask;
               for (int j = 0; j < g; ++j)
