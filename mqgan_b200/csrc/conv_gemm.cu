@@ -1580,7 +1580,8 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
   MQ_REQUIRE(p->out_f32 || p->out_bf16 || p->out_split, "mq_conv_gemm: no output");
   MQ_REQUIRE(p->res_mode == 0 || p->res != nullptr, "mq_conv_gemm: res_mode without res");
   MQ_REQUIRE(!(p->mask_pre || p->mask_post) || p->row_mask != nullptr, "mq_conv_gemm: mask flag without row_mask");
-  if (p->out_f32) MQ_REQUIRE(p->f32_ld % 4 == 0 && p->f32_coff % 4 == 0, "mq_conv_gemm: f32 ld/coff must be multiples of 4");
+  // (fewer than four output channels never take a 16-byte store: the refiner's 3x3 post conv writes one float per pixel)
+  if (p->out_f32) MQ_REQUIRE((p->f32_ld % 4 == 0 && p->f32_coff % 4 == 0) || p->cout < 4, "mq_conv_gemm: f32 ld/coff must be multiples of 4");
   if (p->out_bf16) MQ_REQUIRE(p->bf16_ld % 8 == 0 && p->bf16_coff % 8 == 0, "mq_conv_gemm: bf16 ld/coff must be multiples of 8");
   if (p->out_split) MQ_REQUIRE(p->split_ld % 8 == 0 && p->split_seg % 8 == 0, "mq_conv_gemm: split ld/seg must be multiples of 8");
   if (p->res_mode) MQ_REQUIRE(p->res_ld % 8 == 0 && p->res_coff % 8 == 0, "mq_conv_gemm: res ld/coff must be multiples of 8");

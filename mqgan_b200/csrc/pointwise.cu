@@ -837,7 +837,8 @@ refiner_stem_kernel(const float* __restrict__ r, const uint8_t* __restrict__ mas
 constexpr int kTailT = 8;
 
 // taps: (B, T8, F, ldp) fp32, channel k = 3*(dt+1)+(df+1) holds sum_c x[.., c] * w[k][c] (a 1x1
-// tcgen05 GEMM, C -> 9).  post(x)[t,f] = bias + sum_k taps[t+dt, f+df, k].
+// tcgen05 GEMM, C -> 9).  post(x)[t,f] = bias + sum_k taps[t+dt, f+df, k].  ldp == 1: taps is post(x) itself
+// (without the bias), produced by the 3x3 halo kernel with one output channel: 4 bytes per pixel instead of 48.
 // Phase 2 (reproj, F -> M per frame) was one global load per FMA; now a thread owns one output channel m of four
 // frames and walks f four at a time: 4 coalesced weight loads + 4 shared-memory float4 reads feed 16 FMAs.
 __global__ void __launch_bounds__(256)
@@ -854,6 +855,10 @@ refiner_tail_kernel(const float* __restrict__ taps, int ldp, const uint8_t* __re
     float acc = 0.0f;
     if (f < F && t < T && !(mask != nullptr && mask[static_cast<int64_t>(b) * T + t] != 0)) {
       acc = bias;
+      if (ldp == 1) {             // post already contracted over its 3x3 taps (the halo conv kernel, C -> 1)
+        osm[i] = acc + __ldg(taps + (static_cast<int64_t>(b) * T8 + t) * F + f);
+        continue;
+      }
 #pragma unroll
       for (int dt = -1; dt <= 1; ++dt) {
         const int tt = t + dt;
@@ -1154,8 +1159,8 @@ extern "C" int mq_refiner_stem_split(const float* r, const uint8_t* mask, int B,
 extern "C" int mq_refiner_tail(const float* taps, int ldp, const uint8_t* mask, int B, int T, int T8, int F,
                                float bias, const float* reproj_t, int M, const float* r, float* out,
                                mq_stream_t stream) {
-  MQ_REQUIRE(taps && reproj_t && r && out && B > 0 && T > 0 && T8 >= T && F >= M && ldp >= 9,
-             "mq_refiner_tail: bad args");
+  MQ_REQUIRE(taps && reproj_t && r && out && B > 0 && T > 0 && T8 >= T && F >= M && (ldp >= 9 || ldp == 1),
+             "mq_refiner_tail: bad args (ldp = 9.. tap planes, or 1 = post already summed)");
   const size_t smem = kTailT * static_cast<size_t>((F + 3) & ~3) * sizeof(float);
   dim3 grid((T + kTailT - 1) / kTailT, B);
   refiner_tail_kernel<<<grid, 256, smem, STREAM(stream)>>>(taps, ldp, mask, T, T8, F, bias, reproj_t, M, r, out);

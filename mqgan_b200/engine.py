@@ -24,6 +24,7 @@ Precision modes
 """
 from __future__ import annotations
 
+import os
 from typing import Sequence, Dict, List, Optional, Tuple
 
 import torch
@@ -239,6 +240,10 @@ class PreEncoderEngine:
         w9 = torch.zeros(12, chs[0])
         w9[:9] = w["refiner.post.weight"].reshape(chs[0], 9).t()
         self.tail = pack_conv(w9, None, "linear", dp).to(dev)
+        # ... or as the 3x3 convolution it is, one output channel on the CTA-pair halo kernel (N tile of 32, weights
+        # resident): the tail then reads 4 bytes per pixel instead of nine 4-byte taps out of a 48-byte record
+        self.tail3 = pack_conv(w["refiner.post.weight"], None, "conv2d3", dp).to(dev)
+        self.post_direct = os.environ.get("MQ_POST_DIRECT", "1") != "0"
         self.tail_b = float(w["refiner.post.bias"].reshape(()))
         self.reproj_t = w["refiner.reproj.weight"].t().float().contiguous().to(dev)       # (F, M)
 
@@ -558,9 +563,20 @@ class PreEncoderEngine:
             x = convblock(u, self.ref_ups[i], l, up[l], chs[l], tag=f"ref.up{i}")
             if taps is not None:
                 taps[f"refiner.ups.{i}"] = x
-        tp = torch.empty(B, T8, F, 12, dtype=torch.float32, device=dev)
-        ops.conv_gemm(x, self.tail, B, T8, F, out_f32=tp, tag="ref.post")
-        ops.refiner_tail(tp, m8, B, T, T8, F, self.tail_b, self.reproj_t, cfg.mel_channels, R, out=out)
+        self._post_tail(x, m8, B, T, T8, F, R, out)
+
+    def _post_tail(self, x, m8, B, T, T8, F, R, out):
+        """refiner.post (C -> 1, 3x3; preencoder.py:191) + crop / mask / reproj / + x_recon (:192-200, :499)."""
+        dev = x.device
+        if self.post_direct and ops.PAIR_DEFAULT and F >= 8:
+            # always the CTA-pair kernel, whatever T8: a length group of a few frames must produce the bits the padded
+            # batch produces (one K order per output pixel), and F is a property of the model, not of the batch
+            tp = torch.empty(B, T8, F, 1, dtype=torch.float32, device=dev)
+            ops.conv_gemm(x, self.tail3, B, T8, F, out_f32=tp, pair=True, tag="ref.post")
+        else:
+            tp = torch.empty(B, T8, F, 12, dtype=torch.float32, device=dev)
+            ops.conv_gemm(x, self.tail, B, T8, F, out_f32=tp, tag="ref.post")               # as 9 tap planes
+        ops.refiner_tail(tp, m8, B, T, T8, F, self.tail_b, self.reproj_t, self.cfg.mel_channels, R, out=out)
 
     def _refiner(self, R, m8, B, T, out, taps):
         if self.dec_split:
@@ -624,6 +640,4 @@ class PreEncoderEngine:
                 x = convblock(u, self.ref_ups[i], l, up[l], chs[l + 1] + chs[l], chs[l], tag=f"ref.up{i}")
             if taps is not None:
                 taps[f"refiner.ups.{i}"] = x
-        tp = torch.empty(B, T8, F, 12, dtype=torch.float32, device=dev)
-        ops.conv_gemm(x, self.tail, B, T8, F, out_f32=tp, tag="ref.post")                   # :191 as 9 tap planes
-        ops.refiner_tail(tp, m8, B, T, T8, F, self.tail_b, self.reproj_t, cfg.mel_channels, R, out=out)  # :192-200, :499
+        self._post_tail(x, m8, B, T, T8, F, R, out)                                         # :191-200, :499
