@@ -134,6 +134,17 @@ def test_weight_packing_layout():
     assert (p2.bn, p2.cout_pad, p2.taps) == (256, 768, 9) and p2.tap_dh[0] == -1 and p2.tap_dw[2] == 1
     assert ops.choose_bn(384) == (192, 384) and ops.choose_bn(96) == (96, 96) and ops.choose_bn(16) == (32, 32)
     assert ops.choose_tile(1024, 1) == (128, 1) and ops.choose_tile(128, 144) == (8, 16)
+    # CTA-pair sub-tiles per CTA on the refiner's shapes (32 utterances, F = 144): the variants the sustained
+    # per-launch energy table picks (profiles/conv_bench_r02_sustained.log)
+    assert ops.choose_msub_pair(64, 32, 1024, 144, False) == 4        # pre.conv2, up2.conv2
+    assert ops.choose_msub_pair(128, 32, 512, 144, False) == 2        # down0.conv1/2, up1.conv2
+    assert ops.choose_msub_pair(256, 32, 256, 144, False) == 1        # wide layers: two TMEM buffers
+    assert ops.choose_msub_pair(64, 32, 512, 144, True) == 2          # fused up-concat: two skip-parity boxes per slot
+    assert ops.choose_msub_pair(32, 32, 1024, 144, False) == 4        # refiner.post as a one-channel 3x3 conv
+    assert ops.choose_msub_pair(64, 1, 16, 24, False) == 1            # an image smaller than one pair tile
+    # refiner.post packed as the 3x3 convolution it is: one live output channel in an N tile of 32
+    pp = ops.pack_conv(torch.randn(1, 64, 3, 3), None, "conv2d3", False)
+    assert (pp.bn, pp.cout, pp.cout_pad, pp.taps, pp.kchunks) == (32, 1, 32, 9, 1)
 
 
 def test_fsq_params_match_reference_constants():
