@@ -321,8 +321,11 @@ int mq_refiner_stem_split(const float* r, const uint8_t* mask, int B, int T, int
  * taps (B, T8, F, ldp) fp32, and this kernel: post[t,f] = bias + sum_k taps[t+dt, f+df, k]
  * (zero outside the image), crop to T, mask, reproj_t (F, M) = reproj.weight transposed,
  * out (B, T, M) fp32 = r[..., :M] + residual, r (B, T, F) = cat[x_recon, hidden].
+ * ldp == 4: taps (B, T8, F, 4) holds three ROW sums per pixel, channel dt + 1 = sum over df and c of kernel row dt
+ * applied at that pixel's own row (mq_conv_gemm, "taps2d" weight (4, C, 3) with taps dh = 0, dw = -1, 0, 1), and
+ * post[t,f] = bias + taps[t-1,f,0] + taps[t,f,1] + taps[t+1,f,2]: what the engine uses.
  * ldp == 1: taps (B, T8, F, 1) already holds the 3x3 sum (mq_conv_gemm with the (1, C, 3, 3) weight packed as
- * "conv2d3", one output channel) and post[t,f] = bias + taps[t, f]: what the engine uses. */
+ * "conv2d3", one output channel) and post[t,f] = bias + taps[t, f]. */
 int mq_refiner_tail(const float* taps, int ldp, const uint8_t* mask, int B, int T, int T8, int F,
                     float bias, const float* reproj_t, int M, const float* r, float* out,
                     mq_stream_t stream);

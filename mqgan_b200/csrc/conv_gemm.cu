@@ -1144,7 +1144,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a,
   const int tile0 = blockIdx.x >> 1, tstep = gridDim.x >> 1;
   const int R = kHaloSubRows * a.msub;          // rows of this CTA's share of a tile
   const int hoff = static_cast<int>(rank) * R;
-  const int ntap0 = a.up_mode ? a.up_taps : 9;
+  const int ntap0 = a.up_mode ? a.up_taps : a.taps;
   const int nsegs = a.up_mode ? 1 : a.nseg;
 
   if (warp == 0) {
@@ -1634,9 +1634,13 @@ extern "C" int mq_conv_gemm(const mq_conv_params* p, mq_stream_t stream_) {
     MQ_REQUIRE(!halo && (p->nseg == 1 || !up) && p->bw == 8 && p->bh == kHaloSubRows && p->bn % 32 == 0,
                "mq_conv_gemm: pair mode needs a 16x8 sub-tile, bn a multiple of 32 and nseg == 1 for the fused up-conv");
     if (!up) {
-      MQ_REQUIRE(p->taps == 9, "mq_conv_gemm: pair mode needs a 3x3 convolution");
-      for (int t = 0; t < 9; ++t)
-        MQ_REQUIRE(p->tap_dh[t] == t / 3 - 1 && p->tap_dw[t] == t % 3 - 1, "mq_conv_gemm: pair mode needs the standard 3x3 tap order");
+      // the 3x3 convolution in its standard tap order, or one row of it (three taps along W: the refiner's post conv
+      // computes its three row sums as three output channels); either way every tap is a shifted view of the halo box
+      MQ_REQUIRE(p->taps == 9 || p->taps == 3, "mq_conv_gemm: pair mode needs a 3x3 convolution or one row of it");
+      for (int t = 0; t < p->taps; ++t)
+        MQ_REQUIRE(p->taps == 9 ? (p->tap_dh[t] == t / 3 - 1 && p->tap_dw[t] == t % 3 - 1)
+                                : (p->tap_dh[t] == 0 && p->tap_dw[t] == t - 1),
+                   "mq_conv_gemm: pair mode needs the standard 3x3 tap order (or dh = 0, dw = -1, 0, 1)");
     } else {
       for (int t = 0; t < p->taps; ++t) {
         MQ_REQUIRE(p->tap_dw[t] >= -1 && p->tap_dw[t] <= 1 && p->tap_dh[t] >= -1 && p->tap_dh[t] <= 1,

@@ -860,6 +860,14 @@ refiner_tail_kernel(const float* __restrict__ taps, int ldp, const uint8_t* __re
         osm[i] = acc + __ldg(taps + (static_cast<int64_t>(b) * T8 + t) * F + f);
         continue;
       }
+      if (ldp == 4) {             // three row sums per pixel (channel dt + 1 = sum over df and c of row t's taps): add down T
+        const float4* rec = reinterpret_cast<const float4*>(taps) + (static_cast<int64_t>(b) * T8 + t) * F + f;
+        if (t > 0) acc += __ldg(rec - F).x;          // row t-1 evaluated with the dt = -1 weights
+        acc += __ldg(rec).y;
+        if (t + 1 < T8) acc += __ldg(rec + F).z;
+        osm[i] = acc;
+        continue;
+      }
 #pragma unroll
       for (int dt = -1; dt <= 1; ++dt) {
         const int tt = t + dt;
@@ -1163,8 +1171,9 @@ extern "C" int mq_refiner_stem_split(const float* r, const uint8_t* mask, int B,
 extern "C" int mq_refiner_tail(const float* taps, int ldp, const uint8_t* mask, int B, int T, int T8, int F,
                                float bias, const float* reproj_t, int M, const float* r, float* out,
                                mq_stream_t stream) {
-  MQ_REQUIRE(taps && reproj_t && r && out && B > 0 && T > 0 && T8 >= T && F >= M && (ldp >= 9 || ldp == 1),
-             "mq_refiner_tail: bad args (ldp = 9.. tap planes, or 1 = post already summed)");
+  MQ_REQUIRE(taps && reproj_t && r && out && B > 0 && T > 0 && T8 >= T && F >= M && (ldp >= 9 || ldp == 1 || ldp == 4),
+             "mq_refiner_tail: bad args (ldp = 9.. tap planes, 4 = row sums, 1 = post already summed)");
+  MQ_REQUIRE(ldp != 4 || (reinterpret_cast<uintptr_t>(taps) & 15) == 0, "mq_refiner_tail: row sums must be 16-byte aligned");
   const size_t smem = kTailT * static_cast<size_t>((F + 3) & ~3) * sizeof(float);
   dim3 grid((T + kTailT - 1) / kTailT, B);
   refiner_tail_kernel<<<grid, 256, smem, STREAM(stream)>>>(taps, ldp, mask, T, T8, F, bias, reproj_t, M, r, out);

@@ -243,7 +243,13 @@ class PreEncoderEngine:
         # ... or as the 3x3 convolution it is, one output channel on the CTA-pair halo kernel (N tile of 32, weights
         # resident): the tail then reads 4 bytes per pixel instead of nine 4-byte taps out of a 48-byte record
         self.tail3 = pack_conv(w["refiner.post.weight"], None, "conv2d3", dp).to(dev)
-        self.post_direct = os.environ.get("MQ_POST_DIRECT", "1") != "0"
+        # ... or as its three ROW sums: output channel dt + 1 = the taps of kernel row dt applied along F (three taps in
+        # the K loop instead of nine; N tiles of 32 cost the tensor pipe the same whether one or four columns are live),
+        # which the tail adds down T.  16 bytes per pixel between the passes.
+        wr = torch.zeros(4, chs[0], 3)
+        wr[:3] = w["refiner.post.weight"][0].permute(1, 0, 2)            # (dt, C, df)
+        self.tail_rows = pack_conv(wr, None, "taps2d", dp, taps=([0, 0, 0], [-1, 0, 1])).to(dev)
+        self.post_mode = os.environ.get("MQ_POST_MODE", "rows")           # rows | direct | planes
         self.tail_b = float(w["refiner.post.bias"].reshape(()))
         self.reproj_t = w["refiner.reproj.weight"].t().float().contiguous().to(dev)       # (F, M)
 
@@ -568,9 +574,13 @@ class PreEncoderEngine:
     def _post_tail(self, x, m8, B, T, T8, F, R, out):
         """refiner.post (C -> 1, 3x3; preencoder.py:191) + crop / mask / reproj / + x_recon (:192-200, :499)."""
         dev = x.device
-        if self.post_direct and ops.PAIR_DEFAULT and F >= 8:
-            # always the CTA-pair kernel, whatever T8: a length group of a few frames must produce the bits the padded
-            # batch produces (one K order per output pixel), and F is a property of the model, not of the batch
+        mode = self.post_mode if (ops.PAIR_DEFAULT and F >= 8) else "planes"
+        # rows / direct: always the CTA-pair kernel, whatever T8 - a length group of a few frames must produce the bits
+        # the padded batch produces (one K order per output pixel), and F is a property of the model, not of the batch
+        if mode == "rows":
+            tp = torch.empty(B, T8, F, 4, dtype=torch.float32, device=dev)
+            ops.conv_gemm(x, self.tail_rows, B, T8, F, out_f32=tp, pair=True, tag="ref.post")
+        elif mode == "direct":
             tp = torch.empty(B, T8, F, 1, dtype=torch.float32, device=dev)
             ops.conv_gemm(x, self.tail3, B, T8, F, out_f32=tp, pair=True, tag="ref.post")
         else:

@@ -201,24 +201,26 @@ def test_decode_in_length_groups_is_bit_identical():
 
 @pytest.mark.parametrize("decoder_precision", ["bf16", "f16x2"])
 def test_refiner_post_direct_conv_matches_tap_planes(decoder_precision):
-    """refiner.post (C -> 1, 3x3; reference preencoder.py:191) as one output channel of the CTA-pair halo kernel against
-    the older formulation (a 1x1 GEMM into nine tap planes that the tail shift-adds): the same sum in another order."""
+    """refiner.post (C -> 1, 3x3; reference preencoder.py:191) as three row sums (default) or as one output channel of the
+    CTA-pair halo kernel, against the older formulation (a 1x1 GEMM into nine tap planes that the tail shift-adds):
+    the same sum in another order."""
     cfg, sd, _, lengths, _ = load_golden("hifispeech")
     B, T = 3, 200
     lens = torch.tensor([200, 133, 57])
     mask = sequence_mask(T, lens).unsqueeze(1).cuda()
     idx = torch.randint(0, cfg.codebook_size, (B, T), generator=torch.Generator().manual_seed(11)).cuda()
     outs = {}
-    for direct in (True, False):
+    for mode in ("rows", "direct", "planes"):
         eng = _model(cfg, sd, decoder_precision=decoder_precision).engine()
-        eng.post_direct = direct
-        outs[direct] = eng.decode(idx, mask)
-    ref = outs[False]
-    err = float((outs[True] - ref).abs().max())
-    print("post direct vs tap planes: max abs diff", err, "max |ref|", float(ref.abs().max()))
-    # bf16 decoder: identical bf16 inputs, fp32 sums in another order; f16x2: three product segments per tap
-    assert err <= (2e-5 if decoder_precision == "bf16" else 2e-6) * max(1.0, float(ref.abs().max()))
-    assert torch.equal(outs[True][1, 133:], ref[1, 133:])          # masked frames: x_recon only, both ways
+        eng.post_mode = mode
+        outs[mode] = eng.decode(idx, mask)
+    ref = outs["planes"]
+    for mode in ("rows", "direct"):
+        err = float((outs[mode] - ref).abs().max())
+        print("post", mode, "vs tap planes: max abs diff", err, "max |ref|", float(ref.abs().max()))
+        # bf16 decoder: identical bf16 inputs, fp32 sums in another order; f16x2: three product segments per tap
+        assert err <= (2e-5 if decoder_precision == "bf16" else 2e-6) * max(1.0, float(ref.abs().max()))
+        assert torch.equal(outs[mode][1, 133:], ref[1, 133:])          # masked frames: x_recon only, every way
 
 
 def test_decode_in_length_groups_hifispeech_sizes():
