@@ -482,3 +482,26 @@ def test_native_npy_io_property_random_shapes_and_dtypes(tmp_path):
     check()
     bad = np.full((2, 3), np.nan, np.float32)
     assert lib.mq_npy_read_f32(path, bad.ctypes.data, 2, 999, None) in (1, 4, 5)      # column mismatch is reported, not read
+
+
+def test_refiner_post_row_sum_decomposition():
+    """The engine runs refiner.post (C -> 1, 3x3; reference preencoder.py:191) as a one-row convolution with three output
+    channels (channel dt + 1 = kernel row dt along F) whose outputs the tail adds down T: P0[t-1] + P1[t] + P2[t+1].
+    Same weights, same zero padding - checked here against F.conv2d with the packing the engine uses."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    C, T, Fq = 8, 11, 13
+    w = torch.randn(1, C, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(2, C, T, Fq, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w, padding=1)[:, 0]
+    wr = torch.zeros(4, C, 3, dtype=torch.float64)
+    wr[:3] = w[0].permute(1, 0, 2)                                   # engine.py: (dt, C, df)
+    P = F.conv2d(x, wr.unsqueeze(2), padding=(0, 1))                 # (B, 4, T, F): a 1x3 convolution per output channel
+    Pz = F.pad(P, (0, 0, 1, 1))                                      # zero rows above and below the image
+    got = Pz[:, 0, 0:T] + Pz[:, 1, 1:T + 1] + Pz[:, 2, 2:T + 2]      # P0[t-1] + P1[t] + P2[t+1]
+    assert torch.allclose(got, ref, atol=1e-12, rtol=0)
+    assert float(P[:, 3].abs().max()) == 0.0                         # the fourth (padding) channel stays zero
+    pc = ops.pack_conv(wr.float(), None, "taps2d", False, taps=([0, 0, 0], [-1, 0, 1]))
+    assert (pc.taps, pc.tap_dh[:3], pc.tap_dw[:3], pc.cout, pc.bn) == (3, [0, 0, 0], [-1, 0, 1], 4, 32)
+    # K order of the packed weight: tap-major, then channel (padded to 64)
+    assert torch.equal(pc.wpack[2, 64:64 + C].float(), wr[2, :, 1].float().to(torch.bfloat16).float())
